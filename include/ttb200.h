@@ -1,0 +1,156 @@
+/* ttb200.h -- C ABI of libttb200.so: the B200 (sm_100a) hot path of TensorTrains.jl.
+ *
+ * The reference (stecrotti/TensorTrains.jl v0.14.0, pure Julia) has no FFI of its own; the seam is
+ * Julia dispatch on the storage type of TensorTrain{F,N,T,Z} / PeriodicTensorTrain{F,N,T,Z}
+ * (src/tensor_train.jl:8-12, src/periodic_tensor_train.jl:8-12).  Each entry point below names the
+ * reference method it replaces (file:line relative to the reference root).  INTEGRATION.md shows the
+ * `ccall` stubs a maintainer adds on the Julia side and the ctypes mirror used in this repo.
+ *
+ * Conventions
+ *  - Float64 only.  Site tensor t (0-based) has dims (d_t, d_{t+1}, Q), Q = prod(q), COLUMN-MAJOR
+ *    exactly like the Julia arrays: element (m,n,x) at m + d_t*(n + d_{t+1}*x).
+ *  - A handle owns the device memory of `batch` tensor trains that share L, Q and the ORIGINAL bond
+ *    dimensions (capacity); current bond dimensions are tracked per train and only ever shrink.
+ *  - Host buffers are caller-owned.  Every call is synchronous on return and returns a status code;
+ *    nothing throws or aborts across the boundary.  ttb_last_error() gives the message (thread-local).
+ *  - z (LogarithmicNumbers.Logarithmic in the reference) crosses the boundary as (log|z|, sign).
+ */
+#ifndef TTB200_H
+#define TTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttb_tt* ttb_handle;
+
+enum {
+  TTB_OK = 0,
+  TTB_EINVAL = 1,       /* ArgumentError in the reference (bad indices / is_orthogonal / arguments) */
+  TTB_ESHAPE = 2,       /* ArgumentError: incompatible bond dimensions / boundary bonds != 1       */
+  TTB_ENEGATIVE = 3,    /* ErrorException("Cannot sample from a tensor train with negative values") */
+  TTB_ENONFINITE = 4,   /* NaN/Inf met where the reference would propagate it                        */
+  TTB_ECUDA = 5,        /* CUDA runtime error (message has the CUDA string)                          */
+  TTB_ENOMEM = 6,
+  TTB_EUNSUPPORTED = 7, /* shape outside what the kernels cover (message says which limit)          */
+  TTB_EDOMAIN = 8       /* DomainError: log of a negative normalization                              */
+};
+
+/* SVD truncation policy: src/svd_trunc.jl:33-50 (THRESH), :69-77 (BOND), :91-103 (BONDMAX),
+ * :123-143 (BONDTHRESH).  The rank rule runs on the device right after the factorisation. */
+enum { TTB_TRUNC_THRESH = 0, TTB_TRUNC_BOND = 1, TTB_TRUNC_BONDMAX = 2, TTB_TRUNC_BONDTHRESH = 3 };
+typedef struct {
+  int32_t kind;
+  int32_t _pad;
+  double eps;     /* THRESH, BONDTHRESH */
+  int64_t mprime; /* BOND, BONDMAX, BONDTHRESH */
+} ttb_trunc;
+
+/* is_orthogonal of compress! (src/abstract_tensor_train.jl:261-274) */
+enum { TTB_ORTH_NONE = 0, TTB_ORTH_LEFT = 1, TTB_ORTH_RIGHT = 2 };
+
+int ttb_version(void);
+const char* ttb_last_error(void);
+int ttb_device_count(int* n);
+int ttb_set_device(int dev);
+
+/* pinned host staging memory for the e2e path */
+int ttb_host_alloc(void** p, size_t bytes);
+int ttb_host_free(void* p);
+
+/* ---- container: TensorTrain / PeriodicTensorTrain (src/tensor_train.jl:8-24,
+ *      src/periodic_tensor_train.jl:8-27; validation = check_bond_dims,
+ *      src/abstract_tensor_train.jl:40-52).  bond has L+1 entries; open trains need
+ *      bond[0]==bond[L]==1, periodic ones bond[L]==bond[0].  z starts at 1. */
+int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_handle* out);
+int ttb_destroy(ttb_handle h);
+int ttb_clone(ttb_handle h, ttb_handle* out); /* deepcopy */
+int ttb_info(ttb_handle h, int64_t* L, int64_t* Q, int* periodic, int64_t* batch);
+/* current bond dims of train b: L+1 entries (bond_dims(A) of the reference = the first L) */
+int ttb_get_bonds(ttb_handle h, int64_t b, int64_t* out);
+/* doubles needed by ttb_download_all for train b at its CURRENT dims */
+int ttb_nparams(ttb_handle h, int64_t b, int64_t* n); /* src/abstract_tensor_train.jl:31-37 */
+int ttb_upload_site(ttb_handle h, int64_t b, int64_t t, const double* host);
+int ttb_download_site(ttb_handle h, int64_t b, int64_t t, double* host);
+/* all sites of all trains, packed train-major then site-major, each at its current dims */
+int ttb_upload_all(ttb_handle h, const double* host);
+int ttb_download_all(ttb_handle h, double* host);
+int ttb_get_z(ttb_handle h, int64_t b, double* logabs, int* sign);
+int ttb_set_z(ttb_handle h, int64_t b, double logabs, int sign);
+
+/* ---- sweeps.  lo..hi are 1-based inclusive site indices like the reference's `indices`
+ *      (pass 0,0 for the default range).  Open right sweep needs hi==L and lo>=2
+ *      (src/tensor_train.jl:151-179); open left sweep needs lo==1 and hi<=L-1 (:190-218).
+ *      Periodic trains ignore lo/hi (src/periodic_tensor_train.jl:83-141). */
+int ttb_orthogonalize_right(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_t hi);
+int ttb_orthogonalize_left(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_t hi);
+/* orthogonalize_center! / orthogonalize_two_site_center! (src/tensor_train.jl:220-236) */
+int ttb_orthogonalize_center(ttb_handle h, const ttb_trunc* tr, int64_t l);
+int ttb_orthogonalize_two_site_center(ttb_handle h, const ttb_trunc* tr, int64_t k);
+/* compress! (src/abstract_tensor_train.jl:261-274) */
+int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal);
+/* per-bond results of the LAST sweep of train b: rank[i] = retained dimension of bond i (0 where the
+ * sweep did not touch bond i), err[i] = relative truncation error (the quantity _debug_svd prints,
+ * src/svd_trunc.jl:8-13; max over bonds = TruncBondMax.maxerr). Both have L+1 entries. */
+int ttb_sweep_stats(ttb_handle h, int64_t b, int64_t* rank, double* err);
+/* keep every singular-value vector of truncating sweeps (test/diagnostic aid; costs L*dmax doubles) */
+int ttb_record_spectrum(ttb_handle h, int on);
+/* singular values (descending, BEFORE truncation) seen at bond i in the last truncating sweep */
+int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t* n);
+/* is_left_canonical / is_right_canonical residual max|A'A - I| (src/tensor_train.jl:263-273) */
+int ttb_canonical_residual(ttb_handle h, int64_t b, int64_t t, int left, double* resid);
+
+/* ---- environments (src/abstract_tensor_train.jl:89-117).  l_out/r_out may be NULL; otherwise they
+ *      receive, per train, the L matrices packed site-major: l[t] is d_1 x d_{t+1}, r[t] is
+ *      d_t x d_{L+1}, column-major, with the reference's scaling (normalize!=0: stored l[t<L-1]
+ *      max-abs 1, last one unscaled; mirrored for r).  logabs/sign: one entry per train. */
+int ttb_env_size(ttb_handle h, int64_t b, int left, int64_t* n_doubles);
+int ttb_accumulate_L(ttb_handle h, int normalize, double* l_out, double* logabs, int* sign);
+int ttb_accumulate_R(ttb_handle h, int normalize, double* r_out, double* logabs, int* sign);
+/* normalization(A) = accumulate_L(A)[2] / A.z   (src/abstract_tensor_train.jl:154-157) */
+int ttb_normalization(ttb_handle h, double* logabs, int* sign);
+/* normalize!(A): returns log(|Z|/z_old) per train (src/abstract_tensor_train.jl:184-197) */
+int ttb_normalize(ttb_handle h, double* logz_out);
+/* normalize_eachmatrix! (src/abstract_tensor_train.jl:165-176) */
+int ttb_normalize_eachmatrix(ttb_handle h);
+/* marginals (src/abstract_tensor_train.jl:208-220): out[b][t][x], batch*L*Q doubles */
+int ttb_marginals(ttb_handle h, double* out);
+/* twovar_marginals (src/abstract_tensor_train.jl:231-254): pairs t<u<=t+maxdist in lexicographic
+ * order, each Q*Q doubles column-major (x_t fastest); *npairs receives the count per train. */
+int ttb_twovar_count(ttb_handle h, int64_t maxdist, int64_t* npairs);
+int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out);
+
+/* ---- evaluate (src/abstract_tensor_train.jl:80-83): X is n x L row-major int32 of 0-based flat
+ *      physical indices; evaluates train b at n points; out = tr(prod A_t(x_t)) / z */
+int ttb_evaluate(ttb_handle h, int64_t b, const int32_t* X, int64_t n, double* out);
+
+/* ---- sample (src/abstract_tensor_train.jl:335-384, draw = src/utils.jl:9-20) on train b.
+ *      Draw i uses uniforms[i*L + t] at site t when `uniforms` != NULL, else the Philox4x32-10 stream
+ *      key=(seed), counter=(first_index+i, t).  x_out: nsamples*L flat 0-based indices (uint8 when
+ *      Q<=256) ; p_out (nullable): the normalised probability of each draw, tr(Q)/z_R. */
+int ttb_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
+               const double* uniforms, uint8_t* x_out, double* p_out);
+/* device-resident variant for throughput runs: draws stay in HBM, only site histograms
+ * (L*Q int64, accumulated) come back.  hist may be NULL. */
+int ttb_sample_stats(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
+                     int64_t* hist, double* sum_logp);
+
+/* ---- dot / norm (src/abstract_tensor_train.jl:395-432), same-shape-class trains a[ba], b[bb] */
+int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, double* out);
+
+/* timing aid for bench.py: milliseconds spent on the device inside the last call that ran kernels
+ * (CUDA events on the handle's stream) and how many kernels it launched */
+int ttb_last_timing(ttb_handle h, double* ms, int64_t* launches);
+
+/* per-kernel profiling for the roofline: after ttb_profile(h,1) every kernel launch of this handle is
+ * bracketed by CUDA events; ttb_profile_report writes lines "<kernel> <launches> <total ms>". */
+int ttb_profile(ttb_handle h, int on);
+int ttb_profile_report(ttb_handle h, char* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTB200_H */

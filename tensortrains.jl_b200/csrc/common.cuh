@@ -1,0 +1,186 @@
+// common.cuh -- handle layout, error plumbing and small device helpers shared by the ttb200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ttb200.h"
+
+namespace ttb {
+
+extern thread_local std::string g_err;
+int fail(int code, const char* fmt, ...);
+
+#define TTB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ttb::fail(TTB_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define TTB_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != TTB_OK) return rc__; \
+  } while (0)
+
+// device status bits (ttb_tt::d_status)
+enum { ST_NEGATIVE = 1, ST_NONFINITE = 2, ST_NOCONV = 4 };
+
+// per-train state of the sweep step in flight
+struct StepState {
+  int mprime;                        // retained rank of the current step (written by the rank rule)
+  int pad;
+  unsigned long long maxabs_bits[2]; // max|D| of the absorb output, as ordered bits (ping-pong)
+};
+
+struct Workspace {
+  // sweep
+  double* X[2] = {nullptr, nullptr};  // folded site / absorb output, p_max x n_max col-major
+  int64_t x_stride = 0;
+  double* T = nullptr;                // compact-WY T factors, n_max x bw
+  int64_t t_stride = 0;
+  double* Bv = nullptr;               // Jacobi vectors [nv][ldv]  (rows of R or of X)
+  double* Jv = nullptr;               // accumulated rotations, vector-major [nv][ldj]
+  int64_t bv_stride = 0, jv_stride = 0;
+  int ldv = 0, ldj = 0;
+  int* perm = nullptr;                // [n_max] order of singular values (descending)
+  double* sigma = nullptr;            // [n_max]
+  StepState* st = nullptr;            // [batch]
+  double* stat_err = nullptr;         // [batch][L+1]
+  int* stat_rank = nullptr;           // [batch][L+1]
+  double* spectrum = nullptr;         // [batch][L+1][n_max] (optional)
+  int p_max = 0, n_max = 0, bw = 0;
+  bool sweep_ready = false;
+  // environments
+  double* envL = nullptr;             // [batch][env_stride]
+  double* envR = nullptr;
+  int64_t env_stride = 0;
+  double* env_log = nullptr;          // [batch] log|z| of the last accumulate
+  int* env_sign = nullptr;            // [batch]
+  bool env_ready = false;
+};
+
+}  // namespace ttb
+
+namespace ttb {
+struct ProfEvent { const char* name; cudaEvent_t a, b; };
+}
+
+struct ttb_tt {
+  bool prof_on = false;
+  std::vector<ttb::ProfEvent> prof;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t L = 0, Q = 0, batch = 0;
+  int periodic = 0;
+  std::vector<int64_t> bond0;  // original (capacity) bonds, L+1
+  std::vector<int64_t> off;    // per-site offset in doubles, L+1 entries (off[L] = used length)
+  int64_t tt_stride = 0;       // doubles per train
+  int64_t dmax = 0;            // largest original bond
+  double* slab = nullptr;      // batch * tt_stride
+  int64_t* d_off = nullptr;    // device copy of off
+  int* d_bond = nullptr;       // [batch][L+1] current bonds (device)
+  std::vector<int> h_bond;     // host mirror
+  double* d_logz = nullptr;    // [batch]
+  int* d_signz = nullptr;      // [batch]
+  int* d_status = nullptr;     // [1]
+  ttb::Workspace ws;
+  bool record_spectrum = false;
+  double last_ms = 0.0;
+  int64_t last_launches = 0;
+  int64_t launches = 0;        // running counter inside a call
+};
+
+namespace ttb {
+
+// RAII-ish timing bracket used by every entry point that launches kernels
+struct CallTimer {
+  ttb_tt* h;
+  explicit CallTimer(ttb_tt* h_) : h(h_) {
+    h->launches = 0;
+    cudaEventRecord(h->ev0, h->stream);
+  }
+  int finish() {
+    cudaEventRecord(h->ev1, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(TTB_ECUDA, "stream sync: %s", cudaGetErrorString(e));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TTB_ECUDA, "kernel: %s", cudaGetErrorString(e));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms = ms;
+    h->last_launches = h->launches;
+    return TTB_OK;
+  }
+};
+
+int check_handle(ttb_tt* h);
+void prof_pre(ttb_tt* h, const char* name);
+void prof_post(ttb_tt* h);
+// every kernel launch goes through this: counts the launch and, in profiling mode, brackets it with
+// CUDA events on the handle's stream (per-kernel device time for bench.py's roofline)
+#define TTB_LAUNCH(h, name, ...)     \
+  do {                               \
+    ttb::prof_pre((h), (name));      \
+    __VA_ARGS__;                     \
+    ttb::prof_post((h));             \
+    (h)->launches++;                 \
+  } while (0)
+int sync_bonds_to_host(ttb_tt* h);
+int ensure_sweep_ws(ttb_tt* h);
+int ensure_env_ws(ttb_tt* h);
+int read_status(ttb_tt* h, int* st);  // reads and clears the device status word
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` must hold >= 33 doubles; all threads get the result
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+// max-abs with NaN propagation (fmax drops NaN, the reference's maximum(abs, .) keeps it)
+__device__ __forceinline__ double absmax_nan(double acc, double v) {
+  double a = fabs(v);
+  return (a != a || acc != acc) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(acc, a);
+}
+
+}  // namespace ttb

@@ -1,0 +1,352 @@
+// container.cu -- device container behind TensorTrain / PeriodicTensorTrain
+// (reference: src/tensor_train.jl:8-24, src/periodic_tensor_train.jl:8-27,
+//  check_bond_dims src/abstract_tensor_train.jl:40-52).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ttb {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int check_handle(ttb_tt* h) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return TTB_OK;
+}
+
+void prof_pre(ttb_tt* h, const char* name) {
+  if (!h->prof_on) return;
+  ProfEvent e;
+  e.name = name;
+  cudaEventCreate(&e.a);
+  cudaEventCreate(&e.b);
+  cudaEventRecord(e.a, h->stream);
+  h->prof.push_back(e);
+}
+void prof_post(ttb_tt* h) {
+  if (!h->prof_on) return;
+  cudaEventRecord(h->prof.back().b, h->stream);
+}
+
+int sync_bonds_to_host(ttb_tt* h) {
+  TTB_CUDA(cudaMemcpyAsync(h->h_bond.data(), h->d_bond, sizeof(int) * h->h_bond.size(), cudaMemcpyDeviceToHost,
+                           h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+int read_status(ttb_tt* h, int* st) {
+  TTB_CUDA(cudaMemcpyAsync(st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  if (*st) TTB_CUDA(cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
+  return TTB_OK;
+}
+
+static void free_ws(ttb_tt* h) {
+  Workspace& w = h->ws;
+  cudaFree(w.X[0]); cudaFree(w.X[1]); cudaFree(w.T); cudaFree(w.Bv); cudaFree(w.Jv);
+  cudaFree(w.perm); cudaFree(w.sigma); cudaFree(w.st); cudaFree(w.stat_err); cudaFree(w.stat_rank);
+  cudaFree(w.spectrum); cudaFree(w.envL); cudaFree(w.envR); cudaFree(w.env_log); cudaFree(w.env_sign);
+  w = Workspace();
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_version(void) { return 100; }
+const char* ttb_last_error(void) { return g_err.c_str(); }
+
+int ttb_device_count(int* n) {
+  if (!n) return fail(TTB_EINVAL, "null argument");
+  TTB_CUDA(cudaGetDeviceCount(n));
+  return TTB_OK;
+}
+int ttb_set_device(int dev) {
+  TTB_CUDA(cudaSetDevice(dev));
+  return TTB_OK;
+}
+int ttb_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(TTB_EINVAL, "null argument");
+  TTB_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return TTB_OK;
+}
+int ttb_host_free(void* p) {
+  TTB_CUDA(cudaFreeHost(p));
+  return TTB_OK;
+}
+
+int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_handle* out) {
+  if (!bond || !out) return fail(TTB_EINVAL, "null argument");
+  if (L < 1 || Q < 1 || batch < 1) return fail(TTB_EINVAL, "L, Q and batch must be >= 1 (got %lld, %lld, %lld)",
+                                               (long long)L, (long long)Q, (long long)batch);
+  for (int64_t t = 0; t <= L; ++t)
+    if (bond[t] < 1) return fail(TTB_ESHAPE, "bond %lld is %lld, must be >= 1", (long long)t, (long long)bond[t]);
+  if (!periodic && !(bond[0] == 1 && bond[L] == 1))
+    return fail(TTB_ESHAPE, "First matrix must have 1 row, last matrix must have 1 column");
+  if (periodic && bond[L] != bond[0])
+    return fail(TTB_ESHAPE, "Matrix indices for matrix product non compatible (bond[L]=%lld != bond[0]=%lld)",
+                (long long)bond[L], (long long)bond[0]);
+  ttb_tt* h = new ttb_tt();
+  cudaGetDevice(&h->device);
+  h->L = L; h->Q = Q; h->batch = batch; h->periodic = periodic ? 1 : 0;
+  h->bond0.assign(bond, bond + L + 1);
+  h->off.resize(L + 1);
+  int64_t o = 0;
+  h->dmax = 0;
+  for (int64_t t = 0; t < L; ++t) {
+    h->off[t] = o;
+    int64_t n = bond[t] * bond[t + 1] * Q;
+    o += (n + 15) & ~int64_t(15);  // keep every site 128-byte aligned
+    h->dmax = std::max(h->dmax, std::max(bond[t], bond[t + 1]));
+  }
+  h->off[L] = o;
+  h->tt_stride = o;
+  if (h->dmax > (1 << 20) || h->dmax * Q > (int64_t(1) << 28)) {
+    delete h;
+    return fail(TTB_EUNSUPPORTED, "bond*Q too large");
+  }
+  auto bail = [&](cudaError_t e, const char* what) {
+    int rc = fail(e == cudaErrorMemoryAllocation ? TTB_ENOMEM : TTB_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    ttb_destroy(h);
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "event");
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "event");
+  if ((e = cudaMalloc(&h->slab, sizeof(double) * batch * h->tt_stride)) != cudaSuccess) return bail(e, "slab");
+  if ((e = cudaMemsetAsync(h->slab, 0, sizeof(double) * batch * h->tt_stride, h->stream)) != cudaSuccess)
+    return bail(e, "memset");
+  if ((e = cudaMalloc(&h->d_off, sizeof(int64_t) * (L + 1))) != cudaSuccess) return bail(e, "off");
+  if ((e = cudaMalloc(&h->d_bond, sizeof(int) * batch * (L + 1))) != cudaSuccess) return bail(e, "bond");
+  if ((e = cudaMalloc(&h->d_logz, sizeof(double) * batch)) != cudaSuccess) return bail(e, "logz");
+  if ((e = cudaMalloc(&h->d_signz, sizeof(int) * batch)) != cudaSuccess) return bail(e, "signz");
+  if ((e = cudaMalloc(&h->d_status, sizeof(int))) != cudaSuccess) return bail(e, "status");
+  h->h_bond.resize(batch * (L + 1));
+  for (int64_t b = 0; b < batch; ++b)
+    for (int64_t t = 0; t <= L; ++t) h->h_bond[b * (L + 1) + t] = (int)bond[t];
+  std::vector<int> ones(batch, 1);
+  cudaMemcpyAsync(h->d_off, h->off.data(), sizeof(int64_t) * (L + 1), cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(h->d_bond, h->h_bond.data(), sizeof(int) * h->h_bond.size(), cudaMemcpyHostToDevice, h->stream);
+  cudaMemsetAsync(h->d_logz, 0, sizeof(double) * batch, h->stream);
+  cudaMemcpyAsync(h->d_signz, ones.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, h->stream);
+  cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(e, "init");
+  *out = h;
+  return TTB_OK;
+}
+
+int ttb_destroy(ttb_handle h) {
+  if (!h) return TTB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_ws(h);
+  cudaFree(h->slab); cudaFree(h->d_off); cudaFree(h->d_bond); cudaFree(h->d_logz); cudaFree(h->d_signz);
+  cudaFree(h->d_status);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TTB_OK;
+}
+
+int ttb_clone(ttb_handle h, ttb_handle* out) {
+  TTB_TRY(check_handle(h));
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  ttb_handle c = nullptr;
+  TTB_TRY(ttb_create(h->L, h->bond0.data(), h->Q, h->periodic, h->batch, &c));
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpyAsync(c->slab, h->slab, sizeof(double) * h->batch * h->tt_stride, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(c->d_bond, h->d_bond, sizeof(int) * h->h_bond.size(), cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(c->d_logz, h->d_logz, sizeof(double) * h->batch, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(c->d_signz, h->d_signz, sizeof(int) * h->batch, cudaMemcpyDeviceToDevice, c->stream);
+  c->h_bond = h->h_bond;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    ttb_destroy(c);
+    return fail(TTB_ECUDA, "clone: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return TTB_OK;
+}
+
+int ttb_info(ttb_handle h, int64_t* L, int64_t* Q, int* periodic, int64_t* batch) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  if (L) *L = h->L;
+  if (Q) *Q = h->Q;
+  if (periodic) *periodic = h->periodic;
+  if (batch) *batch = h->batch;
+  return TTB_OK;
+}
+
+static int check_bt(ttb_tt* h, int64_t b, int64_t t) {
+  if (b < 0 || b >= h->batch) return fail(TTB_EINVAL, "train index %lld out of range 0:%lld", (long long)b, (long long)h->batch - 1);
+  if (t < 0 || t >= h->L) return fail(TTB_EINVAL, "site index %lld out of range 0:%lld", (long long)t, (long long)h->L - 1);
+  return TTB_OK;
+}
+
+int ttb_get_bonds(ttb_handle h, int64_t b, int64_t* out) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, 0));
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  for (int64_t t = 0; t <= h->L; ++t) out[t] = h->h_bond[b * (h->L + 1) + t];
+  return TTB_OK;
+}
+
+static int64_t site_len(ttb_tt* h, int64_t b, int64_t t) {
+  const int* bd = &h->h_bond[b * (h->L + 1)];
+  return (int64_t)bd[t] * bd[t + 1] * h->Q;
+}
+
+int ttb_nparams(ttb_handle h, int64_t b, int64_t* n) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, 0));
+  int64_t s = 0;
+  for (int64_t t = 0; t < h->L; ++t) s += site_len(h, b, t);
+  *n = s;
+  return TTB_OK;
+}
+
+int ttb_upload_site(ttb_handle h, int64_t b, int64_t t, const double* host) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, t));
+  TTB_CUDA(cudaMemcpyAsync(h->slab + b * h->tt_stride + h->off[t], host, sizeof(double) * site_len(h, b, t),
+                           cudaMemcpyHostToDevice, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+int ttb_download_site(ttb_handle h, int64_t b, int64_t t, double* host) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, t));
+  TTB_CUDA(cudaMemcpyAsync(host, h->slab + b * h->tt_stride + h->off[t], sizeof(double) * site_len(h, b, t),
+                           cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+// Copies between a packed host buffer and the slab, merging device-contiguous runs of sites into one
+// cudaMemcpyAsync (a site is followed contiguously when its current length equals its padded capacity).
+static int copy_all(ttb_tt* h, double* host, bool to_device) {
+  double* p = host;
+  int64_t run_dev = -1, run_len = 0;
+  double* run_host = nullptr;
+  auto flush = [&]() -> cudaError_t {
+    if (run_len == 0) return cudaSuccess;
+    cudaError_t e = to_device ? cudaMemcpyAsync(h->slab + run_dev, run_host, sizeof(double) * run_len,
+                                                cudaMemcpyHostToDevice, h->stream)
+                              : cudaMemcpyAsync(run_host, h->slab + run_dev, sizeof(double) * run_len,
+                                                cudaMemcpyDeviceToHost, h->stream);
+    run_len = 0;
+    return e;
+  };
+  for (int64_t b = 0; b < h->batch; ++b)
+    for (int64_t t = 0; t < h->L; ++t) {
+      int64_t n = site_len(h, b, t);
+      int64_t dev = b * h->tt_stride + h->off[t];
+      if (run_len > 0 && dev == run_dev + run_len) {
+        run_len += n;
+      } else {
+        TTB_CUDA(flush());
+        run_dev = dev; run_host = p; run_len = n;
+      }
+      p += n;
+    }
+  TTB_CUDA(flush());
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+int ttb_upload_all(ttb_handle h, const double* host) {
+  TTB_TRY(check_handle(h));
+  if (!host) return fail(TTB_EINVAL, "null argument");
+  return copy_all(h, const_cast<double*>(host), true);
+}
+
+int ttb_download_all(ttb_handle h, double* host) {
+  TTB_TRY(check_handle(h));
+  if (!host) return fail(TTB_EINVAL, "null argument");
+  return copy_all(h, host, false);
+}
+
+int ttb_get_z(ttb_handle h, int64_t b, double* logabs, int* sign) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, 0));
+  TTB_CUDA(cudaMemcpyAsync(logabs, h->d_logz + b, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(sign, h->d_signz + b, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+int ttb_set_z(ttb_handle h, int64_t b, double logabs, int sign) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_bt(h, b, 0));
+  int s = sign < 0 ? -1 : 1;
+  TTB_CUDA(cudaMemcpyAsync(h->d_logz + b, &logabs, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(h->d_signz + b, &s, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+int ttb_record_spectrum(ttb_handle h, int on) {
+  TTB_TRY(check_handle(h));
+  h->record_spectrum = on != 0;
+  return TTB_OK;
+}
+
+int ttb_profile(ttb_handle h, int on) {
+  TTB_TRY(check_handle(h));
+  for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  h->prof.clear();
+  h->prof_on = on != 0;
+  return TTB_OK;
+}
+
+int ttb_profile_report(ttb_handle h, char* out, size_t cap) {
+  TTB_TRY(check_handle(h));
+  if (!out || cap == 0) return fail(TTB_EINVAL, "null argument");
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  struct Acc { const char* name; long n; double ms; };
+  std::vector<Acc> acc;
+  for (auto& e : h->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    bool found = false;
+    for (auto& a : acc)
+      if (strcmp(a.name, e.name) == 0) { a.n++; a.ms += ms; found = true; break; }
+    if (!found) acc.push_back({e.name, 1, (double)ms});
+  }
+  std::string s;
+  char line[256];
+  for (auto& a : acc) {
+    snprintf(line, sizeof(line), "%s %ld %.6f\n", a.name, a.n, a.ms);
+    s += line;
+  }
+  snprintf(out, cap, "%s", s.c_str());
+  return TTB_OK;
+}
+
+int ttb_last_timing(ttb_handle h, double* ms, int64_t* launches) {
+  if (!h) return fail(TTB_EINVAL, "null handle");
+  if (ms) *ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  return TTB_OK;
+}
+
+}  // extern "C"

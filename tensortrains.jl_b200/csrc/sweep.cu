@@ -1,0 +1,997 @@
+// sweep.cu -- orthogonalize_right!/left! and compress! on the device.
+//
+// Reference: src/tensor_train.jl:151-218, src/periodic_tensor_train.jl:83-141,
+//            src/abstract_tensor_train.jl:261-274, rank rules src/svd_trunc.jl:33-143.
+//
+// One sweep step factorises the folded site X (p x n, p = bond*Q) as X ~= W * S with W (p x m')
+// orthonormal and S = W^T X (m' x n); W becomes the new site tensor, S is absorbed into the
+// neighbour (D = S * C_nbr(x) or C_nbr(x) * S^T), D is max-abs rescaled and becomes the next X.
+// Both sweep directions share this form: the right sweep factorises X = M^T, the left sweep X = M.
+//   * eps = 0 TruncThresh steps keep every direction, so W S = Q R from a blocked Householder QR
+//     (gauge-equivalent to the reference's U / lambda V^T; only gauge-invariant results are compared).
+//   * truncating steps: tall X -> QR then one-sided (Hestenes) Jacobi on the rows of R with the
+//     rotations accumulated in J; wide X -> Jacobi directly on the rows of X.  The rotated rows ARE
+//     S = Sigma V^T, W = Q J[:, sel] (or J[:, sel]); the rank rule runs in the same kernel so the
+//     retained bond never visits the host.  Jacobi keeps the tiny singular values accurate to
+//     O(eps * sigma_1), which the TruncThresh(1e-10) rank decision needs (a Gram-based SVD does not).
+// All kernels read the current dimensions from the device bond array; a whole sweep is enqueued with
+// no host synchronisation.
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ttb {
+
+struct SweepCtx {
+  double* slab; int64_t tt_stride; const int64_t* off; int* bond; int L1; int Q;
+  double* X0; double* X1; int64_t x_stride;
+  double* T; int64_t t_stride; int bw;
+  double* Bv; double* Jv; int64_t bv_stride, jv_stride; int ldv, ldj;
+  int* perm; double* sigma; int n_max;
+  StepState* st;
+  double* logz;
+  double* stat_err; int* stat_rank; double* spectrum;
+  int* status;
+};
+
+struct StepDesc {
+  int site, nbr, dir;      // dir 0 = right sweep (X = M^T), 1 = left sweep (X = M)
+  int xin;                 // which X buffer holds the folded input
+  int rescale;             // max-abs rescale of the absorb output (0 only on the periodic wrap step)
+  int qr_only;             // TruncThresh(0): keep everything -> QR
+  int kind; double eps; int cap;
+  int bond_idx, bond_idx2; // bond entries that receive m'
+  int last;                // absorb output goes to the neighbour's site storage
+  int slot;                // maxabs ping-pong slot
+};
+
+struct Dims { int p, n, k, mode, N; };  // mode 0 = QR, 1 = SVD tall (p>=n), 2 = SVD wide
+
+__device__ __forceinline__ Dims get_dims(const SweepCtx& c, const StepDesc& s, int b) {
+  const int* bond = c.bond + (int64_t)b * c.L1;
+  Dims d;
+  if (s.dir == 0) { d.p = bond[s.site + 1] * c.Q; d.n = bond[s.site]; d.N = bond[s.nbr]; }
+  else            { d.p = bond[s.site] * c.Q;     d.n = bond[s.site + 1]; d.N = bond[s.nbr + 1]; }
+  d.k = min(d.p, d.n);
+  d.mode = s.qr_only ? 0 : (d.p >= d.n ? 1 : 2);
+  return d;
+}
+
+__device__ __forceinline__ double* xbuf(const SweepCtx& c, int which, int b) {
+  return (which ? c.X1 : c.X0) + (int64_t)b * c.x_stride;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold: site storage -> X   (src/tensor_train.jl:159 right: free reshape, we store its transpose;
+//                            :198 left: M[(m,x),n] |= C[m,n,x])
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fold(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  const double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.site];
+  double* X = xbuf(c, s.xin, b);
+  const int64_t tot = (int64_t)d.p * d.n;
+  const int dl = d.p / c.Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    if (s.dir == 0) {
+      // site = X row-major (ld n): read coalesced, write strided
+      const int j = (int)(i % d.n); const int r = (int)(i / d.n);
+      X[r + (int64_t)d.p * j] = site[i];
+    } else {
+      const int r = (int)(i % d.p); const int j = (int)(i / d.p);
+      const int m = r % dl, x = r / dl;
+      X[i] = site[m + (int64_t)dl * (j + (int64_t)d.n * x)];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked Householder QR: panel factorisation (one CTA per train)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_qr_panel(SweepCtx c, StepDesc s, int panel) {
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 2) return;
+  const int bw = c.bw;
+  const int j0 = panel * bw;
+  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime = d.k;
+  if (j0 >= d.k) return;
+  const int bwc = min(bw, d.k - j0);
+  const int rows = d.p - j0;
+  double* X = xbuf(c, s.xin, b);
+  extern __shared__ double sm[];
+  double* Tm = sm;                 // bw*bw
+  double* G = Tm + bw * bw;        // bw*bw
+  double* tau = G + bw * bw;       // bw
+  double* w = tau + bw;            // bw
+  double* red = w + bw;            // 40
+  double* P = red + 40;            // rows*bwc
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+
+  for (int i = tid; i < rows * bwc; i += nt) {
+    const int r = i % rows, cc = i / rows;
+    P[i] = X[(j0 + r) + (int64_t)d.p * (j0 + cc)];
+  }
+  for (int i = tid; i < bw * bw; i += nt) { Tm[i] = 0.0; G[i] = 0.0; }
+  __syncthreads();
+
+  for (int cc = 0; cc < bwc; ++cc) {
+    double* col = P + (size_t)rows * cc;
+    double part = 0.0;
+    for (int r = cc + 1 + tid; r < rows; r += nt) part += col[r] * col[r];
+    const double xn2 = block_sum(part, red);
+    const double alpha = col[cc];
+    double tc = 0.0;
+    if (xn2 > 0.0) {
+      const double beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+      tc = (beta - alpha) / beta;
+      const double scal = 1.0 / (alpha - beta);
+      __syncthreads();  // everyone has read alpha
+      for (int r = cc + 1 + tid; r < rows; r += nt) col[r] *= scal;
+      if (tid == 0) col[cc] = beta;
+    }
+    if (tid == 0) tau[cc] = tc;
+    __syncthreads();
+    if (tc != 0.0 && cc + 1 < bwc) {
+      for (int c2 = cc + 1 + wid; c2 < bwc; c2 += nw) {
+        const double* col2 = P + (size_t)rows * c2;
+        double sacc = 0.0;
+        for (int r = cc + 1 + lane; r < rows; r += 32) sacc += col[r] * col2[r];
+        sacc = warp_sum(sacc);
+        if (lane == 0) w[c2] = tc * (sacc + col2[cc]);
+      }
+      __syncthreads();
+      const int hr = rows - cc, hc = bwc - cc - 1;
+      for (int i = tid; i < hr * hc; i += nt) {
+        const int r = cc + i % hr, c2 = cc + 1 + i / hr;
+        const double vr = (r == cc) ? 1.0 : col[r];
+        P[r + (size_t)rows * c2] -= vr * w[c2];
+      }
+      __syncthreads();
+    }
+  }
+  // Gram of the unit-lower-trapezoidal V for the compact-WY T factor (dlarft, forward columnwise)
+  for (int pr = wid; pr < bwc * bwc; pr += nw) {
+    const int l = pr % bwc, c2 = pr / bwc;
+    if (l >= c2) continue;
+    const double* cl = P + (size_t)rows * l;
+    const double* cr = P + (size_t)rows * c2;
+    double sacc = 0.0;
+    for (int r = c2 + 1 + lane; r < rows; r += 32) sacc += cl[r] * cr[r];
+    sacc = warp_sum(sacc);
+    if (lane == 0) G[l + bw * c2] = sacc + cl[c2];
+  }
+  __syncthreads();
+  if (wid == 0) {
+    for (int c2 = 0; c2 < bwc; ++c2) {
+      const double tc = tau[c2];
+      if (lane == c2) Tm[c2 + bw * c2] = tc;
+      if (lane < c2) {
+        double acc = 0.0;
+        for (int l = lane; l < c2; ++l) acc += Tm[lane + bw * l] * G[l + bw * c2];
+        Tm[lane + bw * c2] = -tc * acc;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < rows * bwc; i += nt) {
+    const int r = i % rows, cc = i / rows;
+    X[(j0 + r) + (int64_t)d.p * (j0 + cc)] = P[i];
+  }
+  double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * bw * bw;
+  for (int i = tid; i < bw * bw; i += nt) Tg[i] = Tm[i];
+}
+
+// trailing update  A <- (I - V T^T V^T) A  for one chunk of columns
+__global__ void k_qr_update(SweepCtx c, StepDesc s, int panel, int cw) {
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 2) return;
+  const int bw = c.bw;
+  const int j0 = panel * bw;
+  if (j0 >= d.k) return;
+  const int bwc = min(bw, d.k - j0);
+  const int rows = d.p - j0;
+  const int jc0 = j0 + bwc + blockIdx.x * cw;
+  if (jc0 >= d.n) return;
+  const int cwc = min(cw, d.n - jc0);
+  double* X = xbuf(c, s.xin, b);
+  extern __shared__ double sm[];
+  double* Ts = sm;                    // bw*bw
+  double* W = Ts + bw * bw;           // bw*cw
+  double* W2 = W + bw * cw;           // bw*cw
+  double* Vs = W2 + bw * cw;          // rows*bwc
+  double* As = Vs + (size_t)rows * bwc;  // rows*cwc
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * bw * bw;
+  for (int i = tid; i < bw * bw; i += nt) Ts[i] = Tg[i];
+  for (int i = tid; i < rows * bwc; i += nt) {
+    const int r = i % rows, cc = i / rows;
+    Vs[i] = r > cc ? X[(j0 + r) + (int64_t)d.p * (j0 + cc)] : (r == cc ? 1.0 : 0.0);
+  }
+  for (int i = tid; i < rows * cwc; i += nt) {
+    const int r = i % rows, cc = i / rows;
+    As[i] = X[(j0 + r) + (int64_t)d.p * (jc0 + cc)];
+  }
+  __syncthreads();
+  for (int o = wid; o < bwc * cwc; o += nw) {
+    const int i = o % bwc, cc = o / bwc;
+    const double* v = Vs + (size_t)rows * i;
+    const double* a = As + (size_t)rows * cc;
+    double acc = 0.0;
+    for (int r = i + lane; r < rows; r += 32) acc += v[r] * a[r];
+    acc = warp_sum(acc);
+    if (lane == 0) W[i + bw * cc] = acc;
+  }
+  __syncthreads();
+  for (int o = tid; o < bwc * cwc; o += nt) {
+    const int i = o % bwc, cc = o / bwc;
+    double acc = 0.0;
+    for (int l = 0; l <= i; ++l) acc += Ts[l + bw * i] * W[l + bw * cc];
+    W2[i + bw * cc] = acc;
+  }
+  __syncthreads();
+  for (int o = tid; o < rows * cwc; o += nt) {
+    const int r = o % rows, cc = o / rows;
+    double acc = 0.0;
+    const int imax = min(r, bwc - 1);
+    for (int i = 0; i <= imax; ++i) acc += Vs[r + (size_t)rows * i] * W2[i + bw * cc];
+    X[(j0 + r) + (int64_t)d.p * (jc0 + cc)] = As[o] - acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// W = H_1 ... H_k * E for one chunk of columns, written straight into the site tensor
+// (unfold: src/tensor_train.jl:165 right, :204 left)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime;
+  const int c0 = blockIdx.x * cw;
+  if (c0 >= mprime) return;
+  const int cwc = min(cw, mprime - c0);
+  const int bw = c.bw, p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  extern __shared__ double sm[];
+  double* Ts = sm;                 // bw*bw
+  double* W = Ts + bw * bw;        // bw*cw
+  double* W2 = W + bw * cw;        // bw*cw
+  double* Wc = W2 + bw * cw;       // p*cwc
+  double* Vs = Wc + (size_t)p * cw;  // rows*bwc
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* Jv = c.Jv + (int64_t)b * c.jv_stride;
+  for (int i = tid; i < p * cwc; i += nt) {
+    const int r = i % p, cc = i / p;
+    double v;
+    if (d.mode == 0) v = (r == c0 + cc) ? 1.0 : 0.0;
+    else {
+      const int nv = d.k;
+      v = r < nv ? Jv[(int64_t)perm[c0 + cc] * c.ldj + r] : 0.0;
+    }
+    Wc[i] = v;
+  }
+  __syncthreads();
+  if (d.mode != 2) {
+    const int np = (d.k + bw - 1) / bw;
+    for (int panel = np - 1; panel >= 0; --panel) {
+      const int j0 = panel * bw;
+      if (d.mode == 0 && j0 > c0 + cwc - 1) continue;  // e_c untouched by panels right of it
+      const int bwc = min(bw, d.k - j0);
+      const int rows = p - j0;
+      const double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * bw * bw;
+      for (int i = tid; i < bw * bw; i += nt) Ts[i] = Tg[i];
+      for (int i = tid; i < rows * bwc; i += nt) {
+        const int r = i % rows, cc = i / rows;
+        Vs[i] = r > cc ? X[(j0 + r) + (int64_t)p * (j0 + cc)] : (r == cc ? 1.0 : 0.0);
+      }
+      __syncthreads();
+      for (int o = wid; o < bwc * cwc; o += nw) {
+        const int i = o % bwc, cc = o / bwc;
+        const double* v = Vs + (size_t)rows * i;
+        const double* a = Wc + (size_t)p * cc + j0;
+        double acc = 0.0;
+        for (int r = i + lane; r < rows; r += 32) acc += v[r] * a[r];
+        acc = warp_sum(acc);
+        if (lane == 0) W[i + bw * cc] = acc;
+      }
+      __syncthreads();
+      for (int o = tid; o < bwc * cwc; o += nt) {
+        const int i = o % bwc, cc = o / bwc;
+        double acc = 0.0;
+        for (int l = i; l < bwc; ++l) acc += Ts[i + bw * l] * W[l + bw * cc];
+        W2[i + bw * cc] = acc;
+      }
+      __syncthreads();
+      for (int o = tid; o < rows * cwc; o += nt) {
+        const int r = o % rows, cc = o / rows;
+        double acc = 0.0;
+        const int imax = min(r, bwc - 1);
+        for (int i = 0; i <= imax; ++i) acc += Vs[r + (size_t)rows * i] * W2[i + bw * cc];
+        Wc[(size_t)p * cc + j0 + r] -= acc;
+      }
+      __syncthreads();
+    }
+  }
+  double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.site];
+  if (s.dir == 0) {
+    for (int i = tid; i < p * cwc; i += nt) {
+      const int cc = i % cwc, r = i / cwc;
+      site[(c0 + cc) + (int64_t)mprime * r] = Wc[r + (size_t)p * cc];
+    }
+  } else {
+    const int dl = p / c.Q;
+    for (int i = tid; i < p * cwc; i += nt) {
+      const int r = i % p, cc = i / p;
+      const int m = r % dl, x = r / dl;
+      site[m + (int64_t)dl * ((c0 + cc) + (int64_t)mprime * x)] = Wc[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank rules  (src/svd_trunc.jl:38-47, :74, :98-100, :130-140); lam descending, m = length
+// ---------------------------------------------------------------------------------------------
+__device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap, double* err_out) {
+  double total = 0.0;
+  for (int i = m - 1; i >= 0; --i) total += lam[i] * lam[i];
+  int mprime = 1;
+  if (kind == TTB_TRUNC_THRESH || kind == TTB_TRUNC_BONDTHRESH) {
+    const double ln = sqrt(total) * eps;
+    const double thr = ln * ln;
+    double sacc = (kind == TTB_TRUNC_THRESH) ? lam[m - 1] * lam[m - 1] : 0.0;
+    for (int k = m - 1; k >= 1; --k) {  // 1-based k
+      sacc += lam[k - 1] * lam[k - 1];
+      if (sacc >= thr) { mprime = k + 1; break; }
+    }
+    if (kind == TTB_TRUNC_BONDTHRESH) mprime = min(mprime, cap);
+  } else {
+    mprime = min(m, cap);
+  }
+  if (mprime < 1) mprime = 1;
+  double tail = 0.0;
+  for (int i = m - 1; i >= mprime; --i) tail += lam[i] * lam[i];
+  *err_out = total > 0.0 ? sqrt(tail / total) : 0.0;
+  return mprime;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-sided Jacobi SVD on the rows of R (tall) or X (wide) + rank rule.  One CTA per train.
+// ---------------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void k_jacobi(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;
+  const int nv = d.k, len = d.n, p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  double* Bg = c.Bv + (int64_t)b * c.bv_stride;
+  double* Jg = c.Jv + (int64_t)b * c.jv_stride;
+  extern __shared__ double sm[];
+  double* sig = sm;                 // n_max
+  double* srt = sig + c.n_max;      // n_max
+  double* B = SMEM ? (srt + c.n_max) : Bg;
+  const int ldb = SMEM ? len : c.ldv;
+  double* J = SMEM ? (B + (size_t)nv * ldb) : Jg;
+  const int ldjj = SMEM ? nv : c.ldj;
+  __shared__ int rotated;
+  __shared__ int sh_mprime;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+
+  for (int i = tid; i < nv * len; i += nt) {
+    const int r = i % nv, j = i / nv;  // coalesced read of column j of X
+    double v = X[r + (int64_t)p * j];
+    if (d.mode == 1 && r > j) v = 0.0;
+    B[(size_t)r * ldb + j] = v;
+  }
+  for (int i = tid; i < nv * nv; i += nt) {
+    const int e = i % nv, v = i / nv;
+    J[(size_t)v * ldjj + e] = (e == v) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  const int nvp = (nv + 1) & ~1;
+  const int npairs = nvp / 2, rounds = nvp - 1;
+  const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
+  bool conv = (nv < 2);
+  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int rd = 0; rd < rounds; ++rd) {
+      for (int q = wid; q < npairs; q += nw) {
+        int i, j;
+        if (q == 0) { i = nvp - 1; j = rd; }
+        else { i = (rd + q) % (nvp - 1); j = (rd - q + (nvp - 1)) % (nvp - 1); }
+        if (i > j) { const int t = i; i = j; j = t; }
+        if (j >= nv) continue;
+        double* bi = B + (size_t)i * ldb;
+        double* bj = B + (size_t)j * ldb;
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int e = lane; e < len; e += 32) {
+          const double x = bi[e], y = bj[e];
+          al += x * x; be += y * y; ga += x * y;
+        }
+        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        if (al > 0.0 && be > 0.0 && fabs(ga) > tol * sqrt(al) * sqrt(be)) {
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (int e = lane; e < len; e += 32) {
+            const double x = bi[e], y = bj[e];
+            bi[e] = cs * x - sn * y;
+            bj[e] = sn * x + cs * y;
+          }
+          double* ji = J + (size_t)i * ldjj;
+          double* jj = J + (size_t)j * ldjj;
+          for (int e = lane; e < nv; e += 32) {
+            const double x = ji[e], y = jj[e];
+            ji[e] = cs * x - sn * y;
+            jj[e] = sn * x + cs * y;
+          }
+          if (lane == 0) rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    conv = (rotated == 0);
+    __syncthreads();
+  }
+  if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
+
+  for (int v = wid; v < nv; v += nw) {
+    const double* bi = B + (size_t)v * ldb;
+    double al = 0.0;
+    for (int e = lane; e < len; e += 32) al += bi[e] * bi[e];
+    al = warp_sum(al);
+    if (lane == 0) sig[v] = sqrt(al);
+  }
+  __syncthreads();
+  int* perm = c.perm + (int64_t)b * c.n_max;
+  for (int i = tid; i < nv; i += nt) {
+    const double si = sig[i];
+    int pos = 0;
+    for (int j = 0; j < nv; ++j) {
+      const double sj = sig[j];
+      pos += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    srt[pos] = si;
+    perm[pos] = i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double err = 0.0;
+    const int mp = rank_rule(srt, nv, s.kind, s.eps, s.cap, &err);
+    sh_mprime = mp;
+    c.st[b].mprime = mp;
+    c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = err;
+  }
+  __syncthreads();
+  double* sg = c.sigma + (int64_t)b * c.n_max;
+  for (int i = tid; i < nv; i += nt) sg[i] = srt[i];
+  if (c.spectrum) {
+    double* sp = c.spectrum + ((int64_t)b * c.L1 + s.bond_idx) * c.n_max;
+    for (int i = tid; i < c.n_max; i += nt) sp[i] = i < nv ? srt[i] : -1.0;
+  }
+  if (SMEM) {
+    for (int i = tid; i < nv * len; i += nt) {
+      const int e = i % len, v = i / len;
+      Bg[(int64_t)v * c.ldv + e] = B[(size_t)v * ldb + e];
+    }
+    for (int i = tid; i < nv * nv; i += nt) {
+      const int e = i % nv, v = i / nv;
+      Jg[(int64_t)v * c.ldj + e] = J[(size_t)v * ldjj + e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// absorb: Xn[(a + m'x), j] = sum_l S(a,l) * Nbr_x(l,j)   (src/tensor_train.jl:168 / :207)
+// plus max|D| for the rescale (:169-173 / :208-212).  FP64 tile GEMM, 64x64 tile, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+#define AB_TM 64
+#define AB_TN 64
+#define AB_TK 16
+__global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime;
+  const int i0 = blockIdx.x * AB_TM, j0 = blockIdx.y * AB_TN;
+  if (i0 >= mprime || j0 >= d.N) return;
+  const int n = d.n, N = d.N, p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  const double* Bv = c.Bv + (int64_t)b * c.bv_stride;
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+  double* Xn = xbuf(c, s.xin ^ 1, b);
+  __shared__ double Ss[AB_TK][AB_TM + 1];
+  __shared__ double Bs[AB_TK][AB_TN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
+
+  for (int l0 = 0; l0 < n; l0 += AB_TK) {
+    // S tile: AB_TM x AB_TK
+    for (int i = tid; i < AB_TM * AB_TK; i += 256) {
+      int ii, ll;
+      if (d.mode == 0) { ii = i % AB_TM; ll = i / AB_TM; }   // X col-major: rows fastest
+      else { ll = i % AB_TK; ii = i / AB_TK; }                // Bv vector-major: l fastest
+      const int gi = i0 + ii, gl = l0 + ll;
+      double v = 0.0;
+      if (gi < mprime && gl < n) {
+        if (d.mode == 0) v = gi <= gl ? X[gi + (int64_t)p * gl] : 0.0;
+        else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
+      }
+      Ss[ll][ii] = v;
+    }
+    // neighbour tile: AB_TK x AB_TN
+    for (int i = tid; i < AB_TK * AB_TN; i += 256) {
+      int ll, jj;
+      if (s.dir == 1) { ll = i % AB_TK; jj = i / AB_TK; }     // nbr (n x N x Q): l fastest
+      else { jj = i % AB_TN; ll = i / AB_TN; }                // nbr (N x n x Q): j fastest
+      const int gl = l0 + ll, gj = j0 + jj;
+      double v = 0.0;
+      if (gl < n && gj < N)
+        v = s.dir == 1 ? nbr[gl + (int64_t)n * (gj + (int64_t)N * x)] : nbr[gj + (int64_t)N * (gl + (int64_t)n * x)];
+      Bs[ll][jj] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ll = 0; ll < AB_TK; ++ll) {
+      double sa[4], sb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) sa[a] = Ss[ll][tx + 16 * a];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sb[e] = Bs[ll][ty + 16 * e];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[a][e] += sa[a] * sb[e];
+    }
+    __syncthreads();
+  }
+  const int64_t ldo = (int64_t)mprime * c.Q;
+  double mx = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gi = i0 + tx + 16 * a, gj = j0 + ty + 16 * e;
+      if (gi < mprime && gj < N) {
+        Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[a][e];
+        mx = absmax_nan(mx, acc[a][e]);
+      }
+    }
+  // block max with NaN propagation through the ordered-bits trick
+  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = other > bits ? other : bits;
+  }
+  if ((tid & 31) == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
+}
+
+// rescale the absorb output: in place, or unfolded into the neighbour's site storage on the last step
+__global__ void k_rescale(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.y;
+  const int mprime = c.st[b].mprime;
+  const int* bond = c.bond + (int64_t)b * c.L1;
+  const int N = s.dir == 0 ? bond[s.nbr] : bond[s.nbr + 1];
+  const double m = __longlong_as_double((long long)c.st[b].maxabs_bits[s.slot]);
+  const bool ok = s.rescale && !(m != m) && !isinf(m) && m != 0.0;
+  if (!ok && !s.last) return;
+  const int64_t pn = (int64_t)mprime * c.Q;
+  const int64_t tot = pn * N;
+  double* Xn = xbuf(c, s.xin ^ 1, b);
+  double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = Xn[i];
+    if (ok) v /= m;
+    if (!s.last) {
+      Xn[i] = v;
+    } else {
+      // site layouts: right sweep site (N, m', Q): [j + N*(a + m'x)] = Xn[(a+m'x) + pn*j]
+      //               left  sweep site (m', N, Q): [a + m'*(j + N*x)] = Xn[(a+m'x) + pn*j]
+      const int64_t r = i % pn, j = i / pn;
+      if (s.dir == 0) site[j + (int64_t)N * r] = v;
+      else {
+        const int a = (int)(r % mprime), x = (int)(r / mprime);
+        site[a + (int64_t)mprime * (j + (int64_t)N * x)] = v;
+      }
+    }
+  }
+}
+
+// commit the step (one thread per train): z /= m, bond <- m', stats, reset the other maxabs slot
+__global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  int* bond = c.bond + (int64_t)b * c.L1;
+  const int mp = c.st[b].mprime;
+  const double m = __longlong_as_double((long long)c.st[b].maxabs_bits[s.slot]);
+  const bool bad = (m != m) || isinf(m);
+  if (s.rescale && !bad && m != 0.0) c.logz[b] -= log(m);
+  if (s.rescale && bad) atomicOr(c.status, ST_NONFINITE);
+  c.st[b].maxabs_bits[s.slot ^ 1] = 0ull;
+  c.stat_rank[(int64_t)b * c.L1 + s.bond_idx] = mp;
+  if (s.qr_only) c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = 0.0;
+  bond[s.bond_idx] = mp;
+  if (s.bond_idx2 >= 0) bond[s.bond_idx2] = mp;
+}
+
+__global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) { st[i].mprime = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull; }
+  if (i < batch * L1) { stat_err[i] = 0.0; stat_rank[i] = 0; }
+}
+
+// canonical-form residual max|A'A - I| (src/tensor_train.jl:263-273); one CTA
+__global__ void k_canon_resid(const double* site, int dl, int dr, int Q, int left, double* out) {
+  __shared__ double red[40];
+  const int n = left ? dr : dl;
+  double mx = 0.0;
+  for (int o = threadIdx.x; o < n * n; o += blockDim.x) {
+    const int i = o % n, j = o / n;
+    double acc = 0.0;
+    if (left) {
+      for (int x = 0; x < Q; ++x)
+        for (int k = 0; k < dl; ++k)
+          acc += site[k + (int64_t)dl * (i + (int64_t)dr * x)] * site[k + (int64_t)dl * (j + (int64_t)dr * x)];
+    } else {
+      for (int x = 0; x < Q; ++x)
+        for (int k = 0; k < dr; ++k)
+          acc += site[i + (int64_t)dl * (k + (int64_t)dr * x)] * site[j + (int64_t)dl * (k + (int64_t)dr * x)];
+    }
+    mx = fmax(mx, fabs(acc - (i == j ? 1.0 : 0.0)));
+  }
+  mx = block_max(mx, red);
+  if (threadIdx.x == 0) *out = mx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static const int kMaxSmem = 227 * 1024;
+static const int kCw = 4;
+
+int ensure_sweep_ws(ttb_tt* h) {
+  Workspace& w = h->ws;
+  if (w.sweep_ready) return TTB_OK;
+  const int64_t p_max = h->dmax * h->Q, n_max = h->dmax;
+  int bw = 32;
+  while (bw > 4 && (p_max * (bw + kCw) + 3 * bw * bw + 128) * 8 > 200 * 1024) bw >>= 1;
+  if ((p_max * (bw + kCw) + 3 * bw * bw + 128) * 8 > 200 * 1024)
+    return fail(TTB_EUNSUPPORTED, "sweeps support bond*Q <= ~3000 (got %lld)", (long long)p_max);
+  w.p_max = (int)p_max; w.n_max = (int)n_max; w.bw = bw;
+  const int64_t B = h->batch;
+  w.x_stride = (p_max * n_max + 15) & ~int64_t(15);
+  w.t_stride = ((n_max + bw - 1) / bw) * bw * bw;
+  w.ldv = (int)n_max; w.ldj = (int)n_max;
+  w.bv_stride = n_max * n_max; w.jv_stride = n_max * n_max;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  A((void**)&w.X[0], sizeof(double) * B * w.x_stride);
+  A((void**)&w.X[1], sizeof(double) * B * w.x_stride);
+  A((void**)&w.T, sizeof(double) * B * w.t_stride);
+  A((void**)&w.Bv, sizeof(double) * B * w.bv_stride);
+  A((void**)&w.Jv, sizeof(double) * B * w.jv_stride);
+  A((void**)&w.perm, sizeof(int) * B * n_max);
+  A((void**)&w.sigma, sizeof(double) * B * n_max);
+  A((void**)&w.st, sizeof(StepState) * B);
+  A((void**)&w.stat_err, sizeof(double) * B * (h->L + 1));
+  A((void**)&w.stat_rank, sizeof(int) * B * (h->L + 1));
+  if (e != cudaSuccess) return fail(TTB_ENOMEM, "sweep workspace: %s", cudaGetErrorString(e));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    attr_done = true;
+  }
+  w.sweep_ready = true;
+  return TTB_OK;
+}
+
+static int ensure_spectrum(ttb_tt* h) {
+  Workspace& w = h->ws;
+  if (!h->record_spectrum) return TTB_OK;
+  if (!w.spectrum) {
+    const size_t n = (size_t)h->batch * (h->L + 1) * w.n_max;
+    TTB_CUDA(cudaMalloc(&w.spectrum, sizeof(double) * n));
+  }
+  return TTB_OK;
+}
+
+static SweepCtx make_ctx(ttb_tt* h) {
+  Workspace& w = h->ws;
+  SweepCtx c;
+  c.slab = h->slab; c.tt_stride = h->tt_stride; c.off = h->d_off; c.bond = h->d_bond; c.L1 = (int)h->L + 1;
+  c.Q = (int)h->Q;
+  c.X0 = w.X[0]; c.X1 = w.X[1]; c.x_stride = w.x_stride;
+  c.T = w.T; c.t_stride = w.t_stride; c.bw = w.bw;
+  c.Bv = w.Bv; c.Jv = w.Jv; c.bv_stride = w.bv_stride; c.jv_stride = w.jv_stride; c.ldv = w.ldv; c.ldj = w.ldj;
+  c.perm = w.perm; c.sigma = w.sigma; c.n_max = w.n_max;
+  c.st = w.st; c.logz = h->d_logz;
+  c.stat_err = w.stat_err; c.stat_rank = w.stat_rank; c.spectrum = h->record_spectrum ? w.spectrum : nullptr;
+  c.status = h->d_status;
+  return c;
+}
+
+struct HostStep { int site, nbr, rescale, bond_idx, bond_idx2, last; };
+
+static int check_trunc(const ttb_trunc* tr) {
+  if (!tr) return fail(TTB_EINVAL, "null svd_trunc");
+  if (tr->kind < 0 || tr->kind > 3) return fail(TTB_EINVAL, "unknown svd_trunc kind %d", tr->kind);
+  if (tr->kind != TTB_TRUNC_THRESH && tr->mprime < 1) return fail(TTB_EINVAL, "mprime must be >= 1");
+  return TTB_OK;
+}
+
+// Enqueue one sweep (no host synchronisation inside).  dir 0 = right, 1 = left.
+static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vector<HostStep>& steps,
+                         std::vector<int>& ub, bool& exact) {
+  TTB_TRY(ensure_sweep_ws(h));
+  TTB_TRY(ensure_spectrum(h));
+  Workspace& w = h->ws;
+  const SweepCtx c = make_ctx(h);
+  const int B = (int)h->batch, Q = (int)h->Q, bw = w.bw, L1 = (int)h->L + 1;
+  cudaStream_t st = h->stream;
+  const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
+  {
+    const int n = std::max(B, B * L1);
+    TTB_LAUNCH(h, "k_reset_state", k_reset_state<<<(n + 255) / 256, 256, 0, st>>>(w.st, w.stat_err, w.stat_rank, B, L1));
+  }
+  int xin = 0, slot = 0;
+  for (size_t si = 0; si < steps.size(); ++si) {
+    const HostStep& hs = steps[si];
+    StepDesc s;
+    s.site = hs.site; s.nbr = hs.nbr; s.dir = dir; s.xin = xin; s.rescale = hs.rescale; s.qr_only = qr_only ? 1 : 0;
+    s.kind = tr->kind; s.eps = tr->eps;
+    s.cap = (int)std::min<int64_t>(tr->mprime, 1 << 30);
+    s.bond_idx = hs.bond_idx; s.bond_idx2 = hs.bond_idx2; s.last = hs.last; s.slot = slot;
+    int p_ub, n_ub, N_ub;
+    if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; }
+    else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; }
+    const int k_ub = std::min(p_ub, n_ub);
+    if (si == 0) {
+      const int64_t tot = (int64_t)p_ub * n_ub;
+      dim3 g((unsigned)std::min<int64_t>((tot + 255) / 256, 2048), B);
+      TTB_LAUNCH(h, "k_fold", k_fold<<<g, 256, 0, st>>>(c, s));
+    }
+    const bool maybe_qr = qr_only || !(exact && p_ub < n_ub);
+    if (maybe_qr) {
+      const int np = (k_ub + bw - 1) / bw;
+      for (int panel = 0; panel < np; ++panel) {
+        const int j0 = panel * bw;
+        const int rows_ub = p_ub - j0;
+        const int thr = std::min(512, std::max(64, ((rows_ub + 31) / 32) * 32));
+        size_t smem = sizeof(double) * ((size_t)2 * bw * bw + 2 * bw + 40 + (size_t)rows_ub * bw);
+        TTB_LAUNCH(h, "k_qr_panel", k_qr_panel<<<B, thr, smem, st>>>(c, s, panel));
+        const int trail = n_ub - j0 - 1;
+        if (trail > 0) {
+          dim3 g((trail + kCw - 1) / kCw, B);
+          size_t sm2 = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)rows_ub * (bw + kCw));
+          TTB_LAUNCH(h, "k_qr_update", k_qr_update<<<g, 256, sm2, st>>>(c, s, panel, kCw));
+        }
+      }
+    }
+    int mp_ub = k_ub;
+    if (!qr_only) {
+      if (tr->kind != TTB_TRUNC_THRESH) mp_ub = (int)std::min<int64_t>(mp_ub, tr->mprime);
+      const int nv_ub = k_ub, len_ub = n_ub;
+      const size_t need = sizeof(double) * (2 * (size_t)w.n_max + (size_t)nv_ub * (len_ub + nv_ub));
+      const int thr = std::min(512, std::max(64, ((nv_ub / 2 + 1) * 32)));
+      if (need <= (size_t)200 * 1024)
+        TTB_LAUNCH(h, "k_jacobi_smem", k_jacobi<true><<<B, thr, need, st>>>(c, s));
+      else
+        TTB_LAUNCH(h, "k_jacobi_gmem", k_jacobi<false><<<B, 1024, sizeof(double) * 2 * w.n_max, st>>>(c, s));
+    }
+    {
+      dim3 g((mp_ub + kCw - 1) / kCw, B);
+      const int rows_ub = p_ub;
+      size_t smem = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)p_ub * kCw + (size_t)rows_ub * bw);
+      TTB_LAUNCH(h, "k_apply_q", k_apply_q<<<g, 256, smem, st>>>(c, s, kCw));
+    }
+    {
+      dim3 g((mp_ub + AB_TM - 1) / AB_TM, (N_ub + AB_TN - 1) / AB_TN, Q * B);
+      TTB_LAUNCH(h, "k_absorb", k_absorb<<<g, 256, 0, st>>>(c, s));
+    }
+    {
+      const int64_t tot = (int64_t)mp_ub * Q * N_ub;
+      dim3 g((unsigned)std::min<int64_t>((tot + 1023) / 1024, 1024), B);
+      TTB_LAUNCH(h, "k_rescale", k_rescale<<<g, 256, 0, st>>>(c, s));
+      TTB_LAUNCH(h, "k_commit", k_commit<<<(B + 127) / 128, 128, 0, st>>>(c, s, B));
+    }
+    ub[hs.bond_idx] = mp_ub;
+    if (hs.bond_idx2 >= 0) ub[hs.bond_idx2] = mp_ub;
+    if (!qr_only) exact = false;
+    xin ^= 1; slot ^= 1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
+  return TTB_OK;
+}
+
+static void bond_upper_bounds(ttb_tt* h, std::vector<int>& ub, bool& exact) {
+  const int L1 = (int)h->L + 1;
+  ub.assign(L1, 0);
+  exact = true;
+  for (int64_t b = 0; b < h->batch; ++b)
+    for (int t = 0; t < L1; ++t) {
+      const int v = h->h_bond[b * L1 + t];
+      if (b > 0 && v != ub[t]) exact = false;
+      ub[t] = std::max(ub[t], v);
+    }
+}
+
+static int build_right(ttb_tt* h, int64_t lo, int64_t hi, std::vector<HostStep>& steps) {
+  const int L = (int)h->L;
+  steps.clear();
+  if (h->periodic) {
+    if (L < 2) return fail(TTB_EUNSUPPORTED, "periodic sweeps need L >= 2");
+    steps.push_back({0, L - 1, 0, 0, L, 0});                       // wrap step, no rescale (:84-92)
+    for (int t = L - 1; t >= 1; --t) steps.push_back({t, t - 1, 1, t, -1, t == 1 ? 1 : 0});
+    return TTB_OK;
+  }
+  if (lo == 0 && hi == 0) { lo = 2; hi = L; }
+  if (lo > hi) return TTB_OK;  // isempty(indices)
+  if (lo < 2 || hi > L) return fail(TTB_EINVAL, "Indices not compatible with tensor train positions 1:%d: got %lld:%lld", L, (long long)lo, (long long)hi);
+  if (hi != L) return fail(TTB_EUNSUPPORTED, "orthogonalize_right! always seeds from the last site (tensor_train.jl:157); ranges must end at L");
+  for (int t = (int)hi; t >= (int)lo; --t) steps.push_back({t - 1, t - 2, 1, t - 1, -1, t == (int)lo ? 1 : 0});
+  return TTB_OK;
+}
+
+static int build_left(ttb_tt* h, int64_t lo, int64_t hi, std::vector<HostStep>& steps) {
+  const int L = (int)h->L;
+  steps.clear();
+  if (h->periodic) {
+    if (L < 2) return fail(TTB_EUNSUPPORTED, "periodic sweeps need L >= 2");
+    for (int t = 0; t <= L - 2; ++t) steps.push_back({t, t + 1, 1, t + 1, -1, 0});
+    steps.push_back({L - 1, 0, 0, L, 0, 1});                       // wrap step, no rescale (:133-138)
+    return TTB_OK;
+  }
+  if (lo == 0 && hi == 0) { lo = 1; hi = L - 1; }
+  if (lo > hi) return TTB_OK;
+  if (lo < 1 || hi > L - 1) return fail(TTB_EINVAL, "Indices not compatible with tensor train positions 1:%d: got %lld:%lld", L, (long long)lo, (long long)hi);
+  if (lo != 1) return fail(TTB_EUNSUPPORTED, "orthogonalize_left! always seeds from the first site (tensor_train.jl:196); ranges must start at 1");
+  for (int t = (int)lo; t <= (int)hi; ++t) steps.push_back({t - 1, t, 1, t, -1, t == (int)hi ? 1 : 0});
+  return TTB_OK;
+}
+
+static int finish_sweeps(ttb_tt* h, CallTimer& tm) {
+  TTB_TRY(tm.finish());
+  TTB_TRY(sync_bonds_to_host(h));
+  int st = 0;
+  TTB_TRY(read_status(h, &st));
+  if (st & ST_NONFINITE) return fail(TTB_ENONFINITE, "non-finite values met during the sweep");
+  return TTB_OK;
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_orthogonalize_right(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_t hi) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_trunc(tr));
+  std::vector<HostStep> steps;
+  TTB_TRY(build_right(h, lo, hi, steps));
+  if (steps.empty()) return TTB_OK;
+  std::vector<int> ub; bool exact;
+  bond_upper_bounds(h, ub, exact);
+  CallTimer tm(h);
+  TTB_TRY(enqueue_sweep(h, 0, tr, steps, ub, exact));
+  return finish_sweeps(h, tm);
+}
+
+int ttb_orthogonalize_left(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_t hi) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_trunc(tr));
+  std::vector<HostStep> steps;
+  TTB_TRY(build_left(h, lo, hi, steps));
+  if (steps.empty()) return TTB_OK;
+  std::vector<int> ub; bool exact;
+  bond_upper_bounds(h, ub, exact);
+  CallTimer tm(h);
+  TTB_TRY(enqueue_sweep(h, 1, tr, steps, ub, exact));
+  return finish_sweeps(h, tm);
+}
+
+int ttb_orthogonalize_center(ttb_handle h, const ttb_trunc* tr, int64_t l) {
+  TTB_TRY(check_handle(h));
+  if (h->periodic) return fail(TTB_EINVAL, "orthogonalize_center! is defined for TensorTrain only");
+  if (l < 1 || l > h->L) return fail(TTB_EINVAL, "center %lld out of range", (long long)l);
+  if (l - 1 >= 1) TTB_TRY(ttb_orthogonalize_left(h, tr, 1, l - 1));
+  if (l + 1 <= h->L) TTB_TRY(ttb_orthogonalize_right(h, tr, l + 1, h->L));
+  return TTB_OK;
+}
+
+int ttb_orthogonalize_two_site_center(ttb_handle h, const ttb_trunc* tr, int64_t k) {
+  TTB_TRY(check_handle(h));
+  if (h->periodic) return fail(TTB_EINVAL, "orthogonalize_two_site_center! is defined for TensorTrain only");
+  if (k < 1 || k >= h->L) return fail(TTB_EINVAL, "k must be between 1 and length(C)-1 for two-site update");
+  if (k - 1 >= 1) TTB_TRY(ttb_orthogonalize_left(h, tr, 1, k - 1));
+  if (k + 2 <= h->L) TTB_TRY(ttb_orthogonalize_right(h, tr, k + 2, h->L));
+  return TTB_OK;
+}
+
+int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
+  TTB_TRY(check_handle(h));
+  TTB_TRY(check_trunc(tr));
+  if (is_orthogonal == TTB_ORTH_LEFT) return ttb_orthogonalize_right(h, tr, 0, 0);
+  if (is_orthogonal == TTB_ORTH_RIGHT) return ttb_orthogonalize_left(h, tr, 0, 0);
+  if (is_orthogonal != TTB_ORTH_NONE)
+    return fail(TTB_EINVAL, "Keyword `is_orthogonal` only supports: :none, :left, :right");
+  // both sweeps are enqueued back to back; the left sweep sizes its launches from the bond
+  // dimensions the eps=0 right sweep is known to produce
+  std::vector<HostStep> rs, ls;
+  TTB_TRY(build_right(h, 0, 0, rs));
+  TTB_TRY(build_left(h, 0, 0, ls));
+  std::vector<int> ub; bool exact;
+  bond_upper_bounds(h, ub, exact);
+  ttb_trunc t0;
+  t0.kind = TTB_TRUNC_THRESH; t0._pad = 0; t0.eps = 0.0; t0.mprime = 0;
+  CallTimer tm(h);
+  if (!rs.empty()) TTB_TRY(enqueue_sweep(h, 0, &t0, rs, ub, exact));
+  if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, exact));
+  return finish_sweeps(h, tm);
+}
+
+int ttb_sweep_stats(ttb_handle h, int64_t b, int64_t* rank, double* err) {
+  TTB_TRY(check_handle(h));
+  if (b < 0 || b >= h->batch) return fail(TTB_EINVAL, "train index out of range");
+  const int L1 = (int)h->L + 1;
+  if (!h->ws.sweep_ready) {
+    for (int i = 0; i < L1; ++i) { if (rank) rank[i] = 0; if (err) err[i] = 0.0; }
+    return TTB_OK;
+  }
+  std::vector<int> r(L1);
+  std::vector<double> e(L1);
+  TTB_CUDA(cudaMemcpyAsync(r.data(), h->ws.stat_rank + b * L1, sizeof(int) * L1, cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(e.data(), h->ws.stat_err + b * L1, sizeof(double) * L1, cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < L1; ++i) { if (rank) rank[i] = r[i]; if (err) err[i] = e[i]; }
+  return TTB_OK;
+}
+
+int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t* n) {
+  TTB_TRY(check_handle(h));
+  if (!h->ws.spectrum) return fail(TTB_EINVAL, "spectrum recording is off (ttb_record_spectrum)");
+  if (b < 0 || b >= h->batch || bond_index < 0 || bond_index > h->L) return fail(TTB_EINVAL, "index out of range");
+  const int nm = h->ws.n_max;
+  std::vector<double> tmp(nm);
+  TTB_CUDA(cudaMemcpyAsync(tmp.data(), h->ws.spectrum + (b * (h->L + 1) + bond_index) * nm, sizeof(double) * nm,
+                           cudaMemcpyDeviceToHost, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  int64_t cnt = 0;
+  while (cnt < nm && tmp[cnt] >= 0.0) { out[cnt] = tmp[cnt]; ++cnt; }
+  *n = cnt;
+  return TTB_OK;
+}
+
+int ttb_canonical_residual(ttb_handle h, int64_t b, int64_t t, int left, double* resid) {
+  TTB_TRY(check_handle(h));
+  if (b < 0 || b >= h->batch || t < 0 || t >= h->L) return fail(TTB_EINVAL, "index out of range");
+  const int* bd = &h->h_bond[b * (h->L + 1)];
+  double* d_out = nullptr;
+  TTB_CUDA(cudaMalloc(&d_out, sizeof(double)));
+  TTB_LAUNCH(h, "k_canon_resid", k_canon_resid<<<1, 256, 0, h->stream>>>(h->slab + b * h->tt_stride + h->off[t], bd[t], bd[t + 1], (int)h->Q, left,
+                                          d_out));
+  cudaError_t e = cudaMemcpyAsync(resid, d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "canonical_residual: %s", cudaGetErrorString(e));
+  return TTB_OK;
+}
+
+}  // extern "C"

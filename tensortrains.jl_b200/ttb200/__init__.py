@@ -1,0 +1,679 @@
+"""ttb200 -- host-side mirror of the TensorTrains.jl hot-path API over libttb200.so (sm_100a).
+
+The names, argument meaning and error behaviour follow the reference (stecrotti/TensorTrains.jl
+v0.14.0; file:line citations are relative to its root).  Julia's ``f!`` becomes ``f_``.  Site
+tensors live in device memory behind an opaque handle of the C ABI declared in ``include/ttb200.h``;
+every function here is a thin ctypes call -- there is NO CPU fallback: importing this package fails
+if the CUDA library is missing, and every call fails if no CUDA device is present.
+
+Conventions carried over from the reference:
+  * a site tensor has shape ``(d_t, d_{t+1}, q_1, ...)``, column-major like Julia arrays;
+  * physical indices passed to/returned from this module are 0-based (Julia's are 1-based);
+  * ``z`` is a :class:`Logarithmic` (sign, log|z|) like ``LogarithmicNumbers.Logarithmic``.
+A handle may hold a *batch* of independent trains with identical shapes (the reference would hold a
+``Vector`` of trains); batched objects return arrays with a leading batch axis.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+__all__ = [
+    "TensorTrain", "PeriodicTensorTrain", "Logarithmic",
+    "TruncThresh", "TruncBond", "TruncBondMax", "TruncBondThresh",
+    "flat_tt", "rand_tt", "randn_tt", "flat_periodic_tt", "rand_periodic_tt",
+    "bond_dims", "nparams", "evaluate", "accumulate_L", "accumulate_R", "normalization", "lognormalization",
+    "normalize_", "normalize_eachmatrix_", "marginals", "twovar_marginals", "compress_",
+    "orthogonalize_right_", "orthogonalize_left_", "orthogonalize_center_", "orthogonalize_two_site_center_",
+    "is_left_canonical", "is_right_canonical", "is_canonical", "sample", "sample_stats", "lib", "TTBError",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libttb200.so")
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+lib = C.CDLL(_LIB_PATH)
+
+_h = C.c_void_p
+_i64 = C.c_int64
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int)
+_pi64 = C.POINTER(C.c_int64)
+
+
+class _Trunc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("eps", C.c_double), ("mprime", C.c_int64)]
+
+
+def _sig(name, *args):
+    f = getattr(lib, name)
+    f.restype = C.c_int
+    f.argtypes = list(args)
+    return f
+
+
+lib.ttb_last_error.restype = C.c_char_p
+_sig("ttb_device_count", _pi)
+_sig("ttb_set_device", C.c_int)
+_sig("ttb_host_alloc", C.POINTER(C.c_void_p), C.c_size_t)
+_sig("ttb_host_free", C.c_void_p)
+_sig("ttb_create", _i64, _pi64, _i64, C.c_int, _i64, C.POINTER(_h))
+_sig("ttb_destroy", _h)
+_sig("ttb_clone", _h, C.POINTER(_h))
+_sig("ttb_info", _h, _pi64, _pi64, _pi, _pi64)
+_sig("ttb_get_bonds", _h, _i64, _pi64)
+_sig("ttb_nparams", _h, _i64, _pi64)
+_sig("ttb_upload_site", _h, _i64, _i64, _pd)
+_sig("ttb_download_site", _h, _i64, _i64, _pd)
+_sig("ttb_upload_all", _h, _pd)
+_sig("ttb_download_all", _h, _pd)
+_sig("ttb_get_z", _h, _i64, _pd, _pi)
+_sig("ttb_set_z", _h, _i64, C.c_double, C.c_int)
+_sig("ttb_orthogonalize_right", _h, C.POINTER(_Trunc), _i64, _i64)
+_sig("ttb_orthogonalize_left", _h, C.POINTER(_Trunc), _i64, _i64)
+_sig("ttb_orthogonalize_center", _h, C.POINTER(_Trunc), _i64)
+_sig("ttb_orthogonalize_two_site_center", _h, C.POINTER(_Trunc), _i64)
+_sig("ttb_compress", _h, C.POINTER(_Trunc), C.c_int)
+_sig("ttb_sweep_stats", _h, _i64, _pi64, _pd)
+_sig("ttb_record_spectrum", _h, C.c_int)
+_sig("ttb_get_spectrum", _h, _i64, _i64, _pd, _pi64)
+_sig("ttb_canonical_residual", _h, _i64, _i64, C.c_int, _pd)
+_sig("ttb_env_size", _h, _i64, C.c_int, _pi64)
+_sig("ttb_accumulate_L", _h, C.c_int, _pd, _pd, _pi)
+_sig("ttb_accumulate_R", _h, C.c_int, _pd, _pd, _pi)
+_sig("ttb_normalization", _h, _pd, _pi)
+_sig("ttb_normalize", _h, _pd)
+_sig("ttb_normalize_eachmatrix", _h)
+_sig("ttb_marginals", _h, _pd)
+_sig("ttb_twovar_count", _h, _i64, _pi64)
+_sig("ttb_twovar_marginals", _h, _i64, _pd)
+_sig("ttb_evaluate", _h, _i64, C.POINTER(C.c_int32), _i64, _pd)
+_sig("ttb_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
+_sig("ttb_sample_stats", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
+_sig("ttb_dot", _h, _i64, _h, _i64, _pd)
+_sig("ttb_last_timing", _h, _pd, _pi64)
+lib.ttb_version.restype = C.c_int
+
+
+class TTBError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class NegativeValuesError(TTBError):
+    """ErrorException("Cannot sample from a tensor train with negative values")
+    (src/abstract_tensor_train.jl:371)."""
+
+
+_EINVAL, _ESHAPE, _ENEGATIVE, _ENONFINITE, _ECUDA, _ENOMEM, _EUNSUPPORTED, _EDOMAIN = 1, 2, 3, 4, 5, 6, 7, 8
+
+
+def _ck(rc):
+    if rc == 0:
+        return
+    msg = lib.ttb_last_error().decode("utf-8", "replace")
+    if rc in (_EINVAL, _ESHAPE):
+        raise ValueError("ArgumentError: " + msg)          # Julia ArgumentError
+    if rc == _EDOMAIN:
+        raise ValueError("DomainError: " + msg)
+    if rc == _ENEGATIVE:
+        raise NegativeValuesError(rc, msg)
+    if rc == _ENOMEM:
+        raise MemoryError(msg)
+    if rc == _EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise TTBError(rc, msg)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_pd)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _ck(lib.ttb_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(dev: int):
+    _ck(lib.ttb_set_device(int(dev)))
+
+
+# ------------------------------------------------------------------------------------------------
+class Logarithmic:
+    """sign * exp(logabs); mirrors LogarithmicNumbers.Logarithmic as used for ``z``
+    (src/tensor_train.jl:10,12)."""
+    __slots__ = ("logabs", "sign")
+
+    def __init__(self, x=1.0, *, logabs=None, sign=1):
+        if logabs is not None:
+            self.logabs, self.sign = float(logabs), (1 if sign >= 0 else -1)
+        else:
+            x = float(x)
+            self.sign = -1 if x < 0 else 1
+            self.logabs = -math.inf if x == 0 else math.log(abs(x))
+
+    def __float__(self):
+        return self.sign * math.exp(self.logabs)
+
+    def __repr__(self):
+        return f"{'+' if self.sign > 0 else '-'}exp({self.logabs})"
+
+
+# ---- SVD truncators (src/svd_trunc.jl) -----------------------------------------------------------
+class SVDTrunc:
+    def _c(self) -> _Trunc:  # pragma: no cover
+        raise NotImplementedError
+
+    def _after(self, A):
+        pass
+
+
+@dataclass
+class TruncThresh(SVDTrunc):
+    """src/svd_trunc.jl:29-50"""
+    eps: float
+
+    def _c(self):
+        return _Trunc(0, 0, float(self.eps), 0)
+
+    def summary(self):
+        return f"SVD truncation with threshold ε={self.eps}"
+
+
+@dataclass
+class TruncBond(SVDTrunc):
+    """src/svd_trunc.jl:66-77"""
+    mprime: int
+
+    def _c(self):
+        return _Trunc(1, 0, 0.0, int(self.mprime))
+
+    def summary(self):
+        return f"SVD truncation to bond size m'={self.mprime}"
+
+
+@dataclass
+class TruncBondMax(SVDTrunc):
+    """src/svd_trunc.jl:91-103: also keeps the largest truncation error seen so far."""
+    mprime: int
+    maxerr: List[float] = field(default_factory=lambda: [0.0])
+
+    def _c(self):
+        return _Trunc(2, 0, 0.0, int(self.mprime))
+
+    def _after(self, A):
+        for b in range(A.batch):
+            _, err = A.sweep_stats(b)
+            self.maxerr[0] = max(self.maxerr[0], float(np.max(err)))
+
+    def summary(self):
+        return f"SVD truncation to bond size m'={self.mprime}. Max error {self.maxerr[0]}"
+
+
+@dataclass
+class TruncBondThresh(SVDTrunc):
+    """src/svd_trunc.jl:118-143"""
+    mprime: int
+    eps: float = 0.0
+
+    def _c(self):
+        return _Trunc(3, 0, float(self.eps), int(self.mprime))
+
+    def summary(self):
+        return ("SVD truncation with truncation to bond size given by the minimum of threshold "
+                f"ε={self.eps} and m'={self.mprime}")
+
+
+# ---- containers ----------------------------------------------------------------------------------
+class AbstractTensorTrain:
+    """Device-resident train(s).  ``tensors``: list over sites of arrays ``(d_t, d_{t+1}, q...)``
+    (or, with ``batched=True``, ``(B, d_t, d_{t+1}, q...)``)."""
+    periodic = False
+
+    def __init__(self, tensors: Sequence[np.ndarray], z=1.0, batched: bool = False, _handle=None, _q=None):
+        self._hd = _h()
+        if _handle is not None:
+            self._hd, self.q, self.batched = _handle, tuple(_q), batched
+            self._refresh()
+            return
+        tensors = [np.asarray(a, dtype=np.float64) for a in tensors]
+        if not batched:
+            tensors = [a[None] for a in tensors]
+        if any(a.ndim <= 3 for a in tensors):
+            raise ValueError("ArgumentError: Tensors should have at least 3 indices: 2 virtual and 1 physical")
+        B = tensors[0].shape[0]
+        self.q = tuple(tensors[0].shape[3:])
+        L = len(tensors)
+        if any(tuple(a.shape[3:]) != self.q or a.shape[0] != B for a in tensors):
+            raise ValueError("ArgumentError: all sites must share the physical dimensions and the batch size")
+        for t in range(L):
+            if tensors[t].shape[2] != tensors[(t + 1) % L].shape[1] and (self.periodic or t + 1 < L):
+                raise ValueError("ArgumentError: Matrix indices for matrix product non compatible")
+        bond = np.array([a.shape[1] for a in tensors] + [tensors[-1].shape[2]], dtype=np.int64)
+        self.batched = batched
+        _ck(lib.ttb_create(L, bond.ctypes.data_as(_pi64), int(np.prod(self.q)), int(self.periodic), B,
+                           C.byref(self._hd)))
+        self._refresh()
+        # pack train-major, site-major, each site column-major
+        Qf = int(np.prod(self.q))
+        buf = np.concatenate([np.reshape(tensors[t][b].reshape(tensors[t].shape[1], tensors[t].shape[2], Qf, order="F"),
+                                         -1, order="F") for b in range(B) for t in range(L)])
+        _ck(lib.ttb_upload_all(self._hd, _dp(np.ascontiguousarray(buf))))
+        if not (isinstance(z, (int, float)) and z == 1.0):
+            zz = z if isinstance(z, Logarithmic) else Logarithmic(z)
+            for b in range(B):
+                _ck(lib.ttb_set_z(self._hd, b, zz.logabs, zz.sign))
+
+    def _refresh(self):
+        L, Q, per, B = _i64(), _i64(), C.c_int(), _i64()
+        _ck(lib.ttb_info(self._hd, C.byref(L), C.byref(Q), C.byref(per), C.byref(B)))
+        self.L, self.Q, self.batch = L.value, Q.value, B.value
+
+    def __del__(self):
+        try:
+            if self._hd:
+                lib.ttb_destroy(self._hd)
+                self._hd = _h()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.L
+
+    def copy(self):
+        """deepcopy(A)"""
+        nh = _h()
+        _ck(lib.ttb_clone(self._hd, C.byref(nh)))
+        return type(self)(None, batched=self.batched, _handle=nh, _q=self.q)
+
+    __deepcopy__ = lambda self, memo: self.copy()
+
+    # -- metadata
+    def bonds(self, b: int = 0) -> np.ndarray:
+        out = np.zeros(self.L + 1, dtype=np.int64)
+        _ck(lib.ttb_get_bonds(self._hd, b, out.ctypes.data_as(_pi64)))
+        return out
+
+    @property
+    def z(self):
+        zs = []
+        for b in range(self.batch):
+            la, sg = C.c_double(), C.c_int()
+            _ck(lib.ttb_get_z(self._hd, b, C.byref(la), C.byref(sg)))
+            zs.append(Logarithmic(logabs=la.value, sign=sg.value))
+        return zs if self.batched else zs[0]
+
+    @z.setter
+    def z(self, v):
+        vs = v if isinstance(v, (list, tuple)) else [v] * self.batch
+        for b, x in enumerate(vs):
+            x = x if isinstance(x, Logarithmic) else Logarithmic(x)
+            _ck(lib.ttb_set_z(self._hd, b, x.logabs, x.sign))
+
+    # -- site access (getindex / setindex!, src/tensor_train.jl:27-29); copies through the host
+    def site(self, t: int, b: int = 0) -> np.ndarray:
+        bd = self.bonds(b)
+        out = np.zeros(int(bd[t] * bd[t + 1] * self.Q))
+        _ck(lib.ttb_download_site(self._hd, b, t, _dp(out)))
+        return out.reshape((int(bd[t]), int(bd[t + 1])) + self.q, order="F")
+
+    def __getitem__(self, t):
+        return self.site(t % self.L)
+
+    def set_site(self, t: int, a: np.ndarray, b: int = 0):
+        bd = self.bonds(b)
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape[:2] != (bd[t], bd[t + 1]) or a.size != bd[t] * bd[t + 1] * self.Q:
+            raise ValueError("ArgumentError: site shape does not match the current bond dimensions")
+        _ck(lib.ttb_upload_site(self._hd, b, t, _dp(np.ascontiguousarray(a.reshape(-1, order="F")))))
+
+    def tensors(self, b: int = 0) -> List[np.ndarray]:
+        return [self.site(t, b) for t in range(self.L)]
+
+    def sweep_stats(self, b: int = 0):
+        rank = np.zeros(self.L + 1, dtype=np.int64)
+        err = np.zeros(self.L + 1)
+        _ck(lib.ttb_sweep_stats(self._hd, b, rank.ctypes.data_as(_pi64), _dp(err)))
+        return rank, err
+
+    def record_spectrum(self, on: bool = True):
+        _ck(lib.ttb_record_spectrum(self._hd, int(on)))
+
+    def spectrum(self, bond_index: int, b: int = 0) -> np.ndarray:
+        out = np.zeros(int(max(self.bonds(b).max(), 1)) * max(self.Q, 1) + 8)
+        n = _i64()
+        _ck(lib.ttb_get_spectrum(self._hd, b, bond_index, _dp(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def last_timing(self):
+        ms, n = C.c_double(), _i64()
+        _ck(lib.ttb_last_timing(self._hd, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def _sq(self, a):
+        return a if self.batched else a[0]
+
+
+class TensorTrain(AbstractTensorTrain):
+    """Open-boundary train (src/tensor_train.jl:8-24): first bond and last bond must be 1."""
+    periodic = False
+
+
+class PeriodicTensorTrain(AbstractTensorTrain):
+    """Periodic train (src/periodic_tensor_train.jl:8-27)."""
+    periodic = True
+
+
+# ---- constructors (host-side init + upload; src/tensor_train.jl:42-108,
+#      src/periodic_tensor_train.jl:39-59) -----------------------------------------------------------
+def _open_bonds(args):
+    if len(args) >= 2 and np.isscalar(args[0]) and np.isscalar(args[1]):
+        d, L = int(args[0]), int(args[1])
+        return [1] + [d] * (L - 1) + [1], args[2:]
+    return list(args[0]), args[1:]
+
+
+def flat_tt(*args):
+    bonds, q = _open_bonds(args)
+    return TensorTrain([np.ones((bonds[t], bonds[t + 1]) + tuple(q)) for t in range(len(bonds) - 1)])
+
+
+def rand_tt(rng: np.random.Generator, *args):
+    bonds, q = _open_bonds(args)
+    return TensorTrain([rng.random((bonds[t], bonds[t + 1]) + tuple(q)) for t in range(len(bonds) - 1)])
+
+
+def randn_tt(rng: np.random.Generator, *args):
+    bonds, q = _open_bonds(args)
+    s = 1.0 / math.sqrt(max(bonds))
+    return TensorTrain([s * rng.standard_normal((bonds[t], bonds[t + 1]) + tuple(q)) for t in range(len(bonds) - 1)])
+
+
+def _per_bonds(args):
+    if len(args) >= 2 and np.isscalar(args[0]) and np.isscalar(args[1]):
+        # reference quirk: (d, L, q...) builds fill(d, L-1), i.e. L-1 sites (periodic_tensor_train.jl:44,59)
+        return [int(args[0])] * (int(args[1]) - 1), args[2:]
+    return list(args[0]), args[1:]
+
+
+def flat_periodic_tt(*args):
+    bonds, q = _per_bonds(args)
+    n = len(bonds)
+    x = 1.0 / (float(np.prod(np.array(bonds, dtype=np.float64))) ** (1.0 / n) * float(np.prod(q)))
+    return PeriodicTensorTrain([np.full((bonds[t], bonds[(t + 1) % n]) + tuple(q), x) for t in range(n)])
+
+
+def rand_periodic_tt(rng: np.random.Generator, *args):
+    bonds, q = _per_bonds(args)
+    n = len(bonds)
+    return PeriodicTensorTrain([rng.random((bonds[t], bonds[(t + 1) % n]) + tuple(q)) for t in range(n)])
+
+
+# ---- metadata ------------------------------------------------------------------------------------
+def bond_dims(A: AbstractTensorTrain, b: int = 0) -> List[int]:
+    """Left bond of every site (src/abstract_tensor_train.jl:23)."""
+    return [int(v) for v in A.bonds(b)[:-1]]
+
+
+def nparams(A: AbstractTensorTrain, b: int = 0) -> int:
+    """src/abstract_tensor_train.jl:31-37"""
+    n = _i64()
+    _ck(lib.ttb_nparams(A._hd, b, C.byref(n)))
+    return n.value
+
+
+def _flat_x(A, X) -> np.ndarray:
+    """Accepts per-site ints or per-site tuples of 0-based physical indices; returns flat indices."""
+    out = np.zeros(len(X), dtype=np.int32)
+    for t, x in enumerate(X):
+        if np.isscalar(x):
+            out[t] = int(x)
+        else:
+            x = tuple(int(v) for v in x)
+            if len(x) != len(A.q) or any(not (0 <= xi < qi) for xi, qi in zip(x, A.q)):
+                raise ValueError("ArgumentError: X outside the domain")
+            out[t] = int(np.ravel_multi_index(x, A.q, order="F"))
+    return out
+
+
+def evaluate(A: AbstractTensorTrain, X, b: int = 0):
+    """``tr(prod A[t][:,:,x_t...]) / z`` (src/abstract_tensor_train.jl:80-83).  ``X`` is one point
+    (sequence over sites) or an ``(n, L)`` int array of flat indices; returns a float or ``n`` floats."""
+    if isinstance(X, np.ndarray) and X.ndim == 2:
+        Xf = np.ascontiguousarray(X, dtype=np.int32)
+        single = False
+    else:
+        Xf = _flat_x(A, X)[None]
+        single = True
+    if Xf.shape[1] != A.L:
+        raise ValueError("ArgumentError: X must have one entry per site")
+    out = np.zeros(Xf.shape[0])
+    _ck(lib.ttb_evaluate(A._hd, b, Xf.ctypes.data_as(C.POINTER(C.c_int32)), Xf.shape[0], _dp(out)))
+    return float(out[0]) if single else out
+
+
+# ---- environments --------------------------------------------------------------------------------
+def _accumulate(A, left: bool, normalize: bool):
+    fn = lib.ttb_accumulate_L if left else lib.ttb_accumulate_R
+    sizes = []
+    for b in range(A.batch):
+        n = _i64()
+        _ck(lib.ttb_env_size(A._hd, b, int(left), C.byref(n)))
+        sizes.append(n.value)
+    buf = np.zeros(sum(sizes))
+    la = np.zeros(A.batch)
+    sg = np.zeros(A.batch, dtype=np.int32)
+    _ck(fn(A._hd, int(normalize), _dp(buf), _dp(la), sg.ctypes.data_as(_pi)))
+    envs, o = [], 0
+    for b in range(A.batch):
+        bd = A.bonds(b)
+        per = []
+        for t in range(A.L):
+            shp = (int(bd[0]), int(bd[t + 1])) if left else (int(bd[t]), int(bd[A.L]))
+            n = shp[0] * shp[1]
+            per.append(buf[o:o + n].reshape(shp, order="F").copy())
+            o += n
+        envs.append(per)
+    zs = [Logarithmic(logabs=la[b], sign=int(sg[b])) for b in range(A.batch)]
+    return (envs, zs) if A.batched else (envs[0], zs[0])
+
+
+def accumulate_L(A, normalize: bool = True):
+    """src/abstract_tensor_train.jl:89-102 -> ``(l, z)``"""
+    return _accumulate(A, True, normalize)
+
+
+def accumulate_R(A, normalize: bool = True):
+    """src/abstract_tensor_train.jl:104-117 -> ``(r, z)``"""
+    return _accumulate(A, False, normalize)
+
+
+def normalization(A):
+    """``accumulate_L(A)[2] / A.z`` (src/abstract_tensor_train.jl:154-157)"""
+    la = np.zeros(A.batch)
+    sg = np.zeros(A.batch, dtype=np.int32)
+    _ck(lib.ttb_normalization(A._hd, _dp(la), sg.ctypes.data_as(_pi)))
+    zs = [Logarithmic(logabs=la[b], sign=int(sg[b])) for b in range(A.batch)]
+    return zs if A.batched else zs[0]
+
+
+def lognormalization(A):
+    """src/abstract_tensor_train.jl:145-147 (DomainError on negative Z)"""
+    zs = normalization(A)
+    zl = zs if A.batched else [zs]
+    if any(z.sign < 0 for z in zl):
+        raise ValueError("DomainError: log of a negative normalization")
+    out = np.array([z.logabs for z in zl])
+    return out if A.batched else float(out[0])
+
+
+def normalize_(A):
+    """``normalize!`` (src/abstract_tensor_train.jl:184-197): returns ``log(|Z|/z_old)``"""
+    out = np.zeros(A.batch)
+    _ck(lib.ttb_normalize(A._hd, _dp(out)))
+    return out if A.batched else float(out[0])
+
+
+def normalize_eachmatrix_(A):
+    """src/abstract_tensor_train.jl:165-176"""
+    _ck(lib.ttb_normalize_eachmatrix(A._hd))
+
+
+def marginals(A):
+    """src/abstract_tensor_train.jl:208-220: list over sites of arrays shaped ``q``"""
+    out = np.zeros((A.batch, A.L, A.Q))
+    _ck(lib.ttb_marginals(A._hd, _dp(out)))
+    res = [[out[b, t].reshape(A.q, order="F") for t in range(A.L)] for b in range(A.batch)]
+    return res if A.batched else res[0]
+
+
+def twovar_marginals(A, maxdist: Optional[int] = None):
+    """src/abstract_tensor_train.jl:231-254: dict ``(t,u) -> (q..., q...)`` array, 0-based t<u<=t+maxdist
+    (the reference's other entries are empty arrays)."""
+    md = A.L - 1 if maxdist is None else int(maxdist)
+    n = _i64()
+    _ck(lib.ttb_twovar_count(A._hd, md, C.byref(n)))
+    out = np.zeros((A.batch, n.value, A.Q * A.Q))
+    if n.value:
+        _ck(lib.ttb_twovar_marginals(A._hd, md, _dp(out)))
+    res = []
+    for b in range(A.batch):
+        d, i = {}, 0
+        for t in range(A.L - 1):
+            for u in range(t + 1, min(A.L - 1, t + md) + 1):
+                d[(t, u)] = out[b, i].reshape(A.q + A.q, order="F")
+                i += 1
+        res.append(d)
+    return res if A.batched else res[0]
+
+
+# ---- sweeps --------------------------------------------------------------------------------------
+def _range(indices):
+    if indices is None:
+        return 0, 0
+    idx = list(indices)
+    if len(idx) == 0:
+        return 1, 0
+    if idx != sorted(idx):
+        raise ValueError("ArgumentError: Indices must be sorted")
+    if idx != list(range(idx[0], idx[-1] + 1)):
+        raise NotImplementedError("only contiguous index ranges are supported")
+    return idx[0], idx[-1]
+
+
+def orthogonalize_right_(A, svd_trunc: Optional[SVDTrunc] = None, indices=None):
+    """``orthogonalize_right!`` (src/tensor_train.jl:151-179, periodic: src/periodic_tensor_train.jl:83-111).
+    ``indices`` are 1-based site numbers like the reference's."""
+    tr = svd_trunc if svd_trunc is not None else (TruncThresh(0.0) if A.periodic else TruncThresh(1e-6))
+    lo, hi = _range(indices)
+    if lo > hi:
+        return A
+    ct = tr._c()
+    _ck(lib.ttb_orthogonalize_right(A._hd, C.byref(ct), lo, hi))
+    tr._after(A)
+    return A
+
+
+def orthogonalize_left_(A, svd_trunc: Optional[SVDTrunc] = None, indices=None):
+    """``orthogonalize_left!`` (src/tensor_train.jl:190-218, periodic :113-141)"""
+    tr = svd_trunc if svd_trunc is not None else (TruncThresh(0.0) if A.periodic else TruncThresh(1e-6))
+    lo, hi = _range(indices)
+    if lo > hi:
+        return A
+    ct = tr._c()
+    _ck(lib.ttb_orthogonalize_left(A._hd, C.byref(ct), lo, hi))
+    tr._after(A)
+    return A
+
+
+def orthogonalize_center_(A, l: int, svd_trunc: Optional[SVDTrunc] = None):
+    """src/tensor_train.jl:220-223 (1-based ``l``)"""
+    tr = svd_trunc if svd_trunc is not None else TruncThresh(1e-6)
+    ct = tr._c()
+    _ck(lib.ttb_orthogonalize_center(A._hd, C.byref(ct), int(l)))
+    tr._after(A)
+    return A
+
+
+def orthogonalize_two_site_center_(A, k: int, svd_trunc: Optional[SVDTrunc] = None):
+    """src/tensor_train.jl:232-236"""
+    tr = svd_trunc if svd_trunc is not None else TruncThresh(1e-6)
+    ct = tr._c()
+    _ck(lib.ttb_orthogonalize_two_site_center(A._hd, C.byref(ct), int(k)))
+    tr._after(A)
+    return A
+
+
+_ORTH = {"none": 0, "left": 1, "right": 2}
+
+
+def compress_(A, svd_trunc: Optional[SVDTrunc] = None, is_orthogonal: str = "none"):
+    """``compress!`` (src/abstract_tensor_train.jl:261-274)"""
+    tr = svd_trunc if svd_trunc is not None else TruncThresh(1e-6)
+    if is_orthogonal not in _ORTH:
+        raise ValueError(f"ArgumentError: Keyword `is_orthogonal` only supports: :none, :left, :right, got :{is_orthogonal}")
+    ct = tr._c()
+    _ck(lib.ttb_compress(A._hd, C.byref(ct), _ORTH[is_orthogonal]))
+    tr._after(A)
+    return A
+
+
+def _resid(A, t, left, b=0):
+    r = C.c_double()
+    _ck(lib.ttb_canonical_residual(A._hd, b, t, int(left), C.byref(r)))
+    return r.value
+
+
+def is_left_canonical(A, t: int, atol: float = 1e-10, b: int = 0) -> bool:
+    """src/tensor_train.jl:263-267 applied to site ``t`` (0-based)"""
+    return _resid(A, t, True, b) <= atol
+
+
+def is_right_canonical(A, t: int, atol: float = 1e-10, b: int = 0) -> bool:
+    """src/tensor_train.jl:269-273"""
+    return _resid(A, t, False, b) <= atol
+
+
+def is_canonical(A, central_idx: int, atol: float = 1e-10, b: int = 0) -> bool:
+    """src/tensor_train.jl:275-280 (1-based ``central_idx``)"""
+    return (all(is_left_canonical(A, t, atol, b) for t in range(0, central_idx - 1)) and
+            all(is_right_canonical(A, t, atol, b) for t in range(central_idx, A.L)))
+
+
+# ---- sampling ------------------------------------------------------------------------------------
+def sample(A, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None, b: int = 0):
+    """``sample`` (src/abstract_tensor_train.jl:335-384).  Without ``nsamples`` returns one draw
+    ``(x, p)`` like the reference (x = list over sites of 0-based multi-indices); with ``nsamples``
+    returns ``(X, p)`` with ``X`` an ``(nsamples, L)`` uint8 array of flat 0-based indices.
+    ``uniforms`` (``(nsamples, L)`` doubles) replaces the Philox stream (one ``rand`` per site)."""
+    n = 1 if nsamples is None else int(nsamples)
+    up = None
+    if uniforms is not None:
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(n, A.L))
+        up = _dp(u)
+    X = np.zeros((n, A.L), dtype=np.uint8)
+    p = np.zeros(n)
+    _ck(lib.ttb_sample(A._hd, b, n, C.c_uint64(seed), C.c_uint64(first_index), up,
+                       X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(p)))
+    if nsamples is None:
+        x = [list(np.unravel_index(int(xi), A.q, order="F")) for xi in X[0]]
+        return x, float(p[0])
+    return X, p
+
+
+def sample_stats(A, nsamples: int, seed: int = 0, first_index: int = 0, b: int = 0):
+    """Throughput variant: draws stay on the device; returns the ``(L, Q)`` histogram of the drawn
+    values and the sum of log-probabilities."""
+    hist = np.zeros((A.L, A.Q), dtype=np.int64)
+    slp = C.c_double(0.0)
+    _ck(lib.ttb_sample_stats(A._hd, b, int(nsamples), C.c_uint64(seed), C.c_uint64(first_index),
+                             hist.ctypes.data_as(_pi64), C.byref(slp)))
+    return hist, slp.value

@@ -1,0 +1,463 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes mirror) against the CPU oracle on the
+same seeded inputs.  Tolerances are the ones BASELINE.json's north_star states:
+  evaluate, log Z, marginals: rel 1e-10;  singular values |Δσ_k| <= 1e-8 σ_1;  post-truncation evaluate
+  rel 1e-8;  retained bond dimensions identical;  sampling: identical draws for injected uniforms,
+  chi-square for the Philox stream."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+from oracle import tt_oracle as O
+
+T = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global T
+    import ttb200
+    T = ttb200
+    T.set_device(0)
+    yield
+
+
+RNG = lambda s: np.random.Generator(np.random.Philox(s))
+REL = 1e-10
+
+
+def close(a, b, rel=REL, abs_=0.0):
+    return abs(a - b) <= rel * max(abs(a), abs(b)) + abs_
+
+
+def pair(tensors, periodic=False, z=1.0):
+    cls_g = T.PeriodicTensorTrain if periodic else T.TensorTrain
+    cls_o = O.PeriodicTensorTrain if periodic else O.TensorTrain
+    return cls_g(tensors, z=z), cls_o([a.copy() for a in tensors], z=z)
+
+
+def rand_open(rng, bonds, q, fill="rand"):
+    f = (lambda s: rng.random(s)) if fill == "rand" else (lambda s: rng.standard_normal(s) / math.sqrt(max(bonds)))
+    return [f((bonds[t], bonds[t + 1]) + tuple(q)) for t in range(len(bonds) - 1)]
+
+
+def rand_per(rng, bonds, q):
+    n = len(bonds)
+    return [rng.random((bonds[t], bonds[(t + 1) % n]) + tuple(q)) for t in range(n)]
+
+
+def rand_points(rng, Ao, n):
+    Qs = [int(np.prod(a.shape[2:])) for a in Ao]
+    return np.stack([rng.integers(0, Q, n) for Q in Qs], axis=1).astype(np.int32)
+
+
+def o_eval_flat(Ao, xf):
+    return O.evaluate(Ao, [np.unravel_index(int(x), a.shape[2:], order="F") for x, a in zip(xf, Ao)])
+
+
+def check_evals(A, Ao, X, rel, signed=False):
+    """signed=True (randn fills): values cancel, so the error is measured against the largest |value|
+    of the point set instead of each value."""
+    g = T.evaluate(A, X)
+    e = np.array([o_eval_flat(Ao, X[i]) for i in range(X.shape[0])])
+    if signed:
+        assert np.max(np.abs(g - e)) <= rel * np.max(np.abs(e)), (g, e)
+    else:
+        for i in range(X.shape[0]):
+            assert close(g[i], e[i], rel, 1e-300), (i, g[i], e[i])
+
+
+# ---- container -------------------------------------------------------------------------------------
+def test_container_roundtrip_and_metadata():
+    rng = RNG(100)
+    ts = rand_open(rng, [1, 3, 4, 10, 1], (2, 2))
+    A, Ao = pair(ts, z=12.3)
+    assert T.bond_dims(A) == [1, 3, 4, 10] == O.bond_dims(Ao)
+    assert T.nparams(A) == O.nparams(Ao)
+    for t in range(4):
+        assert np.array_equal(A.site(t), ts[t])
+    assert close(float(A.z), 12.3)
+    B = A.copy()
+    B.set_site(1, 2 * ts[1])
+    assert np.array_equal(A.site(1), ts[1]) and np.array_equal(B.site(1), 2 * ts[1])
+    with pytest.raises(ValueError):
+        T.TensorTrain([rng.random((2, 3, 2)), rng.random((3, 1, 2))])          # first bond != 1
+    with pytest.raises(ValueError):
+        T.TensorTrain([rng.random((1, 4, 2)), rng.random((3, 1, 2))])          # incompatible bonds
+    with pytest.raises(ValueError):
+        T.PeriodicTensorTrain([rng.random((2, 3, 2)), rng.random((3, 4, 2))])  # ring does not close
+
+
+# ---- evaluate / environments / marginals -------------------------------------------------------------
+@pytest.mark.parametrize("q", [(2,), (2, 3), (3, 1, 2)])
+def test_evaluate_and_environments_open(q):
+    rng = RNG(101 + len(q))
+    ts = rand_open(rng, [1, 5, 7, 3, 6, 1], q)
+    A, Ao = pair(ts, z=-0.37)
+    check_evals(A, Ao, rand_points(rng, Ao, 16), REL)
+    for norm in (True, False):
+        (l, zl), (lo, zlo) = T.accumulate_L(A, norm), O.accumulate_L(Ao, norm)
+        (r, zr), (ro, zro) = T.accumulate_R(A, norm), O.accumulate_R(Ao, norm)
+        for a, b in zip(l + r, lo + ro):
+            assert np.allclose(a, b, rtol=1e-10, atol=0)
+        assert close(zl.logabs, zlo.logabs, REL, 1e-12) and zl.sign == zlo.sign
+        assert close(zr.logabs, zro.logabs, REL, 1e-12) and zr.sign == zro.sign
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    assert zg.sign == zo.sign == -1 and close(zg.logabs, zo.logabs, REL, 1e-12)
+    with pytest.raises(ValueError):
+        T.lognormalization(A)
+    for a, b in zip(T.marginals(A), O.marginals(Ao)):
+        assert np.allclose(a, b, rtol=1e-10, atol=0)
+    m2, m2o = T.twovar_marginals(A), O.twovar_marginals(Ao)
+    assert set(m2) == set(m2o)
+    for k in m2o:
+        assert np.allclose(m2[k], m2o[k], rtol=1e-10, atol=0), k
+    m2 = T.twovar_marginals(A, maxdist=2)
+    m2o = O.twovar_marginals(Ao, maxdist=2)
+    assert set(m2) == set(m2o)
+    for k in m2o:
+        assert np.allclose(m2[k], m2o[k], rtol=1e-10, atol=0), k
+
+
+def test_evaluate_and_environments_periodic():
+    rng = RNG(110)
+    ts = rand_per(rng, [3, 5, 2, 4], (2, 2))
+    A, Ao = pair(ts, periodic=True)
+    check_evals(A, Ao, rand_points(rng, Ao, 16), REL)
+    (l, zl), (lo, zlo) = T.accumulate_L(A), O.accumulate_L(Ao)
+    (r, zr), (ro, zro) = T.accumulate_R(A), O.accumulate_R(Ao)
+    for a, b in zip(l + r, lo + ro):
+        assert np.allclose(a, b, rtol=1e-10, atol=0)
+    assert close(zl.logabs, zlo.logabs, REL) and close(zr.logabs, zro.logabs, REL)
+    assert close(float(T.normalization(A)), O.exact_normalization(Ao), 1e-10)
+    for a, b in zip(T.marginals(A), O.marginals(Ao)):
+        assert np.allclose(a, b, rtol=1e-10, atol=0)
+    m2, m2o = T.twovar_marginals(A), O.twovar_marginals(Ao)
+    for k in m2o:
+        assert np.allclose(m2[k], m2o[k], rtol=1e-10, atol=0), k
+    A2 = T.flat_periodic_tt([3, 5, 2, 4], 2, 3)
+    assert close(float(T.normalization(A2)), 1.0, 1e-12)
+
+
+def test_flat_known_normalization_and_normalize():
+    q, bonds = (2, 4), [1, 3, 5, 2, 1]
+    A = T.flat_tt(bonds, *q)
+    assert close(float(T.normalization(A)), np.prod(bonds) * np.prod(q) ** 4, 1e-12)
+    rng = RNG(111)
+    ts = rand_open(rng, [1, 6, 9, 4, 1], (3,))
+    A, Ao = pair(ts, z=5.0)
+    lg, lo = T.normalize_(A), O.normalize(Ao)
+    assert close(lg, lo, REL)
+    assert close(float(T.normalization(A)), 1.0, 1e-10) and close(float(A.z), 1.0)
+    for t in range(4):
+        assert np.allclose(A.site(t), Ao[t], rtol=1e-12)
+    A, Ao = pair(ts, z=-3.0)
+    T.normalize_eachmatrix_(A)
+    O.normalize_eachmatrix(Ao)
+    for t in range(4):
+        assert np.allclose(A.site(t), Ao[t], rtol=1e-14)
+    assert close(A.z.logabs, Ao.z.logabs, 1e-12) and A.z.sign == Ao.z.sign == -1
+
+
+def test_long_chain_stays_finite():
+    """test/tensor_train.jl:232-258 (L = 10 000, bonds 10..15)."""
+    rng = RNG(112)
+    L = 10000
+    bonds = [1] + list(rng.integers(10, 16, L - 1)) + [1]
+    ts = rand_open(rng, bonds, (2, 2))
+    A, Ao = pair(ts)
+    assert close(T.lognormalization(A), O.lognormalization(Ao), REL)
+    T.normalize_(A)
+    assert close(float(T.normalization(A)), 1.0, 1e-8)
+    A, Ao = pair([a * 1e-50 for a in ts])
+    assert close(T.lognormalization(A), O.lognormalization(Ao), REL)
+
+
+# ---- sweeps ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fill", ["rand", "randn"])
+def test_orthogonalize_eps0_gauge_invariance(fill):
+    rng = RNG(120)
+    ts = rand_open(rng, [1, 3, 4, 10, 7, 1], (2, 2), fill)
+    A, Ao = pair(ts, z=12.3)
+    X = rand_points(rng, Ao, 12)
+    z0 = O.normalization(Ao)
+    sg = fill == "randn"
+    T.orthogonalize_right_(A, T.TruncThresh(0.0))
+    check_evals(A, Ao, X, 1e-10, sg)
+    assert all(T.is_right_canonical(A, t) for t in range(1, 5))
+    Bo = Ao.copy(); O.orthogonalize_right(Bo, O.TruncThresh(0.0))
+    assert T.bond_dims(A) == O.bond_dims(Bo)
+    zg = T.normalization(A)
+    assert zg.sign == z0.sign and close(zg.logabs, z0.logabs, REL, 1e-12)
+    T.orthogonalize_left_(A, T.TruncThresh(0.0))
+    O.orthogonalize_left(Bo, O.TruncThresh(0.0))
+    check_evals(A, Ao, X, 1e-10, sg)
+    assert all(T.is_left_canonical(A, t) for t in range(0, 4))
+    assert T.bond_dims(A) == O.bond_dims(Bo)
+
+
+@pytest.mark.parametrize("trunc", ["thresh1e-3", "thresh1e-8", "bond3", "bondmax2", "bondthresh", "thresh1e-15"])
+@pytest.mark.parametrize("fill", ["rand", "randn"])
+def test_compress_matches_oracle(trunc, fill):
+    rng = RNG(130)
+    ts = rand_open(rng, [1, 4, 9, 12, 8, 5, 1], (3, 2), fill)
+    A, Ao = pair(ts)
+    mk = {"thresh1e-3": (T.TruncThresh(1e-3), O.TruncThresh(1e-3)), "thresh1e-8": (T.TruncThresh(1e-8), O.TruncThresh(1e-8)),
+          "bond3": (T.TruncBond(3), O.TruncBond(3)), "bondmax2": (T.TruncBondMax(2), O.TruncBondMax(2)),
+          "bondthresh": (T.TruncBondThresh(4, 1e-4), O.TruncBondThresh(4, 1e-4)),
+          "thresh1e-15": (T.TruncThresh(1e-15), O.TruncThresh(1e-15))}[trunc]
+    X = rand_points(rng, Ao, 12)
+    A.record_spectrum(True)
+    stats = []
+    T.compress_(A, mk[0])
+    O.compress(Ao, mk[1], stats=stats)
+    assert T.bond_dims(A) == O.bond_dims(Ao), (T.bond_dims(A), O.bond_dims(Ao))
+    for (t, lam_o, kept) in stats:      # left sweep at 1-based site t decides bond index t
+        lam_g = A.spectrum(t)
+        assert len(lam_g) == len(lam_o)
+        assert np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], (t, lam_g, lam_o)
+    check_evals(A, Ao, X, 1e-8, fill == "randn")
+    if trunc != "thresh1e-15":
+        assert all(T.is_left_canonical(A, t) for t in range(0, 5))
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    assert zg.sign == zo.sign and close(zg.logabs, zo.logabs, 1e-8, 1e-10)
+    if trunc == "bondmax2":
+        assert close(mk[0].maxerr[0], mk[1].maxerr[0], 1e-6, 1e-14)
+
+
+def test_compress_routes_and_errors():
+    """test/tensor_train.jl:217-230."""
+    rng = RNG(131)
+    ts = rand_open(rng, [1, 4, 4, 4, 4, 1], (3, 2), "randn")
+    tr = T.TruncThresh(1e-2)
+    A, Ao = pair(ts)
+    X = rand_points(rng, Ao, 8)
+    B = A.copy(); Cc = A.copy()
+    Bo = Ao.copy(); Co = Ao.copy()
+    T.compress_(A, tr); O.compress(Ao, O.TruncThresh(1e-2))
+    T.orthogonalize_right_(B, T.TruncThresh(0.0)); T.compress_(B, tr, is_orthogonal="right")
+    O.orthogonalize_right(Bo, O.TruncThresh(0.0)); O.compress(Bo, O.TruncThresh(1e-2), is_orthogonal="right")
+    T.orthogonalize_left_(Cc, T.TruncThresh(0.0)); T.compress_(Cc, tr, is_orthogonal="left")
+    O.orthogonalize_left(Co, O.TruncThresh(0.0)); O.compress(Co, O.TruncThresh(1e-2), is_orthogonal="left")
+    assert T.bond_dims(A) == O.bond_dims(Ao) and T.bond_dims(B) == O.bond_dims(Bo) and T.bond_dims(Cc) == O.bond_dims(Co)
+    check_evals(A, Ao, X, 1e-8, True); check_evals(B, Bo, X, 1e-8, True); check_evals(Cc, Co, X, 1e-8, True)
+    with pytest.raises(ValueError):
+        T.compress_(A, tr, is_orthogonal="something")
+    with pytest.raises(ValueError):
+        T.orthogonalize_right_(A, tr, indices=[1, 2])
+    with pytest.raises(ValueError):
+        T.orthogonalize_left_(A, tr, indices=[3, 2])
+
+
+def test_orthogonalize_center():
+    """test/tensor_train.jl:198-215."""
+    rng = RNG(132)
+    ts = rand_open(rng, [1, 3, 3, 3, 1], (2, 2), "randn")
+    A, Ao = pair(ts)
+    T.orthogonalize_center_(A, 2, T.TruncBond(3))
+    O.orthogonalize_center(Ao, 2, O.TruncBond(3))
+    assert T.is_canonical(A, 2)
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    assert zg.sign == zo.sign and close(zg.logabs, zo.logabs, 1e-8, 1e-10)
+    T.orthogonalize_two_site_center_(A, 2, T.TruncThresh(0.0))
+    assert T.is_right_canonical(A, 3)
+
+
+def test_periodic_sweeps_match_oracle():
+    """src/periodic_tensor_train.jl:83-141 incl. the wrap-around step order."""
+    rng = RNG(140)
+    ts = rand_per(rng, [4, 3, 5, 2, 6], (2, 3))
+    A, Ao = pair(ts, periodic=True)
+    X = rand_points(rng, Ao, 12)
+    T.orthogonalize_right_(A); Bo = Ao.copy(); O.orthogonalize_right(Bo)
+    assert T.bond_dims(A) == O.bond_dims(Bo)
+    check_evals(A, Ao, X, 1e-9)
+    T.orthogonalize_left_(A); O.orthogonalize_left(Bo)
+    assert T.bond_dims(A) == O.bond_dims(Bo)
+    check_evals(A, Ao, X, 1e-9)
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    assert close(zg.logabs, zo.logabs, 1e-9, 1e-10)
+    A, Ao = pair(ts, periodic=True)
+    T.compress_(A, T.TruncThresh(1e-6)); O.compress(Ao, O.TruncThresh(1e-6))
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    check_evals(A, Ao, X, 1e-8)
+    F = T.flat_periodic_tt([4, 4, 4, 4], 2); Fo = O.flat_periodic_tt([4, 4, 4, 4], 2)
+    T.compress_(F, T.TruncThresh(3e-2)); O.compress(Fo, O.TruncThresh(3e-2))
+    assert T.bond_dims(F) == O.bond_dims(Fo) and max(T.bond_dims(F)) < 4
+    assert close(float(T.normalization(F)), 1.0, 1e-8)
+
+
+def test_truncation_error_bound():
+    """test/svd_trunc.jl:1-24: norm2m(A,B) < (L eps)^2 (dot/norm evaluated by the oracle on the
+    downloaded tensors -- dot is a `next` row)."""
+    rng = RNG(141)
+    L = 10
+    ts = rand_open(rng, [1] + list(rng.integers(1, 4, L - 1)) + [1], (4, 4))
+    Bo = O.TensorTrain([a.copy() for a in ts]); O.normalize(Bo)
+    for eps in 10.0 ** np.arange(0.0, -5.5, -1.0):
+        A = T.TensorTrain([a.copy() for a in Bo.tensors])
+        T.compress_(A, T.TruncThresh(eps))
+        Ad = O.TensorTrain(A.tensors(), z=O.LogNum(logabs=A.z.logabs, sign=A.z.sign))
+        assert O.norm2m(Ad, Bo) < (L * eps) ** 2 + 1e-13
+
+
+def test_batched_periodic_matches_single():
+    rng = RNG(150)
+    B, bonds, q = 5, [4, 6, 3, 5], (2,)
+    n = len(bonds)
+    tsb = [rng.random((B, bonds[t], bonds[(t + 1) % n]) + q) for t in range(n)]
+    A = T.PeriodicTensorTrain(tsb, batched=True)
+    lz = T.normalize_(A)
+    m2 = T.twovar_marginals(A)
+    T.compress_(A, T.TruncThresh(1e-6))
+    for b in range(B):
+        Ao = O.PeriodicTensorTrain([a[b].copy() for a in tsb])
+        assert close(lz[b], O.normalize(Ao), REL)
+        m2o = O.twovar_marginals(Ao)
+        for k in m2o:
+            assert np.allclose(m2[b][k], m2o[k], rtol=1e-10, atol=0)
+        O.compress(Ao, O.TruncThresh(1e-6))
+        assert T.bond_dims(A, b) == O.bond_dims(Ao)
+        X = rand_points(rng, Ao, 4)
+        g = T.evaluate(A, X, b=b)
+        for i in range(4):
+            assert close(g[i], o_eval_flat(Ao, X[i]), 1e-8)
+
+
+# ---- sampling ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_sampling_injected_uniforms_bit_parity(periodic):
+    rng = RNG(160)
+    if periodic:
+        ts = rand_per(rng, [3, 4, 2, 3, 3], (3,))
+    else:
+        ts = rand_open(rng, [1, 5, 7, 3, 6, 1], (2, 2))
+    A, Ao = pair(ts, periodic=periodic)
+    n = 64
+    us = rng.random((n, len(ts)))
+    X, p = T.sample(A, n, uniforms=us)
+    rz = O.accumulate_R(Ao)
+    for i in range(n):
+        xo, po = O.sample(lambda t: us[i, t], Ao, rz=rz)
+        assert list(X[i]) == xo, i
+        assert close(p[i], po, 1e-9)
+    T.normalize_(A); O.normalize(Ao)
+    X2, p2 = T.sample(A, n, uniforms=us)
+    assert np.array_equal(X, X2)
+    g = T.evaluate(A, X2.astype(np.int32))
+    assert np.allclose(g, p2, rtol=1e-9)
+    x1, p1 = T.sample(A, uniforms=us[:1])
+    assert [int(np.ravel_multi_index(tuple(v), A.q, order="F")) for v in x1] == list(X[0])
+
+
+def test_sampling_philox_stream_and_chi_square():
+    rng = RNG(161)
+    ts = rand_open(rng, [1, 4, 6, 5, 1], (3,))
+    A, Ao = pair(ts)
+    T.normalize_(A); O.normalize(Ao)
+    n, seed, first = 20000, 1234, 77
+    X, p = T.sample(A, n, seed=seed, first_index=first)
+    # exact stream parity on a subset
+    rz = O.accumulate_R(Ao)
+    for i in range(32):
+        xo, _ = O.sample(lambda t: float(O.philox_uniform(seed, first + i, t)), Ao, rz=rz)
+        assert list(X[i]) == xo
+    # independence of the launch split: same global indices, two calls
+    Xa, _ = T.sample(A, 100, seed=seed, first_index=first)
+    Xb, _ = T.sample(A, 60, seed=seed, first_index=first + 40)
+    assert np.array_equal(X[:100], Xa) and np.array_equal(X[40:100], Xb)
+    # chi-square on single- and two-site marginals (critical values at p = 1e-6)
+    m1 = O.marginals(Ao)
+    for t in range(4):
+        cnt = np.bincount(X[:, t], minlength=3)
+        chi = np.sum((cnt - n * m1[t]) ** 2 / (n * m1[t]))
+        assert chi < 27.6, (t, chi)          # dof 2
+    m2 = O.twovar_marginals(Ao)
+    for (t, u), b in m2.items():
+        cnt = np.zeros((3, 3))
+        np.add.at(cnt, (X[:, t], X[:, u]), 1)
+        chi = np.sum((cnt - n * b) ** 2 / (n * b))
+        assert chi < 44.0, (t, u, chi)       # dof 8
+    hist, slp = T.sample_stats(A, n, seed=seed, first_index=first)
+    assert np.array_equal(hist, np.stack([np.bincount(X[:, t], minlength=3) for t in range(4)]))
+    assert close(slp, float(np.sum(np.log(p))), 1e-9)
+
+
+def test_sampling_negative_values_raise():
+    rng = RNG(162)
+    ts = rand_open(rng, [1, 6, 7, 5, 1], (2, 2))
+    ts[0] = -ts[0]
+    A, Ao = pair(ts)
+    zg = T.normalization(A)
+    assert zg.sign == -1 and close(float(zg), O.exact_normalization(Ao), 1e-10)
+    with pytest.raises(T.TTBError):
+        T.sample(A, 4, seed=1)
+
+
+# ---- the named configurations (reduced where the CPU oracle would take minutes) -----------------------
+def test_config2_pipeline():
+    """C2: L=128, q=2, d=64: orthogonalize_right!(eps=0) + compress!(TruncBond(32), :right) +
+    normalize! + marginals."""
+    rng = RNG(2)
+    L, d = 128, 64
+    ts = rand_open(rng, [1] + [d] * (L - 1) + [1], (2,))
+    A, Ao = pair(ts)
+    X = rand_points(rng, Ao, 6)
+    T.orthogonalize_right_(A, T.TruncThresh(0.0)); O.orthogonalize_right(Ao, O.TruncThresh(0.0))
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    A.record_spectrum(True)
+    stats = []
+    T.compress_(A, T.TruncBond(32), is_orthogonal="right")
+    O.compress(Ao, O.TruncBond(32), is_orthogonal="right", stats=stats)
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    for (t, lam_o, kept) in stats:
+        lam_g = A.spectrum(t)
+        assert len(lam_g) == len(lam_o) and np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], t
+    lg, lo = T.normalize_(A), O.normalize(Ao)
+    assert close(lg, lo, 1e-8)
+    for a, b in zip(T.marginals(A), O.marginals(Ao)):
+        assert np.allclose(a, b, rtol=1e-8, atol=1e-12)
+    g = T.evaluate(A, X)
+    for i in range(X.shape[0]):
+        assert close(g[i], o_eval_flat(Ao, X[i]), 1e-7, 1e-300)
+
+
+@pytest.mark.parametrize("fill", ["rand", "randn"])
+def test_config3_reduced(fill):
+    """C3 at reduced length: L=12, q=2, d=256, compress!(TruncThresh(1e-10))."""
+    rng = RNG(3)
+    L, d = 12, 256
+    bonds = [1] + [d] * (L - 1) + [1]
+    ts = rand_open(rng, bonds, (2,), fill)
+    A, Ao = pair(ts)
+    X = rand_points(rng, Ao, 6)
+    A.record_spectrum(True)
+    stats = []
+    T.compress_(A, T.TruncThresh(1e-10)); O.compress(Ao, O.TruncThresh(1e-10), stats=stats)
+    assert T.bond_dims(A) == O.bond_dims(Ao), (T.bond_dims(A), O.bond_dims(Ao))
+    for (t, lam_o, kept) in stats:
+        lam_g = A.spectrum(t)
+        assert len(lam_g) == len(lam_o) and np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], t
+    check_evals(A, Ao, X, 1e-8, fill == "randn")
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    if fill == "rand":
+        assert zg.sign == zo.sign and close(zg.logabs, zo.logabs, 1e-8, 1e-10)
+
+
+def test_config4_reduced_sampling():
+    """C4 at reduced length: L=24, q=4, d=128; normalize! then sample."""
+    rng = RNG(4)
+    L, d = 24, 128
+    ts = rand_open(rng, [1] + [d] * (L - 1) + [1], (4,))
+    A, Ao = pair(ts)
+    T.normalize_(A); O.normalize(Ao)
+    n = 16
+    us = rng.random((n, L))
+    X, p = T.sample(A, n, uniforms=us)
+    rz = O.accumulate_R(Ao)
+    for i in range(n):
+        xo, po = O.sample(lambda t: us[i, t], Ao, rz=rz)
+        assert list(X[i]) == xo and close(p[i], po, 1e-9)
