@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+Workload (N=1): config 3 of BASELINE.json -- one open TensorTrain, L=256, q=2, d=256, Float64,
+`rand_tt` fill (U[0,1), NumPy Philox seed 3+rank), full `compress!(TruncThresh(1e-10))` =
+eps=0 right sweep + truncating left sweep = 2(L-1) = 510 site-steps.  A bench "step" is one whole
+compress! on a fresh copy of the train.  metric = compress! site-steps/s.
+N>1: a single-train sweep is sequential in L and does not shard (DESIGN.md "replicas only"), so every
+rank compresses its own train (seed 3+rank): weak scaling, no data-path collective.
+
+JSON line keys beyond the base contract:
+  roofline     dominant kernel of the step, algorithmic FLOPs per launch / CUDA-event time per launch
+               against an FP64 peak measured in this run (cuBLAS DGEMM through torch.matmul)
+  cpu_baseline the CPU oracle (NumPy/SciPy-OpenBLAS gesdd restatement of the reference; Julia is not
+               installed) on the same workload, host cores of this box
+  extra        the second half of the metric string: sample draws/s on config 4 (L=256,q=4,d=128), and
+               the randn fill of config 3
+`--impl reference` times the CPU oracle (the reference's algorithm; kind "port") on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tensortrains.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+L3, D3, Q3 = 256, 256, 2
+L4, D4, Q4 = 256, 128, 4
+EPS3 = 1e-10
+
+
+def make_open(seed, L, d, q, fill="rand"):
+    rng = np.random.Generator(np.random.Philox(seed))
+    bonds = [1] + [d] * (L - 1) + [1]
+    if fill == "rand":
+        return bonds, [rng.random((bonds[t], bonds[t + 1], q)) for t in range(L)]
+    s = 1.0 / math.sqrt(d)
+    return bonds, [s * rng.standard_normal((bonds[t], bonds[t + 1], q)) for t in range(L)]
+
+
+def pack(tensors):
+    return np.concatenate([np.reshape(a, -1, order="F") for a in tensors])
+
+
+# ---- algorithmic work ----------------------------------------------------
+def qr_sweep_flops(bonds, Q, bw=32):
+    """eps=0 right sweep over an open train: per-kernel-class algorithmic FLOPs and launch counts.
+    Factor 2 m^2 (n - m/3) split into panel + trailing update, thin-Q formation, absorb 2 a m m' Q."""
+    L = len(bonds) - 1
+    b = list(bonds)
+    out = {"k_qr_panel": [0, 0.0], "k_qr_update": [0, 0.0], "k_apply_q": [0, 0.0], "k_absorb": [0, 0.0]}
+    for t in range(L - 1, 0, -1):
+        p, n, a = b[t + 1] * Q, b[t], b[t - 1]
+        k = min(p, n)
+        for j0 in range(0, k, bw):
+            bwc, rows = min(bw, k - j0), p - j0
+            out["k_qr_panel"][0] += 1
+            out["k_qr_panel"][1] += 2.0 * bwc * bwc * (rows - bwc / 3.0)
+            trail = n - j0 - bwc
+            if n - j0 - 1 > 0:
+                out["k_qr_update"][0] += 1
+                out["k_qr_update"][1] += 4.0 * rows * bwc * max(trail, 0)
+        out["k_apply_q"][0] += 1
+        out["k_apply_q"][1] += 2.0 * k * k * (p - k / 3.0)
+        out["k_absorb"][0] += 1
+        out["k_absorb"][1] += 2.0 * a * n * k * Q
+        b[t] = k
+    return out, b
+
+
+def clocks_sampler(stop, out, dev):
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active,"
+                              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                              "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+    except Exception:
+        return
+    def rd():
+        for line in p.stdout:
+            out.append(line.strip())
+    th = threading.Thread(target=rd, daemon=True)
+    th.start()
+    stop.wait()
+    p.terminate()
+
+
+def summarize_clocks(lines):
+    sm, mx, reasons = [], 0.0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        try:
+            sm.append(float(f[0])); mx = max(mx, float(f[1]))
+        except Exception:
+            continue
+        for nm, v in zip(names, f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(nm)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch, dev):
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_compress_steps_per_s(L, d, q, seed, reps=1):
+    from oracle import tt_oracle as O
+    _, ts = make_open(seed, L, d, q)
+    best = 1e99
+    for _ in range(reps):
+        A = O.TensorTrain([a.copy() for a in ts])
+        t0 = time.perf_counter()
+        O.compress(A, O.TruncThresh(EPS3))
+        best = min(best, time.perf_counter() - t0)
+    return 2 * (L - 1) / best, best
+
+
+def cpu_sample_draws_per_s(L, d, q, seed, n):
+    from oracle import tt_oracle as O
+    _, ts = make_open(seed, L, d, q)
+    A = O.TensorTrain(ts)
+    O.normalize(A)
+    rz = O.accumulate_R(A)
+    rng = np.random.default_rng(0)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        us = rng.random(L)
+        O.sample(lambda t: us[t], A, rz=rz)
+    return n / (time.perf_counter() - t0)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; Julia+MKL cannot run
+    here).  Each step = compress! of an L=32 slice of the config-3 shape (62 site-steps)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Ls = 32
+    for _ in range(args.warmup):
+        cpu_compress_steps_per_s(Ls, D3, Q3, 3)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_compress_steps_per_s(Ls, D3, Q3, 3)
+    dt = time.perf_counter() - t0
+    # the timed region includes input generation (~5%); subtract nothing, say so
+    val = args.steps * 2 * (Ls - 1) / dt
+    line = {"impl": "reference", "metric": "compress_site_steps_per_s", "value": val, "unit": "site-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 single TT q=2 d=256 rand_tt compress!(TruncThresh(1e-10))",
+                       "sample": "L=32 slice of the L=256 chain per step (62 of 510 site-steps, same 256x512 bulk matrices)"},
+            "cpu_baseline": {"value": val, "unit": "site-steps/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "L=32 slice, NumPy/SciPy-OpenBLAS gesdd restatement, not Julia/MKL"},
+            "e2e": {"value": val, "unit": "site-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sampling / randn / cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import ttb200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    T.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, max(args.warmup, 0)
+    bonds, ts = make_open(3 + rank, L3, D3, Q3)
+    nbytes = sum(a.size for a in ts) * 8
+    pin = T.PinnedBuffer(nbytes // 8)
+    pin.array[:] = pack(ts)
+    del ts
+    tr = T.TruncThresh(EPS3)
+    nsteps_unit = 2 * (L3 - 1)
+
+    # ---- device-resident arm: fresh copies made outside the timed region ----
+    base = T.TensorTrain.empty(bonds, (Q3,))
+    base.upload_all(pin.array)
+    copies = [base.copy() for _ in range(W + K)]
+    stop, clk = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, clk, local), daemon=True)
+    th.start()
+    for i in range(W):
+        T.compress_(copies[i], tr)
+    barrier()
+    dev_ms, launches = 0.0, 0
+    w0 = time.perf_counter()
+    for i in range(W, W + K):
+        T.compress_(copies[i], tr)
+        ms, nl = copies[i].last_timing()
+        dev_ms += ms; launches += nl
+    barrier()
+    wall = time.perf_counter() - w0
+    dev_ms = max_over_ranks(dev_ms)
+    bonds_after = T.bond_dims(copies[-1])
+    out_params = T.nparams(copies[-1])
+
+    # ---- end-to-end arm: pinned host -> device -> compress! -> host, every step ----
+    e2e_h = T.TensorTrain.empty(bonds, (Q3,))
+    outbuf = T.PinnedBuffer(nbytes // 8)
+    def e2e_step():
+        hh = T.TensorTrain.empty(bonds, (Q3,))
+        hh.upload_all(pin.array)
+        T.compress_(hh, tr)
+        n = T.nparams(hh)
+        hh.download_all(outbuf.array[:n])
+        return n
+    e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(K):
+        nout = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - e0)
+    stop.set()
+    del e2e_h
+
+    value = world * K * nsteps_unit / (dev_ms * 1e-3)
+    e2e_val = world * K * nsteps_unit / e2e_s
+
+    line = {"metric": "compress_site_steps_per_s", "value": value, "unit": "site-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: single TensorTrain L=256 q=2 d=256 Float64, rand_tt fill, compress!(TruncThresh(1e-10)) "
+                                   "= 510 site-steps per step; one train per GPU (replicas, no collective)",
+                       "l2": "input 254 MiB per train > 126 MB L2; every step runs on a fresh copy",
+                       "timing": "CUDA events on the library stream around each compress! call, summed over steps, max over ranks",
+                       "wall_s": wall, "bonds_after_max": int(max(bonds_after))},
+            "e2e": {"value": e2e_val, "unit": "site-steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(nout) * 8,
+                    "note": "pinned host tensors -> ttb_upload_all -> ttb_compress -> ttb_download_all, wall clock"},
+            "gpu_launches": int(launches),
+            "clocks": summarize_clocks(clk)}
+
+    if rank == 0:
+        # ---- roofline: per-kernel CUDA-event times of one more compress! ----
+        prof = base.copy()
+        prof.profile(True)
+        T.compress_(prof, tr)
+        rep = prof.profile_report()
+        prof.profile(False)
+        peak = measure_fp64_peak(torch, dev)
+        fl, _ = qr_sweep_flops(bonds, Q3)
+        tot_ms = sum(v[1] for v in rep.values())
+        dom = max(rep, key=lambda k: rep[k][1])
+        n_l, ms = rep[dom]
+        # algorithmic FLOPs of the dominant class over the step (right sweep; the left sweep of the
+        # rand fill works on <=16-row matrices and is negligible) -- DESIGN.md states the formulas
+        key = dom if dom in fl else None
+        alg = fl[key][1] if key else 0.0
+        per_launch = alg / max(n_l, 1)
+        achieved = per_launch / (ms / n_l * 1e-3) / 1e12 if ms > 0 else 0.0
+        line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
+                                           "MEASURED_PEAKS.json has no FP64 entry",
+                            "share_of_step": ms / tot_ms if tot_ms else None,
+                            "flops_per_launch": per_launch, "launches": n_l, "ms_per_launch": ms / n_l,
+                            "kernels": {k: {"launches": v[0], "ms": v[1], "alg_gflop": fl.get(k, [0, 0.0])[1] / 1e9}
+                                        for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
+                            "whole_step": {"alg_gflop": sum(v[1] for v in fl.values()) / 1e9,
+                                           "tflops": sum(v[1] for v in fl.values()) / (dev_ms / K * 1e-3) / 1e12}}
+        if world == 1 and not args.no_extra:
+            v, secs = cpu_compress_steps_per_s(L3, D3, Q3, 3)
+            line["cpu_baseline"] = {"value": v, "unit": "site-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"the full C3 compress! once ({secs:.1f} s): NumPy/SciPy-OpenBLAS gesdd "
+                                              "restatement of the reference, not Julia/MKL"}
+            extra = {}
+            try:
+                # sampling half of the metric: config 4
+                b4, t4 = make_open(4, L4, D4, Q4)
+                A4 = T.TensorTrain(t4)
+                T.normalize_(A4)
+                nd = 20000
+                T.sample_stats(A4, 2000, seed=1)
+                t0 = time.perf_counter()
+                T.sample_stats(A4, nd, seed=1, first_index=0)
+                ms4, _ = A4.last_timing()
+                extra["sample"] = {"workload": "C4: L=256 q=4 d=128 rand_tt, normalize! then sample", "draws": nd,
+                                   "draws_per_s": nd / (ms4 * 1e-3), "wall_draws_per_s": nd / (time.perf_counter() - t0),
+                                   "cpu_draws_per_s": cpu_sample_draws_per_s(L4, D4, Q4, 4, 20),
+                                   "alg_mflop_per_draw": 8.65}
+                del A4
+                # randn fill of config 3 (both sweeps full rank): reduced length
+                Lr = 16
+                br, tsr = make_open(3, Lr, D3, Q3, "randn")
+                Ar = T.TensorTrain(tsr)
+                T.compress_(Ar.copy(), tr)
+                T.compress_(Ar, tr)
+                msr, _ = Ar.last_timing()
+                extra["randn_fill"] = {"workload": f"C3 shape, randn_tt fill, L={Lr}", "site_steps_per_s": 2 * (Lr - 1) / (msr * 1e-3)}
+            except Exception as ex:  # the headline line must still be printed
+                extra["error"] = repr(ex)
+            line["extra"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ struct EnvCtx {
 #define ENV_AC 8  // environment rows handled per pass
 
 // l[t] (r x d_{t+1}) = (l[t-1] / nt) * sum_x A_t(:,:,x);  one CTA per train
-__global__ void k_accumulate_L(EnvCtx c) {
+__global__ void __launch_bounds__(1024) k_accumulate_L(EnvCtx c) {
   const int b = blockIdx.x;
   const int* bond = c.bond + (int64_t)b * c.L1;
   const double* tt = c.slab + (int64_t)b * c.tt_stride;
@@ -107,7 +107,7 @@ __global__ void k_accumulate_L(EnvCtx c) {
 }
 
 // r[t] (d_t x rr) = sum_x A_t(:,:,x) * (r[t+1] / nt);  one CTA per train
-__global__ void k_accumulate_R(EnvCtx c) {
+__global__ void __launch_bounds__(1024) k_accumulate_R(EnvCtx c) {
   const int b = blockIdx.x;
   const int* bond = c.bond + (int64_t)b * c.L1;
   const double* tt = c.slab + (int64_t)b * c.tt_stride;
@@ -500,7 +500,7 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
   } else {
     const size_t smem = sizeof(double) * (size_t)thr * ENV_AC;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
     TTB_LAUNCH(h, "k_accumulate_R", k_accumulate_R<<<(unsigned)h->batch, thr, smem, h->stream>>>(c));
   }
   return TTB_OK;
@@ -708,7 +708,7 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
       c.out = d_out; c.npairs = npairs;
       dim3 g((unsigned)(L - 1), (unsigned)h->batch);
       static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_twovar, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+      if (!attr) { cudaFuncSetAttribute(k_twovar, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
       TTB_LAUNCH(h, "k_twovar", k_twovar<<<g, 256, scr_in_smem ? smem_need : sizeof(double) * Q * Q, h->stream>>>(c));
       rc = tm.finish();
     }

@@ -276,7 +276,7 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     c.uniforms = d_u; c.seed = seed; c.first = first;
     c.x_out = d_x; c.p_out = d_p; c.hist = d_hist; c.sum_logp = d_slp; c.status = h->d_status; c.nsamples = nsamples;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
     CallTimer tm(h);
     TTB_LAUNCH(h, "k_sample_prep", k_sample_prep<<<dim3(L, Q), 128, 0, h->stream>>>(c));
     const int thr = dmax <= 32 ? 64 : 128;

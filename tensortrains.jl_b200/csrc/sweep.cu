@@ -362,7 +362,7 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // one-sided Jacobi SVD on the rows of R (tall) or X (wide) + rank rule.  One CTA per train.
 // ---------------------------------------------------------------------------------------------
 template <bool SMEM>
-__global__ void k_jacobi(SweepCtx c, StepDesc s) {
+__global__ void __launch_bounds__(SMEM ? 512 : 1024) k_jacobi(SweepCtx c, StepDesc s) {
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
@@ -658,7 +658,7 @@ __global__ void k_canon_resid(const double* site, int dl, int dr, int Q, int lef
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static const int kMaxSmem = 227 * 1024;
+static const int kMaxSmem = 208 * 1024;
 static const int kCw = 4;
 
 int ensure_sweep_ws(ttb_tt* h) {

@@ -98,6 +98,8 @@ _sig("ttb_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_ui
 _sig("ttb_sample_stats", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
 _sig("ttb_dot", _h, _i64, _h, _i64, _pd)
 _sig("ttb_last_timing", _h, _pd, _pi64)
+_sig("ttb_profile", _h, C.c_int)
+_sig("ttb_profile_report", _h, C.c_char_p, C.c_size_t)
 lib.ttb_version.restype = C.c_int
 
 
@@ -358,8 +360,50 @@ class AbstractTensorTrain:
         _ck(lib.ttb_last_timing(self._hd, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def _sq(self, a):
-        return a if self.batched else a[0]
+    def profile(self, on: bool = True):
+        """Bracket every kernel launch of this handle with CUDA events (bench.py's roofline)."""
+        _ck(lib.ttb_profile(self._hd, int(on)))
+
+    def profile_report(self):
+        """``{kernel: (launches, total_ms)}`` since :meth:`profile` was switched on."""
+        buf = C.create_string_buffer(1 << 16)
+        _ck(lib.ttb_profile_report(self._hd, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
+
+    def upload_all(self, packed: np.ndarray):
+        """Raw packed upload (train-major, site-major, column-major sites at their current dims)."""
+        _ck(lib.ttb_upload_all(self._hd, _dp(packed)))
+
+    def download_all(self, out: np.ndarray):
+        _ck(lib.ttb_download_all(self._hd, _dp(out)))
+
+
+    @classmethod
+    def empty(cls, bonds: Sequence[int], q: Sequence[int], batch: int = 1):
+        """Allocate device storage only (zeros); fill it with :meth:`upload_all`."""
+        bond = np.array(list(bonds), dtype=np.int64)
+        hd = _h()
+        _ck(lib.ttb_create(len(bond) - 1, bond.ctypes.data_as(_pi64), int(np.prod(q)), int(cls.periodic), int(batch),
+                           C.byref(hd)))
+        return cls(None, batched=batch > 1, _handle=hd, _q=tuple(q))
+
+
+class PinnedBuffer:
+    """Page-locked host staging buffer (cudaHostAlloc) viewed as a float64 NumPy array."""
+
+    def __init__(self, n_doubles: int):
+        self._p = C.c_void_p()
+        _ck(lib.ttb_host_alloc(C.byref(self._p), int(n_doubles) * 8))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, _pd), shape=(int(n_doubles),))
+
+    def free(self):
+        if self._p:
+            lib.ttb_host_free(self._p)
+            self._p = C.c_void_p()
 
 
 class TensorTrain(AbstractTensorTrain):

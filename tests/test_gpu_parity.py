@@ -69,6 +69,14 @@ def check_evals(A, Ao, X, rel, signed=False):
             assert close(g[i], e[i], rel, 1e-300), (i, g[i], e[i])
 
 
+def spectra_close(lam_g, lam_o):
+    """|Δσ_k| <= 1e-8 σ_1 on the scale-normalised spectrum.  The absolute scale of the matrix a sweep
+    step factorises is NOT gauge invariant: the reference divides the previous step's D by max|D|
+    (tensor_train.jl:169-173), and max|.| changes under the orthogonal gauge freedom of the eps=0
+    sweep (QR here, U*lambda there).  Ratios sigma_k/sigma_1 -- all the rank rules use -- are."""
+    return len(lam_g) == len(lam_o) and np.max(np.abs(lam_g / lam_g[0] - lam_o / lam_o[0])) <= 1e-8
+
+
 # ---- container -------------------------------------------------------------------------------------
 def test_container_roundtrip_and_metadata():
     rng = RNG(100)
@@ -216,8 +224,7 @@ def test_compress_matches_oracle(trunc, fill):
     assert T.bond_dims(A) == O.bond_dims(Ao), (T.bond_dims(A), O.bond_dims(Ao))
     for (t, lam_o, kept) in stats:      # left sweep at 1-based site t decides bond index t
         lam_g = A.spectrum(t)
-        assert len(lam_g) == len(lam_o)
-        assert np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], (t, lam_g, lam_o)
+        assert spectra_close(lam_g, lam_o), (t, lam_g, lam_o)
     check_evals(A, Ao, X, 1e-8, fill == "randn")
     if trunc != "thresh1e-15":
         assert all(T.is_left_canonical(A, t) for t in range(0, 5))
@@ -415,7 +422,7 @@ def test_config2_pipeline():
     assert T.bond_dims(A) == O.bond_dims(Ao)
     for (t, lam_o, kept) in stats:
         lam_g = A.spectrum(t)
-        assert len(lam_g) == len(lam_o) and np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], t
+        assert spectra_close(lam_g, lam_o), (t, lam_g, lam_o)
     lg, lo = T.normalize_(A), O.normalize(Ao)
     assert close(lg, lo, 1e-8)
     for a, b in zip(T.marginals(A), O.marginals(Ao)):
@@ -440,7 +447,7 @@ def test_config3_reduced(fill):
     assert T.bond_dims(A) == O.bond_dims(Ao), (T.bond_dims(A), O.bond_dims(Ao))
     for (t, lam_o, kept) in stats:
         lam_g = A.spectrum(t)
-        assert len(lam_g) == len(lam_o) and np.max(np.abs(lam_g - lam_o)) <= 1e-8 * lam_o[0], t
+        assert spectra_close(lam_g, lam_o), (t, lam_g, lam_o)
     check_evals(A, Ao, X, 1e-8, fill == "randn")
     zg, zo = T.normalization(A), O.normalization(Ao)
     if fill == "rand":
