@@ -1,0 +1,407 @@
+// qr_fast.cuh -- the bw = 32 fast path of the blocked Householder QR (included by sweep.cu).
+//
+//  * k_qr_panel_reg : panel factorisation with the panel held in REGISTERS.  16 warps, warp w owns
+//    panel columns w and w+16, lane l holds rows l, l+32, ...  Per column: the owner warp forms the
+//    reflector (one warp-level reduction), publishes v through shared memory, ONE block barrier,
+//    then every warp applies it to its own columns with a warp-level dot -- no cross-warp reduction.
+//    The V^T V products the compact-WY T factor needs fall out of the same dots.
+//  * k_qr_update_tma / k_apply_q_tma : block-reflector application with the V panel staged in shared
+//    memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier), one copy per panel column.
+#pragma once
+
+namespace ttb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a transaction that never completes traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 26)) __trap();
+}
+
+// Stage `ncols` columns of `rows` doubles (column stride ld_g in global, `rows` in shared) into smem.
+// Bulk (TMA) path when every column start is 16-byte aligned, plain loads otherwise.  Called by all
+// threads; returns after the data is visible to the whole CTA.
+__device__ __forceinline__ void stage_columns(double* dst, const double* src, int rows, int ncols, int64_t ld_g,
+                                              uint64_t* bar, uint32_t& phase, bool aligned) {
+  if (aligned) {
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, (uint32_t)(rows * ncols * 8));
+      for (int cc = 0; cc < ncols; ++cc) bulk_g2s(dst + (size_t)rows * cc, src + ld_g * cc, (uint32_t)(rows * 8), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int cc = 0; cc < ncols; ++cc) {
+      const double* g = src + ld_g * cc;
+      double* sd = dst + (size_t)rows * cc;
+      for (int r = threadIdx.x; r < rows; r += blockDim.x) sd[r] = g[r];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int RPL>
+__global__ void __launch_bounds__(512, 1) k_qr_panel_reg(SweepCtx c, StepDesc s, int panel) {
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 2) return;
+  const int j0 = panel * 32;
+  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime = d.k;
+  if (j0 >= d.k) return;
+  const int bwc = min(32, d.k - j0);
+  const int rows = d.p - j0;  // host guarantees rows <= 32*RPL
+  const int64_t p = d.p;
+  double* X = xbuf(c, s.xin, b) + j0 + p * j0;  // panel origin
+  __shared__ double vs[2][32 * RPL];
+  __shared__ double sh_tau[32];
+  __shared__ double G[32 * 32];
+  __shared__ double Tm[32 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;  // 16 warps
+  double a[2][RPL];
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int cs = wid + 16 * s2;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = lane + 32 * i;
+      a[s2][i] = (cs < bwc && r < rows) ? X[r + p * cs] : 0.0;
+    }
+  }
+  for (int i = tid; i < 1024; i += 512) { G[i] = 0.0; Tm[i] = 0.0; }
+
+  // NOT unrolled: the body is executed once per column; unrolling 32x made the kernel a 50 KB
+  // straight line that ran at instruction-fetch speed (ncu: stall_no_inst + barrier, r1 profile).
+#pragma unroll 1
+  for (int cc = 0; cc < bwc; ++cc) {
+    const int buf = cc & 1;
+    const int ow = cc & 15;
+    const bool os = (cc >> 4) != 0;
+    if (wid == ow) {
+      double col[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) col[i] = os ? a[1][i] : a[0][i];
+      double part = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        if (r > cc) part += col[i] * col[i];
+      }
+      const double xn2 = warp_sum(part);
+      const double alpha = __shfl_sync(0xffffffffu, col[0], cc);
+      double tau = 0.0, scal = 0.0, beta = alpha;
+      if (xn2 > 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        // one division instead of two: r = 1/((alpha-beta)*beta)
+        const double den = alpha - beta;
+        const double rinv = 1.0 / (den * beta);
+        scal = beta * rinv;        // 1/(alpha-beta)
+        tau = -den * den * rinv;   // (beta-alpha)/beta
+      }
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        double v = 0.0;
+        if (r > cc) { v = col[i] * scal; col[i] = v; }
+        else if (r == cc) { v = 1.0; col[i] = beta; }
+        vs[buf][r] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        if (os) a[1][i] = col[i]; else a[0][i] = col[i];
+      }
+      if (lane == 0) sh_tau[cc] = tau;
+    }
+    __syncthreads();
+    const double tau = sh_tau[cc];
+    double v[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) v[i] = vs[buf][lane + 32 * i];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int cs = wid + 16 * s2;
+      if (cs < bwc && cs != cc) {  // warp-uniform
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) dot += v[i] * a[s2][i];
+        dot = warp_sum(dot);
+        if (cs > cc) {
+          if (tau != 0.0) {
+            const double w = tau * dot;
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+          }
+        } else if (lane == 0) {
+          G[cs + 32 * cc] = dot;  // V_cs^T v_cc for the T factor
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (wid == 0) {
+    for (int c2 = 0; c2 < bwc; ++c2) {
+      const double tc = sh_tau[c2];
+      if (lane == c2) Tm[c2 + 32 * c2] = tc;
+      if (lane < c2) {
+        double acc = 0.0;
+        for (int l = lane; l < c2; ++l) acc += Tm[lane + 32 * l] * G[l + 32 * c2];
+        Tm[lane + 32 * c2] = -tc * acc;
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int cs = wid + 16 * s2;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = lane + 32 * i;
+      if (cs < bwc && r < rows) X[r + p * cs] = a[s2][i];
+    }
+  }
+  __syncthreads();
+  double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * 1024;
+  for (int i = tid; i < 1024; i += 512) Tg[i] = Tm[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block reflector on a chunk held in shared memory:  Wc <- (I - V op(T) V^T) Wc,  op = T^T if TRANS.
+// Vs: rows x bwc unit-lower-trapezoidal (explicit 1 / 0), ld = rows.  Ts: 32 x 32 upper, ld 32.
+// Wc: rows x cwc, ld = ldw (cwc <= 4).  256 threads.  W, W2: 32*4 scratch each.
+// ---------------------------------------------------------------------------------------------
+template <bool TRANS>
+__device__ __forceinline__ void block_reflect(const double* Vs, const double* Ts, double* Wc, int ldw, int rows, int bwc,
+                                              int cwc, double* W, double* W2) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;  // 8 warps
+  // W = V^T Wc : warp handles i in [4*wid, 4*wid+4), all cc
+  {
+    double acc[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[ii][cc] = 0.0;
+    const int i0 = 4 * wid;
+    if (i0 < bwc) {
+      for (int r = lane; r < rows; r += 32) {
+        double vv[4], ww[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) vv[ii] = (i0 + ii < bwc) ? Vs[r + (size_t)rows * (i0 + ii)] : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) ww[cc] = (cc < cwc) ? Wc[r + (size_t)ldw * cc] : 0.0;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) acc[ii][cc] += vv[ii] * ww[cc];
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const double t = warp_sum(acc[ii][cc]);
+          if (lane == 0) W[(i0 + ii) + 32 * cc] = t;
+        }
+    }
+  }
+  __syncthreads();
+  // W2 = op(T) W without ever forming T: T^{-1} = diag(1/tau) + striu(V^T V) (compact-WY identity), so
+  // op(T) w is a 32-step triangular substitution on the Gram matrix the panel kernel produced for
+  // free.  One warp per right-hand side, lane = row.  Ts[lane + 32 i] must be G[lane][i] for the
+  // backward solve (T w) and G[i][lane] for the forward solve (T^T w; the caller stages G transposed);
+  // the diagonal holds tau.  tau = 0 (H = I) gives y_i = 0, like a zero row/column of T.
+  if (wid < 4) {
+    const int cc = wid;
+    double w = (lane < bwc && cc < cwc) ? W[lane + 32 * cc] : 0.0;
+    double y = 0.0;
+    if (TRANS) {
+      for (int i = 0; i < bwc; ++i) {
+        const double yi = __shfl_sync(0xffffffffu, w, i) * Ts[i + 32 * i];
+        if (lane > i) w -= Ts[lane + 32 * i] * yi;
+        if (lane == i) y = yi;
+      }
+    } else {
+      for (int i = bwc - 1; i >= 0; --i) {
+        const double yi = __shfl_sync(0xffffffffu, w, i) * Ts[i + 32 * i];
+        if (lane < i) w -= Ts[lane + 32 * i] * yi;
+        if (lane == i) y = yi;
+      }
+    }
+    W2[lane + 32 * cc] = y;
+  }
+  __syncthreads();
+  for (int r = tid; r < rows; r += 256) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int imax = min(r, bwc - 1);
+    for (int i = 0; i <= imax; ++i) {
+      const double vv = Vs[r + (size_t)rows * i];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[cc] += vv * W2[i + 32 * cc];
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      if (cc < cwc) Wc[r + (size_t)ldw * cc] -= acc[cc];
+  }
+  __syncthreads();
+}
+
+// make the staged panel explicit unit-lower-trapezoidal
+__device__ __forceinline__ void fix_unit_lower(double* Vs, int rows, int bwc) {
+  for (int i = threadIdx.x; i < bwc * bwc; i += blockDim.x) {
+    const int r = i % bwc, cc = i / bwc;
+    if (r < cc) Vs[r + (size_t)rows * cc] = 0.0;
+    else if (r == cc) Vs[r + (size_t)rows * cc] = 1.0;
+  }
+}
+
+// trailing update  A <- (I - V T^T V^T) A  for one chunk of <= 4 columns (bw == 32)
+__global__ void __launch_bounds__(256) k_qr_update_tma(SweepCtx c, StepDesc s, int panel) {
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 2) return;
+  const int j0 = panel * 32;
+  if (j0 >= d.k) return;
+  const int bwc = min(32, d.k - j0);
+  const int rows = d.p - j0;
+  const int jc0 = j0 + bwc + blockIdx.x * 4;
+  if (jc0 >= d.n) return;
+  const int cwc = min(4, d.n - jc0);
+  const int64_t p = d.p;
+  double* X = xbuf(c, s.xin, b);
+  extern __shared__ __align__(128) double smx[];
+  double* Ts = smx;               // 1024
+  double* W = Ts + 1024;          // 128
+  double* W2 = W + 128;           // 128
+  double* As = W2 + 128;          // rows*4
+  double* Vs = As + (size_t)rows * 4;  // rows*32
+  __shared__ __align__(8) uint64_t bar;
+  uint32_t phase = 0;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(&bar, 1);
+  const double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * 1024;
+  __syncthreads();
+  const bool aligned = ((p & 1) == 0);
+  // one barrier phase covers both the V panel and the chunk; the T factor is fetched while TMA runs
+  if (aligned) {
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar, (uint32_t)(rows * (bwc + cwc) * 8));
+      for (int cc = 0; cc < bwc; ++cc)
+        bulk_g2s(Vs + (size_t)rows * cc, X + j0 + p * (j0 + cc), (uint32_t)(rows * 8), &bar);
+      for (int cc = 0; cc < cwc; ++cc)
+        bulk_g2s(As + (size_t)rows * cc, X + j0 + p * (jc0 + cc), (uint32_t)(rows * 8), &bar);
+    }
+    {
+      double t4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t4[u] = Tg[tid + 256 * u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // staged TRANSPOSED: the forward solve reads G[i][lane]
+        const int idx = tid + 256 * u;
+        Ts[(idx >> 5) + 32 * (idx & 31)] = t4[u];
+      }
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = tid; i < 1024; i += 256) Ts[(i >> 5) + 32 * (i & 31)] = Tg[i];
+    stage_columns(Vs, X + j0 + p * j0, rows, bwc, p, &bar, phase, false);
+    stage_columns(As, X + j0 + p * jc0, rows, cwc, p, &bar, phase, false);
+  }
+  fix_unit_lower(Vs, rows, bwc);
+  __syncthreads();
+  block_reflect<true>(Vs, Ts, As, rows, rows, bwc, cwc, W, W2);
+  for (int i = tid; i < rows * cwc; i += 256) {
+    const int r = i % rows, cc = i / rows;
+    X[(j0 + r) + p * (jc0 + cc)] = As[i];
+  }
+}
+
+// W = H_1 ... H_k E for one chunk of <= 4 columns, written into the site tensor (bw == 32)
+__global__ void __launch_bounds__(256) k_apply_q_tma(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime;
+  const int c0 = blockIdx.x * 4;
+  if (c0 >= mprime) return;
+  const int cwc = min(4, mprime - c0);
+  const int p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  extern __shared__ __align__(128) double smx[];
+  double* Ts = smx;               // 1024
+  double* W = Ts + 1024;          // 128
+  double* W2 = W + 128;           // 128
+  double* Wc = W2 + 128;          // p*4
+  double* Vs = Wc + (size_t)p * 4;  // rows*32
+  __shared__ __align__(8) uint64_t bar;
+  uint32_t phase = 0;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(&bar, 1);
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* Jv = c.Jv + (int64_t)b * c.jv_stride;
+  for (int i = tid; i < p * cwc; i += 256) {
+    const int r = i % p, cc = i / p;
+    double v;
+    if (d.mode == 0) v = (r == c0 + cc) ? 1.0 : 0.0;
+    else v = r < d.k ? Jv[(int64_t)perm[c0 + cc] * c.ldj + r] : 0.0;
+    Wc[i] = v;
+  }
+  __syncthreads();
+  if (d.mode != 2) {
+    const bool aligned = ((p & 1) == 0);
+    const int np = (d.k + 31) / 32;
+    for (int panel = np - 1; panel >= 0; --panel) {
+      const int j0 = panel * 32;
+      if (d.mode == 0 && j0 > c0 + cwc - 1) continue;
+      const int bwc = min(32, d.k - j0);
+      const int rows = p - j0;
+      const double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * 1024;
+      for (int i = tid; i < 1024; i += 256) Ts[i] = Tg[i];
+      stage_columns(Vs, X + j0 + (int64_t)p * j0, rows, bwc, p, &bar, phase, aligned);
+      fix_unit_lower(Vs, rows, bwc);
+      __syncthreads();
+      block_reflect<false>(Vs, Ts, Wc + j0, p, rows, bwc, cwc, W, W2);
+    }
+  }
+  double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.site];
+  if (s.dir == 0) {
+    for (int i = tid; i < p * cwc; i += 256) {
+      const int cc = i % cwc, r = i / cwc;
+      site[(c0 + cc) + (int64_t)mprime * r] = Wc[r + (size_t)p * cc];
+    }
+  } else {
+    const int dl = p / c.Q;
+    for (int i = tid; i < p * cwc; i += 256) {
+      const int r = i % p, cc = i / p;
+      const int m = r % dl, x = r / dl;
+      site[m + (int64_t)dl * ((c0 + cc) + (int64_t)mprime * x)] = Wc[i];
+    }
+  }
+}
+
+}  // namespace ttb

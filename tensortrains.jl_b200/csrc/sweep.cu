@@ -332,6 +332,11 @@ __global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
   }
 }
 
+}  // namespace ttb
+#include "qr_fast.cuh"
+#include "qr_panel.cuh"
+namespace ttb {
+
 // ---------------------------------------------------------------------------------------------
 // rank rules  (src/svd_trunc.jl:38-47, :74, :98-100, :130-140); lam descending, m = length
 // ---------------------------------------------------------------------------------------------
@@ -361,8 +366,9 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // ---------------------------------------------------------------------------------------------
 // one-sided Jacobi SVD on the rows of R (tall) or X (wide) + rank rule.  One CTA per train.
 // ---------------------------------------------------------------------------------------------
-template <bool SMEM>
-__global__ void __launch_bounds__(SMEM ? 512 : 1024) k_jacobi(SweepCtx c, StepDesc s) {
+// `smem_doubles` = dynamic shared memory the launch provides; the vectors live in shared memory when
+// the ACTUAL (device-known) sizes fit, in the global workspace otherwise.
+__global__ void __launch_bounds__(512) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 1024) k_jacobi(SweepCtx c, StepDe
   extern __shared__ double sm[];
   double* sig = sm;                 // n_max
   double* srt = sig + c.n_max;      // n_max
+  const bool SMEM = 2 * (int64_t)c.n_max + (int64_t)nv * (len + nv) <= (int64_t)smem_doubles;
   double* B = SMEM ? (srt + c.n_max) : Bg;
   const int ldb = SMEM ? len : c.ldv;
   double* J = SMEM ? (B + (size_t)nv * ldb) : Jg;
@@ -396,6 +403,7 @@ __global__ void __launch_bounds__(SMEM ? 512 : 1024) k_jacobi(SweepCtx c, StepDe
   const int nvp = (nv + 1) & ~1;
   const int npairs = nvp / 2, rounds = nvp - 1;
   const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
   bool conv = (nv < 2);
   for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
     if (tid == 0) rotated = 0;
@@ -415,10 +423,11 @@ __global__ void __launch_bounds__(SMEM ? 512 : 1024) k_jacobi(SweepCtx c, StepDe
           al += x * x; be += y * y; ga += x * y;
         }
         al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-        if (al > 0.0 && be > 0.0 && fabs(ga) > tol * sqrt(al) * sqrt(be)) {
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
+          // tan(theta) from tan(2 theta) = 2 ga / (be - al): one sqrt, one division, one rsqrt
+          const double da = be - al, b2 = 2.0 * ga;
+          const double t = b2 / (da + copysign(sqrt(da * da + b2 * b2), da));
+          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
           for (int e = lane; e < len; e += 32) {
             const double x = bi[e], y = bj[e];
             bi[e] = cs * x - sn * y;
@@ -578,6 +587,126 @@ __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
   if ((tid & 31) == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
 }
 
+// DMMA variant: 32x32 output tile per CTA (4 warps, each 16x16 = two m16n8k8 FP64 tensor-core tiles),
+// K staged 32 at a time through shared memory with register prefetch of the next stage.
+#define AM_T 32
+#define AM_K 32
+#define AM_LD 36  // row stride == 4 (mod 16): fragment loads are conflict-free per half-warp
+__device__ __forceinline__ void dmma_16x8x8(double (&d)[4], const double (&a)[4], const double (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
+__global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
+  const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime;
+  const int i0 = blockIdx.x * AM_T, j0 = blockIdx.y * AM_T;
+  if (i0 >= mprime || j0 >= d.N) return;
+  const int n = d.n, N = d.N;
+  const int64_t p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  const double* Bv = c.Bv + (int64_t)b * c.bv_stride;
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+  double* Xn = xbuf(c, s.xin ^ 1, b);
+  __shared__ double Ss[AM_K][AM_LD];
+  __shared__ double Bs[AM_K][AM_LD];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = (wid & 1) * 16, wn = (wid >> 1) * 16;
+  double acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
+  double rs[8], rb[8];  // prefetch registers: 1024 elements / 128 threads
+  auto fetch = [&](int l0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = tid + 128 * u;
+      int ii, ll;
+      if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
+      else { ll = i % AM_K; ii = i / AM_K; }
+      const int gi = i0 + ii, gl = l0 + ll;
+      double v = 0.0;
+      if (gi < mprime && gl < n) {
+        if (d.mode == 0) v = gi <= gl ? X[gi + p * gl] : 0.0;
+        else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
+      }
+      rs[u] = v;
+      int l2, jj;
+      if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
+      else { jj = i % AM_T; l2 = i / AM_T; }
+      const int gl2 = l0 + l2, gj = j0 + jj;
+      double w = 0.0;
+      if (gl2 < n && gj < N)
+        w = s.dir == 1 ? nbr[gl2 + (int64_t)n * (gj + (int64_t)N * x)] : nbr[gj + (int64_t)N * (gl2 + (int64_t)n * x)];
+      rb[u] = w;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = tid + 128 * u;
+      int ii, ll;
+      if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
+      else { ll = i % AM_K; ii = i / AM_K; }
+      Ss[ll][ii] = rs[u];
+      int l2, jj;
+      if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
+      else { jj = i % AM_T; l2 = i / AM_T; }
+      Bs[l2][jj] = rb[u];
+    }
+  };
+  // mode 0: S is upper triangular -> K range starts at the tile's first row
+  const int lstart = (d.mode == 0) ? (i0 / AM_K) * AM_K : 0;
+  fetch(lstart);
+  for (int l0 = lstart; l0 < n; l0 += AM_K) {
+    __syncthreads();
+    stash();
+    __syncthreads();
+    if (l0 + AM_K < n) fetch(l0 + AM_K);
+#pragma unroll
+    for (int kk = 0; kk < AM_K; kk += 8) {
+      double af[4];
+      af[0] = Ss[kk + t4][wm + g];
+      af[1] = Ss[kk + t4][wm + g + 8];
+      af[2] = Ss[kk + t4 + 4][wm + g];
+      af[3] = Ss[kk + t4 + 4][wm + g + 8];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        double bf[2];
+        bf[0] = Bs[kk + t4][wn + nt * 8 + g];
+        bf[1] = Bs[kk + t4 + 4][wn + nt * 8 + g];
+        dmma_16x8x8(acc[nt], af, bf);
+      }
+    }
+  }
+  const int64_t ldo = (int64_t)mprime * c.Q;
+  double mx = 0.0;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gi = i0 + wm + g + ((e & 2) ? 8 : 0);
+      const int gj = j0 + wn + nt * 8 + t4 * 2 + (e & 1);
+      if (gi < mprime && gj < N) {
+        Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[nt][e];
+        mx = absmax_nan(mx, acc[nt][e]);
+      }
+    }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = other > bits ? other : bits;
+  }
+  if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
+}
+
 // rescale the absorb output: in place, or unfolded into the neighbour's site storage on the last step
 __global__ void k_rescale(SweepCtx c, StepDesc s) {
   const int b = blockIdx.y;
@@ -660,6 +789,7 @@ __global__ void k_canon_resid(const double* site, int dl, int dr, int Q, int lef
 // ---------------------------------------------------------------------------------------------
 static const int kMaxSmem = 208 * 1024;
 static const int kCw = 4;
+static const int kRankHintEvery = 4;  // truncating sweeps: bond read-back period (launch sizing only)
 
 int ensure_sweep_ws(ttb_tt* h) {
   Workspace& w = h->ws;
@@ -693,8 +823,13 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_jacobi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_jacobi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     attr_done = true;
   }
   w.sweep_ready = true;
@@ -737,7 +872,7 @@ static int check_trunc(const ttb_trunc* tr) {
 
 // Enqueue one sweep (no host synchronisation inside).  dir 0 = right, 1 = left.
 static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vector<HostStep>& steps,
-                         std::vector<int>& ub, bool& exact) {
+                         std::vector<int>& ub, std::vector<int>& lb) {
   TTB_TRY(ensure_sweep_ws(h));
   TTB_TRY(ensure_spectrum(h));
   Workspace& w = h->ws;
@@ -757,29 +892,62 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.kind = tr->kind; s.eps = tr->eps;
     s.cap = (int)std::min<int64_t>(tr->mprime, 1 << 30);
     s.bond_idx = hs.bond_idx; s.bond_idx2 = hs.bond_idx2; s.last = hs.last; s.slot = slot;
-    int p_ub, n_ub, N_ub;
-    if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; }
-    else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; }
+    // Launch-sizing hint: every few truncating steps read back the bond array the device has already
+    // committed.  The rank DECISION never leaves the device; the host only learns that later grids can
+    // be smaller (and that whole QR phases can be skipped when p < n is certain).
+    if (!qr_only && si > 0 && kRankHintEvery > 0 && si % kRankHintEvery == 0) {
+      TTB_TRY(sync_bonds_to_host(h));
+      const int L1h = (int)h->L + 1;
+      for (int t = 0; t < L1h; ++t) {
+        int v = 0, lo = 1 << 30;
+        for (int64_t bb = 0; bb < h->batch; ++bb) {
+          v = std::max(v, h->h_bond[bb * L1h + t]);
+          lo = std::min(lo, h->h_bond[bb * L1h + t]);
+        }
+        ub[t] = v; lb[t] = lo;
+      }
+    }
+    int p_ub, n_ub, N_ub, p_lb, n_lb;
+    if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
+    else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; p_lb = lb[hs.site] * Q; n_lb = lb[hs.site + 1]; }
     const int k_ub = std::min(p_ub, n_ub);
     if (si == 0) {
       const int64_t tot = (int64_t)p_ub * n_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 255) / 256, 2048), B);
       TTB_LAUNCH(h, "k_fold", k_fold<<<g, 256, 0, st>>>(c, s));
     }
-    const bool maybe_qr = qr_only || !(exact && p_ub < n_ub);
+    const bool maybe_qr = qr_only || !(p_ub < n_lb);  // p < n for every train => wide => Jacobi on X directly
+    // register-panel / TMA kernels (they exchange V^T V + tau instead of an explicit T factor)
+    const bool fast = (bw == 32 && p_ub <= 512);
     if (maybe_qr) {
       const int np = (k_ub + bw - 1) / bw;
       for (int panel = 0; panel < np; ++panel) {
         const int j0 = panel * bw;
         const int rows_ub = p_ub - j0;
-        const int thr = std::min(512, std::max(64, ((rows_ub + 31) / 32) * 32));
-        size_t smem = sizeof(double) * ((size_t)2 * bw * bw + 2 * bw + 40 + (size_t)rows_ub * bw);
-        TTB_LAUNCH(h, "k_qr_panel", k_qr_panel<<<B, thr, smem, st>>>(c, s, panel));
+        if (fast) {
+#define TTB_PANEL(RPL_)                                                                                   \
+  TTB_LAUNCH(h, "k_qr_panel_flag",                                                                        \
+             k_qr_panel_flag<RPL_><<<B, 512, sizeof(double) * (1024 * RPL_ + 2080) + 128, st>>>(c, s, panel))
+          if (rows_ub <= 64) TTB_PANEL(2);
+          else if (rows_ub <= 128) TTB_PANEL(4);
+          else if (rows_ub <= 256) TTB_PANEL(8);
+          else TTB_PANEL(16);
+#undef TTB_PANEL
+        } else {
+          const int thr = std::min(512, std::max(64, ((rows_ub + 31) / 32) * 32));
+          size_t smem = sizeof(double) * ((size_t)2 * bw * bw + 2 * bw + 40 + (size_t)rows_ub * bw);
+          TTB_LAUNCH(h, "k_qr_panel", k_qr_panel<<<B, thr, smem, st>>>(c, s, panel));
+        }
         const int trail = n_ub - j0 - 1;
         if (trail > 0) {
           dim3 g((trail + kCw - 1) / kCw, B);
-          size_t sm2 = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)rows_ub * (bw + kCw));
-          TTB_LAUNCH(h, "k_qr_update", k_qr_update<<<g, 256, sm2, st>>>(c, s, panel, kCw));
+          if (fast) {
+            size_t sm2 = sizeof(double) * ((size_t)1280 + (size_t)rows_ub * 36);
+            TTB_LAUNCH(h, "k_qr_update_tma", k_qr_update_tma<<<g, 256, sm2, st>>>(c, s, panel));
+          } else {
+            size_t sm2 = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)rows_ub * (bw + kCw));
+            TTB_LAUNCH(h, "k_qr_update", k_qr_update<<<g, 256, sm2, st>>>(c, s, panel, kCw));
+          }
         }
       }
     }
@@ -788,21 +956,23 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       if (tr->kind != TTB_TRUNC_THRESH) mp_ub = (int)std::min<int64_t>(mp_ub, tr->mprime);
       const int nv_ub = k_ub, len_ub = n_ub;
       const size_t need = sizeof(double) * (2 * (size_t)w.n_max + (size_t)nv_ub * (len_ub + nv_ub));
+      const size_t give = std::min<size_t>(need, (size_t)200 * 1024);
       const int thr = std::min(512, std::max(64, ((nv_ub / 2 + 1) * 32)));
-      if (need <= (size_t)200 * 1024)
-        TTB_LAUNCH(h, "k_jacobi_smem", k_jacobi<true><<<B, thr, need, st>>>(c, s));
-      else
-        TTB_LAUNCH(h, "k_jacobi_gmem", k_jacobi<false><<<B, 1024, sizeof(double) * 2 * w.n_max, st>>>(c, s));
+      TTB_LAUNCH(h, "k_jacobi", k_jacobi<<<B, thr, give, st>>>(c, s, (int)(give / sizeof(double))));
     }
     {
       dim3 g((mp_ub + kCw - 1) / kCw, B);
-      const int rows_ub = p_ub;
-      size_t smem = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)p_ub * kCw + (size_t)rows_ub * bw);
-      TTB_LAUNCH(h, "k_apply_q", k_apply_q<<<g, 256, smem, st>>>(c, s, kCw));
+      if (fast) {
+        size_t smem = sizeof(double) * ((size_t)1280 + (size_t)p_ub * 36);
+        TTB_LAUNCH(h, "k_apply_q_tma", k_apply_q_tma<<<g, 256, smem, st>>>(c, s));
+      } else {
+        size_t smem = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)p_ub * kCw + (size_t)p_ub * bw);
+        TTB_LAUNCH(h, "k_apply_q", k_apply_q<<<g, 256, smem, st>>>(c, s, kCw));
+      }
     }
     {
-      dim3 g((mp_ub + AB_TM - 1) / AB_TM, (N_ub + AB_TN - 1) / AB_TN, Q * B);
-      TTB_LAUNCH(h, "k_absorb", k_absorb<<<g, 256, 0, st>>>(c, s));
+      dim3 g((mp_ub + AM_T - 1) / AM_T, (N_ub + AM_T - 1) / AM_T, Q * B);
+      TTB_LAUNCH(h, "k_absorb_mma", k_absorb_mma<<<g, 128, 0, st>>>(c, s));
     }
     {
       const int64_t tot = (int64_t)mp_ub * Q * N_ub;
@@ -810,9 +980,9 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       TTB_LAUNCH(h, "k_rescale", k_rescale<<<g, 256, 0, st>>>(c, s));
       TTB_LAUNCH(h, "k_commit", k_commit<<<(B + 127) / 128, 128, 0, st>>>(c, s, B));
     }
-    ub[hs.bond_idx] = mp_ub;
-    if (hs.bond_idx2 >= 0) ub[hs.bond_idx2] = mp_ub;
-    if (!qr_only) exact = false;
+    const int mp_lb = qr_only ? std::min(p_lb, n_lb) : 1;
+    ub[hs.bond_idx] = mp_ub; lb[hs.bond_idx] = mp_lb;
+    if (hs.bond_idx2 >= 0) { ub[hs.bond_idx2] = mp_ub; lb[hs.bond_idx2] = mp_lb; }
     xin ^= 1; slot ^= 1;
   }
   cudaError_t e = cudaGetLastError();
@@ -820,15 +990,15 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   return TTB_OK;
 }
 
-static void bond_upper_bounds(ttb_tt* h, std::vector<int>& ub, bool& exact) {
+static void bond_upper_bounds(ttb_tt* h, std::vector<int>& ub, std::vector<int>& lb) {
   const int L1 = (int)h->L + 1;
   ub.assign(L1, 0);
-  exact = true;
+  lb.assign(L1, 1 << 30);
   for (int64_t b = 0; b < h->batch; ++b)
     for (int t = 0; t < L1; ++t) {
       const int v = h->h_bond[b * L1 + t];
-      if (b > 0 && v != ub[t]) exact = false;
       ub[t] = std::max(ub[t], v);
+      lb[t] = std::min(lb[t], v);
     }
 }
 
@@ -887,10 +1057,10 @@ int ttb_orthogonalize_right(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64
   std::vector<HostStep> steps;
   TTB_TRY(build_right(h, lo, hi, steps));
   if (steps.empty()) return TTB_OK;
-  std::vector<int> ub; bool exact;
-  bond_upper_bounds(h, ub, exact);
+  std::vector<int> ub, lb;
+  bond_upper_bounds(h, ub, lb);
   CallTimer tm(h);
-  TTB_TRY(enqueue_sweep(h, 0, tr, steps, ub, exact));
+  TTB_TRY(enqueue_sweep(h, 0, tr, steps, ub, lb));
   return finish_sweeps(h, tm);
 }
 
@@ -900,10 +1070,10 @@ int ttb_orthogonalize_left(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_
   std::vector<HostStep> steps;
   TTB_TRY(build_left(h, lo, hi, steps));
   if (steps.empty()) return TTB_OK;
-  std::vector<int> ub; bool exact;
-  bond_upper_bounds(h, ub, exact);
+  std::vector<int> ub, lb;
+  bond_upper_bounds(h, ub, lb);
   CallTimer tm(h);
-  TTB_TRY(enqueue_sweep(h, 1, tr, steps, ub, exact));
+  TTB_TRY(enqueue_sweep(h, 1, tr, steps, ub, lb));
   return finish_sweeps(h, tm);
 }
 
@@ -937,13 +1107,13 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
   std::vector<HostStep> rs, ls;
   TTB_TRY(build_right(h, 0, 0, rs));
   TTB_TRY(build_left(h, 0, 0, ls));
-  std::vector<int> ub; bool exact;
-  bond_upper_bounds(h, ub, exact);
+  std::vector<int> ub, lb;
+  bond_upper_bounds(h, ub, lb);
   ttb_trunc t0;
   t0.kind = TTB_TRUNC_THRESH; t0._pad = 0; t0.eps = 0.0; t0.mprime = 0;
   CallTimer tm(h);
-  if (!rs.empty()) TTB_TRY(enqueue_sweep(h, 0, &t0, rs, ub, exact));
-  if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, exact));
+  if (!rs.empty()) TTB_TRY(enqueue_sweep(h, 0, &t0, rs, ub, lb));
+  if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, lb));
   return finish_sweeps(h, tm);
 }
 
