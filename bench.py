@@ -235,12 +235,12 @@ def main():
     for i in range(W):
         T.compress_(copies[i], tr)
     barrier()
-    dev_ms, launches = 0.0, 0
+    dev_ms, launches, ms_each = 0.0, 0, []
     w0 = time.perf_counter()
     for i in range(W, W + K):
         T.compress_(copies[i], tr)
         ms, nl = copies[i].last_timing()
-        dev_ms += ms; launches += nl
+        dev_ms += ms; launches += nl; ms_each.append(round(ms, 3))
     barrier()
     wall = time.perf_counter() - w0
     dev_ms = max_over_ranks(dev_ms)
@@ -277,7 +277,7 @@ def main():
                                    "= 510 site-steps per step; one train per GPU (replicas, no collective)",
                        "l2": "input 254 MiB per train > 126 MB L2; every step runs on a fresh copy",
                        "timing": "CUDA events on the library stream around each compress! call, summed over steps, max over ranks",
-                       "wall_s": wall, "bonds_after_max": int(max(bonds_after))},
+                       "wall_s": wall, "ms_each": ms_each, "bonds_after_max": int(max(bonds_after))},
             "e2e": {"value": e2e_val, "unit": "site-steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(nout) * 8,
                     "note": "pinned host tensors -> ttb_upload_all -> ttb_compress -> ttb_download_all, wall clock"},
             "gpu_launches": int(launches),

@@ -44,6 +44,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 }  // namespace ttb
 #include "qr_panel.cuh"
 using namespace ttb;
+#ifndef NSV
+#define NSV 2
+#endif
 
 int main() {
   const int p = 512, n = 256;
@@ -57,15 +60,15 @@ int main() {
   c.L1 = 3; c.Q = 2; c.bw = 32; c.x_stride = (int64_t)p * n; c.t_stride = 8 * 1024;
   cudaMalloc(&c.X0, h.size() * 8); cudaMalloc(&c.T, 8 * 1024 * 8); cudaMalloc(&c.st, sizeof(StepState));
   s.site = 1; s.nbr = 0; s.dir = 0; s.xin = 0; s.qr_only = 1;
-  const size_t smem = sizeof(double) * (1024 * 16 + 2080) + 128;
-  cudaFuncSetAttribute(k_qr_panel_flag<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = sizeof(double) * (1024 * 16 + 1056) + 128;
+  cudaFuncSetAttribute(k_qr_panel_flag<16, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int panel = 0; panel < 2; ++panel) {
     float best = 1e9f;
     for (int rep = 0; rep < 5; ++rep) {
       cudaMemcpy(c.X0, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
       cudaEventRecord(e0);
-      k_qr_panel_flag<16><<<1, 512, smem>>>(c, s, panel);
+      k_qr_panel_flag<16, NSV><<<1, 1024 / NSV, smem>>>(c, s, panel);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
     }

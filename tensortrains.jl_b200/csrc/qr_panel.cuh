@@ -1,12 +1,16 @@
 // qr_panel.cuh -- k_qr_panel_flag: register-resident Householder panel (32 columns, <= 512 rows) whose
 // warps hand reflectors to each other through shared-memory flags instead of block barriers.
 //
-// Why (r1 ncu profiles of the barrier version): the panel is a chain of 32 dependent columns; with a
-// __syncthreads per column every column paid owner latency + the slowest warp + the barrier, ~2.4 us.
-// Here all 32 reflectors stay in shared memory (no buffer reuse => no WAR hazard), the owner of column
-// c publishes v_c and raises ready[c]; every warp consumes the reflectors in order at its own pace and
-// the owner of column c+1 updates THAT column first, so the chain per column is one warp's
-// norm -> rsqrt/rcp -> publish plus one dot+update.  Dots use 4 independent accumulators.
+// Layout: NW = 32/NS warps, warp w owns the NS panel columns w, w+NW, ...; lane l holds rows l+32i.
+// The panel is a chain of 32 dependent columns: reflector c can only be formed after reflector c-1
+// has been applied to column c.  All 32 reflectors stay in shared memory (no buffer reuse => no WAR
+// hazard); the owner of column c publishes v_c and raises ready[c]; every warp consumes the reflectors
+// in order at its own pace.  The owner of column c+1 applies v_c to THAT column first, forms and
+// publishes v_{c+1}, and only then catches up on its other columns.  The V^T V products that define the
+// compact-WY T factor (T^{-1} = diag(1/tau) + striu(V^T V)) fall out of the same dots and are shipped
+// as they are: no T factor is ever built (its serial recurrence cost a quarter of the kernel).
+// Measured building blocks (profiles/micro_lat.cu, B200): dependent DFMA 8, shfl+DADD 35, rsqrt ~80,
+// 1/x ~80, LDS ~70 cycles.
 #pragma once
 
 #ifndef TTB_PANEL_BACKOFF_NS
@@ -72,8 +76,11 @@ __device__ __forceinline__ double make_reflector(double (&col)[RPL], double* vco
   return tau;
 }
 
-template <int RPL>
-__global__ void __launch_bounds__(512, 1) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
+template <int RPL, int NS>
+__global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
+  constexpr int NW = 32 / NS;
+  constexpr int NT = 32 * NW;
+  constexpr int LDV = 32 * RPL;
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 2) return;
@@ -86,89 +93,93 @@ __global__ void __launch_bounds__(512, 1) k_qr_panel_flag(SweepCtx c, StepDesc s
   double* X = xbuf(c, s.xin, b) + j0 + p * j0;  // panel origin
   extern __shared__ __align__(16) double dyn[];
   double* vs = dyn;                       // [32][32*RPL] all reflectors of the panel
-  double* G = vs + 32 * 32 * RPL;         // 32*32
-  double* Tm = G + 1024;                  // 32*32
-  double* sh_tau = Tm + 1024;             // 32
+  double* G = vs + 32 * LDV;              // 32*32: striu = V^T V, diagonal = tau
+  double* sh_tau = G + 1024;              // 32
   int* ready = reinterpret_cast<int*>(sh_tau + 32);  // 32 flags
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;  // 16 warps
-  constexpr int LDV = 32 * RPL;
-  double a[2][RPL];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double a[NS][RPL];
 #pragma unroll
-  for (int s2 = 0; s2 < 2; ++s2) {
-    const int cs = wid + 16 * s2;
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid + NW * s2;
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + 32 * i;
       a[s2][i] = (cs < bwc && r < rows) ? X[r + p * cs] : 0.0;
     }
   }
-  for (int i = tid; i < 1024; i += 512) { G[i] = 0.0; Tm[i] = 0.0; }
+  for (int i = tid; i < 1024; i += NT) G[i] = 0.0;
   if (tid < 32) ready[tid] = 0;
   __syncthreads();
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[0] = clock64();
 #endif
 
-  // apply reflector ccv (already in registers as v) to one of this warp's two columns
-  auto apply_slot = [&](int ccv, const double (&v)[RPL], double tau, int s2) {
-    const int cs = wid + 16 * s2;
-    if (cs < bwc && cs != ccv) {  // warp-uniform
-      double dot = s2 ? dot_rpl<RPL>(v, a[1]) : dot_rpl<RPL>(v, a[0]);
-      dot = warp_sum(dot);
-      if (cs > ccv) {
-        if (tau != 0.0) {
-          const double w = tau * dot;
-          if (s2) {
+  // apply reflector ccv (in registers as v) to this warp's column slot `slot` (runtime index resolved
+  // by predication over the unrolled slots, so `a` stays in registers)
+  auto apply_slot = [&](int ccv, const double (&v)[RPL], double tau, int slot) {
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) a[1][i] -= v[i] * w;
-          } else {
+    for (int s2 = 0; s2 < NS; ++s2) {
+      if (s2 != slot) continue;
+      const int cs = wid + NW * s2;
+      if (cs < bwc && cs != ccv) {  // warp-uniform
+        const double dot = warp_sum(dot_rpl<RPL>(v, a[s2]));
+        if (cs > ccv) {
+          if (tau != 0.0) {
+            const double w = tau * dot;
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) a[0][i] -= v[i] * w;
+            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
           }
+        } else {
+          G[cs + 32 * ccv] = dot;  // V_cs^T v_ccv (same value from every lane)
         }
-      } else if (lane == 0) {
-        G[cs + 32 * ccv] = dot;  // V_cs^T v_ccv for the T factor
       }
     }
   };
-  bool pending = false;  // this warp still owes reflector cc-1 to its non-priority column
-  int pend_slot = 0;
+  bool pending = false;  // this warp still owes reflector cc-1 to its non-priority columns
+  int pend_pri = 0;
 #pragma unroll 1
   for (int cc = 0; cc < bwc; ++cc) {
-    const int ow = cc & 15;
-    const bool os = (cc >> 4) != 0;
+    const int ow = cc % NW;
+    const int os = cc / NW;
     if (wid == ow) {
       // ---- owner: form reflector cc from its (fully updated) column, in place ----
       double* vcol = vs + (size_t)cc * LDV;
-      const double tau = os ? make_reflector<RPL>(a[1], vcol, cc, lane) : make_reflector<RPL>(a[0], vcol, cc, lane);
-      if (lane == 0) sh_tau[cc] = tau;
-      // No MEMBAR here: shared-memory stores of one warp are performed in order, __syncwarp orders the
-      // lanes, and the flag is the last store (a CTA fence with 16 STS in flight cost ~600 cycles per
-      // column in the micro-benchmark, profiles/micro_panel.cu).
+      double tau = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 == os) tau = make_reflector<RPL>(a[s2], vcol, cc, lane);
+      // All lanes store the same tau / flag (no divergent region on the chain).  No MEMBAR: shared-memory
+      // stores of one warp are performed in order and the flag is the last store instruction.
+      sh_tau[cc] = tau;
       __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
+      *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
 #ifdef TTB_PANEL_STAMPS
       if (lane == 0) TTB_PANEL_STAMPS[8 + cc] = clock64();
 #endif
     } else {
       // ---- consumer: wait for reflector cc ----
-      if (lane == 0) {
+      // every lane polls the same word (a broadcast load): no divergence, no reconvergence barrier
+      {
         unsigned it = 0;
-        const bool hot = (wid == ((cc + 1) & 15));  // next link of the chain polls tightly
+        const bool hot = (wid == ((cc + 1) % NW));  // next link of the chain polls tightly
         while (ld_flag(&ready[cc]) == 0) {
-          if (!hot) __nanosleep(TTB_PANEL_BACKOFF_NS);  // keep the other pollers off the shared-memory pipe
+          if (!hot) __nanosleep(TTB_PANEL_BACKOFF_NS);
           if (++it > (1u << 26)) __trap();
         }
       }
-      __syncwarp();
     }
     double v[RPL];
-    if (pending) {  // catch up the column that was skipped while this warp hurried to publish
+#ifdef TTB_PANEL_CHAIN_ONLY  // timing experiment: only the critical chain does work (results are wrong)
+    pending = false;
+#endif
+    if (pending) {  // catch up the columns that were skipped while this warp hurried to publish
       const double taup = *reinterpret_cast<volatile double*>(&sh_tau[cc - 1]);
       const double* vp = vs + (size_t)(cc - 1) * LDV;
 #pragma unroll
       for (int i = 0; i < RPL; ++i) v[i] = vp[lane + 32 * i];
-      apply_slot(cc - 1, v, taup, pend_slot);
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 != pend_pri) apply_slot(cc - 1, v, taup, s2);
       pending = false;
     }
     const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
@@ -177,30 +188,33 @@ __global__ void __launch_bounds__(512, 1) k_qr_panel_flag(SweepCtx c, StepDesc s
 #pragma unroll
       for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
     }
-    // the slot that holds column cc+1 goes first: its owner is the next link of the chain and
-    // defers its other column until after it has published reflector cc+1
-    const int first = ((cc + 1) >> 4) & 1;
-    apply_slot(cc, v, tau, first);
-    if (cc + 1 < bwc && wid == ((cc + 1) & 15)) {
+    // the slot that holds column cc+1 goes first: its owner is the next link of the chain
+    const int pri = ((cc + 1) / NW) % NS;
+#ifdef TTB_PANEL_CHAIN_ONLY
+    if (wid == ((cc + 1) % NW)) apply_slot(cc, v, tau, pri);
+    continue;
+#endif
+    apply_slot(cc, v, tau, pri);
+    if (cc + 1 < bwc && wid == ((cc + 1) % NW)) {
       pending = true;
-      pend_slot = 1 - first;
+      pend_pri = pri;
     } else {
-      apply_slot(cc, v, tau, 1 - first);
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 != pri) apply_slot(cc, v, tau, s2);
     }
   }
   __syncthreads();
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[1] = clock64();
 #endif
-  // No T factor is built (that serial 32-step recurrence cost ~31k cycles, a quarter of the kernel):
-  // consumers solve with T^{-1} = diag(1/tau) + striu(V^T V) directly, so ship G with tau on the diagonal.
   if (tid < 32) G[tid + 32 * tid] = tid < bwc ? sh_tau[tid] : 0.0;
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[2] = clock64();
 #endif
 #pragma unroll
-  for (int s2 = 0; s2 < 2; ++s2) {
-    const int cs = wid + 16 * s2;
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid + NW * s2;
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + 32 * i;
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(512, 1) k_qr_panel_flag(SweepCtx c, StepDesc s
   if (tid == 0) TTB_PANEL_STAMPS[3] = clock64();
 #endif
   double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * 1024;
-  for (int i = tid; i < 1024; i += 512) Tg[i] = G[i];
+  for (int i = tid; i < 1024; i += NT) Tg[i] = G[i];
 }
 
 }  // namespace ttb

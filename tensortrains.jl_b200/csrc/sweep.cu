@@ -333,6 +333,9 @@ __global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
 }
 
 }  // namespace ttb
+#ifndef TTB_PANEL_NS
+#define TTB_PANEL_NS 4
+#endif
 #include "qr_fast.cuh"
 #include "qr_panel.cuh"
 namespace ttb {
@@ -789,6 +792,7 @@ __global__ void k_canon_resid(const double* site, int dl, int dr, int Q, int lef
 // ---------------------------------------------------------------------------------------------
 static const int kMaxSmem = 208 * 1024;
 static const int kCw = 4;
+static constexpr int kPanelNS = TTB_PANEL_NS;  // panel columns per warp (2 -> 16 warps, 4 -> 8 warps)
 static const int kRankHintEvery = 4;  // truncating sweeps: bond read-back period (launch sizing only)
 
 int ensure_sweep_ws(ttb_tt* h) {
@@ -826,10 +830,10 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_qr_panel_flag<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_qr_panel_flag<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_qr_panel_flag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_qr_panel_flag<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<2, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<4, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<8, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_panel_flag<16, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     attr_done = true;
   }
   w.sweep_ready = true;
@@ -927,7 +931,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         if (fast) {
 #define TTB_PANEL(RPL_)                                                                                   \
   TTB_LAUNCH(h, "k_qr_panel_flag",                                                                        \
-             k_qr_panel_flag<RPL_><<<B, 512, sizeof(double) * (1024 * RPL_ + 2080) + 128, st>>>(c, s, panel))
+             k_qr_panel_flag<RPL_, kPanelNS><<<B, 1024 / kPanelNS, sizeof(double) * (1024 * RPL_ + 1056) + 128, st>>>(c, s, panel))
           if (rows_ub <= 64) TTB_PANEL(2);
           else if (rows_ub <= 128) TTB_PANEL(4);
           else if (rows_ub <= 256) TTB_PANEL(8);
