@@ -1,48 +1,11 @@
 // qr_fast.cuh -- the bw = 32 fast path of the blocked Householder QR (included by sweep.cu).
 //
-//  * k_qr_panel_reg : panel factorisation with the panel held in REGISTERS.  16 warps, warp w owns
-//    panel columns w and w+16, lane l holds rows l, l+32, ...  Per column: the owner warp forms the
-//    reflector (one warp-level reduction), publishes v through shared memory, ONE block barrier,
-//    then every warp applies it to its own columns with a warp-level dot -- no cross-warp reduction.
-//    The V^T V products the compact-WY T factor needs fall out of the same dots.
+//  * the panel factorisation itself is k_qr_panel_flag in qr_panel.cuh.
 //  * k_qr_update_tma / k_apply_q_tma : block-reflector application with the V panel staged in shared
 //    memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier), one copy per panel column.
 #pragma once
 
 namespace ttb {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a transaction that never completes traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
-    if (it > (1u << 26)) __trap();
-}
 
 // Stage `ncols` columns of `rows` doubles (column stride ld_g in global, `rows` in shared) into smem.
 // Bulk (TMA) path when every column start is 16-byte aligned, plain loads otherwise.  Called by all
@@ -65,130 +28,6 @@ __device__ __forceinline__ void stage_columns(double* dst, const double* src, in
     }
     __syncthreads();
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-template <int RPL>
-__global__ void __launch_bounds__(512, 1) k_qr_panel_reg(SweepCtx c, StepDesc s, int panel) {
-  const int b = blockIdx.x;
-  const Dims d = get_dims(c, s, b);
-  if (d.mode == 2) return;
-  const int j0 = panel * 32;
-  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime = d.k;
-  if (j0 >= d.k) return;
-  const int bwc = min(32, d.k - j0);
-  const int rows = d.p - j0;  // host guarantees rows <= 32*RPL
-  const int64_t p = d.p;
-  double* X = xbuf(c, s.xin, b) + j0 + p * j0;  // panel origin
-  __shared__ double vs[2][32 * RPL];
-  __shared__ double sh_tau[32];
-  __shared__ double G[32 * 32];
-  __shared__ double Tm[32 * 32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;  // 16 warps
-  double a[2][RPL];
-#pragma unroll
-  for (int s2 = 0; s2 < 2; ++s2) {
-    const int cs = wid + 16 * s2;
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      const int r = lane + 32 * i;
-      a[s2][i] = (cs < bwc && r < rows) ? X[r + p * cs] : 0.0;
-    }
-  }
-  for (int i = tid; i < 1024; i += 512) { G[i] = 0.0; Tm[i] = 0.0; }
-
-  // NOT unrolled: the body is executed once per column; unrolling 32x made the kernel a 50 KB
-  // straight line that ran at instruction-fetch speed (ncu: stall_no_inst + barrier, r1 profile).
-#pragma unroll 1
-  for (int cc = 0; cc < bwc; ++cc) {
-    const int buf = cc & 1;
-    const int ow = cc & 15;
-    const bool os = (cc >> 4) != 0;
-    if (wid == ow) {
-      double col[RPL];
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) col[i] = os ? a[1][i] : a[0][i];
-      double part = 0.0;
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        const int r = lane + 32 * i;
-        if (r > cc) part += col[i] * col[i];
-      }
-      const double xn2 = warp_sum(part);
-      const double alpha = __shfl_sync(0xffffffffu, col[0], cc);
-      double tau = 0.0, scal = 0.0, beta = alpha;
-      if (xn2 > 0.0) {
-        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-        // one division instead of two: r = 1/((alpha-beta)*beta)
-        const double den = alpha - beta;
-        const double rinv = 1.0 / (den * beta);
-        scal = beta * rinv;        // 1/(alpha-beta)
-        tau = -den * den * rinv;   // (beta-alpha)/beta
-      }
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        const int r = lane + 32 * i;
-        double v = 0.0;
-        if (r > cc) { v = col[i] * scal; col[i] = v; }
-        else if (r == cc) { v = 1.0; col[i] = beta; }
-        vs[buf][r] = v;
-      }
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        if (os) a[1][i] = col[i]; else a[0][i] = col[i];
-      }
-      if (lane == 0) sh_tau[cc] = tau;
-    }
-    __syncthreads();
-    const double tau = sh_tau[cc];
-    double v[RPL];
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) v[i] = vs[buf][lane + 32 * i];
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const int cs = wid + 16 * s2;
-      if (cs < bwc && cs != cc) {  // warp-uniform
-        double dot = 0.0;
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) dot += v[i] * a[s2][i];
-        dot = warp_sum(dot);
-        if (cs > cc) {
-          if (tau != 0.0) {
-            const double w = tau * dot;
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-          }
-        } else if (lane == 0) {
-          G[cs + 32 * cc] = dot;  // V_cs^T v_cc for the T factor
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (wid == 0) {
-    for (int c2 = 0; c2 < bwc; ++c2) {
-      const double tc = sh_tau[c2];
-      if (lane == c2) Tm[c2 + 32 * c2] = tc;
-      if (lane < c2) {
-        double acc = 0.0;
-        for (int l = lane; l < c2; ++l) acc += Tm[lane + 32 * l] * G[l + 32 * c2];
-        Tm[lane + 32 * c2] = -tc * acc;
-      }
-      __syncwarp();
-    }
-  }
-#pragma unroll
-  for (int s2 = 0; s2 < 2; ++s2) {
-    const int cs = wid + 16 * s2;
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      const int r = lane + 32 * i;
-      if (cs < bwc && r < rows) X[r + p * cs] = a[s2][i];
-    }
-  }
-  __syncthreads();
-  double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)panel * 1024;
-  for (int i = tid; i < 1024; i += 512) Tg[i] = Tm[i];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 // (bit-parity tests) or from Philox4x32-10 keyed by (seed; global sample index, site).
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -216,7 +217,41 @@ __global__ void k_sample(SampCtx c, int64_t base) {
   }
 }
 
+// ---- packing for the tiled sampler: A_t as [site][k-chunk][x][n][8] and G_t as [site][m][8], zero padded
+struct PackCtx {
+  const double* slab; int64_t tt_stride; const int64_t* off; const int* bond; int L, L1, Q;
+  const double* envR; const int64_t* eoffR;
+  double* Ap; double* Gp; int b; int DP;
+};
+
+__global__ void k_sample_pack(PackCtx c) {
+  const int t = blockIdx.x, x = blockIdx.y;
+  const int* bond = c.bond + (int64_t)c.b * c.L1;
+  const int dl = bond[t], dr = bond[t + 1];
+  const int DP = c.DP, NKC = DP / 8;
+  const double* A = c.slab + (int64_t)c.b * c.tt_stride + c.off[t] + (int64_t)dl * dr * x;
+  const double* r = t < c.L - 1 ? c.envR + c.eoffR[t + 1] : nullptr;  // dr x 1 (open train)
+  double* Ap = c.Ap + (int64_t)t * NKC * c.Q * DP * 8;
+  for (int i = threadIdx.x; i < DP * DP; i += blockDim.x) {
+    const int k8 = i & 7, n = (i >> 3) % DP, kc = (i >> 3) / DP;
+    const int m = kc * 8 + k8;
+    Ap[(((int64_t)kc * c.Q + x) * DP + n) * 8 + k8] = (m < dl && n < dr) ? A[m + (int64_t)dl * n] : 0.0;
+  }
+  double* Gp = c.Gp + (int64_t)t * DP * 8;
+  for (int m = threadIdx.x; m < DP; m += blockDim.x) {
+    double acc = 0.0;
+    if (m < dl) {
+      if (r) for (int n = 0; n < dr; ++n) acc += A[m + (int64_t)dl * n] * r[n];
+      else acc = A[m];  // last site: dr == 1, r = 1
+    }
+    Gp[m * 8 + x] = acc;
+  }
+}
+
 }  // namespace ttb
+
+#include "tma_mma.cuh"
+#include "sample_tile.cuh"
 
 using namespace ttb;
 
@@ -277,14 +312,55 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     c.x_out = d_x; c.p_out = d_p; c.hist = d_hist; c.sum_logp = d_slp; c.status = h->d_status; c.nsamples = nsamples;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
+    // Tiled tensor-core sampler for open trains whose state fits (d <= 128); the generic one-CTA-per-draw
+    // kernel covers periodic trains, larger bonds and tiny requests.
+    const int DP = dmax <= 32 ? 32 : (dmax <= 64 ? 64 : 128);
+    const size_t tile_smem = sizeof(double) * ((size_t)(ST_SMAX + 1) * (DP + 4) + 2 * (size_t)Q * DP * 8 + (size_t)DP * 8 +
+                                               ST_SMAX * 10) +
+                             sizeof(int) * (ST_SMAX + ST_MAXTILES * 17 + 4) + sizeof(unsigned) * (size_t)L * Q + 64;
+    const bool tiled = !h->periodic && rmax == 1 && dmax <= 128 && Q <= 8 && nsamples >= 32 && tile_smem <= 200 * 1024 &&
+                       getenv("TTB_SAMPLE_GENERIC") == nullptr;
+    double *d_Ap = nullptr, *d_Gp = nullptr;
     CallTimer tm(h);
-    TTB_LAUNCH(h, "k_sample_prep", k_sample_prep<<<dim3(L, Q), 128, 0, h->stream>>>(c));
-    const int thr = dmax <= 32 ? 64 : 128;
-    for (int64_t base = 0; base < nsamples; base += (int64_t)1 << 30) {
-      const unsigned g = (unsigned)std::min<int64_t>(nsamples - base, (int64_t)1 << 30);
-      TTB_LAUNCH(h, "k_sample", k_sample<<<g, thr, smem, h->stream>>>(c, base));
+    if (tiled) {
+      const size_t nAp = (size_t)L * DP * DP * Q, nGp = (size_t)L * DP * 8;
+      e = cudaMalloc(&d_Ap, sizeof(double) * nAp);
+      if (e == cudaSuccess) e = cudaMalloc(&d_Gp, sizeof(double) * nGp);
+      if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "sample pack buffers: %s", cudaGetErrorString(e));
+      if (rc == TTB_OK) {
+        cudaMemsetAsync(d_Gp, 0, sizeof(double) * nGp, h->stream);
+        PackCtx pc;
+        pc.slab = h->slab; pc.tt_stride = h->tt_stride; pc.off = h->d_off; pc.bond = h->d_bond; pc.L = L; pc.L1 = L + 1;
+        pc.Q = Q; pc.envR = w.envR + b * w.env_stride; pc.eoffR = d_eoff; pc.Ap = d_Ap; pc.Gp = d_Gp; pc.b = (int)b; pc.DP = DP;
+        TTB_LAUNCH(h, "k_sample_pack", k_sample_pack<<<dim3(L, Q), 256, 0, h->stream>>>(pc));
+        TileCtx tc;
+        tc.Ap = d_Ap; tc.Gp = d_Gp; tc.L = L; tc.Q = Q; tc.uniforms = d_u; tc.seed = seed; tc.first = first;
+        tc.x_out = d_x; tc.p_out = d_p; tc.hist = d_hist; tc.sum_logp = d_slp; tc.status = h->d_status; tc.nsamples = nsamples;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        const int64_t nb = (nsamples + ST_SMAX - 1) / ST_SMAX;
+        const unsigned g = (unsigned)std::min<int64_t>(nb, nsm);
+        static bool tattr = false;
+        if (!tattr) {
+          cudaFuncSetAttribute(k_sample_tile<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+          cudaFuncSetAttribute(k_sample_tile<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+          cudaFuncSetAttribute(k_sample_tile<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+          tattr = true;
+        }
+        if (DP == 32) TTB_LAUNCH(h, "k_sample_tile", k_sample_tile<32><<<g, ST_THREADS, tile_smem, h->stream>>>(tc));
+        else if (DP == 64) TTB_LAUNCH(h, "k_sample_tile", k_sample_tile<64><<<g, ST_THREADS, tile_smem, h->stream>>>(tc));
+        else TTB_LAUNCH(h, "k_sample_tile", k_sample_tile<128><<<g, ST_THREADS, tile_smem, h->stream>>>(tc));
+      }
+    } else {
+      TTB_LAUNCH(h, "k_sample_prep", k_sample_prep<<<dim3(L, Q), 128, 0, h->stream>>>(c));
+      const int thr = dmax <= 32 ? 64 : 128;
+      for (int64_t base = 0; base < nsamples; base += (int64_t)1 << 30) {
+        const unsigned g = (unsigned)std::min<int64_t>(nsamples - base, (int64_t)1 << 30);
+        TTB_LAUNCH(h, "k_sample", k_sample<<<g, thr, smem, h->stream>>>(c, base));
+      }
     }
-    rc = tm.finish();
+    if (rc == TTB_OK) rc = tm.finish();
+    cudaFree(d_Ap); cudaFree(d_Gp);
     h->last_ms += ms_acc; h->last_launches += l_acc;
   }
   if (rc == TTB_OK) {

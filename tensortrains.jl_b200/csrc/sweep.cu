@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tma_mma.cuh"
 
 namespace ttb {
 
@@ -595,13 +596,6 @@ __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
 #define AM_T 32
 #define AM_K 32
 #define AM_LD 36  // row stride == 4 (mod 16): fragment loads are conflict-free per half-warp
-__device__ __forceinline__ void dmma_16x8x8(double (&d)[4], const double (&a)[4], const double (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
-      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
-}
-
 __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
   const Dims d = get_dims(c, s, b);

@@ -461,7 +461,7 @@ def test_config4_reduced_sampling():
     ts = rand_open(rng, [1] + [d] * (L - 1) + [1], (4,))
     A, Ao = pair(ts)
     T.normalize_(A); O.normalize(Ao)
-    n = 16
+    n = 64          # >= 32 draws: the tiled DMMA sampler (DP = 128)
     us = rng.random((n, L))
     X, p = T.sample(A, n, uniforms=us)
     rz = O.accumulate_R(Ao)
