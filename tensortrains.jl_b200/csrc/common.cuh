@@ -30,10 +30,12 @@ int fail(int code, const char* fmt, ...);
 enum { ST_NEGATIVE = 1, ST_NONFINITE = 2, ST_NOCONV = 4 };
 
 // per-train state of the sweep step in flight
+// Two slots (step parity): thin-Q formation of step t runs on a side stream while step t+1 is already
+// being factorised, so nothing a step's kernels read may be overwritten by the next step.
 struct StepState {
-  int mprime;                        // retained rank of the current step (written by the rank rule)
-  int pad;
-  unsigned long long maxabs_bits[2]; // max|D| of the absorb output, as ordered bits (ping-pong)
+  int mprime[2];                     // retained rank of the step (written by the rank rule)
+  unsigned long long maxabs_bits[2]; // max|D| of the absorb output, as ordered bits
+  int p[2], n[2], N[2];              // dimensions of the step, snapshotted from the bond array
 };
 
 struct Workspace {
@@ -74,7 +76,9 @@ struct ttb_tt {
   std::vector<ttb::ProfEvent> prof;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // side stream: thin-Q formation overlaps the next factorisation
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_qr[2] = {nullptr, nullptr}, ev_aq[2] = {nullptr, nullptr};
   int64_t L = 0, Q = 0, batch = 0;
   int periodic = 0;
   std::vector<int64_t> bond0;  // original (capacity) bonds, L+1

@@ -128,6 +128,11 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
   };
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&h->ev_qr[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->ev_aq[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+  }
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "event");
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "event");
   if ((e = cudaMalloc(&h->slab, sizeof(double) * batch * h->tt_stride)) != cudaSuccess) return bail(e, "slab");
@@ -155,12 +160,18 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
 int ttb_destroy(ttb_handle h) {
   if (!h) return TTB_OK;
   cudaSetDevice(h->device);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_ws(h);
   cudaFree(h->slab); cudaFree(h->d_off); cudaFree(h->d_bond); cudaFree(h->d_logz); cudaFree(h->d_signz);
   cudaFree(h->d_status);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_qr[i]) cudaEventDestroy(h->ev_qr[i]);
+    if (h->ev_aq[i]) cudaEventDestroy(h->ev_aq[i]);
+  }
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return TTB_OK;

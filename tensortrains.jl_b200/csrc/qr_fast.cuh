@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_qr_update_tma(SweepCtx c, StepDesc s, i
 __global__ void __launch_bounds__(256) k_apply_q_tma(SweepCtx c, StepDesc s) {
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
-  const int mprime = c.st[b].mprime;
+  const int mprime = c.st[b].mprime[s.slot];
   const int c0 = blockIdx.x * 4;
   if (c0 >= mprime) return;
   const int cwc = min(4, mprime - c0);

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
   const Dims d = get_dims(c, s, b);
   if (d.mode == 2) return;
   const int j0 = panel * 32;
-  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime = d.k;
+  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime[s.slot] = d.k;
   if (j0 >= d.k) return;
   const int bwc = min(32, d.k - j0);
   const int rows = d.p - j0;  // host guarantees rows <= 32*RPL

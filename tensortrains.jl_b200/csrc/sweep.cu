@@ -18,6 +18,7 @@
 // no host synchronisation.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tma_mma.cuh"
@@ -49,14 +50,24 @@ struct StepDesc {
 
 struct Dims { int p, n, k, mode, N; };  // mode 0 = QR, 1 = SVD tall (p>=n), 2 = SVD wide
 
+// dimensions of the step in flight, from the snapshot k_snapshot took when the step started (the bond
+// array itself is rewritten by k_commit while side-stream kernels of the same step may still run)
 __device__ __forceinline__ Dims get_dims(const SweepCtx& c, const StepDesc& s, int b) {
-  const int* bond = c.bond + (int64_t)b * c.L1;
+  const StepState& st = c.st[b];
   Dims d;
-  if (s.dir == 0) { d.p = bond[s.site + 1] * c.Q; d.n = bond[s.site]; d.N = bond[s.nbr]; }
-  else            { d.p = bond[s.site] * c.Q;     d.n = bond[s.site + 1]; d.N = bond[s.nbr + 1]; }
+  d.p = st.p[s.slot]; d.n = st.n[s.slot]; d.N = st.N[s.slot];
   d.k = min(d.p, d.n);
   d.mode = s.qr_only ? 0 : (d.p >= d.n ? 1 : 2);
   return d;
+}
+
+__global__ void k_snapshot(SweepCtx c, StepDesc s, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int* bond = c.bond + (int64_t)b * c.L1;
+  StepState& st = c.st[b];
+  if (s.dir == 0) { st.p[s.slot] = bond[s.site + 1] * c.Q; st.n[s.slot] = bond[s.site]; st.N[s.slot] = bond[s.nbr]; }
+  else            { st.p[s.slot] = bond[s.site] * c.Q;     st.n[s.slot] = bond[s.site + 1]; st.N[s.slot] = bond[s.nbr + 1]; }
 }
 
 __device__ __forceinline__ double* xbuf(const SweepCtx& c, int which, int b) {
@@ -96,7 +107,7 @@ __global__ void k_qr_panel(SweepCtx c, StepDesc s, int panel) {
   if (d.mode == 2) return;
   const int bw = c.bw;
   const int j0 = panel * bw;
-  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime = d.k;
+  if (panel == 0 && d.mode == 0 && threadIdx.x == 0) c.st[b].mprime[s.slot] = d.k;
   if (j0 >= d.k) return;
   const int bwc = min(bw, d.k - j0);
   const int rows = d.p - j0;
@@ -250,7 +261,7 @@ __global__ void k_qr_update(SweepCtx c, StepDesc s, int panel, int cw) {
 __global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
-  const int mprime = c.st[b].mprime;
+  const int mprime = c.st[b].mprime[s.slot];
   const int c0 = blockIdx.x * cw;
   if (c0 >= mprime) return;
   const int cwc = min(cw, mprime - c0);
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(512) k_jacobi(SweepCtx c, StepDesc s, int smem
     double err = 0.0;
     const int mp = rank_rule(srt, nv, s.kind, s.eps, s.cap, &err);
     sh_mprime = mp;
-    c.st[b].mprime = mp;
+    c.st[b].mprime[s.slot] = mp;
     c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = err;
   }
   __syncthreads();
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(512) k_jacobi(SweepCtx c, StepDesc s, int smem
 __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
   const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
   const Dims d = get_dims(c, s, b);
-  const int mprime = c.st[b].mprime;
+  const int mprime = c.st[b].mprime[s.slot];
   const int i0 = blockIdx.x * AB_TM, j0 = blockIdx.y * AB_TN;
   if (i0 >= mprime || j0 >= d.N) return;
   const int n = d.n, N = d.N, p = d.p;
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
 __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
   const Dims d = get_dims(c, s, b);
-  const int mprime = c.st[b].mprime;
+  const int mprime = c.st[b].mprime[s.slot];
   const int i0 = blockIdx.x * AM_T, j0 = blockIdx.y * AM_T;
   if (i0 >= mprime || j0 >= d.N) return;
   const int n = d.n, N = d.N;
@@ -707,9 +718,8 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
 // rescale the absorb output: in place, or unfolded into the neighbour's site storage on the last step
 __global__ void k_rescale(SweepCtx c, StepDesc s) {
   const int b = blockIdx.y;
-  const int mprime = c.st[b].mprime;
-  const int* bond = c.bond + (int64_t)b * c.L1;
-  const int N = s.dir == 0 ? bond[s.nbr] : bond[s.nbr + 1];
+  const int mprime = c.st[b].mprime[s.slot];
+  const int N = c.st[b].N[s.slot];
   const double m = __longlong_as_double((long long)c.st[b].maxabs_bits[s.slot]);
   const bool ok = s.rescale && !(m != m) && !isinf(m) && m != 0.0;
   if (!ok && !s.last) return;
@@ -740,7 +750,7 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   int* bond = c.bond + (int64_t)b * c.L1;
-  const int mp = c.st[b].mprime;
+  const int mp = c.st[b].mprime[s.slot];
   const double m = __longlong_as_double((long long)c.st[b].maxabs_bits[s.slot]);
   const bool bad = (m != m) || isinf(m);
   if (s.rescale && !bad && m != 0.0) c.logz[b] -= log(m);
@@ -754,7 +764,7 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
 
 __global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < batch) { st[i].mprime = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull; }
+  if (i < batch) { st[i].mprime[0] = st[i].mprime[1] = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull; }
   if (i < batch * L1) { stat_err[i] = 0.0; stat_rank[i] = 0; }
 }
 
@@ -807,7 +817,7 @@ int ensure_sweep_ws(ttb_tt* h) {
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   A((void**)&w.X[0], sizeof(double) * B * w.x_stride);
   A((void**)&w.X[1], sizeof(double) * B * w.x_stride);
-  A((void**)&w.T, sizeof(double) * B * w.t_stride);
+  A((void**)&w.T, sizeof(double) * 2 * B * w.t_stride);  // two step slots
   A((void**)&w.Bv, sizeof(double) * B * w.bv_stride);
   A((void**)&w.Jv, sizeof(double) * B * w.jv_stride);
   A((void**)&w.perm, sizeof(int) * B * n_max);
@@ -874,9 +884,14 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   TTB_TRY(ensure_sweep_ws(h));
   TTB_TRY(ensure_spectrum(h));
   Workspace& w = h->ws;
-  const SweepCtx c = make_ctx(h);
+  const SweepCtx cbase = make_ctx(h);
   const int B = (int)h->batch, Q = (int)h->Q, bw = w.bw, L1 = (int)h->L + 1;
   cudaStream_t st = h->stream;
+  // thin-Q formation runs on the side stream unless per-kernel profiling wants a serial timeline
+  const bool overlap = !h->prof_on && getenv("TTB_NO_OVERLAP") == nullptr;
+  cudaStream_t st2 = overlap ? h->stream2 : h->stream;
+  bool side_pending = false;  // apply_q of the previous step may still be running on st2
+  int side_slot = 0;
   const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
   {
     const int n = std::max(B, B * L1);
@@ -890,6 +905,8 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.kind = tr->kind; s.eps = tr->eps;
     s.cap = (int)std::min<int64_t>(tr->mprime, 1 << 30);
     s.bond_idx = hs.bond_idx; s.bond_idx2 = hs.bond_idx2; s.last = hs.last; s.slot = slot;
+    SweepCtx c = cbase;
+    c.T = cbase.T + (int64_t)slot * B * w.t_stride;
     // Launch-sizing hint: every few truncating steps read back the bond array the device has already
     // committed.  The rank DECISION never leaves the device; the host only learns that later grids can
     // be smaller (and that whole QR phases can be skipped when p < n is certain).
@@ -909,6 +926,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
     else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; p_lb = lb[hs.site] * Q; n_lb = lb[hs.site + 1]; }
     const int k_ub = std::min(p_ub, n_ub);
+    TTB_LAUNCH(h, "k_snapshot", k_snapshot<<<(B + 127) / 128, 128, 0, st>>>(c, s, B));
     if (si == 0) {
       const int64_t tot = (int64_t)p_ub * n_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 255) / 256, 2048), B);
@@ -956,16 +974,32 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const size_t need = sizeof(double) * (2 * (size_t)w.n_max + (size_t)nv_ub * (len_ub + nv_ub));
       const size_t give = std::min<size_t>(need, (size_t)200 * 1024);
       const int thr = std::min(512, std::max(64, ((nv_ub / 2 + 1) * 32)));
+      if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
       TTB_LAUNCH(h, "k_jacobi", k_jacobi<<<B, thr, give, st>>>(c, s, (int)(give / sizeof(double))));
     }
     {
       dim3 g((mp_ub + kCw - 1) / kCw, B);
+      // The new site tensor W = Q E (or Q J[:,sel]) is consumed by nobody in this sweep: form it on the
+      // side stream while the main stream absorbs S and factorises the next site.  It reads X[xin], the
+      // T slot and Bv/Jv/perm of this step; the next step's absorb (writes X[xin]) / Jacobi wait for it.
+      if (overlap) {
+        cudaEventRecord(h->ev_qr[slot], st);
+        cudaStreamWaitEvent(st2, h->ev_qr[slot], 0);
+      }
       if (fast) {
         size_t smem = sizeof(double) * ((size_t)1280 + (size_t)p_ub * 36);
-        TTB_LAUNCH(h, "k_apply_q_tma", k_apply_q_tma<<<g, 256, smem, st>>>(c, s));
+        TTB_LAUNCH(h, "k_apply_q_tma", k_apply_q_tma<<<g, 256, smem, st2>>>(c, s));
       } else {
         size_t smem = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)p_ub * kCw + (size_t)p_ub * bw);
-        TTB_LAUNCH(h, "k_apply_q", k_apply_q<<<g, 256, smem, st>>>(c, s, kCw));
+        TTB_LAUNCH(h, "k_apply_q", k_apply_q<<<g, 256, smem, st2>>>(c, s, kCw));
+      }
+      if (overlap) {
+        // absorb of THIS step only reads; the wait for the PREVIOUS step's apply_q must come before it
+        // because absorb writes X[xin ^ 1], which that apply_q read as its X[xin]
+        if (side_pending) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
+        cudaEventRecord(h->ev_aq[slot], st2);
+        side_pending = true;
+        side_slot = slot;
       }
     }
     {
@@ -983,6 +1017,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     if (hs.bond_idx2 >= 0) { ub[hs.bond_idx2] = mp_ub; lb[hs.bond_idx2] = mp_lb; }
     xin ^= 1; slot ^= 1;
   }
+  if (side_pending && overlap) cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0);  // join the side stream
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TTB_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
   return TTB_OK;
