@@ -6,7 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
-__device__ long long g_stamps[64];
+__device__ long long g_stamps[1024];
 #define TTB_PANEL_STAMPS g_stamps
 #include "common.cuh"
 namespace ttb {
@@ -72,8 +72,17 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
     }
-    long long st[64];
+    long long st[1024];
     cudaMemcpyFromSymbol(st, g_stamps, sizeof(st));
+#ifdef TTB_PANEL_FINE
+    printf("  col: flag->vload | dot+red+upd | (loop) | norm+red | rsqrt/rcp | v store | publish->next sees\n");
+    for (int cc = 2; cc < 31; cc += 6) {
+      long long* a = &st[64 + 16 * cc];        // stamps of reflector cc (next owner side: 0,1,2 ; owner side: 4..7)
+      long long* nx = &st[64 + 16 * (cc + 1)];
+      printf("  %2d: %5lld | %5lld | %5lld | %5lld | %5lld | %5lld | %5lld\n", cc, a[1] - a[0], a[2] - a[1], nx[4] - a[2],
+             nx[5] - nx[4], nx[6] - nx[5], nx[7] - nx[6], nx[0] - nx[7]);
+    }
+#endif
     printf("panel %d: kernel %.1f us (%s)  cycles: loop %lld  Tbuild %lld  store %lld\n", panel, best * 1e3,
            cudaGetErrorString(cudaGetLastError()), st[1] - st[0], st[2] - st[1], st[3] - st[2]);
     printf("  ready-to-ready:");

@@ -1,21 +1,19 @@
 // qr_panel.cuh -- k_qr_panel_flag: register-resident Householder panel (32 columns, <= 512 rows) whose
 // warps hand reflectors to each other through shared-memory flags instead of block barriers.
 //
-// Layout: NW = 32/NS warps, warp w owns the NS panel columns w, w+NW, ...; lane l holds rows l+32i.
-// The panel is a chain of 32 dependent columns: reflector c can only be formed after reflector c-1
-// has been applied to column c.  All 32 reflectors stay in shared memory (no buffer reuse => no WAR
-// hazard); the owner of column c publishes v_c and raises ready[c]; every warp consumes the reflectors
-// in order at its own pace.  The owner of column c+1 applies v_c to THAT column first, forms and
-// publishes v_{c+1}, and only then catches up on its other columns.  The V^T V products that define the
-// compact-WY T factor (T^{-1} = diag(1/tau) + striu(V^T V)) fall out of the same dots and are shipped
-// as they are: no T factor is ever built (its serial recurrence cost a quarter of the kernel).
-// Measured building blocks (profiles/micro_lat.cu, B200): dependent DFMA 8, shfl+DADD 35, rsqrt ~80,
-// 1/x ~80, LDS ~70 cycles.
+// Layout: NW = 32/NS warps; warp w owns the NS CONSECUTIVE panel columns NS*w .. NS*w+NS-1, lane l holds
+// rows l + 32 i.  The panel is a chain of 32 dependent columns (reflector c needs reflector c-1 applied
+// to column c).  Inside a warp's block the chain never leaves the warp: the reflector it has just
+// formed is applied to its own later columns straight from registers, so only every NS-th link pays the
+// shared-memory hand-off (publish 32*RPL doubles, raise ready[c], next warp polls).  All 32 reflectors
+// stay in shared memory (no buffer reuse => no WAR hazard); the other warps consume them in order at
+// their own pace, all NS columns at once (independent dots, interleaved warp reductions).
+// The V^T V products that define the compact-WY T factor (T^{-1} = diag(1/tau) + striu(V^T V)) fall out
+// of the same dots and are shipped as they are: no T factor is ever built.
+// Measured (profiles/micro_lat.cu, micro_panel2.cu, B200): dependent DFMA 8, shfl+DADD 35, rsqrt ~80,
+// 1/x ~80, LDS ~70 cycles; round-robin ownership cost ~2450 cycles per column of which ~600 were the
+// hand-off, block ownership removes it from NS-1 of NS links.
 #pragma once
-
-#ifndef TTB_PANEL_BACKOFF_NS
-#define TTB_PANEL_BACKOFF_NS 200
-#endif
 
 namespace ttb {
 
@@ -38,19 +36,18 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
   return (d0 + d1) + (d2 + d3);
 }
 
-// Householder reflector of column `cc` held as col[i] = row (lane + 32 i); overwrites the column with
-// (R_cc on the diagonal, v below) and publishes v (unit diagonal, zeros above) to vcol.  Returns tau.
+// Householder reflector of panel column `cc` (< 32) held as col[i] = row (lane + 32 i).  Overwrites the
+// column with (R_cc on the diagonal, v below), returns v in registers (unit diagonal, zeros above) and
+// publishes it to vcol.  Only the first 32 rows (i = 0) can lie on or above the diagonal.
 template <int RPL>
-__device__ __forceinline__ double make_reflector(double (&col)[RPL], double* vcol, int cc, int lane) {
-  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+__device__ __forceinline__ double make_reflector(double (&col)[RPL], double (&v)[RPL], double* vcol, int cc, int lane) {
+  double p0 = (lane > cc) ? col[0] * col[0] : 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
-  for (int i = 0; i < RPL; ++i) {
-    const int r = lane + 32 * i;
-    const double x = (r > cc) ? col[i] : 0.0;
-    if ((i & 3) == 0) p0 += x * x;
-    else if ((i & 3) == 1) p1 += x * x;
-    else if ((i & 3) == 2) p2 += x * x;
-    else p3 += x * x;
+  for (int i = 1; i < RPL; ++i) {
+    if ((i & 3) == 0) p0 += col[i] * col[i];
+    else if ((i & 3) == 1) p1 += col[i] * col[i];
+    else if ((i & 3) == 2) p2 += col[i] * col[i];
+    else p3 += col[i] * col[i];
   }
   const double xn2 = warp_sum((p0 + p1) + (p2 + p3));
   const double alpha = __shfl_sync(0xffffffffu, col[0], cc);
@@ -65,13 +62,19 @@ __device__ __forceinline__ double make_reflector(double (&col)[RPL], double* vco
     scal = 1.0 / den;
     tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
   }
+  {
+    double v0 = 0.0;
+    if (lane > cc) { v0 = col[0] * scal; col[0] = v0; }
+    else if (lane == cc) { v0 = 1.0; col[0] = beta; }
+    v[0] = v0;
+    vcol[lane] = v0;
+  }
 #pragma unroll
-  for (int i = 0; i < RPL; ++i) {
-    const int r = lane + 32 * i;
-    double v = 0.0;
-    if (r > cc) { v = col[i] * scal; col[i] = v; }
-    else if (r == cc) { v = 1.0; col[i] = beta; }
-    vcol[r] = v;
+  for (int i = 1; i < RPL; ++i) {
+    const double vi = col[i] * scal;
+    col[i] = vi;
+    v[i] = vi;
+    vcol[lane + 32 * i] = vi;
   }
   return tau;
 }
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
   double a[NS][RPL];
 #pragma unroll
   for (int s2 = 0; s2 < NS; ++s2) {
-    const int cs = wid + NW * s2;
+    const int cs = wid * NS + s2;
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + 32 * i;
@@ -114,41 +117,19 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
   if (tid == 0) TTB_PANEL_STAMPS[0] = clock64();
 #endif
 
-  // apply reflector ccv (in registers as v) to this warp's column slot `slot` (runtime index resolved
-  // by predication over the unrolled slots, so `a` stays in registers)
-  auto apply_slot = [&](int ccv, const double (&v)[RPL], double tau, int slot) {
-#pragma unroll
-    for (int s2 = 0; s2 < NS; ++s2) {
-      if (s2 != slot) continue;
-      const int cs = wid + NW * s2;
-      if (cs < bwc && cs != ccv) {  // warp-uniform
-        const double dot = warp_sum(dot_rpl<RPL>(v, a[s2]));
-        if (cs > ccv) {
-          if (tau != 0.0) {
-            const double w = tau * dot;
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-          }
-        } else {
-          G[cs + 32 * ccv] = dot;  // V_cs^T v_ccv (same value from every lane)
-        }
-      }
-    }
-  };
-  bool pending = false;  // this warp still owes reflector cc-1 to its non-priority columns
-  int pend_pri = 0;
 #pragma unroll 1
   for (int cc = 0; cc < bwc; ++cc) {
-    const int ow = cc % NW;
-    const int os = cc / NW;
+    const int ow = cc / NS;
+    const int os = cc % NS;
+    double v[RPL];
+    double tau = 0.0;
     if (wid == ow) {
-      // ---- owner: form reflector cc from its (fully updated) column, in place ----
+      // ---- owner: form reflector cc from its (fully updated) column, in place; publish for the others
       double* vcol = vs + (size_t)cc * LDV;
-      double tau = 0.0;
 #pragma unroll
       for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 == os) tau = make_reflector<RPL>(a[s2], vcol, cc, lane);
-      // All lanes store the same tau / flag (no divergent region on the chain).  No MEMBAR: shared-memory
+        if (s2 == os) tau = make_reflector<RPL>(a[s2], v, vcol, cc, lane);
+      // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared
       // stores of one warp are performed in order and the flag is the last store instruction.
       sh_tau[cc] = tau;
       __syncwarp();
@@ -157,51 +138,37 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
       if (lane == 0) TTB_PANEL_STAMPS[8 + cc] = clock64();
 #endif
     } else {
-      // ---- consumer: wait for reflector cc ----
-      // every lane polls the same word (a broadcast load): no divergence, no reconvergence barrier
-      {
-        unsigned it = 0;
-        const bool hot = (wid == ((cc + 1) % NW));  // next link of the chain polls tightly
-        while (ld_flag(&ready[cc]) == 0) {
-          if (!hot) __nanosleep(TTB_PANEL_BACKOFF_NS);
-          if (++it > (1u << 26)) __trap();
-        }
+      // ---- consumer: every lane polls the same word (broadcast load, no divergence)
+      unsigned it = 0;
+      while (ld_flag(&ready[cc]) == 0) {
+        if (++it > (1u << 26)) __trap();
       }
-    }
-    double v[RPL];
-#ifdef TTB_PANEL_CHAIN_ONLY  // timing experiment: only the critical chain does work (results are wrong)
-    pending = false;
-#endif
-    if (pending) {  // catch up the columns that were skipped while this warp hurried to publish
-      const double taup = *reinterpret_cast<volatile double*>(&sh_tau[cc - 1]);
-      const double* vp = vs + (size_t)(cc - 1) * LDV;
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) v[i] = vp[lane + 32 * i];
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 != pend_pri) apply_slot(cc - 1, v, taup, s2);
-      pending = false;
-    }
-    const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
-    {
+      tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
       const double* vcol = vs + (size_t)cc * LDV;
 #pragma unroll
       for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
     }
-    // the slot that holds column cc+1 goes first: its owner is the next link of the chain
-    const int pri = ((cc + 1) / NW) % NS;
-#ifdef TTB_PANEL_CHAIN_ONLY
-    if (wid == ((cc + 1) % NW)) apply_slot(cc, v, tau, pri);
-    continue;
-#endif
-    apply_slot(cc, v, tau, pri);
-    if (cc + 1 < bwc && wid == ((cc + 1) % NW)) {
-      pending = true;
-      pend_pri = pri;
-    } else {
+    // ---- apply reflector cc to all NS columns of this warp at once: independent dots, interleaved
+    //      butterfly reductions, then the rank-1 updates (finished columns only need the dot: V^T V)
+    double dot[NS];
 #pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 != pri) apply_slot(cc, v, tau, s2);
+    for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) dot[s2] += __shfl_xor_sync(0xffffffffu, dot[s2], o);
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const int cs = wid * NS + s2;
+      if (cs >= bwc || cs == cc) continue;  // warp-uniform
+      if (cs > cc) {
+        const double w = tau * dot[s2];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+      } else {
+        G[cs + 32 * cc] = dot[s2];  // V_cs^T v_cc (same value from every lane)
+      }
     }
   }
   __syncthreads();
@@ -214,7 +181,7 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
 #endif
 #pragma unroll
   for (int s2 = 0; s2 < NS; ++s2) {
-    const int cs = wid + NW * s2;
+    const int cs = wid * NS + s2;
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + 32 * i;
