@@ -283,8 +283,36 @@ def main():
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk)}
 
+    # ---- sampling half of the metric (config 4): the train is replicated, the draws are sharded by
+    #      global draw index (Philox key), the only collective is the all-reduce of the histogram ----
+    sample_info = None
+    if not args.no_extra:
+        from ttb200 import parallel as P
+        _, t4 = make_open(4, L4, D4, Q4)
+        A4 = T.TensorTrain(t4)
+        del t4
+        T.normalize_(A4)
+        nd = 1_000_000                                   # draws per rank
+        T.sample_stats(A4, 20000, seed=1, first_index=0)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        hist, slp = T.sample_stats(A4, nd, seed=1, first_index=rank * nd)
+        wall4 = time.perf_counter() - t0
+        ms4, _ = A4.last_timing()
+        ms4 = max_over_ranks(ms4)
+        wall4 = max_over_ranks(wall4)
+        hist_tot = P.allreduce_sum(hist)
+        assert int(hist_tot.sum()) == world * nd * L4
+        sample_info = {"workload": "C4: TensorTrain L=256 q=4 d=128 rand_tt, normalize! then sample; draws sharded over ranks",
+                       "draws": world * nd, "draws_per_s": world * nd / (ms4 * 1e-3),
+                       "e2e_draws_per_s": world * nd / wall4,
+                       "alg_mflop_per_draw": 8.65,
+                       "note": "device time of ttb_sample_stats (accumulate_R + pack + tiled DMMA sampler); histogram "
+                               "(L x Q int64) is the only result copied back"}
+        del A4
+
     if rank == 0:
-        # ---- roofline: per-kernel CUDA-event times of one more compress! ----
+        # ---- roofline: per-kernel CUDA-event times of one more compress! (serial timeline) ----
         prof = base.copy()
         prof.profile(True)
         T.compress_(prof, tr)
@@ -292,46 +320,43 @@ def main():
         prof.profile(False)
         peak = measure_fp64_peak(torch, dev)
         fl, _ = qr_sweep_flops(bonds, Q3)
+        alias = {"k_qr_panel_flag": "k_qr_panel", "k_qr_update_tma": "k_qr_update", "k_apply_q_tma": "k_apply_q",
+                 "k_absorb_mma": "k_absorb"}
         tot_ms = sum(v[1] for v in rep.values())
         dom = max(rep, key=lambda k: rep[k][1])
         n_l, ms = rep[dom]
         # algorithmic FLOPs of the dominant class over the step (right sweep; the left sweep of the
         # rand fill works on <=16-row matrices and is negligible) -- DESIGN.md states the formulas
-        key = dom if dom in fl else None
-        alg = fl[key][1] if key else 0.0
-        per_launch = alg / max(n_l, 1)
-        achieved = per_launch / (ms / n_l * 1e-3) / 1e12 if ms > 0 else 0.0
+        n_alg, alg = fl.get(alias.get(dom, dom), [n_l, 0.0])
+        per_launch = alg / max(n_alg, 1)
+        achieved = alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": None,
                             "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
                             "share_of_step": ms / tot_ms if tot_ms else None,
-                            "flops_per_launch": per_launch, "launches": n_l, "ms_per_launch": ms / n_l,
-                            "kernels": {k: {"launches": v[0], "ms": v[1], "alg_gflop": fl.get(k, [0, 0.0])[1] / 1e9}
+                            "flops_per_launch": per_launch, "launches": n_l, "working_launches": n_alg,
+                            "ms_per_launch": ms / n_l,
+                            "note": "one CTA per panel: a chain of 32 dependent Householder columns, latency bound by "
+                                    "construction (profiles/r1_micro_panel.txt); achieved = algorithmic panel FLOPs / "
+                                    "CUDA-event time of all launches of the class",
+                            "kernels": {k: {"launches": v[0], "ms": v[1],
+                                            "alg_gflop": fl.get(alias.get(k, k), [0, 0.0])[1] / 1e9}
                                         for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
                             "whole_step": {"alg_gflop": sum(v[1] for v in fl.values()) / 1e9,
                                            "tflops": sum(v[1] for v in fl.values()) / (dev_ms / K * 1e-3) / 1e12}}
+        extra = {}
+        if sample_info is not None:
+            sample_info["tflops_minimal_algorithm"] = sample_info["draws_per_s"] * 8.65e6 / 1e12
+            sample_info["frac_of_fp64_peak"] = sample_info["tflops_minimal_algorithm"] / (peak * world) if peak else None
+            extra["sample"] = sample_info
         if world == 1 and not args.no_extra:
             v, secs = cpu_compress_steps_per_s(L3, D3, Q3, 3)
             line["cpu_baseline"] = {"value": v, "unit": "site-steps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"the full C3 compress! once ({secs:.1f} s): NumPy/SciPy-OpenBLAS gesdd "
                                               "restatement of the reference, not Julia/MKL"}
-            extra = {}
             try:
-                # sampling half of the metric: config 4
-                b4, t4 = make_open(4, L4, D4, Q4)
-                A4 = T.TensorTrain(t4)
-                T.normalize_(A4)
-                nd = 20000
-                T.sample_stats(A4, 2000, seed=1)
-                t0 = time.perf_counter()
-                T.sample_stats(A4, nd, seed=1, first_index=0)
-                ms4, _ = A4.last_timing()
-                extra["sample"] = {"workload": "C4: L=256 q=4 d=128 rand_tt, normalize! then sample", "draws": nd,
-                                   "draws_per_s": nd / (ms4 * 1e-3), "wall_draws_per_s": nd / (time.perf_counter() - t0),
-                                   "cpu_draws_per_s": cpu_sample_draws_per_s(L4, D4, Q4, 4, 20),
-                                   "alg_mflop_per_draw": 8.65}
-                del A4
+                extra["sample"]["cpu_draws_per_s"] = cpu_sample_draws_per_s(L4, D4, Q4, 4, 20)
                 # randn fill of config 3 (both sweeps full rank): reduced length
                 Lr = 16
                 br, tsr = make_open(3, Lr, D3, Q3, "randn")
@@ -342,6 +367,7 @@ def main():
                 extra["randn_fill"] = {"workload": f"C3 shape, randn_tt fill, L={Lr}", "site_steps_per_s": 2 * (Lr - 1) / (msr * 1e-3)}
             except Exception as ex:  # the headline line must still be printed
                 extra["error"] = repr(ex)
+        if extra:
             line["extra"] = extra
         print(json.dumps(line))
     if world > 1:

@@ -9,6 +9,7 @@
 // log|z| + sign, like the reference's Logarithmic accumulator.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -426,6 +427,10 @@ __global__ void k_twovar(TwoCtx c) {
   (void)dcur;
 }
 
+}  // namespace ttb
+#include "twovar_fast.cuh"
+namespace ttb {
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -699,7 +704,36 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
     CallTimer tm(h);
     rc = launch_acc(h, true, 1, s);
     if (rc == TTB_OK) rc = launch_acc(h, false, 1, s);
-    if (rc == TTB_OK) {
+    // fast path: GT_u(x), T_u once per call, then Frobenius products + one small GEMM per pair
+    const int64_t kcap = h->bond0[0] * h->dmax;
+    const size_t fast_smem = sizeof(double) * (3 * (size_t)Q * kcap + (size_t)h->dmax * h->dmax + 8 * (Q * Q + 1) + Q * Q);
+    const bool use_fast = fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr;
+    double *d_GT = nullptr, *d_Tm = nullptr;
+    if (rc == TTB_OK && use_fast) {
+      const int64_t gstride = (kcap + 15) & ~int64_t(15), tstride = (h->dmax * h->dmax + 15) & ~int64_t(15);
+      e = cudaMalloc(&d_GT, sizeof(double) * h->batch * L * Q * gstride);
+      if (e == cudaSuccess) e = cudaMalloc(&d_Tm, sizeof(double) * h->batch * L * tstride);
+      if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
+      if (rc == TTB_OK) {
+        TwoPre pc;
+        pc.slab = h->slab; pc.tt_stride = h->tt_stride; pc.off = h->d_off; pc.bond = h->d_bond;
+        pc.L = (int)L; pc.L1 = (int)L + 1; pc.Q = (int)Q;
+        pc.envR = w.envR; pc.env_stride = w.env_stride; pc.eoffR = s.d_eoffR;
+        pc.GT = d_GT; pc.Tm = d_Tm; pc.gstride = gstride; pc.tstride = tstride;
+        TTB_LAUNCH(h, "k_twovar_pre", k_twovar_pre<<<dim3((unsigned)L, (unsigned)h->batch), 256, 0, h->stream>>>(pc));
+        TwoFast fc;
+        fc.slab = h->slab; fc.tt_stride = h->tt_stride; fc.off = h->d_off; fc.bond = h->d_bond;
+        fc.L = (int)L; fc.L1 = (int)L + 1; fc.Q = (int)Q;
+        fc.envL = w.envL; fc.env_stride = w.env_stride; fc.eoffL = s.d_eoffL;
+        fc.GT = d_GT; fc.Tm = d_Tm; fc.gstride = gstride; fc.tstride = tstride;
+        fc.pair_off = d_poff; fc.maxdist = (int)std::min<int64_t>(maxdist, L); fc.out = d_out; fc.npairs = npairs;
+        fc.kcap = (int)kcap; fc.dmax = (int)h->dmax;
+        static bool fattr = false;
+        if (!fattr) { cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); fattr = true; }
+        TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<dim3((unsigned)(L - 1), (unsigned)h->batch), 256, fast_smem, h->stream>>>(fc));
+        rc = tm.finish();
+      }
+    } else if (rc == TTB_OK) {
       TwoCtx c;
       c.slab = h->slab; c.tt_stride = h->tt_stride; c.off = h->d_off; c.bond = h->d_bond;
       c.L = (int)L; c.L1 = (int)L + 1; c.Q = (int)Q;
@@ -712,6 +746,7 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
       TTB_LAUNCH(h, "k_twovar", k_twovar<<<g, 256, scr_in_smem ? smem_need : sizeof(double) * Q * Q, h->stream>>>(c));
       rc = tm.finish();
     }
+    cudaFree(d_GT); cudaFree(d_Tm);
     if (rc == TTB_OK) {
       e = cudaMemcpy(out, d_out, sizeof(double) * h->batch * npairs * Q * Q, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = fail(TTB_ECUDA, "twovar copy: %s", cudaGetErrorString(e));

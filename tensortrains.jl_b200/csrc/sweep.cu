@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "common.cuh"
 #include "tma_mma.cuh"
@@ -1145,9 +1146,22 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
   ttb_trunc t0;
   t0.kind = TTB_TRUNC_THRESH; t0._pad = 0; t0.eps = 0.0; t0.mprime = 0;
   CallTimer tm(h);
+  const bool dbg = getenv("TTB_TIMING") != nullptr;
+  timespec t_a, t_b, t_c, t_d;
+  if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_a);
   if (!rs.empty()) TTB_TRY(enqueue_sweep(h, 0, &t0, rs, ub, lb));
+  if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_b);
   if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, lb));
-  return finish_sweeps(h, tm);
+  if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_c);
+  const int rc = finish_sweeps(h, tm);
+  if (dbg) {
+    clock_gettime(CLOCK_MONOTONIC, &t_d);
+    auto ms = [](const timespec& x, const timespec& y) { return (y.tv_sec - x.tv_sec) * 1e3 + (y.tv_nsec - x.tv_nsec) * 1e-6; };
+    fprintf(stderr, "[ttb timing] compress: host enqueue right %.1f ms, left (incl. rank-hint syncs) %.1f ms, drain %.1f ms; "
+                    "device %.1f ms, %lld launches\n", ms(t_a, t_b), ms(t_b, t_c), ms(t_c, t_d), h->last_ms,
+            (long long)h->last_launches);
+  }
+  return rc;
 }
 
 int ttb_sweep_stats(ttb_handle h, int64_t b, int64_t* rank, double* err) {
