@@ -384,7 +384,7 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // ---------------------------------------------------------------------------------------------
 // `smem_doubles` = dynamic shared memory the launch provides; the vectors live in shared memory when
 // the ACTUAL (device-known) sizes fit, in the global workspace otherwise.
-__global__ void __launch_bounds__(512) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
+__global__ void __launch_bounds__(1024) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
@@ -416,47 +416,69 @@ __global__ void __launch_bounds__(512) k_jacobi(SweepCtx c, StepDesc s, int smem
   }
   __syncthreads();
 
+  // Cyclic one-sided Jacobi, round-robin ordering: nvp-1 rounds of nvp/2 disjoint pairs, one warp per
+  // pair.  Squared norms are cached (refreshed every sweep; a rotation updates them exactly:
+  // |bi'|^2 = al - t ga, |bj'|^2 = be + t ga), so a pair costs ONE dot + one warp reduction; B and the
+  // accumulated rotations J are updated in the same pass.  ~10 sweeps on the sweep matrices
+  // (profiles/r1_jacobi_sweeps.txt), each round is one block barrier.
   const int nvp = (nv + 1) & ~1;
   const int npairs = nvp / 2, rounds = nvp - 1;
   const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
+  double* sq = sig;  // cached squared norms live in the sigma scratch until the end
   bool conv = (nv < 2);
   for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
-    if (tid == 0) rotated = 0;
+    for (int v = wid; v < nv; v += nw) {
+      const double* bi = B + (size_t)v * ldb;
+      double a0 = 0.0, a1 = 0.0;
+      int e = lane;
+      for (; e + 32 < len; e += 64) { a0 += bi[e] * bi[e]; a1 += bi[e + 32] * bi[e + 32]; }
+      if (e < len) a0 += bi[e] * bi[e];
+      const double al = warp_sum(a0 + a1);
+      sq[v] = al;
+    }
+    rotated = 0;
     __syncthreads();
     for (int rd = 0; rd < rounds; ++rd) {
       for (int q = wid; q < npairs; q += nw) {
         int i, j;
         if (q == 0) { i = nvp - 1; j = rd; }
-        else { i = (rd + q) % (nvp - 1); j = (rd - q + (nvp - 1)) % (nvp - 1); }
+        else {
+          i = rd + q; if (i >= nvp - 1) i -= nvp - 1;
+          j = rd - q; if (j < 0) j += nvp - 1;
+        }
         if (i > j) { const int t = i; i = j; j = t; }
         if (j >= nv) continue;
         double* bi = B + (size_t)i * ldb;
         double* bj = B + (size_t)j * ldb;
-        double al = 0.0, be = 0.0, ga = 0.0;
-        for (int e = lane; e < len; e += 32) {
-          const double x = bi[e], y = bj[e];
-          al += x * x; be += y * y; ga += x * y;
-        }
-        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        const double al = sq[i], be = sq[j];
+        double g0 = 0.0, g1 = 0.0;
+        int e = lane;
+        for (; e + 32 < len; e += 64) { g0 += bi[e] * bj[e]; g1 += bi[e + 32] * bj[e + 32]; }
+        if (e < len) g0 += bi[e] * bj[e];
+        const double ga = warp_sum(g0 + g1);
         if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
           // tan(theta) from tan(2 theta) = 2 ga / (be - al): one sqrt, one division, one rsqrt
           const double da = be - al, b2 = 2.0 * ga;
           const double t = b2 / (da + copysign(sqrt(da * da + b2 * b2), da));
           const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-          for (int e = lane; e < len; e += 32) {
-            const double x = bi[e], y = bj[e];
-            bi[e] = cs * x - sn * y;
-            bj[e] = sn * x + cs * y;
+#pragma unroll 4
+          for (int e2 = lane; e2 < len; e2 += 32) {
+            const double x = bi[e2], y = bj[e2];
+            bi[e2] = cs * x - sn * y;
+            bj[e2] = sn * x + cs * y;
           }
           double* ji = J + (size_t)i * ldjj;
           double* jj = J + (size_t)j * ldjj;
-          for (int e = lane; e < nv; e += 32) {
-            const double x = ji[e], y = jj[e];
-            ji[e] = cs * x - sn * y;
-            jj[e] = sn * x + cs * y;
+#pragma unroll 4
+          for (int e2 = lane; e2 < nv; e2 += 32) {
+            const double x = ji[e2], y = jj[e2];
+            ji[e2] = cs * x - sn * y;
+            jj[e2] = sn * x + cs * y;
           }
-          if (lane == 0) rotated = 1;
+          sq[i] = al - t * ga;  // same value from every lane
+          sq[j] = be + t * ga;
+          rotated = 1;
         }
       }
       __syncthreads();
@@ -974,7 +996,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const int nv_ub = k_ub, len_ub = n_ub;
       const size_t need = sizeof(double) * (2 * (size_t)w.n_max + (size_t)nv_ub * (len_ub + nv_ub));
       const size_t give = std::min<size_t>(need, (size_t)200 * 1024);
-      const int thr = std::min(512, std::max(64, ((nv_ub / 2 + 1) * 32)));
+      const int thr = std::min(1024, std::max(64, ((nv_ub + 1) / 2) * 32));  // one warp per pair
       if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
       TTB_LAUNCH(h, "k_jacobi", k_jacobi<<<B, thr, give, st>>>(c, s, (int)(give / sizeof(double))));
     }
@@ -1093,6 +1115,7 @@ int ttb_orthogonalize_right(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64
   if (steps.empty()) return TTB_OK;
   std::vector<int> ub, lb;
   bond_upper_bounds(h, ub, lb);
+  TTB_TRY(ensure_sweep_ws(h));  // allocate outside the timed bracket
   CallTimer tm(h);
   TTB_TRY(enqueue_sweep(h, 0, tr, steps, ub, lb));
   return finish_sweeps(h, tm);
@@ -1106,6 +1129,7 @@ int ttb_orthogonalize_left(ttb_handle h, const ttb_trunc* tr, int64_t lo, int64_
   if (steps.empty()) return TTB_OK;
   std::vector<int> ub, lb;
   bond_upper_bounds(h, ub, lb);
+  TTB_TRY(ensure_sweep_ws(h));  // allocate outside the timed bracket
   CallTimer tm(h);
   TTB_TRY(enqueue_sweep(h, 1, tr, steps, ub, lb));
   return finish_sweeps(h, tm);
@@ -1145,21 +1169,27 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
   bond_upper_bounds(h, ub, lb);
   ttb_trunc t0;
   t0.kind = TTB_TRUNC_THRESH; t0._pad = 0; t0.eps = 0.0; t0.mprime = 0;
+  TTB_TRY(ensure_sweep_ws(h));  // allocate outside the timed bracket
   CallTimer tm(h);
   const bool dbg = getenv("TTB_TIMING") != nullptr;
   timespec t_a, t_b, t_c, t_d;
   if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_a);
   if (!rs.empty()) TTB_TRY(enqueue_sweep(h, 0, &t0, rs, ub, lb));
-  if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_b);
+  cudaEvent_t ev_mid = nullptr;
+  if (dbg) { clock_gettime(CLOCK_MONOTONIC, &t_b); cudaEventCreate(&ev_mid); cudaEventRecord(ev_mid, h->stream); }
   if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, lb));
   if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_c);
   const int rc = finish_sweeps(h, tm);
   if (dbg) {
     clock_gettime(CLOCK_MONOTONIC, &t_d);
     auto ms = [](const timespec& x, const timespec& y) { return (y.tv_sec - x.tv_sec) * 1e3 + (y.tv_nsec - x.tv_nsec) * 1e-6; };
+    float g_right = 0.f, g_left = 0.f;
+    cudaEventElapsedTime(&g_right, h->ev0, ev_mid);
+    cudaEventElapsedTime(&g_left, ev_mid, h->ev1);
+    cudaEventDestroy(ev_mid);
     fprintf(stderr, "[ttb timing] compress: host enqueue right %.1f ms, left (incl. rank-hint syncs) %.1f ms, drain %.1f ms; "
-                    "device %.1f ms, %lld launches\n", ms(t_a, t_b), ms(t_b, t_c), ms(t_c, t_d), h->last_ms,
-            (long long)h->last_launches);
+                    "device %.1f ms (right sweep %.1f, left sweep %.1f), %lld launches\n", ms(t_a, t_b), ms(t_b, t_c),
+            ms(t_c, t_d), h->last_ms, g_right, g_left, (long long)h->last_launches);
   }
   return rc;
 }
