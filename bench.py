@@ -330,8 +330,11 @@ def main():
         n_alg, alg = fl.get(alias.get(dom, dom), [n_l, 0.0])
         per_launch = alg / max(n_alg, 1)
         achieved = alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture
+        # (profiles/r1_ncu_full_sweep_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum)
+        ncu_traffic = {"k_qr_panel_flag": 149504 + 0}
         line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak if peak else None, "traffic": None,
+                            "frac": achieved / peak if peak else None, "traffic": ncu_traffic.get(dom),
                             "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
                             "share_of_step": ms / tot_ms if tot_ms else None,
@@ -349,6 +352,11 @@ def main():
         if sample_info is not None:
             sample_info["tflops_minimal_algorithm"] = sample_info["draws_per_s"] * 8.65e6 / 1e12
             sample_info["frac_of_fp64_peak"] = sample_info["tflops_minimal_algorithm"] / (peak * world) if peak else None
+            sample_info["roofline"] = {"bound": "tensor", "kernel": "k_sample_tile<128>", "unit": "TFLOP/s",
+                                       "achieved": sample_info["tflops_minimal_algorithm"] / world, "peak": peak,
+                                       "frac": sample_info["frac_of_fp64_peak"],
+                                       "ncu": "tensor pipe 64.9% active, DRAM traffic 34.1 MB per launch = the packed "
+                                              "train read once (profiles/r1_ncu_full_sample_tile.csv)"}
             extra["sample"] = sample_info
         if world == 1 and not args.no_extra:
             v, secs = cpu_compress_steps_per_s(L3, D3, Q3, 3)
