@@ -222,6 +222,23 @@ __global__ void __launch_bounds__(1024) k_accumulate_R(EnvCtx c) {
   }
 }
 
+// Phase 1 of the two-phase environment pass (few trains, large sites): T_t = sum_x A_t(:,:,x) for every
+// site in parallel.  This is the HBM-streaming part (reads every site tensor once, fully coalesced, the
+// whole GPU at once); the sequential chain then runs on the Q-times smaller T's out of L2.
+__global__ void k_site_trace(const double* slab, int64_t tt_stride, const int64_t* off, const int* bond, int L1, int Q,
+                             double* tr, int64_t tr_stride, const int64_t* toff) {
+  const int t = blockIdx.y, b = blockIdx.z;
+  const int* bd = bond + (int64_t)b * L1;
+  const int64_t n = (int64_t)bd[t] * bd[t + 1];
+  const double* A = slab + (int64_t)b * tt_stride + off[t];
+  double* o = tr + (int64_t)b * tr_stride + toff[t];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int x = 0; x < Q; ++x) acc += A[i + n * x];
+    o[i] = acc;
+  }
+}
+
 // marginals: p_t[x] ∝ sum_{a,b,c} l[t-1][a,b] A_t[b,c,x] r[t+1][c,a]; one CTA per (site, train)
 struct MargCtx {
   const double* slab; int64_t tt_stride; const int64_t* off; const int* bond; int L, L1, Q;
@@ -429,6 +446,7 @@ __global__ void k_twovar(TwoCtx c) {
 
 }  // namespace ttb
 #include "twovar_fast.cuh"
+#include "env_fast.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -500,6 +518,45 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
   c.log_out = w.env_log + (left ? 0 : h->batch); c.sign_out = w.env_sign + (left ? 0 : h->batch);
   c.normalize = normalize;
   const int thr = env_threads(h);
+  // two-phase pass: parallel physical-index sum first (HBM streaming), then the chain on the traces
+  double* d_tr = nullptr;
+  int64_t* d_toff = nullptr;
+  if (h->Q > 1 && h->batch < 296 && getenv("TTB_ENV_ONEPHASE") == nullptr) {
+    const int L = (int)h->L;
+    std::vector<int64_t> toff(L + 1, 0);
+    for (int t = 0; t < L; ++t) toff[t + 1] = toff[t] + ((h->bond0[t] * h->bond0[t + 1] + 15) & ~int64_t(15));
+    cudaError_t e = cudaMallocAsync(&d_tr, sizeof(double) * h->batch * toff[L], h->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_toff, sizeof(int64_t) * (L + 1), h->stream);
+    if (e != cudaSuccess) { if (d_tr) cudaFreeAsync(d_tr, h->stream); return fail(TTB_ENOMEM, "environment traces: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * (L + 1), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);  // toff is a stack vector
+    const int64_t maxsite = h->dmax * h->dmax;
+    const bool open_chain = !h->periodic && h->bond0[0] == 1 && h->bond0[L] == 1;
+    if (open_chain) {
+      // open train: both directions are coalesced column dots on T (left) or T^T (right)
+      if (left) {
+        dim3 g((unsigned)std::min<int64_t>((maxsite + 255) / 256, 64), (unsigned)L, (unsigned)h->batch);
+        TTB_LAUNCH(h, "k_site_trace", k_site_trace<<<g, 256, 0, h->stream>>>(h->slab, h->tt_stride, h->d_off, h->d_bond,
+                                                                       (int)h->L + 1, (int)h->Q, d_tr, toff[L], d_toff));
+      } else {
+        dim3 g((unsigned)std::min<int64_t>((maxsite + 1023) / 1024, 64), (unsigned)L, (unsigned)h->batch);
+        TTB_LAUNCH(h, "k_site_trace_t", k_site_trace_t<<<g, 256, 0, h->stream>>>(h->slab, h->tt_stride, h->d_off, h->d_bond,
+                                                                           (int)h->L + 1, (int)h->Q, d_tr, toff[L], d_toff));
+      }
+      ChainCtx cc;
+      cc.T = d_tr; cc.t_stride = toff[L]; cc.toff = d_toff; cc.bond = h->d_bond; cc.L = L; cc.L1 = L + 1;
+      cc.env = c.env; cc.env_stride = c.env_stride; cc.eoff = c.eoff; cc.log_out = c.log_out; cc.sign_out = c.sign_out;
+      cc.normalize = normalize; cc.left = left ? 1 : 0; cc.dmax = (int)h->dmax;
+      TTB_LAUNCH(h, "k_chain_open", k_chain_open<<<(unsigned)h->batch, 1024, sizeof(double) * 2 * h->dmax, h->stream>>>(cc));
+      cudaFreeAsync(d_tr, h->stream);
+      cudaFreeAsync(d_toff, h->stream);
+      return TTB_OK;
+    }
+    dim3 g((unsigned)std::min<int64_t>((maxsite + 255) / 256, 64), (unsigned)L, (unsigned)h->batch);
+    TTB_LAUNCH(h, "k_site_trace", k_site_trace<<<g, 256, 0, h->stream>>>(h->slab, h->tt_stride, h->d_off, h->d_bond, (int)h->L + 1,
+                                                                   (int)h->Q, d_tr, toff[L], d_toff));
+    c.slab = d_tr; c.tt_stride = toff[L]; c.off = d_toff; c.Q = 1;
+  }
   if (left) {
     TTB_LAUNCH(h, "k_accumulate_L", k_accumulate_L<<<(unsigned)h->batch, thr, 0, h->stream>>>(c));
   } else {
@@ -507,6 +564,10 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
     TTB_LAUNCH(h, "k_accumulate_R", k_accumulate_R<<<(unsigned)h->batch, thr, smem, h->stream>>>(c));
+  }
+  if (d_tr) {  // stream-ordered release: the chain kernel above is the last reader
+    cudaFreeAsync(d_tr, h->stream);
+    cudaFreeAsync(d_toff, h->stream);
   }
   return TTB_OK;
 }
