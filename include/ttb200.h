@@ -138,8 +138,10 @@ int ttb_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_
 int ttb_sample_stats(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
                      int64_t* hist, double* sum_logp);
 
-/* ---- dot / norm (src/abstract_tensor_train.jl:395-432), same-shape-class trains a[ba], b[bb] */
-int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, double* out);
+/* ---- dot (src/abstract_tensor_train.jl:395-408) of train ba of `a` with train bb of `b` (same length and
+ * physical dimension, same device; open or periodic, bonds may differ).  The value is returned as
+ * (log|dot|, sign) including both z factors; norm / norm2m / isapprox (:418-437) are host arithmetic on it. */
+int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, double* logabs, int* sign);
 
 /* timing aid for bench.py: milliseconds spent on the device inside the last call that ran kernels
  * (CUDA events on the handle's stream) and how many kernels it launched */

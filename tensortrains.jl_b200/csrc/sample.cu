@@ -432,9 +432,4 @@ int ttb_sample_stats(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, u
   return sample_impl(h, b, nsamples, seed, first_index, nullptr, nullptr, nullptr, hist, sum_logp);
 }
 
-int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, double* out) {
-  (void)a; (void)ba; (void)b; (void)bb; (void)out;
-  return fail(TTB_EUNSUPPORTED, "dot/norm are the next row after the hot path (SURVEY 8f); not built yet");
-}
-
 }  // extern "C"

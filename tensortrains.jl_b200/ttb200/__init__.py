@@ -96,7 +96,7 @@ _sig("ttb_twovar_marginals", _h, _i64, _pd)
 _sig("ttb_evaluate", _h, _i64, C.POINTER(C.c_int32), _i64, _pd)
 _sig("ttb_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
 _sig("ttb_sample_stats", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
-_sig("ttb_dot", _h, _i64, _h, _i64, _pd)
+_sig("ttb_dot", _h, _i64, _h, _i64, _pd, _pi)
 _sig("ttb_last_timing", _h, _pd, _pi64)
 _sig("ttb_profile", _h, C.c_int)
 _sig("ttb_profile_report", _h, C.c_char_p, C.c_size_t)
@@ -721,3 +721,36 @@ def sample_stats(A, nsamples: int, seed: int = 0, first_index: int = 0, b: int =
     _ck(lib.ttb_sample_stats(A._hd, b, int(nsamples), C.c_uint64(seed), C.c_uint64(first_index),
                              hist.ctypes.data_as(_pi64), C.byref(slp)))
     return hist, slp.value
+
+
+# ---- dot / norm / norm2m / isapprox (first row after the hot path) -------------------------
+def dot_log(A, B, ba: int = 0, bb: int = 0) -> Logarithmic:
+    """``dot(A, B)`` as a ``Logarithmic`` (sign, log|.|): long chains do not overflow."""
+    la = C.c_double(0.0)
+    sg = C.c_int(1)
+    _ck(lib.ttb_dot(A._hd, ba, B._hd, bb, C.byref(la), C.byref(sg)))
+    return Logarithmic(logabs=float(la.value), sign=int(sg.value))
+
+
+def dot(A, B, ba: int = 0, bb: int = 0) -> float:
+    """``LinearAlgebra.dot(A, B)`` (src/abstract_tensor_train.jl:395-408), z factors included."""
+    return float(dot_log(A, B, ba, bb))
+
+
+def norm(A, b: int = 0) -> float:
+    """``LinearAlgebra.norm(A)`` = sqrt(A . A) (src/abstract_tensor_train.jl:418-420)"""
+    return math.sqrt(abs(dot(A, A, b, b)))
+
+
+def norm2m(A, B, ba: int = 0, bb: int = 0) -> float:
+    """``norm2m(A, B)`` = |A|^2 + |B|^2 - 2 A.B (src/abstract_tensor_train.jl:430-432)"""
+    return norm(A, ba) ** 2 + norm(B, bb) ** 2 - 2.0 * dot(A, B, ba, bb)
+
+
+def isapprox(A, B, atol: float = 0.0, rtol: float = 1e-6, ba: int = 0, bb: int = 0) -> bool:
+    """``Base.isapprox`` for trains (src/abstract_tensor_train.jl:434-437)"""
+    na, nb = norm(A, ba), norm(B, bb)
+    return na * na + nb * nb - 2.0 * dot(A, B, ba, bb) <= max(atol, rtol * max(na, nb)) ** 2
+
+
+__all__ += ["dot", "dot_log", "norm", "norm2m", "isapprox"]

@@ -468,3 +468,56 @@ def test_config4_reduced_sampling():
     for i in range(n):
         xo, po = O.sample(lambda t: us[i, t], Ao, rz=rz)
         assert list(X[i]) == xo and close(p[i], po, 1e-9)
+
+
+# ---- dot / norm / norm2m (first row after the hot path, src/abstract_tensor_train.jl:395-437) --------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_dot_norm_match_oracle(periodic):
+    rng = RNG(700 + periodic)
+    q = (2, 3)
+    if periodic:
+        ba, bb = [3, 5, 4, 2], [2, 3, 6, 4]
+        ta, tb = rand_per(rng, ba, q), rand_per(rng, bb, q)
+    else:
+        ba, bb = [1, 5, 40, 7, 1], [1, 3, 33, 6, 1]
+        ta, tb = rand_open(rng, ba, q, "randn"), rand_open(rng, bb, q, "randn")
+    A, Ao = pair(ta, periodic, z=-2.5)
+    B, Bo = pair(tb, periodic, z=0.75)
+    assert close(T.dot(A, B), O.dot(Ao, Bo), 1e-10)
+    assert close(T.dot(B, A), O.dot(Ao, Bo), 1e-10)
+    assert close(T.norm(A), O.norm(Ao), 1e-10)
+    assert close(T.norm2m(A, B), O.norm2m(Ao, Bo), 1e-9)
+    # brute force: the dot is the sum over all configurations of the product of the two evaluations
+    assert close(T.dot(A, B), O.exact_dot(Ao, Bo), 1e-10)
+
+
+def test_dot_tracks_truncation_error_and_isapprox():
+    """norm2m(A, compress(A)) is the squared truncation error (test/tensor_train.jl:88-106 uses it as
+    the accuracy measure); isapprox follows (:434-437)."""
+    rng = RNG(710)
+    bonds = [1, 6, 20, 20, 6, 1]
+    A, Ao = pair(rand_open(rng, bonds, (3,)))
+    B = A.copy()
+    T.compress_(B, T.TruncBond(4))
+    e2 = T.norm2m(A, B)
+    assert 0.0 <= e2 <= 1e-2 * T.norm(A) ** 2
+    assert T.isapprox(A, A.copy()) and T.isapprox(A, B, rtol=1.0)
+    C2 = A.copy()
+    T.compress_(C2, T.TruncThresh(1e-12))
+    assert T.isapprox(A, C2, rtol=1e-8)
+    # long chain: the plain value would overflow, the logarithmic one does not
+    L = 400
+    tl = [rng.random((1 if t == 0 else 4, 1 if t == L - 1 else 4, 2)) * 50.0 for t in range(L)]
+    G, Go = pair(tl)
+    d = T.dot_log(G, G)
+    assert d.sign == 1 and math.isfinite(d.logabs) and d.logabs > 709.0
+    n = T.normalization(G)
+    assert d.logabs < 2 * n.logabs + 1e-6     # sum of squares <= (sum)^2 for a positive train
+
+
+def test_dot_shape_errors():
+    rng = RNG(720)
+    A = T.TensorTrain(rand_open(rng, [1, 3, 1], (2,)))
+    B = T.TensorTrain(rand_open(rng, [1, 3, 3, 1], (2,)))
+    with pytest.raises(ValueError):
+        T.dot(A, B)
