@@ -384,7 +384,10 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // ---------------------------------------------------------------------------------------------
 // `smem_doubles` = dynamic shared memory the launch provides; the vectors live in shared memory when
 // the ACTUAL (device-known) sizes fit, in the global workspace otherwise.
-__global__ void __launch_bounds__(1024) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
+// MAXT: largest block the instantiation is launched with (register budget); NE: row elements per lane
+// held in registers across a rotation (32*NE covers the row for the common sizes).
+template <int MAXT, int NE>
+__global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
@@ -451,31 +454,75 @@ __global__ void __launch_bounds__(1024) k_jacobi(SweepCtx c, StepDesc s, int sme
         if (j >= nv) continue;
         double* bi = B + (size_t)i * ldb;
         double* bj = B + (size_t)j * ldb;
+        // The first 256 elements of both rows (and 64 of the rotation rows) stay in registers between
+        // the dot and the update: a round is a latency chain (load -> dot -> 5 shuffles -> angle -> store),
+        // not a throughput problem, so every shared-memory round trip taken off it counts.
+        double xi[NE], yj[NE], jx[2], jy[2];
+        double* ji = J + (size_t)i * ldjj;
+        double* jj = J + (size_t)j * ldjj;
+#pragma unroll
+        for (int m = 0; m < NE; ++m) {
+          const int e = lane + 32 * m;
+          const bool ok = e < len;
+          xi[m] = ok ? bi[e] : 0.0;
+          yj[m] = ok ? bj[e] : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const int e = lane + 32 * m;
+          const bool ok = e < nv;
+          jx[m] = ok ? ji[e] : 0.0;
+          jy[m] = ok ? jj[e] : 0.0;
+        }
         const double al = sq[i], be = sq[j];
         double g0 = 0.0, g1 = 0.0;
-        int e = lane;
-        for (; e + 32 < len; e += 64) { g0 += bi[e] * bj[e]; g1 += bi[e + 32] * bj[e + 32]; }
-        if (e < len) g0 += bi[e] * bj[e];
+#pragma unroll
+        for (int m = 0; m < NE; m += 2) { g0 += xi[m] * yj[m]; g1 += xi[m + 1] * yj[m + 1]; }
+        for (int e = lane + 32 * NE; e < len; e += 32) g0 += bi[e] * bj[e];
         const double ga = warp_sum(g0 + g1);
         if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
-          // tan(theta) from tan(2 theta) = 2 ga / (be - al): one sqrt, one division, one rsqrt
+          // rotation angle from tan(2 theta) = 2 ga / (be - al), |theta| <= pi/4, with two rsqrt and no
+          // division on the critical path:  cos 2th = |da|/h, sin 2th = sign(da) b2/h,
+          // cos th = sqrt((1 + cos 2th)/2), sin th = sin 2th / (2 cos th)
           const double da = be - al, b2 = 2.0 * ga;
-          const double t = b2 / (da + copysign(sqrt(da * da + b2 * b2), da));
-          const double cs = rsqrt(1.0 + t * t), sn = cs * t;
-#pragma unroll 4
-          for (int e2 = lane; e2 < len; e2 += 32) {
-            const double x = bi[e2], y = bj[e2];
-            bi[e2] = cs * x - sn * y;
-            bj[e2] = sn * x + cs * y;
+          const double h2 = da * da + b2 * b2;
+          double r = rsqrt(h2), das = da, b2s = b2;
+          if (!(h2 > 1e-280 && h2 < 1e280)) {  // far outside the normal range: rescale first (rare, warp-uniform)
+            const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+            das = da * sc; b2s = b2 * sc;
+            r = rsqrt(das * das + b2s * b2s);
           }
-          double* ji = J + (size_t)i * ldjj;
-          double* jj = J + (size_t)j * ldjj;
-#pragma unroll 4
-          for (int e2 = lane; e2 < nv; e2 += 32) {
-            const double x = ji[e2], y = jj[e2];
-            ji[e2] = cs * x - sn * y;
-            jj[e2] = sn * x + cs * y;
+          const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+          const double u = 0.5 + 0.5 * c2;
+          const double ic = rsqrt(u);   // = 1 / cos(theta)
+          const double cs = u * ic, sn = 0.5 * s2 * ic;
+#pragma unroll
+          for (int m = 0; m < NE; ++m) {
+            const int e = lane + 32 * m;
+            if (e < len) {
+              bi[e] = cs * xi[m] - sn * yj[m];
+              bj[e] = sn * xi[m] + cs * yj[m];
+            }
           }
+          for (int e = lane + 32 * NE; e < len; e += 32) {
+            const double x = bi[e], y = bj[e];
+            bi[e] = cs * x - sn * y;
+            bj[e] = sn * x + cs * y;
+          }
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const int e = lane + 32 * m;
+            if (e < nv) {
+              ji[e] = cs * jx[m] - sn * jy[m];
+              jj[e] = sn * jx[m] + cs * jy[m];
+            }
+          }
+          for (int e = lane + 64; e < nv; e += 32) {
+            const double x = ji[e], y = jj[e];
+            ji[e] = cs * x - sn * y;
+            jj[e] = sn * x + cs * y;
+          }
+          const double t = sn * ic;   // tan(theta) without a division
           sq[i] = al - t * ga;  // same value from every lane
           sq[j] = be + t * ga;
           rotated = 1;
@@ -856,7 +903,10 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_panel_flag<2, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_panel_flag<4, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_panel_flag<8, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -998,7 +1048,14 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const size_t give = std::min<size_t>(need, (size_t)200 * 1024);
       const int thr = std::min(1024, std::max(64, ((nv_ub + 1) / 2) * 32));  // one warp per pair
       if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
-      TTB_LAUNCH(h, "k_jacobi", k_jacobi<<<B, thr, give, st>>>(c, s, (int)(give / sizeof(double))));
+      const int sd = (int)(give / sizeof(double));
+      if (thr <= 512) {
+        if (len_ub <= 64) TTB_LAUNCH(h, "k_jacobi", (k_jacobi<512, 2><<<B, thr, give, st>>>(c, s, sd)));
+        else TTB_LAUNCH(h, "k_jacobi", (k_jacobi<512, 8><<<B, thr, give, st>>>(c, s, sd)));
+      } else {
+        if (len_ub <= 64) TTB_LAUNCH(h, "k_jacobi", (k_jacobi<1024, 2><<<B, thr, give, st>>>(c, s, sd)));
+        else TTB_LAUNCH(h, "k_jacobi", (k_jacobi<1024, 8><<<B, thr, give, st>>>(c, s, sd)));
+      }
     }
     {
       dim3 g((mp_ub + kCw - 1) / kCw, B);
