@@ -38,7 +38,7 @@ elif which == "c2":
     A.profile(True)
     T.compress_(A, T.TruncBond(32))
     report(A, "C2 compress TruncBond(32)")
-else:
+elif which == "c5":
     Bn, L, d, q = 512, 64, 32, 2
     A = T.PeriodicTensorTrain([rng.random((Bn, d, d, q)) for _ in range(L)], batched=True)
     T.normalize_(A)
@@ -46,3 +46,13 @@ else:
     A.profile(True)
     T.compress_(A, T.TruncThresh(1e-6))
     report(A, "C5 compress B=512")
+if which == "c3right":
+    L = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    bonds = [1] + [256] * (L - 1) + [1]
+    A = T.TensorTrain([rng.random((bonds[t], bonds[t + 1], 2)) for t in range(L)])
+    B = A.copy()
+    T.orthogonalize_right_(B, T.TruncThresh(0.0))
+    print("right sweep unprofiled ms", B.last_timing())
+    A.profile(True)
+    T.orthogonalize_right_(A, T.TruncThresh(0.0))
+    report(A, f"C3 right sweep L={L}")

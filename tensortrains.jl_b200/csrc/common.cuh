@@ -140,6 +140,30 @@ int ensure_env_ws(ttb_tt* h);
 int read_status(ttb_tt* h, int* st);  // reads and clears the device status word
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch.  A sweep is a chain of ~20 short dependent kernels per site; the
+// stream-order gap between two of them is ~4 us on B200, ~1.7 us when the next grid is already resident
+// and parked in griddepcontrol.wait (profiles/micro_pdl.cu).  Contract: EVERY kernel launched through
+// launch_pdl -- and every kernel that can sit between two of them in a stream -- starts with pdl_enter()
+// in all threads, before it touches memory and before any early return; completion of a grid then implies
+// completion of all its predecessors.  On a kernel launched the ordinary way both instructions are no-ops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

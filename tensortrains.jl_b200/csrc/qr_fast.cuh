@@ -30,6 +30,42 @@ __device__ __forceinline__ void stage_columns(double* dst, const double* src, in
   }
 }
 
+// Sum 16 per-lane values over the warp with 16 shuffles instead of 80: every level sends the half of the
+// values the partner keeps.  Afterwards lane l (and its neighbour l^1) hold the total of value
+// index (l >> 1) & 15.
+__device__ __forceinline__ double warp_reduce16(double (&a)[16], int lane) {
+  double b8[8], b4[4], b2[2];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double send = hi ? a[k] : a[k + 8], keep = hi ? a[k + 8] : a[k];
+      b8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double send = hi ? b8[k] : b8[k + 4], keep = hi ? b8[k + 4] : b8[k];
+      b4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = hi ? b4[k] : b4[k + 2], keep = hi ? b4[k + 2] : b4[k];
+      b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool hi = lane & 2;
+  const double send = hi ? b2[0] : b2[1], keep = hi ? b2[1] : b2[0];
+  double r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Block reflector on a chunk held in shared memory:  Wc <- (I - V op(T) V^T) Wc,  op = T^T if TRANS.
 // Vs: rows x bwc unit-lower-trapezoidal (explicit 1 / 0), ld = rows.  Ts: 32 x 32 upper, ld 32.
@@ -59,13 +95,16 @@ __device__ __forceinline__ void block_reflect(const double* Vs, const double* Ts
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) acc[ii][cc] += vv[ii] * ww[cc];
       }
+      double flat[16];
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const double t = warp_sum(acc[ii][cc]);
-          if (lane == 0) W[(i0 + ii) + 32 * cc] = t;
-        }
+        for (int cc = 0; cc < 4; ++cc) flat[ii * 4 + cc] = acc[ii][cc];
+      const double t = warp_reduce16(flat, lane);
+      if (!(lane & 1)) {
+        const int idx = lane >> 1;  // value index = ii * 4 + cc
+        W[(i0 + (idx >> 2)) + 32 * (idx & 3)] = t;
+      }
     }
   }
   __syncthreads();
@@ -120,6 +159,7 @@ __device__ __forceinline__ void fix_unit_lower(double* Vs, int rows, int bwc) {
 
 // trailing update  A <- (I - V T^T V^T) A  for one chunk of <= 4 columns (bw == 32)
 __global__ void __launch_bounds__(256) k_qr_update_tma(SweepCtx c, StepDesc s, int panel) {
+  pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 2) return;
@@ -183,6 +223,7 @@ __global__ void __launch_bounds__(256) k_qr_update_tma(SweepCtx c, StepDesc s, i
 
 // W = H_1 ... H_k E for one chunk of <= 4 columns, written into the site tensor (bw == 32)
 __global__ void __launch_bounds__(256) k_apply_q_tma(SweepCtx c, StepDesc s) {
+  pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
   const int mprime = c.st[b].mprime[s.slot];

@@ -81,6 +81,7 @@ __device__ __forceinline__ double make_reflector(double (&col)[RPL], double (&v)
 
 template <int RPL, int NS>
 __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
+  pdl_enter();
   constexpr int NW = 32 / NS;
   constexpr int NT = 32 * NW;
   constexpr int LDV = 32 * RPL;

@@ -47,6 +47,7 @@ struct StepDesc {
   int bond_idx, bond_idx2; // bond entries that receive m'
   int last;                // absorb output goes to the neighbour's site storage
   int slot;                // maxabs ping-pong slot
+  int next_site, next_nbr; // the step that follows in this sweep (-1: none): k_commit snapshots its dimensions
 };
 
 struct Dims { int p, n, k, mode, N; };  // mode 0 = QR, 1 = SVD tall (p>=n), 2 = SVD wide
@@ -62,13 +63,19 @@ __device__ __forceinline__ Dims get_dims(const SweepCtx& c, const StepDesc& s, i
   return d;
 }
 
-__global__ void k_snapshot(SweepCtx c, StepDesc s, int batch) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
+__device__ __forceinline__ void snapshot_dims(const SweepCtx& c, int b, int dir, int site, int nbr, int slot) {
   const int* bond = c.bond + (int64_t)b * c.L1;
   StepState& st = c.st[b];
-  if (s.dir == 0) { st.p[s.slot] = bond[s.site + 1] * c.Q; st.n[s.slot] = bond[s.site]; st.N[s.slot] = bond[s.nbr]; }
-  else            { st.p[s.slot] = bond[s.site] * c.Q;     st.n[s.slot] = bond[s.site + 1]; st.N[s.slot] = bond[s.nbr + 1]; }
+  if (dir == 0) { st.p[slot] = bond[site + 1] * c.Q; st.n[slot] = bond[site]; st.N[slot] = bond[nbr]; }
+  else          { st.p[slot] = bond[site] * c.Q;     st.n[slot] = bond[site + 1]; st.N[slot] = bond[nbr + 1]; }
+}
+
+// dimensions of the first step of a sweep (later steps are snapshotted by the previous step's k_commit)
+__global__ void k_snapshot(SweepCtx c, StepDesc s, int batch) {
+  pdl_enter();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  snapshot_dims(c, b, s.dir, s.site, s.nbr, s.slot);
 }
 
 __device__ __forceinline__ double* xbuf(const SweepCtx& c, int which, int b) {
@@ -80,6 +87,7 @@ __device__ __forceinline__ double* xbuf(const SweepCtx& c, int which, int b) {
 //                            :198 left: M[(m,x),n] |= C[m,n,x])
 // ---------------------------------------------------------------------------------------------
 __global__ void k_fold(SweepCtx c, StepDesc s) {
+  pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
   const double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.site];
@@ -103,6 +111,7 @@ __global__ void k_fold(SweepCtx c, StepDesc s) {
 // blocked Householder QR: panel factorisation (one CTA per train)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_qr_panel(SweepCtx c, StepDesc s, int panel) {
+  pdl_enter();
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 2) return;
@@ -199,6 +208,7 @@ __global__ void k_qr_panel(SweepCtx c, StepDesc s, int panel) {
 
 // trailing update  A <- (I - V T^T V^T) A  for one chunk of columns
 __global__ void k_qr_update(SweepCtx c, StepDesc s, int panel, int cw) {
+  pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 2) return;
@@ -260,6 +270,7 @@ __global__ void k_qr_update(SweepCtx c, StepDesc s, int panel, int cw) {
 // (unfold: src/tensor_train.jl:165 right, :204 left)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
+  pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
   const int mprime = c.st[b].mprime[s.slot];
@@ -388,6 +399,7 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // held in registers across a rotation (32*NE covers the row for the common sizes).
 template <int MAXT, int NE>
 __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int smem_doubles) {
+  pdl_enter();
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
@@ -589,6 +601,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 #define AB_TN 64
 #define AB_TK 16
 __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
+  pdl_enter();
   const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
   const Dims d = get_dims(c, s, b);
   const int mprime = c.st[b].mprime[s.slot];
@@ -678,6 +691,7 @@ __global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
 #define AM_K 32
 #define AM_LD 36  // row stride == 4 (mod 16): fragment loads are conflict-free per half-warp
 __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
+  pdl_enter();
   const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
   const Dims d = get_dims(c, s, b);
   const int mprime = c.st[b].mprime[s.slot];
@@ -787,6 +801,7 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
 
 // rescale the absorb output: in place, or unfolded into the neighbour's site storage on the last step
 __global__ void k_rescale(SweepCtx c, StepDesc s) {
+  pdl_enter();
   const int b = blockIdx.y;
   const int mprime = c.st[b].mprime[s.slot];
   const int N = c.st[b].N[s.slot];
@@ -817,6 +832,7 @@ __global__ void k_rescale(SweepCtx c, StepDesc s) {
 
 // commit the step (one thread per train): z /= m, bond <- m', stats, reset the other maxabs slot
 __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   int* bond = c.bond + (int64_t)b * c.L1;
@@ -830,9 +846,11 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
   if (s.qr_only) c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = 0.0;
   bond[s.bond_idx] = mp;
   if (s.bond_idx2 >= 0) bond[s.bond_idx2] = mp;
+  if (s.next_site >= 0) snapshot_dims(c, b, s.dir, s.next_site, s.next_nbr, s.slot ^ 1);
 }
 
 __global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) { st[i].mprime[0] = st[i].mprime[1] = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull; }
   if (i < batch * L1) { stat_err[i] = 0.0; stat_rank[i] = 0; }
@@ -966,9 +984,20 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   bool side_pending = false;  // apply_q of the previous step may still be running on st2
   int side_slot = 0;
   const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
+  // Main-stream launches use programmatic dependent launch (common.cuh): the next grid is resident and
+  // parked in griddepcontrol.wait while its predecessor drains.  A launch that follows an event wait (or
+  // opens the sweep) is an ordinary one.
+  const bool use_pdl = !h->prof_on && getenv("TTB_NO_PDL") == nullptr;
+  bool hard_dep = true;
+#define SW_LAUNCH(name, kern, grid, block, smem, ...)                                              \
+  do {                                                                                             \
+    if (hard_dep || !use_pdl) { TTB_LAUNCH(h, name, (kern<<<grid, block, smem, st>>>(__VA_ARGS__))); } \
+    else { TTB_LAUNCH(h, name, launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)); } \
+    hard_dep = false;                                                                              \
+  } while (0)
   {
     const int n = std::max(B, B * L1);
-    TTB_LAUNCH(h, "k_reset_state", k_reset_state<<<(n + 255) / 256, 256, 0, st>>>(w.st, w.stat_err, w.stat_rank, B, L1));
+    SW_LAUNCH("k_reset_state", k_reset_state, (n + 255) / 256, 256, 0, w.st, w.stat_err, w.stat_rank, B, L1);
   }
   int xin = 0, slot = 0;
   for (size_t si = 0; si < steps.size(); ++si) {
@@ -978,6 +1007,8 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.kind = tr->kind; s.eps = tr->eps;
     s.cap = (int)std::min<int64_t>(tr->mprime, 1 << 30);
     s.bond_idx = hs.bond_idx; s.bond_idx2 = hs.bond_idx2; s.last = hs.last; s.slot = slot;
+    s.next_site = si + 1 < steps.size() ? steps[si + 1].site : -1;
+    s.next_nbr = si + 1 < steps.size() ? steps[si + 1].nbr : -1;
     SweepCtx c = cbase;
     c.T = cbase.T + (int64_t)slot * B * w.t_stride;
     // Launch-sizing hint: every few truncating steps read back the bond array the device has already
@@ -999,11 +1030,11 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
     else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; p_lb = lb[hs.site] * Q; n_lb = lb[hs.site + 1]; }
     const int k_ub = std::min(p_ub, n_ub);
-    TTB_LAUNCH(h, "k_snapshot", k_snapshot<<<(B + 127) / 128, 128, 0, st>>>(c, s, B));
+    if (si == 0) SW_LAUNCH("k_snapshot", k_snapshot, (B + 127) / 128, 128, 0, c, s, B);
     if (si == 0) {
       const int64_t tot = (int64_t)p_ub * n_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 255) / 256, 2048), B);
-      TTB_LAUNCH(h, "k_fold", k_fold<<<g, 256, 0, st>>>(c, s));
+      SW_LAUNCH("k_fold", k_fold, g, 256, 0, c, s);
     }
     const bool maybe_qr = qr_only || !(p_ub < n_lb);  // p < n for every train => wide => Jacobi on X directly
     // register-panel / TMA kernels (they exchange V^T V + tau instead of an explicit T factor)
@@ -1014,9 +1045,11 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         const int j0 = panel * bw;
         const int rows_ub = p_ub - j0;
         if (fast) {
-#define TTB_PANEL(RPL_)                                                                                   \
-  TTB_LAUNCH(h, "k_qr_panel_flag",                                                                        \
-             k_qr_panel_flag<RPL_, kPanelNS><<<B, 1024 / kPanelNS, sizeof(double) * (1024 * RPL_ + 1056) + 128, st>>>(c, s, panel))
+#define TTB_PANEL(RPL_)                                                                            \
+  do {                                                                                             \
+    auto kp = k_qr_panel_flag<RPL_, kPanelNS>;                                                     \
+    SW_LAUNCH("k_qr_panel_flag", kp, B, 1024 / kPanelNS, sizeof(double) * (1024 * RPL_ + 1056) + 128, c, s, panel); \
+  } while (0)
           if (rows_ub <= 64) TTB_PANEL(2);
           else if (rows_ub <= 128) TTB_PANEL(4);
           else if (rows_ub <= 256) TTB_PANEL(8);
@@ -1025,17 +1058,17 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         } else {
           const int thr = std::min(512, std::max(64, ((rows_ub + 31) / 32) * 32));
           size_t smem = sizeof(double) * ((size_t)2 * bw * bw + 2 * bw + 40 + (size_t)rows_ub * bw);
-          TTB_LAUNCH(h, "k_qr_panel", k_qr_panel<<<B, thr, smem, st>>>(c, s, panel));
+          SW_LAUNCH("k_qr_panel", k_qr_panel, B, thr, smem, c, s, panel);
         }
         const int trail = n_ub - j0 - 1;
         if (trail > 0) {
           dim3 g((trail + kCw - 1) / kCw, B);
           if (fast) {
             size_t sm2 = sizeof(double) * ((size_t)1280 + (size_t)rows_ub * 36);
-            TTB_LAUNCH(h, "k_qr_update_tma", k_qr_update_tma<<<g, 256, sm2, st>>>(c, s, panel));
+            SW_LAUNCH("k_qr_update_tma", k_qr_update_tma, g, 256, sm2, c, s, panel);
           } else {
             size_t sm2 = sizeof(double) * ((size_t)bw * bw + 2 * bw * kCw + (size_t)rows_ub * (bw + kCw));
-            TTB_LAUNCH(h, "k_qr_update", k_qr_update<<<g, 256, sm2, st>>>(c, s, panel, kCw));
+            SW_LAUNCH("k_qr_update", k_qr_update, g, 256, sm2, c, s, panel, kCw);
           }
         }
       }
@@ -1047,15 +1080,11 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const size_t need = sizeof(double) * (2 * (size_t)w.n_max + (size_t)nv_ub * (len_ub + nv_ub));
       const size_t give = std::min<size_t>(need, (size_t)200 * 1024);
       const int thr = std::min(1024, std::max(64, ((nv_ub + 1) / 2) * 32));  // one warp per pair
-      if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
+      if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; hard_dep = true; }
       const int sd = (int)(give / sizeof(double));
-      if (thr <= 512) {
-        if (len_ub <= 64) TTB_LAUNCH(h, "k_jacobi", (k_jacobi<512, 2><<<B, thr, give, st>>>(c, s, sd)));
-        else TTB_LAUNCH(h, "k_jacobi", (k_jacobi<512, 8><<<B, thr, give, st>>>(c, s, sd)));
-      } else {
-        if (len_ub <= 64) TTB_LAUNCH(h, "k_jacobi", (k_jacobi<1024, 2><<<B, thr, give, st>>>(c, s, sd)));
-        else TTB_LAUNCH(h, "k_jacobi", (k_jacobi<1024, 8><<<B, thr, give, st>>>(c, s, sd)));
-      }
+      auto kj = thr <= 512 ? (len_ub <= 64 ? k_jacobi<512, 2> : k_jacobi<512, 8>)
+                           : (len_ub <= 64 ? k_jacobi<1024, 2> : k_jacobi<1024, 8>);
+      SW_LAUNCH("k_jacobi", kj, B, thr, give, c, s, sd);
     }
     {
       dim3 g((mp_ub + kCw - 1) / kCw, B);
@@ -1076,7 +1105,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       if (overlap) {
         // absorb of THIS step only reads; the wait for the PREVIOUS step's apply_q must come before it
         // because absorb writes X[xin ^ 1], which that apply_q read as its X[xin]
-        if (side_pending) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; }
+        if (side_pending) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; hard_dep = true; }
         cudaEventRecord(h->ev_aq[slot], st2);
         side_pending = true;
         side_slot = slot;
@@ -1084,19 +1113,20 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     }
     {
       dim3 g((mp_ub + AM_T - 1) / AM_T, (N_ub + AM_T - 1) / AM_T, Q * B);
-      TTB_LAUNCH(h, "k_absorb_mma", k_absorb_mma<<<g, 128, 0, st>>>(c, s));
+      SW_LAUNCH("k_absorb_mma", k_absorb_mma, g, 128, 0, c, s);
     }
     {
       const int64_t tot = (int64_t)mp_ub * Q * N_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 1023) / 1024, 1024), B);
-      TTB_LAUNCH(h, "k_rescale", k_rescale<<<g, 256, 0, st>>>(c, s));
-      TTB_LAUNCH(h, "k_commit", k_commit<<<(B + 127) / 128, 128, 0, st>>>(c, s, B));
+      SW_LAUNCH("k_rescale", k_rescale, g, 256, 0, c, s);
+      SW_LAUNCH("k_commit", k_commit, (B + 127) / 128, 128, 0, c, s, B);
     }
     const int mp_lb = qr_only ? std::min(p_lb, n_lb) : 1;
     ub[hs.bond_idx] = mp_ub; lb[hs.bond_idx] = mp_lb;
     if (hs.bond_idx2 >= 0) { ub[hs.bond_idx2] = mp_ub; lb[hs.bond_idx2] = mp_lb; }
     xin ^= 1; slot ^= 1;
   }
+#undef SW_LAUNCH
   if (side_pending && overlap) cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0);  // join the side stream
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TTB_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
