@@ -36,6 +36,7 @@ struct StepState {
   int mprime[2];                     // retained rank of the step (written by the rank rule)
   unsigned long long maxabs_bits[2]; // max|D| of the absorb output, as ordered bits
   int p[2], n[2], N[2];              // dimensions of the step, snapshotted from the bond array
+  double scale_in[2];                // lazy rescale: factor the step applies to its input X (1/max|D| of the previous step)
 };
 
 struct Workspace {

@@ -66,12 +66,14 @@ struct DotCtx {
 };
 
 __global__ void k_dot_init(double* C, int64_t capC, int ra, int rb) {
+  pdl_enter();
   const int s = blockIdx.x, a1 = s % ra, b1 = s / ra;
   for (int i = threadIdx.x; i < ra * rb; i += blockDim.x) C[(int64_t)s * capC + i] = (i == a1 + ra * b1) ? 1.0 : 0.0;
 }
 
 // E_s(x) = A(x) * (scale * C_s)
 __global__ void __launch_bounds__(256) k_dot_ac(DotCtx c) {
+  pdl_enter();
   const int x = blockIdx.y, s = blockIdx.z;
   gemm_tile32<false>(c.da_l, c.db_r, c.da_r, c.A + (int64_t)c.da_l * c.da_r * x, c.da_l, c.C + (int64_t)s * c.capC, c.da_r,
                      c.E + ((int64_t)s * c.Q + x) * c.capC, c.da_l, c.scal[0], blockIdx.x, nullptr);
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256) k_dot_ac(DotCtx c) {
 // C_s' = E_s B^T over the combined (b_{l+1}, x) index.  E_s(x) blocks are capC apart, so the contraction is
 // split per x and accumulated by re-reading the tile: keep it simple -- one launch per site, x looped here.
 __global__ void __launch_bounds__(256) k_dot_eb(DotCtx c) {
+  pdl_enter();
   const int s = blockIdx.z;
   __shared__ double As[32][33], Bs[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(256) k_dot_eb(DotCtx c) {
 
 // turn the max-abs of the step into the scale the next step applies; accumulate its log
 __global__ void k_dot_scale(double* scal, unsigned long long* mx_bits) {
+  pdl_enter();
   const double mx = __longlong_as_double((long long)*mx_bits);
   if (mx != 0.0 && !isnan(mx) && !isinf(mx)) { scal[0] = 1.0 / mx; scal[1] += log(mx); }
   else scal[0] = 1.0;
@@ -131,6 +135,7 @@ __global__ void k_dot_scale(double* scal, unsigned long long* mx_bits) {
 // d = sum_{a1,b1} C_{(a1,b1)}[a1, b1];  out = (log|d| + acc - log z_A - log z_B, sign)
 __global__ void k_dot_final(const double* C, int64_t capC, int ra, int rb, const double* scal,
                             const double* logzA, const int* sgnA, const double* logzB, const int* sgnB, double* out) {
+  pdl_enter();
   __shared__ double red[40];
   double v = 0.0;
   for (int s = threadIdx.x; s < ra * rb; s += blockDim.x) {
@@ -191,13 +196,15 @@ extern "C" int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, doubl
     c.da_l = bA[t]; c.da_r = bA[t + 1]; c.db_l = bB[t]; c.db_r = bB[t + 1];
     const unsigned t1 = (unsigned)(((c.da_l + 31) / 32) * ((c.db_r + 31) / 32));
     const unsigned t2 = (unsigned)(((c.da_l + 31) / 32) * ((c.db_l + 31) / 32));
-    TTB_LAUNCH(a, "k_dot_ac", (k_dot_ac<<<dim3(t1, (unsigned)Q, (unsigned)S), 256, 0, s>>>(c)));
-    TTB_LAUNCH(a, "k_dot_eb", (k_dot_eb<<<dim3(t2, 1, (unsigned)S), 256, 0, s>>>(c)));
-    if (t > 0) TTB_LAUNCH(a, "k_dot_scale", (k_dot_scale<<<1, 1, 0, s>>>(scal, mx_bits)));  // the last product stays unscaled
+    // a chain of 3 L short dependent kernels: programmatic dependent launch (common.cuh)
+    TTB_LAUNCH(a, "k_dot_ac", launch_pdl(k_dot_ac, dim3(t1, (unsigned)Q, (unsigned)S), dim3(256), 0, s, c));
+    TTB_LAUNCH(a, "k_dot_eb", launch_pdl(k_dot_eb, dim3(t2, 1, (unsigned)S), dim3(256), 0, s, c));
+    if (t > 0) TTB_LAUNCH(a, "k_dot_scale", launch_pdl(k_dot_scale, dim3(1), dim3(1), 0, s, scal, mx_bits));  // the last product stays unscaled
     double* tmp = c.C; c.C = c.Cn; c.Cn = tmp;
   }
-  TTB_LAUNCH(a, "k_dot_final", (k_dot_final<<<1, 256, 0, s>>>(c.C, capC, ra, rb, scal, a->d_logz + ba, a->d_signz + ba,
-                                                               b->d_logz + bb, b->d_signz + bb, out_dev)));
+  TTB_LAUNCH(a, "k_dot_final", launch_pdl(k_dot_final, dim3(1), dim3(256), 0, s, (const double*)c.C, capC, ra, rb, (const double*)scal,
+                                          (const double*)(a->d_logz + ba), (const int*)(a->d_signz + ba),
+                                          (const double*)(b->d_logz + bb), (const int*)(b->d_signz + bb), out_dev));
   double h_out[2] = {0.0, 0.0};
   cudaMemcpyAsync(h_out, out_dev, sizeof(h_out), cudaMemcpyDeviceToHost, s);
   int rc = timer.finish();

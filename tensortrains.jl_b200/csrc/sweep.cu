@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
   if (d.mode == 0) return;
   const int nv = d.k, len = d.n, p = d.p;
   const double* X = xbuf(c, s.xin, b);
+  const double scale_in = c.st[b].scale_in[s.slot];  // pending 1/max|D| of the previous step (lazy rescale)
   double* Bg = c.Bv + (int64_t)b * c.bv_stride;
   double* Jg = c.Jv + (int64_t)b * c.jv_stride;
   extern __shared__ double sm[];
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 
   for (int i = tid; i < nv * len; i += nt) {
     const int r = i % nv, j = i / nv;  // coalesced read of column j of X
-    double v = X[r + (int64_t)p * j];
+    double v = X[r + (int64_t)p * j] * scale_in;
     if (d.mode == 1 && r > j) v = 0.0;
     B[(size_t)r * ldb + j] = v;
   }
@@ -597,94 +598,6 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 // absorb: Xn[(a + m'x), j] = sum_l S(a,l) * Nbr_x(l,j)   (src/tensor_train.jl:168 / :207)
 // plus max|D| for the rescale (:169-173 / :208-212).  FP64 tile GEMM, 64x64 tile, 4x4 per thread.
 // ---------------------------------------------------------------------------------------------
-#define AB_TM 64
-#define AB_TN 64
-#define AB_TK 16
-__global__ void __launch_bounds__(256) k_absorb(SweepCtx c, StepDesc s) {
-  pdl_enter();
-  const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
-  const Dims d = get_dims(c, s, b);
-  const int mprime = c.st[b].mprime[s.slot];
-  const int i0 = blockIdx.x * AB_TM, j0 = blockIdx.y * AB_TN;
-  if (i0 >= mprime || j0 >= d.N) return;
-  const int n = d.n, N = d.N, p = d.p;
-  const double* X = xbuf(c, s.xin, b);
-  const double* Bv = c.Bv + (int64_t)b * c.bv_stride;
-  const int* perm = c.perm + (int64_t)b * c.n_max;
-  const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
-  double* Xn = xbuf(c, s.xin ^ 1, b);
-  __shared__ double Ss[AB_TK][AB_TM + 1];
-  __shared__ double Bs[AB_TK][AB_TN + 1];
-  const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
-
-  for (int l0 = 0; l0 < n; l0 += AB_TK) {
-    // S tile: AB_TM x AB_TK
-    for (int i = tid; i < AB_TM * AB_TK; i += 256) {
-      int ii, ll;
-      if (d.mode == 0) { ii = i % AB_TM; ll = i / AB_TM; }   // X col-major: rows fastest
-      else { ll = i % AB_TK; ii = i / AB_TK; }                // Bv vector-major: l fastest
-      const int gi = i0 + ii, gl = l0 + ll;
-      double v = 0.0;
-      if (gi < mprime && gl < n) {
-        if (d.mode == 0) v = gi <= gl ? X[gi + (int64_t)p * gl] : 0.0;
-        else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
-      }
-      Ss[ll][ii] = v;
-    }
-    // neighbour tile: AB_TK x AB_TN
-    for (int i = tid; i < AB_TK * AB_TN; i += 256) {
-      int ll, jj;
-      if (s.dir == 1) { ll = i % AB_TK; jj = i / AB_TK; }     // nbr (n x N x Q): l fastest
-      else { jj = i % AB_TN; ll = i / AB_TN; }                // nbr (N x n x Q): j fastest
-      const int gl = l0 + ll, gj = j0 + jj;
-      double v = 0.0;
-      if (gl < n && gj < N)
-        v = s.dir == 1 ? nbr[gl + (int64_t)n * (gj + (int64_t)N * x)] : nbr[gj + (int64_t)N * (gl + (int64_t)n * x)];
-      Bs[ll][jj] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int ll = 0; ll < AB_TK; ++ll) {
-      double sa[4], sb[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) sa[a] = Ss[ll][tx + 16 * a];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sb[e] = Bs[ll][ty + 16 * e];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[a][e] += sa[a] * sb[e];
-    }
-    __syncthreads();
-  }
-  const int64_t ldo = (int64_t)mprime * c.Q;
-  double mx = 0.0;
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int gi = i0 + tx + 16 * a, gj = j0 + ty + 16 * e;
-      if (gi < mprime && gj < N) {
-        Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[a][e];
-        mx = absmax_nan(mx, acc[a][e]);
-      }
-    }
-  // block max with NaN propagation through the ordered-bits trick
-  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
-    bits = other > bits ? other : bits;
-  }
-  if ((tid & 31) == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
-}
-
 // DMMA variant: 32x32 output tile per CTA (4 warps, each 16x16 = two m16n8k8 FP64 tensor-core tiles),
 // K staged 32 at a time through shared memory with register prefetch of the next stage.
 #define AM_T 32
@@ -704,6 +617,7 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   const int* perm = c.perm + (int64_t)b * c.n_max;
   const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
   double* Xn = xbuf(c, s.xin ^ 1, b);
+  const double scale_in = c.st[b].scale_in[s.slot];  // R of an unscaled X (lazy rescale); Bv is already scaled
   __shared__ double Ss[AM_K][AM_LD];
   __shared__ double Bs[AM_K][AM_LD];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -725,7 +639,7 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
       const int gi = i0 + ii, gl = l0 + ll;
       double v = 0.0;
       if (gi < mprime && gl < n) {
-        if (d.mode == 0) v = gi <= gl ? X[gi + p * gl] : 0.0;
+        if (d.mode == 0) v = gi <= gl ? X[gi + p * gl] * scale_in : 0.0;
         else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
       }
       rs[u] = v;
@@ -799,7 +713,11 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
 }
 
-// rescale the absorb output: in place, or unfolded into the neighbour's site storage on the last step
+// Rescale of the absorb output (src/tensor_train.jl:169-173 / :208-212).  Between steps it is LAZY: the
+// blocked QR is invariant under a uniform scale of X, so the division by max|D| is applied where the
+// numbers are next consumed (k_jacobi's load, the R that k_absorb_mma reads) through StepState::scale_in,
+// written by k_commit.  This kernel only runs on the last step of a sweep, where the scaled output is
+// unfolded into the neighbour's site storage.
 __global__ void k_rescale(SweepCtx c, StepDesc s) {
   pdl_enter();
   const int b = blockIdx.y;
@@ -842,6 +760,7 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
   if (s.rescale && !bad && m != 0.0) c.logz[b] -= log(m);
   if (s.rescale && bad) atomicOr(c.status, ST_NONFINITE);
   c.st[b].maxabs_bits[s.slot ^ 1] = 0ull;
+  c.st[b].scale_in[s.slot ^ 1] = (s.rescale && !bad && m != 0.0 && !s.last) ? 1.0 / m : 1.0;
   c.stat_rank[(int64_t)b * c.L1 + s.bond_idx] = mp;
   if (s.qr_only) c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = 0.0;
   bond[s.bond_idx] = mp;
@@ -852,7 +771,10 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
 __global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < batch) { st[i].mprime[0] = st[i].mprime[1] = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull; }
+  if (i < batch) {
+    st[i].mprime[0] = st[i].mprime[1] = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull;
+    st[i].scale_in[0] = st[i].scale_in[1] = 1.0;
+  }
   if (i < batch * L1) { stat_err[i] = 0.0; stat_rank[i] = 0; }
 }
 
@@ -1118,7 +1040,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     {
       const int64_t tot = (int64_t)mp_ub * Q * N_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 1023) / 1024, 1024), B);
-      SW_LAUNCH("k_rescale", k_rescale, g, 256, 0, c, s);
+      if (hs.last) SW_LAUNCH("k_rescale", k_rescale, g, 256, 0, c, s);
       SW_LAUNCH("k_commit", k_commit, (B + 127) / 128, 128, 0, c, s, B);
     }
     const int mp_lb = qr_only ? std::min(p_lb, n_lb) : 1;
