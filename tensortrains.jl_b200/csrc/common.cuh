@@ -37,6 +37,7 @@ struct StepState {
   unsigned long long maxabs_bits[2]; // max|D| of the absorb output, as ordered bits
   int p[2], n[2], N[2];              // dimensions of the step, snapshotted from the bond array
   double scale_in[2];                // lazy rescale: factor the step applies to its input X (1/max|D| of the previous step)
+  int rot[2];                        // cluster Jacobi: rotations of the sweep in flight (ping-pong), all CTAs
 };
 
 struct Workspace {

@@ -1,0 +1,186 @@
+// jacobi_cluster.cuh -- one-sided Jacobi SVD for matrices that do not fit one CTA's shared memory
+// (k >= ~115 at k = n: the full-rank randn fill of config 3, or a truncating sweep run first on wide bonds).
+//
+// The single-CTA kernel then works out of L2 with 32 warps: ~15 ms per 256 x 256 SVD.  Here a thread-block
+// CLUSTER of 8 CTAs shares the matrix: the k rows form 16 blocks of rb rows; in block-round kr CTA c holds
+// the block pair the circle method assigns to it (8 disjoint block pairs per round, 15 rounds per sweep),
+// with both blocks -- rows of B and of the accumulated rotations J -- in ITS shared memory, and performs
+// every rotation between the two blocks (rb sub-rounds of rb disjoint pairs, one warp per pair) and, in the
+// first block-round of a sweep, every rotation inside each block.  That is exactly the 255 rounds x 128 pairs
+// of the cyclic ordering, 8 SMs wide.  Blocks live at their home rows of the global workspace (L2 resident,
+// 0.5 MB) between block-rounds: store, __threadfence, hardware cluster barrier, load the next pair with
+// L1-bypassing loads.  Convergence is a cluster-wide rotation count exchanged through global memory.
+#pragma once
+#include <cooperative_groups.h>
+
+namespace ttb {
+
+namespace cg = cooperative_groups;
+
+constexpr int kJcCluster = 8;            // CTAs per cluster (portable maximum)
+constexpr int kJcBlocks = 2 * kJcCluster;
+constexpr int kJcThreads = 512;
+
+__host__ __device__ inline int jc_rows_per_block(int nv) {
+  int rb = (nv + kJcBlocks - 1) / kJcBlocks;
+  rb = (rb + 1) & ~1;
+  return rb < 2 ? 2 : rb;
+}
+__host__ __device__ inline size_t jc_smem_bytes(int nv, int len) {
+  const int rb = jc_rows_per_block(nv);
+  return sizeof(double) * ((size_t)2 * rb * (len + nv) + 2 * rb) + 16;
+}
+
+// rows of R (tall) / X (wide), scaled, into the vector-major global workspace; J = I
+__global__ void k_jacobi_init(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  const int b = blockIdx.y;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;
+  const int nv = d.k, len = d.n, p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  const double scale_in = c.st[b].scale_in[s.slot];
+  double* Bg = c.Bv + (int64_t)b * c.bv_stride;
+  double* Jg = c.Jv + (int64_t)b * c.jv_stride;
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tr = (nv + 31) / 32, tc = (len + 31) / 32;
+  for (int tl = blockIdx.x; tl < tr * tc; tl += gridDim.x) {
+    const int r0 = (tl % tr) * 32, j0 = (tl / tr) * 32;
+    for (int jj = ty; jj < 32; jj += 8) {
+      const int r = r0 + tx, j = j0 + jj;
+      double v = 0.0;
+      if (r < nv && j < len && !(d.mode == 1 && r > j)) v = X[r + (int64_t)p * j] * scale_in;
+      tile[jj][tx] = v;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int r = r0 + rr, j = j0 + tx;
+      if (r < nv && j < len) Bg[(int64_t)r * c.ldv + j] = tile[tx][rr];
+    }
+    __syncthreads();
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)nv * nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % nv), v = (int)(i / nv);
+    Jg[(int64_t)v * c.ldj + e] = (e == v) ? 1.0 : 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { c.st[b].rot[0] = 0; c.st[b].rot[1] = 0; }
+}
+
+template <int NE>
+__global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads, 1) k_jacobi_cluster(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  cg::cluster_group cl = cg::this_cluster();
+  const int b = blockIdx.y;
+  const int rank = blockIdx.x;  // gridDim.x == cluster size
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;      // uniform over the cluster
+  const int nv = d.k, len = d.n;
+  const int rb = jc_rows_per_block(nv), rb2 = 2 * rb;
+  double* Bg = c.Bv + (int64_t)b * c.bv_stride;
+  double* Jg = c.Jv + (int64_t)b * c.jv_stride;
+  extern __shared__ __align__(16) double sm[];
+  double* Bs = sm;                          // [2 rb][len]
+  double* Js = Bs + (size_t)rb2 * len;      // [2 rb][nv]
+  double* sq = Js + (size_t)rb2 * nv;       // [2 rb]
+  __shared__ int rotated;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = kJcThreads / 32;
+  const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  int* rot = c.st[b].rot;
+  bool conv = (nv < 2);
+  int sweep = 0;
+  for (; sweep < 60 && !conv; ++sweep) {
+    if (tid == 0) rotated = 0;
+    for (int kr = 0; kr < kJcBlocks - 1; ++kr) {
+      int bi, bj;
+      rr_pair(kJcBlocks, kr, rank, bi, bj);
+      // ---- load the two blocks (home rows bi*rb.., bj*rb..) past L1; rows >= nv are zero padding
+      for (int half = 0; half < 2; ++half) {
+        const int g0 = (half ? bj : bi) * rb;
+        for (int i = tid; i < rb * len; i += kJcThreads) {
+          const int r = i / len, e = i - r * len;
+          Bs[(size_t)(half * rb + r) * len + e] = (g0 + r < nv) ? __ldcg(Bg + (int64_t)(g0 + r) * c.ldv + e) : 0.0;
+        }
+        for (int i = tid; i < rb * nv; i += kJcThreads) {
+          const int r = i / nv, e = i - r * nv;
+          Js[(size_t)(half * rb + r) * nv + e] = (g0 + r < nv) ? __ldcg(Jg + (int64_t)(g0 + r) * c.ldj + e) : 0.0;
+        }
+      }
+      __syncthreads();
+      for (int v = wid; v < rb2; v += NW) {
+        const double* row = Bs + (size_t)v * len;
+        double a0 = 0.0, a1 = 0.0;
+        int e = lane;
+        for (; e + 32 < len; e += 64) { a0 += row[e] * row[e]; a1 += row[e + 32] * row[e + 32]; }
+        if (e < len) a0 += row[e] * row[e];
+        const double al = warp_sum(a0 + a1);
+        if (lane == 0) sq[v] = al;
+      }
+      __syncthreads();
+      bool did = false;
+      // ---- rotations inside each block, once per sweep (first block-round): rb/2 + rb/2 pairs per sub-round
+      if (kr == 0) {
+        for (int rd = 0; rd < rb - 1; ++rd) {
+          if (wid < rb) {
+            const int half = wid >= rb / 2 ? 1 : 0;
+            int i, j;
+            rr_pair(rb, rd, wid - half * (rb / 2), i, j);
+            i += half * rb; j += half * rb;
+            did |= jacobi_pair<NE, NE>(Bs + (size_t)i * len, Bs + (size_t)j * len, Js + (size_t)i * nv, Js + (size_t)j * nv,
+                                       len, nv, sq + i, sq + j, tol2, lane);
+          }
+          __syncthreads();
+        }
+      }
+      // ---- rotations between the two blocks: rb sub-rounds of rb disjoint pairs
+      for (int rd = 0; rd < rb; ++rd) {
+        if (wid < rb) {
+          const int i = wid;
+          int j = wid + rd; if (j >= rb) j -= rb;
+          j += rb;
+          did |= jacobi_pair<NE, NE>(Bs + (size_t)i * len, Bs + (size_t)j * len, Js + (size_t)i * nv, Js + (size_t)j * nv,
+                                     len, nv, sq + i, sq + j, tol2, lane);
+        }
+        __syncthreads();
+      }
+      if (did && lane == 0) rotated = 1;
+      // ---- blocks back to their home rows
+      for (int half = 0; half < 2; ++half) {
+        const int g0 = (half ? bj : bi) * rb;
+        for (int i = tid; i < rb * len; i += kJcThreads) {
+          const int r = i / len, e = i - r * len;
+          if (g0 + r < nv) Bg[(int64_t)(g0 + r) * c.ldv + e] = Bs[(size_t)(half * rb + r) * len + e];
+        }
+        for (int i = tid; i < rb * nv; i += kJcThreads) {
+          const int r = i / nv, e = i - r * nv;
+          if (g0 + r < nv) Jg[(int64_t)(g0 + r) * c.ldj + e] = Js[(size_t)(half * rb + r) * nv + e];
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (kr == kJcBlocks - 2 && tid == 0) {
+        if (rotated) atomicAdd(&rot[sweep & 1], 1);
+        __threadfence();
+      }
+      cl.sync();
+    }
+    const int total = __ldcg(&rot[sweep & 1]);  // L2 load: identical in every CTA after the barrier
+    if (rank == 0 && tid == 0) rot[(sweep + 1) & 1] = 0;  // ordered before its next use by 15 cluster barriers
+    conv = (total == 0);
+  }
+  if (!conv && rank == 0 && tid == 0) atomicOr(c.status, ST_NOCONV);
+}
+
+// singular values, order, rank rule for the cluster path (the rotated rows are in the global workspace)
+__global__ void __launch_bounds__(1024) k_jacobi_finish(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;
+  extern __shared__ double sm[];
+  jacobi_finish(c, s, b, c.Bv + (int64_t)b * c.bv_stride, c.ldv, d.k, d.n, sm, sm + c.n_max);
+}
+
+}  // namespace ttb

@@ -391,6 +391,136 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 }
 
 // ---------------------------------------------------------------------------------------------
+// one-sided (Hestenes) Jacobi: one rotation of the row pair (bi, bj) and of the accumulated rotations
+// (ji, jj), executed by one warp.  Squared norms are cached in sqi/sqj (a rotation updates them exactly:
+// |bi'|^2 = al - t ga, |bj'|^2 = be + t ga), so a pair costs ONE dot + one warp reduction.  The first
+// 32*NE elements of both rows (32*NJ of the rotation rows) stay in registers between the dot and the
+// update: a round is a latency chain (load -> dot -> 5 shuffles -> angle -> store), not a throughput
+// problem, so every shared-memory round trip taken off it counts.  Returns true when it rotated.
+// ---------------------------------------------------------------------------------------------
+template <int NE, int NJ>
+__device__ __forceinline__ bool jacobi_pair(double* bi, double* bj, double* ji, double* jj, int len, int nv,
+                                            double* sqi, double* sqj, double tol2, int lane) {
+  double xi[NE], yj[NE], jx[NJ], jy[NJ];
+#pragma unroll
+  for (int m = 0; m < NE; ++m) {
+    const int e = lane + 32 * m;
+    const bool ok = e < len;
+    xi[m] = ok ? bi[e] : 0.0;
+    yj[m] = ok ? bj[e] : 0.0;
+  }
+#pragma unroll
+  for (int m = 0; m < NJ; ++m) {
+    const int e = lane + 32 * m;
+    const bool ok = e < nv;
+    jx[m] = ok ? ji[e] : 0.0;
+    jy[m] = ok ? jj[e] : 0.0;
+  }
+  const double al = *sqi, be = *sqj;
+  double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+  for (int m = 0; m < NE; m += 2) { g0 += xi[m] * yj[m]; g1 += xi[m + 1] * yj[m + 1]; }
+  for (int e = lane + 32 * NE; e < len; e += 32) g0 += bi[e] * bj[e];
+  const double ga = warp_sum(g0 + g1);
+  if (!(al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be)) return false;
+  // rotation angle from tan(2 theta) = 2 ga / (be - al), |theta| <= pi/4, with two rsqrt and no
+  // division on the critical path:  cos 2th = |da|/h, sin 2th = sign(da) b2/h,
+  // cos th = sqrt((1 + cos 2th)/2), sin th = sin 2th / (2 cos th)
+  const double da = be - al, b2 = 2.0 * ga;
+  const double h2 = da * da + b2 * b2;
+  double r = rsqrt(h2), das = da, b2s = b2;
+  if (!(h2 > 1e-280 && h2 < 1e280)) {  // far outside the normal range: rescale first (rare, warp-uniform)
+    const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+    das = da * sc; b2s = b2 * sc;
+    r = rsqrt(das * das + b2s * b2s);
+  }
+  const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+  const double u = 0.5 + 0.5 * c2;
+  const double ic = rsqrt(u);   // = 1 / cos(theta)
+  const double cs = u * ic, sn = 0.5 * s2 * ic;
+#pragma unroll
+  for (int m = 0; m < NE; ++m) {
+    const int e = lane + 32 * m;
+    if (e < len) {
+      bi[e] = cs * xi[m] - sn * yj[m];
+      bj[e] = sn * xi[m] + cs * yj[m];
+    }
+  }
+  for (int e = lane + 32 * NE; e < len; e += 32) {
+    const double x = bi[e], y = bj[e];
+    bi[e] = cs * x - sn * y;
+    bj[e] = sn * x + cs * y;
+  }
+#pragma unroll
+  for (int m = 0; m < NJ; ++m) {
+    const int e = lane + 32 * m;
+    if (e < nv) {
+      ji[e] = cs * jx[m] - sn * jy[m];
+      jj[e] = sn * jx[m] + cs * jy[m];
+    }
+  }
+  for (int e = lane + 32 * NJ; e < nv; e += 32) {
+    const double x = ji[e], y = jj[e];
+    ji[e] = cs * x - sn * y;
+    jj[e] = sn * x + cs * y;
+  }
+  const double t = sn * ic;   // tan(theta) without a division
+  *sqi = al - t * ga;         // same value from every lane
+  *sqj = be + t * ga;
+  return true;
+}
+
+// round-robin (circle method) pairing of n (even) players: pair q of round rd, i < j
+__device__ __forceinline__ void rr_pair(int n, int rd, int q, int& i, int& j) {
+  if (q == 0) { i = n - 1; j = rd; }
+  else {
+    i = rd + q; if (i >= n - 1) i -= n - 1;
+    j = rd - q; if (j < 0) j += n - 1;
+  }
+  if (i > j) { const int t = i; i = j; j = t; }
+}
+
+// After convergence: singular values = row norms -> sort -> rank rule on the device (the retained rank never
+// visits the host), sigma / spectrum / stats.  B: the rotated rows (shared or global), sig/srt: n_max
+// doubles of shared scratch each.  Called by every thread of the CTA.
+__device__ __forceinline__ void jacobi_finish(const SweepCtx& c, const StepDesc& s, int b, const double* B, int ldb,
+                                              int nv, int len, double* sig, double* srt) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int v = wid; v < nv; v += nw) {
+    const double* bi = B + (size_t)v * ldb;
+    double al = 0.0;
+    for (int e = lane; e < len; e += 32) al += bi[e] * bi[e];
+    al = warp_sum(al);
+    if (lane == 0) sig[v] = sqrt(al);
+  }
+  __syncthreads();
+  int* perm = c.perm + (int64_t)b * c.n_max;
+  for (int i = tid; i < nv; i += nt) {
+    const double si = sig[i];
+    int pos = 0;
+    for (int j = 0; j < nv; ++j) {
+      const double sj = sig[j];
+      pos += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    srt[pos] = si;
+    perm[pos] = i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double err = 0.0;
+    const int mp = rank_rule(srt, nv, s.kind, s.eps, s.cap, &err);
+    c.st[b].mprime[s.slot] = mp;
+    c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = err;
+  }
+  double* sg = c.sigma + (int64_t)b * c.n_max;
+  for (int i = tid; i < nv; i += nt) sg[i] = srt[i];
+  if (c.spectrum) {
+    double* sp = c.spectrum + ((int64_t)b * c.L1 + s.bond_idx) * c.n_max;
+    for (int i = tid; i < c.n_max; i += nt) sp[i] = i < nv ? srt[i] : -1.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // one-sided Jacobi SVD on the rows of R (tall) or X (wide) + rank rule.  One CTA per train.
 // ---------------------------------------------------------------------------------------------
 // `smem_doubles` = dynamic shared memory the launch provides; the vectors live in shared memory when
@@ -417,7 +547,6 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
   double* J = SMEM ? (B + (size_t)nv * ldb) : Jg;
   const int ldjj = SMEM ? nv : c.ldj;
   __shared__ int rotated;
-  __shared__ int sh_mprime;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
 
   for (int i = tid; i < nv * len; i += nt) {
@@ -432,11 +561,8 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
   }
   __syncthreads();
 
-  // Cyclic one-sided Jacobi, round-robin ordering: nvp-1 rounds of nvp/2 disjoint pairs, one warp per
-  // pair.  Squared norms are cached (refreshed every sweep; a rotation updates them exactly:
-  // |bi'|^2 = al - t ga, |bj'|^2 = be + t ga), so a pair costs ONE dot + one warp reduction; B and the
-  // accumulated rotations J are updated in the same pass.  ~10 sweeps on the sweep matrices
-  // (profiles/r1_jacobi_sweeps.txt), each round is one block barrier.
+  // Cyclic ordering: nvp-1 rounds of nvp/2 disjoint pairs, one warp per pair, one block barrier per
+  // round; squared norms refreshed every sweep.  8-10 sweeps on the sweep matrices.
   const int nvp = (nv + 1) & ~1;
   const int npairs = nvp / 2, rounds = nvp - 1;
   const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
@@ -458,88 +584,11 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
     for (int rd = 0; rd < rounds; ++rd) {
       for (int q = wid; q < npairs; q += nw) {
         int i, j;
-        if (q == 0) { i = nvp - 1; j = rd; }
-        else {
-          i = rd + q; if (i >= nvp - 1) i -= nvp - 1;
-          j = rd - q; if (j < 0) j += nvp - 1;
-        }
-        if (i > j) { const int t = i; i = j; j = t; }
+        rr_pair(nvp, rd, q, i, j);
         if (j >= nv) continue;
-        double* bi = B + (size_t)i * ldb;
-        double* bj = B + (size_t)j * ldb;
-        // The first 256 elements of both rows (and 64 of the rotation rows) stay in registers between
-        // the dot and the update: a round is a latency chain (load -> dot -> 5 shuffles -> angle -> store),
-        // not a throughput problem, so every shared-memory round trip taken off it counts.
-        double xi[NE], yj[NE], jx[2], jy[2];
-        double* ji = J + (size_t)i * ldjj;
-        double* jj = J + (size_t)j * ldjj;
-#pragma unroll
-        for (int m = 0; m < NE; ++m) {
-          const int e = lane + 32 * m;
-          const bool ok = e < len;
-          xi[m] = ok ? bi[e] : 0.0;
-          yj[m] = ok ? bj[e] : 0.0;
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const int e = lane + 32 * m;
-          const bool ok = e < nv;
-          jx[m] = ok ? ji[e] : 0.0;
-          jy[m] = ok ? jj[e] : 0.0;
-        }
-        const double al = sq[i], be = sq[j];
-        double g0 = 0.0, g1 = 0.0;
-#pragma unroll
-        for (int m = 0; m < NE; m += 2) { g0 += xi[m] * yj[m]; g1 += xi[m + 1] * yj[m + 1]; }
-        for (int e = lane + 32 * NE; e < len; e += 32) g0 += bi[e] * bj[e];
-        const double ga = warp_sum(g0 + g1);
-        if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
-          // rotation angle from tan(2 theta) = 2 ga / (be - al), |theta| <= pi/4, with two rsqrt and no
-          // division on the critical path:  cos 2th = |da|/h, sin 2th = sign(da) b2/h,
-          // cos th = sqrt((1 + cos 2th)/2), sin th = sin 2th / (2 cos th)
-          const double da = be - al, b2 = 2.0 * ga;
-          const double h2 = da * da + b2 * b2;
-          double r = rsqrt(h2), das = da, b2s = b2;
-          if (!(h2 > 1e-280 && h2 < 1e280)) {  // far outside the normal range: rescale first (rare, warp-uniform)
-            const double sc = 1.0 / fmax(fabs(da), fabs(b2));
-            das = da * sc; b2s = b2 * sc;
-            r = rsqrt(das * das + b2s * b2s);
-          }
-          const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
-          const double u = 0.5 + 0.5 * c2;
-          const double ic = rsqrt(u);   // = 1 / cos(theta)
-          const double cs = u * ic, sn = 0.5 * s2 * ic;
-#pragma unroll
-          for (int m = 0; m < NE; ++m) {
-            const int e = lane + 32 * m;
-            if (e < len) {
-              bi[e] = cs * xi[m] - sn * yj[m];
-              bj[e] = sn * xi[m] + cs * yj[m];
-            }
-          }
-          for (int e = lane + 32 * NE; e < len; e += 32) {
-            const double x = bi[e], y = bj[e];
-            bi[e] = cs * x - sn * y;
-            bj[e] = sn * x + cs * y;
-          }
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            const int e = lane + 32 * m;
-            if (e < nv) {
-              ji[e] = cs * jx[m] - sn * jy[m];
-              jj[e] = sn * jx[m] + cs * jy[m];
-            }
-          }
-          for (int e = lane + 64; e < nv; e += 32) {
-            const double x = ji[e], y = jj[e];
-            ji[e] = cs * x - sn * y;
-            jj[e] = sn * x + cs * y;
-          }
-          const double t = sn * ic;   // tan(theta) without a division
-          sq[i] = al - t * ga;  // same value from every lane
-          sq[j] = be + t * ga;
+        if (jacobi_pair<NE, 2>(B + (size_t)i * ldb, B + (size_t)j * ldb, J + (size_t)i * ldjj, J + (size_t)j * ldjj,
+                               len, nv, sq + i, sq + j, tol2, lane))
           rotated = 1;
-        }
       }
       __syncthreads();
     }
@@ -547,41 +596,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
     __syncthreads();
   }
   if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
-
-  for (int v = wid; v < nv; v += nw) {
-    const double* bi = B + (size_t)v * ldb;
-    double al = 0.0;
-    for (int e = lane; e < len; e += 32) al += bi[e] * bi[e];
-    al = warp_sum(al);
-    if (lane == 0) sig[v] = sqrt(al);
-  }
-  __syncthreads();
-  int* perm = c.perm + (int64_t)b * c.n_max;
-  for (int i = tid; i < nv; i += nt) {
-    const double si = sig[i];
-    int pos = 0;
-    for (int j = 0; j < nv; ++j) {
-      const double sj = sig[j];
-      pos += (sj > si || (sj == si && j < i)) ? 1 : 0;
-    }
-    srt[pos] = si;
-    perm[pos] = i;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double err = 0.0;
-    const int mp = rank_rule(srt, nv, s.kind, s.eps, s.cap, &err);
-    sh_mprime = mp;
-    c.st[b].mprime[s.slot] = mp;
-    c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = err;
-  }
-  __syncthreads();
-  double* sg = c.sigma + (int64_t)b * c.n_max;
-  for (int i = tid; i < nv; i += nt) sg[i] = srt[i];
-  if (c.spectrum) {
-    double* sp = c.spectrum + ((int64_t)b * c.L1 + s.bond_idx) * c.n_max;
-    for (int i = tid; i < c.n_max; i += nt) sp[i] = i < nv ? srt[i] : -1.0;
-  }
+  jacobi_finish(c, s, b, B, ldb, nv, len, sig, srt);
   if (SMEM) {
     for (int i = tid; i < nv * len; i += nt) {
       const int e = i % len, v = i / len;
@@ -593,6 +608,10 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
     }
   }
 }
+
+}  // namespace ttb
+#include "jacobi_cluster.cuh"
+namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
 // absorb: Xn[(a + m'x), j] = sum_l S(a,l) * Nbr_x(l,j)   (src/tensor_train.jl:168 / :207)
@@ -843,6 +862,7 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1004,9 +1024,20 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const int thr = std::min(1024, std::max(64, ((nv_ub + 1) / 2) * 32));  // one warp per pair
       if (side_pending && overlap) { cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0); side_pending = false; hard_dep = true; }
       const int sd = (int)(give / sizeof(double));
+      // too large for one CTA's shared memory: cluster of 8 CTAs (jacobi_cluster.cuh)
+      const bool cluster_path = need > (size_t)200 * 1024 && jc_smem_bytes(nv_ub, len_ub) <= (size_t)200 * 1024 &&
+                                getenv("TTB_JACOBI_NOCLUSTER") == nullptr;
+      if (cluster_path) {
+        const int tiles = ((nv_ub + 31) / 32) * ((len_ub + 31) / 32);
+        SW_LAUNCH("k_jacobi_init", k_jacobi_init, dim3(std::min(tiles, 128), B), 256, 0, c, s);
+        TTB_LAUNCH(h, "k_jacobi_cluster",
+                   (k_jacobi_cluster<8><<<dim3(kJcCluster, B), kJcThreads, jc_smem_bytes(nv_ub, len_ub), st>>>(c, s)));
+        SW_LAUNCH("k_jacobi_finish", k_jacobi_finish, B, 1024, sizeof(double) * 2 * (size_t)w.n_max, c, s);
+      } else {
       auto kj = thr <= 512 ? (len_ub <= 64 ? k_jacobi<512, 2> : k_jacobi<512, 8>)
                            : (len_ub <= 64 ? k_jacobi<1024, 2> : k_jacobi<1024, 8>);
       SW_LAUNCH("k_jacobi", kj, B, thr, give, c, s, sd);
+      }
     }
     {
       dim3 g((mp_ub + kCw - 1) / kCw, B);

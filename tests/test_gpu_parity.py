@@ -521,3 +521,36 @@ def test_dot_shape_errors():
     B = T.TensorTrain(rand_open(rng, [1, 3, 3, 1], (2,)))
     with pytest.raises(ValueError):
         T.dot(A, B)
+
+
+# ---- matrices too large for one CTA's shared memory: the cluster Jacobi (jacobi_cluster.cuh) -----------
+@pytest.mark.parametrize("case", ["randn150_bond97", "rand136_left_first"])
+def test_large_bond_cluster_jacobi(case):
+    rng = RNG(150)
+    if case == "randn150_bond97":
+        L, d = 10, 150                      # k = 150: 16 blocks of 10 rows, the last one padded
+        ts = rand_open(rng, [1] + [d] * (L - 1) + [1], (2,), "randn")
+        A, Ao = pair(ts)
+        X = rand_points(rng, Ao, 6)
+        A.record_spectrum(True)
+        stats = []
+        T.compress_(A, T.TruncBond(97)); O.compress(Ao, O.TruncBond(97), stats=stats)
+        assert T.bond_dims(A) == O.bond_dims(Ao)
+        for (t, lam_o, kept) in stats:
+            assert spectra_close(A.spectrum(t), lam_o), t
+        g = T.evaluate(A, X)
+        e = np.array([o_eval_flat(Ao, X[i]) for i in range(X.shape[0])])
+        assert np.max(np.abs(g - e)) <= 1e-8 * np.max(np.abs(e))
+        assert all(T.is_left_canonical(A, t) for t in range(0, L - 1))
+    else:
+        L, d = 9, 136                       # truncating LEFT sweep first: full-rank 136-wide SVDs of a rand fill
+        ts = rand_open(rng, [1] + [d] * (L - 1) + [1], (2,), "rand")
+        A, Ao = pair(ts)
+        X = rand_points(rng, Ao, 6)
+        A.record_spectrum(True)
+        stats = []
+        T.orthogonalize_left_(A, T.TruncThresh(1e-7)); O.orthogonalize_left(Ao, O.TruncThresh(1e-7), stats=stats)
+        assert T.bond_dims(A) == O.bond_dims(Ao)
+        for (t, lam_o, kept) in stats:
+            assert spectra_close(A.spectrum(t), lam_o), t
+        check_evals(A, Ao, X, 1e-6)
