@@ -31,6 +31,80 @@ __host__ __device__ inline size_t jc_smem_bytes(int nv, int len) {
   return sizeof(double) * ((size_t)2 * rb * (len + nv) + 2 * rb) + 16;
 }
 
+// jacobi_pair with row i (and its rotation row) RESIDENT IN REGISTERS: in the cross-block phase warp w
+// rotates its fixed row i = w against a different row j every sub-round, so only row j moves through
+// shared memory -- the phase is shared-memory-bandwidth bound (16 pairs x 4 rows x 2 KB x load+store per
+// sub-round) and this halves the traffic.  Requires len, nv <= 32*NE.
+template <int NE>
+__device__ __forceinline__ bool jacobi_pair_fixed(double (&xi)[NE], double (&jx)[NE], double& al, double* bj, double* jj,
+                                                  int len, int nv, double* sqj, double tol2, int lane) {
+  double yj[NE], jy[NE];
+#pragma unroll
+  for (int m = 0; m < NE; ++m) {
+    const int e = lane + 32 * m;
+    yj[m] = e < len ? bj[e] : 0.0;
+    jy[m] = e < nv ? jj[e] : 0.0;
+  }
+  const double be = *sqj;
+  double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+  for (int m = 0; m < NE; m += 2) { g0 += xi[m] * yj[m]; g1 += xi[m + 1] * yj[m + 1]; }
+  const double ga = warp_sum(g0 + g1);
+  if (!(al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be)) return false;
+  const double da = be - al, b2 = 2.0 * ga;
+  const double h2 = da * da + b2 * b2;
+  double r = rsqrt(h2), das = da, b2s = b2;
+  if (!(h2 > 1e-280 && h2 < 1e280)) {
+    const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+    das = da * sc; b2s = b2 * sc;
+    r = rsqrt(das * das + b2s * b2s);
+  }
+  const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+  const double u = 0.5 + 0.5 * c2;
+  const double ic = rsqrt(u);
+  const double cs = u * ic, sn = 0.5 * s2 * ic;
+#pragma unroll
+  for (int m = 0; m < NE; ++m) {
+    const int e = lane + 32 * m;
+    const double x = xi[m], y = yj[m];
+    xi[m] = cs * x - sn * y;
+    if (e < len) bj[e] = sn * x + cs * y;
+    const double p = jx[m], q = jy[m];
+    jx[m] = cs * p - sn * q;
+    if (e < nv) jj[e] = sn * p + cs * q;
+  }
+  const double t = sn * ic;
+  al -= t * ga;
+  *sqj = be + t * ga;
+  return true;
+}
+
+// copy `rows` rows of `n` doubles between a strided global matrix and a packed shared block; 16-byte
+// accesses with four requests in flight per thread when the layout allows it (L2 latency, not bandwidth,
+// is what a block exchange costs).  TO_SMEM: global -> shared past L1; otherwise shared -> global.
+template <bool TO_SMEM>
+__device__ __forceinline__ void jc_copy_rows(double* g, int64_t ldg, double* sh, int n, int rows, int row0, int nv, int tid) {
+  if (((n | (int)ldg) & 1) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(sh)) & 15) == 0) {
+    const int n2 = n >> 1, tot = rows * n2;
+#pragma unroll 4
+    for (int i = tid; i < tot; i += kJcThreads) {
+      const int r = i / n2, e = i - r * n2;
+      double2* sp = reinterpret_cast<double2*>(sh + (size_t)r * n) + e;
+      double2* gp = reinterpret_cast<double2*>(g + (int64_t)(row0 + r) * ldg) + e;
+      if (TO_SMEM) *sp = (row0 + r < nv) ? __ldcg(gp) : make_double2(0.0, 0.0);
+      else if (row0 + r < nv) *gp = *sp;
+    }
+  } else {
+    const int tot = rows * n;
+#pragma unroll 4
+    for (int i = tid; i < tot; i += kJcThreads) {
+      const int r = i / n, e = i - r * n;
+      if (TO_SMEM) sh[(size_t)r * n + e] = (row0 + r < nv) ? __ldcg(g + (int64_t)(row0 + r) * ldg + e) : 0.0;
+      else if (row0 + r < nv) g[(int64_t)(row0 + r) * ldg + e] = sh[(size_t)r * n + e];
+    }
+  }
+}
+
 // rows of R (tall) / X (wide), scaled, into the vector-major global workspace; J = I
 __global__ void k_jacobi_init(SweepCtx c, StepDesc s) {
   pdl_enter();
@@ -99,14 +173,8 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
       // ---- load the two blocks (home rows bi*rb.., bj*rb..) past L1; rows >= nv are zero padding
       for (int half = 0; half < 2; ++half) {
         const int g0 = (half ? bj : bi) * rb;
-        for (int i = tid; i < rb * len; i += kJcThreads) {
-          const int r = i / len, e = i - r * len;
-          Bs[(size_t)(half * rb + r) * len + e] = (g0 + r < nv) ? __ldcg(Bg + (int64_t)(g0 + r) * c.ldv + e) : 0.0;
-        }
-        for (int i = tid; i < rb * nv; i += kJcThreads) {
-          const int r = i / nv, e = i - r * nv;
-          Js[(size_t)(half * rb + r) * nv + e] = (g0 + r < nv) ? __ldcg(Jg + (int64_t)(g0 + r) * c.ldj + e) : 0.0;
-        }
+        jc_copy_rows<true>(Bg, c.ldv, Bs + (size_t)half * rb * len, len, rb, g0, nv, tid);
+        jc_copy_rows<true>(Jg, c.ldj, Js + (size_t)half * rb * nv, nv, rb, g0, nv, tid);
       }
       __syncthreads();
       for (int v = wid; v < rb2; v += NW) {
@@ -135,28 +203,53 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
         }
       }
       // ---- rotations between the two blocks: rb sub-rounds of rb disjoint pairs
-      for (int rd = 0; rd < rb; ++rd) {
+      if (len <= 32 * NE && nv <= 32 * NE) {
+        // warp w keeps its row i = w (and the rotation row) in registers through all rb sub-rounds
+        double xi[NE], jx[NE], al = 0.0;
         if (wid < rb) {
-          const int i = wid;
-          int j = wid + rd; if (j >= rb) j -= rb;
-          j += rb;
-          did |= jacobi_pair<NE, NE>(Bs + (size_t)i * len, Bs + (size_t)j * len, Js + (size_t)i * nv, Js + (size_t)j * nv,
-                                     len, nv, sq + i, sq + j, tol2, lane);
+#pragma unroll
+          for (int m = 0; m < NE; ++m) {
+            const int e = lane + 32 * m;
+            xi[m] = e < len ? Bs[(size_t)wid * len + e] : 0.0;
+            jx[m] = e < nv ? Js[(size_t)wid * nv + e] : 0.0;
+          }
+          al = sq[wid];
+        }
+        for (int rd = 0; rd < rb; ++rd) {
+          if (wid < rb) {
+            int j = wid + rd; if (j >= rb) j -= rb;
+            j += rb;
+            did |= jacobi_pair_fixed<NE>(xi, jx, al, Bs + (size_t)j * len, Js + (size_t)j * nv, len, nv, sq + j, tol2, lane);
+          }
+          __syncthreads();
+        }
+        if (wid < rb) {
+#pragma unroll
+          for (int m = 0; m < NE; ++m) {
+            const int e = lane + 32 * m;
+            if (e < len) Bs[(size_t)wid * len + e] = xi[m];
+            if (e < nv) Js[(size_t)wid * nv + e] = jx[m];
+          }
         }
         __syncthreads();
+      } else {
+        for (int rd = 0; rd < rb; ++rd) {
+          if (wid < rb) {
+            const int i = wid;
+            int j = wid + rd; if (j >= rb) j -= rb;
+            j += rb;
+            did |= jacobi_pair<NE, NE>(Bs + (size_t)i * len, Bs + (size_t)j * len, Js + (size_t)i * nv, Js + (size_t)j * nv,
+                                       len, nv, sq + i, sq + j, tol2, lane);
+          }
+          __syncthreads();
+        }
       }
       if (did && lane == 0) rotated = 1;
       // ---- blocks back to their home rows
       for (int half = 0; half < 2; ++half) {
         const int g0 = (half ? bj : bi) * rb;
-        for (int i = tid; i < rb * len; i += kJcThreads) {
-          const int r = i / len, e = i - r * len;
-          if (g0 + r < nv) Bg[(int64_t)(g0 + r) * c.ldv + e] = Bs[(size_t)(half * rb + r) * len + e];
-        }
-        for (int i = tid; i < rb * nv; i += kJcThreads) {
-          const int r = i / nv, e = i - r * nv;
-          if (g0 + r < nv) Jg[(int64_t)(g0 + r) * c.ldj + e] = Js[(size_t)(half * rb + r) * nv + e];
-        }
+        jc_copy_rows<false>(Bg, c.ldv, Bs + (size_t)half * rb * len, len, rb, g0, nv, tid);
+        jc_copy_rows<false>(Jg, c.ldj, Js + (size_t)half * rb * nv, nv, rb, g0, nv, tid);
       }
       __threadfence();
       __syncthreads();
