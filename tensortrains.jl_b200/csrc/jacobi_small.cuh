@@ -1,0 +1,131 @@
+// jacobi_small.cuh -- one-sided Jacobi for k, n <= W (W = 32 or 64): the truncating steps of config 2
+// (k = n = 64) and of a config-5 batch (k = n = 32, hundreds of CTAs).
+//
+// With 8 (or, in a batch, 16) warps per SM sub-partition a Jacobi round is bound by INSTRUCTION ISSUE, not
+// latency: the general kernel executes ~350 instructions per pair (bounds checks, 64-bit address math,
+// library rsqrt with its special-case paths).  Here rows are zero-padded to a compile-time stride W in
+// shared memory -- no predicates, 32-bit offsets, W/32 elements per lane -- and the two rsqrt are the
+// hardware approximation + two Newton steps (their arguments are range-checked / in [0.5, 1]):
+// ~120 instructions per pair.
+#pragma once
+
+namespace ttb {
+
+// 1/sqrt(a) for a normal, positive double: MUFU.RSQ64H seed (2^-22) + two Newton iterations
+__device__ __forceinline__ double rsqrt_nr(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y;
+  double e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = a * y;
+  e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
+
+template <int W>
+__global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  constexpr int EPL = W / 32;       // row elements per lane
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;
+  const int nv = d.k, len = d.n, p = d.p;   // host guarantees nv, len <= W
+  const double* X = xbuf(c, s.xin, b);
+  const double scale_in = c.st[b].scale_in[s.slot];
+  extern __shared__ double sm[];
+  double* sig = sm;                  // W   (cached squared norms, then singular values)
+  double* srt = sig + W;             // W
+  double* B = srt + W;               // [W][W] rows zero-padded to W
+  double* J = B + W * W;             // [W][W]
+  __shared__ int rotated;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int i = tid; i < W * W; i += nt) {
+    const int r = i % W, j = i / W;  // coalesced read of column j of X
+    double v = 0.0;
+    if (r < nv && j < len && !(d.mode == 1 && r > j)) v = X[r + (int64_t)p * j] * scale_in;
+    B[r * W + j] = v;
+    J[j * W + r] = (r == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int nvp = (nv + 1) & ~1;
+  const int npairs = nvp / 2, rounds = nvp - 1;
+  const double tol2 = (double)max(len, 2) * 2.220446049250313e-16 * 2.220446049250313e-16;
+  double* sq = sig;
+  bool conv = (nv < 2);
+  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+    for (int v = wid; v < nv; v += nw) {
+      double a0 = 0.0;
+#pragma unroll
+      for (int m = 0; m < EPL; ++m) { const double x = B[v * W + lane + 32 * m]; a0 += x * x; }
+      a0 = warp_sum(a0);
+      sq[v] = a0;
+    }
+    rotated = 0;
+    __syncthreads();
+    for (int rd = 0; rd < rounds; ++rd) {
+      for (int q = wid; q < npairs; q += nw) {
+        int i, j;
+        rr_pair(nvp, rd, q, i, j);
+        if (j >= nv) continue;
+        double* bi = B + i * W + lane;
+        double* bj = B + j * W + lane;
+        double* ji = J + i * W + lane;
+        double* jj = J + j * W + lane;
+        double x[EPL], y[EPL], u_[EPL], v_[EPL];
+#pragma unroll
+        for (int m = 0; m < EPL; ++m) { x[m] = bi[32 * m]; y[m] = bj[32 * m]; u_[m] = ji[32 * m]; v_[m] = jj[32 * m]; }
+        const double al = sq[i], be = sq[j];
+        double g = 0.0;
+#pragma unroll
+        for (int m = 0; m < EPL; ++m) g += x[m] * y[m];
+        const double ga = warp_sum(g);
+        if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
+          // same rotation as jacobi_pair (sweep.cu): cos 2th = |da|/h, sin 2th = sign(da) b2/h
+          const double da = be - al, b2 = 2.0 * ga;
+          const double h2 = da * da + b2 * b2;
+          double r, das = da, b2s = b2;
+          if (h2 > 1e-280 && h2 < 1e280) r = rsqrt_nr(h2);
+          else {
+            const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+            das = da * sc; b2s = b2 * sc;
+            r = rsqrt(das * das + b2s * b2s);
+          }
+          const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+          const double uu = 0.5 + 0.5 * c2;
+          const double ic = rsqrt_nr(uu);
+          const double cs = uu * ic, sn = 0.5 * s2 * ic;
+#pragma unroll
+          for (int m = 0; m < EPL; ++m) {
+            bi[32 * m] = cs * x[m] - sn * y[m];
+            bj[32 * m] = sn * x[m] + cs * y[m];
+            ji[32 * m] = cs * u_[m] - sn * v_[m];
+            jj[32 * m] = sn * u_[m] + cs * v_[m];
+          }
+          const double t = sn * ic;
+          sq[i] = al - t * ga;
+          sq[j] = be + t * ga;
+          rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    conv = (rotated == 0);
+    __syncthreads();
+  }
+  if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
+  jacobi_finish(c, s, b, B, W, nv, len, sig, srt);
+  double* Bg = c.Bv + (int64_t)b * c.bv_stride;
+  double* Jg = c.Jv + (int64_t)b * c.jv_stride;
+  for (int i = tid; i < nv * len; i += nt) {
+    const int e = i % len, v = i / len;
+    Bg[(int64_t)v * c.ldv + e] = B[v * W + e];
+  }
+  for (int i = tid; i < nv * nv; i += nt) {
+    const int e = i % nv, v = i / nv;
+    Jg[(int64_t)v * c.ldj + e] = J[v * W + e];
+  }
+}
+
+}  // namespace ttb

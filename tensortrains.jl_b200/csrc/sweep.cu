@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 
 }  // namespace ttb
 #include "jacobi_cluster.cuh"
+#include "jacobi_small.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -863,6 +864,7 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1033,6 +1035,12 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         TTB_LAUNCH(h, "k_jacobi_cluster",
                    (k_jacobi_cluster<8><<<dim3(kJcCluster, B), kJcThreads, jc_smem_bytes(nv_ub, len_ub), st>>>(c, s)));
         SW_LAUNCH("k_jacobi_finish", k_jacobi_finish, B, 1024, sizeof(double) * 2 * (size_t)w.n_max, c, s);
+      } else if (nv_ub > 16 && nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
+        // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
+        if (nv_ub <= 32 && len_ub <= 32)
+          SW_LAUNCH("k_jacobi", k_jacobi_small<32>, B, std::min(512, thr), sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
+        else
+          SW_LAUNCH("k_jacobi", k_jacobi_small<64>, B, thr, sizeof(double) * (2 * 64 + 2 * 64 * 64), c, s);
       } else {
       auto kj = thr <= 512 ? (len_ub <= 64 ? k_jacobi<512, 2> : k_jacobi<512, 8>)
                            : (len_ub <= 64 ? k_jacobi<1024, 2> : k_jacobi<1024, 8>);
