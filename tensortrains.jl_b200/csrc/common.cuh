@@ -207,6 +207,19 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   __syncthreads();
   return red[32];
 }
+// 1/sqrt(a) for a normal, positive double: MUFU.RSQ64H seed (2^-22) + two Newton iterations.  No special
+// cases (callers range-check): ~9 instructions instead of the library's ~25 on the Jacobi critical path.
+__device__ __forceinline__ double rsqrt_nr(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y;
+  double e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = a * y;
+  e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
 // max-abs with NaN propagation (fmax drops NaN, the reference's maximum(abs, .) keeps it)
 __device__ __forceinline__ double absmax_nan(double acc, double v) {
   double a = fabs(v);

@@ -26,6 +26,10 @@ __host__ __device__ inline int jc_rows_per_block(int nv) {
   rb = (rb + 1) & ~1;
   return rb < 2 ? 2 : rb;
 }
+// trains the single-CTA kernel handles when both paths are launched (same predicate as k_jacobi's SMEM)
+__device__ __forceinline__ bool jc_single_takes(const SweepCtx& c, const StepDesc& s, const Dims& d) {
+  return s.jc_sd > 0 && 2 * (int64_t)c.n_max + (int64_t)d.k * (d.n + d.k) <= (int64_t)s.jc_sd;
+}
 __host__ __device__ inline size_t jc_smem_bytes(int nv, int len) {
   const int rb = jc_rows_per_block(nv);
   return sizeof(double) * ((size_t)2 * rb * (len + nv) + 2 * rb) + 16;
@@ -53,7 +57,7 @@ __device__ __forceinline__ bool jacobi_pair_fixed(double (&xi)[NE], double (&jx)
   if (!(al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be)) return false;
   const double da = be - al, b2 = 2.0 * ga;
   const double h2 = da * da + b2 * b2;
-  double r = rsqrt(h2), das = da, b2s = b2;
+  double r = rsqrt_nr(h2), das = da, b2s = b2;
   if (!(h2 > 1e-280 && h2 < 1e280)) {
     const double sc = 1.0 / fmax(fabs(da), fabs(b2));
     das = da * sc; b2s = b2 * sc;
@@ -61,7 +65,7 @@ __device__ __forceinline__ bool jacobi_pair_fixed(double (&xi)[NE], double (&jx)
   }
   const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
   const double u = 0.5 + 0.5 * c2;
-  const double ic = rsqrt(u);
+  const double ic = rsqrt_nr(u);
   const double cs = u * ic, sn = 0.5 * s2 * ic;
 #pragma unroll
   for (int m = 0; m < NE; ++m) {
@@ -110,7 +114,7 @@ __global__ void k_jacobi_init(SweepCtx c, StepDesc s) {
   pdl_enter();
   const int b = blockIdx.y;
   const Dims d = get_dims(c, s, b);
-  if (d.mode == 0) return;
+  if (d.mode == 0 || jc_single_takes(c, s, d)) return;
   const int nv = d.k, len = d.n, p = d.p;
   const double* X = xbuf(c, s.xin, b);
   const double scale_in = c.st[b].scale_in[s.slot];
@@ -148,7 +152,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
   const int b = blockIdx.y;
   const int rank = blockIdx.x;  // gridDim.x == cluster size
   const Dims d = get_dims(c, s, b);
-  if (d.mode == 0) return;      // uniform over the cluster
+  if (d.mode == 0 || jc_single_takes(c, s, d)) return;      // uniform over the cluster
   const int nv = d.k, len = d.n;
   const int rb = jc_rows_per_block(nv), rb2 = 2 * rb;
   double* Bg = c.Bv + (int64_t)b * c.bv_stride;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_finish(SweepCtx c, StepDesc s) 
   pdl_enter();
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
-  if (d.mode == 0) return;
+  if (d.mode == 0 || jc_single_takes(c, s, d)) return;
   extern __shared__ double sm[];
   jacobi_finish(c, s, b, c.Bv + (int64_t)b * c.bv_stride, c.ldv, d.k, d.n, sm, sm + c.n_max);
 }

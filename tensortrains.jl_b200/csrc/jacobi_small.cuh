@@ -11,19 +11,6 @@
 
 namespace ttb {
 
-// 1/sqrt(a) for a normal, positive double: MUFU.RSQ64H seed (2^-22) + two Newton iterations
-__device__ __forceinline__ double rsqrt_nr(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double t = a * y;
-  double e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  t = a * y;
-  e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  return y;
-}
-
 template <int W>
 __global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepCtx c, StepDesc s) {
   pdl_enter();

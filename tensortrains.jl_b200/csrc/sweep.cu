@@ -48,6 +48,8 @@ struct StepDesc {
   int last;                // absorb output goes to the neighbour's site storage
   int slot;                // maxabs ping-pong slot
   int next_site, next_nbr; // the step that follows in this sweep (-1: none): k_commit snapshots its dimensions
+  int jc_sd;               // > 0: both Jacobi paths are launched (host bounds cannot tell): trains whose ACTUAL
+                           // 2 n_max + k (n + k) doubles fit jc_sd are done by k_jacobi, the others by the cluster
 };
 
 struct Dims { int p, n, k, mode, N; };  // mode 0 = QR, 1 = SVD tall (p>=n), 2 = SVD wide
@@ -428,7 +430,7 @@ __device__ __forceinline__ bool jacobi_pair(double* bi, double* bj, double* ji, 
   // cos th = sqrt((1 + cos 2th)/2), sin th = sin 2th / (2 cos th)
   const double da = be - al, b2 = 2.0 * ga;
   const double h2 = da * da + b2 * b2;
-  double r = rsqrt(h2), das = da, b2s = b2;
+  double r = rsqrt_nr(h2), das = da, b2s = b2;
   if (!(h2 > 1e-280 && h2 < 1e280)) {  // far outside the normal range: rescale first (rare, warp-uniform)
     const double sc = 1.0 / fmax(fabs(da), fabs(b2));
     das = da * sc; b2s = b2 * sc;
@@ -436,7 +438,7 @@ __device__ __forceinline__ bool jacobi_pair(double* bi, double* bj, double* ji, 
   }
   const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
   const double u = 0.5 + 0.5 * c2;
-  const double ic = rsqrt(u);   // = 1 / cos(theta)
+  const double ic = rsqrt_nr(u);   // = 1 / cos(theta), u in [0.5, 1]
   const double cs = u * ic, sn = 0.5 * s2 * ic;
 #pragma unroll
   for (int m = 0; m < NE; ++m) {
@@ -542,6 +544,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
   double* sig = sm;                 // n_max
   double* srt = sig + c.n_max;      // n_max
   const bool SMEM = 2 * (int64_t)c.n_max + (int64_t)nv * (len + nv) <= (int64_t)smem_doubles;
+  if (s.jc_sd > 0 && !SMEM) return;  // the cluster kernels take this train
   double* B = SMEM ? (srt + c.n_max) : Bg;
   const int ldb = SMEM ? len : c.ldv;
   double* J = SMEM ? (B + (size_t)nv * ldb) : Jg;
@@ -953,6 +956,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.bond_idx = hs.bond_idx; s.bond_idx2 = hs.bond_idx2; s.last = hs.last; s.slot = slot;
     s.next_site = si + 1 < steps.size() ? steps[si + 1].site : -1;
     s.next_nbr = si + 1 < steps.size() ? steps[si + 1].nbr : -1;
+    s.jc_sd = 0;
     SweepCtx c = cbase;
     c.T = cbase.T + (int64_t)slot * B * w.t_stride;
     // Launch-sizing hint: every few truncating steps read back the bond array the device has already
@@ -1030,12 +1034,16 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       const bool cluster_path = need > (size_t)200 * 1024 && jc_smem_bytes(nv_ub, len_ub) <= (size_t)200 * 1024 &&
                                 getenv("TTB_JACOBI_NOCLUSTER") == nullptr;
       if (cluster_path) {
+        // the bounds say "may not fit one CTA"; the device knows: launch both, each train takes one path
+        s.jc_sd = sd;
+        auto kj1 = k_jacobi<1024, 8>;
+        SW_LAUNCH("k_jacobi", kj1, B, 1024, give, c, s, sd);
         const int tiles = ((nv_ub + 31) / 32) * ((len_ub + 31) / 32);
         SW_LAUNCH("k_jacobi_init", k_jacobi_init, dim3(std::min(tiles, 128), B), 256, 0, c, s);
         TTB_LAUNCH(h, "k_jacobi_cluster",
                    (k_jacobi_cluster<8><<<dim3(kJcCluster, B), kJcThreads, jc_smem_bytes(nv_ub, len_ub), st>>>(c, s)));
         SW_LAUNCH("k_jacobi_finish", k_jacobi_finish, B, 1024, sizeof(double) * 2 * (size_t)w.n_max, c, s);
-      } else if (nv_ub > 16 && nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
+      } else if (nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
         if (nv_ub <= 32 && len_ub <= 32)
           SW_LAUNCH("k_jacobi", k_jacobi_small<32>, B, std::min(512, thr), sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
