@@ -81,6 +81,13 @@ struct ttb_tt {
   cudaStream_t stream2 = nullptr;            // side stream: thin-Q formation overlaps the next factorisation
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_qr[2] = {nullptr, nullptr}, ev_aq[2] = {nullptr, nullptr};
+  // rank feedback of truncating sweeps: k_commit writes the retained rank of every train into a ring of
+  // mapped pinned slots; the host enqueues at most two steps ahead of the last slot it has seen complete
+  // (cudaEventQuery, never a blocking sync) and sizes later launches from it
+  static constexpr int kHintRing = 4;
+  cudaEvent_t ev_hint[kHintRing] = {nullptr, nullptr, nullptr, nullptr};
+  int* hint_host = nullptr;    // [kHintRing][batch], cudaHostAllocMapped
+  int* hint_dev = nullptr;     // device alias of hint_host
   int64_t L = 0, Q = 0, batch = 0;
   int periodic = 0;
   std::vector<int64_t> bond0;  // original (capacity) bonds, L+1

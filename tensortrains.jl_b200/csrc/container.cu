@@ -133,6 +133,11 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
     if ((e = cudaEventCreateWithFlags(&h->ev_qr[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->ev_aq[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
   }
+  for (int i = 0; i < ttb_tt::kHintRing; ++i)
+    if ((e = cudaEventCreateWithFlags(&h->ev_hint[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+  if ((e = cudaHostAlloc((void**)&h->hint_host, sizeof(int) * ttb_tt::kHintRing * batch, cudaHostAllocMapped)) != cudaSuccess)
+    return bail(e, "rank feedback buffer");
+  if ((e = cudaHostGetDevicePointer((void**)&h->hint_dev, h->hint_host, 0)) != cudaSuccess) return bail(e, "rank feedback buffer");
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "event");
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "event");
   if ((e = cudaMalloc(&h->slab, sizeof(double) * batch * h->tt_stride)) != cudaSuccess) return bail(e, "slab");
@@ -167,6 +172,9 @@ int ttb_destroy(ttb_handle h) {
   cudaFree(h->d_status);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < ttb_tt::kHintRing; ++i)
+    if (h->ev_hint[i]) cudaEventDestroy(h->ev_hint[i]);
+  if (h->hint_host) cudaFreeHost(h->hint_host);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_qr[i]) cudaEventDestroy(h->ev_qr[i]);
     if (h->ev_aq[i]) cudaEventDestroy(h->ev_aq[i]);

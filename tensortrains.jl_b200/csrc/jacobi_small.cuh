@@ -1,40 +1,41 @@
-// jacobi_small.cuh -- one-sided Jacobi for k, n <= W (W = 32 or 64): the truncating steps of config 2
-// (k = n = 64) and of a config-5 batch (k = n = 32, hundreds of CTAs).
+// jacobi_small.cuh -- one-sided Jacobi for k <= WR rows of length n <= WL, compile-time strides:
+// <64,64> the truncating steps of config 2 (k = n = 64), <32,32> a config-5 batch (k = n = 32, hundreds of
+// CTAs), <32,256> the left sweep of config 3 (k ~ 16 retained directions x Q, n = 256).
 //
 // With 8 (or, in a batch, 16) warps per SM sub-partition a Jacobi round is bound by INSTRUCTION ISSUE, not
-// latency: the general kernel executes ~350 instructions per pair (bounds checks, 64-bit address math,
-// library rsqrt with its special-case paths).  Here rows are zero-padded to a compile-time stride W in
-// shared memory -- no predicates, 32-bit offsets, W/32 elements per lane -- and the two rsqrt are the
-// hardware approximation + two Newton steps (their arguments are range-checked / in [0.5, 1]):
-// ~120 instructions per pair.
+// latency: the general kernel executes ~350 instructions per pair (bounds checks, 64-bit address math).
+// Here rows are zero-padded to compile-time strides in shared memory -- no predicates, 32-bit offsets,
+// WL/32 row elements and WR/32 rotation elements per lane: ~120-180 instructions per pair.  With few warps
+// (config 3) the same leanness shortens the latency chain of a round, which one warp issues alone.
 #pragma once
 
 namespace ttb {
 
-template <int W>
-__global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepCtx c, StepDesc s) {
+template <int WR, int WL>
+__global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jacobi_small(SweepCtx c, StepDesc s) {
   pdl_enter();
-  constexpr int EPL = W / 32;       // row elements per lane
+  constexpr int EPL = WL / 32;      // row elements per lane
+  constexpr int JPL = WR / 32;      // rotation-row elements per lane
   const int b = blockIdx.x;
   const Dims d = get_dims(c, s, b);
   if (d.mode == 0) return;
-  const int nv = d.k, len = d.n, p = d.p;   // host guarantees nv, len <= W
+  const int nv = d.k, len = d.n, p = d.p;   // host guarantees nv <= WR, len <= WL
   const double* X = xbuf(c, s.xin, b);
   const double scale_in = c.st[b].scale_in[s.slot];
   extern __shared__ double sm[];
-  double* sig = sm;                  // W   (cached squared norms, then singular values)
-  double* srt = sig + W;             // W
-  double* B = srt + W;               // [W][W] rows zero-padded to W
-  double* J = B + W * W;             // [W][W]
+  double* sig = sm;                  // WR  (cached squared norms, then singular values)
+  double* srt = sig + WR;            // WR
+  double* B = srt + WR;              // [WR][WL] rows zero-padded
+  double* J = B + WR * WL;           // [WR][WR]
   __shared__ int rotated;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-  for (int i = tid; i < W * W; i += nt) {
-    const int r = i % W, j = i / W;  // coalesced read of column j of X
+  for (int i = tid; i < WR * WL; i += nt) {
+    const int r = i % WR, j = i / WR;  // coalesced read of column j of X
     double v = 0.0;
     if (r < nv && j < len && !(d.mode == 1 && r > j)) v = X[r + (int64_t)p * j] * scale_in;
-    B[r * W + j] = v;
-    J[j * W + r] = (r == j) ? 1.0 : 0.0;
+    B[r * WL + j] = v;
   }
+  for (int i = tid; i < WR * WR; i += nt) J[i] = (i / WR == i % WR) ? 1.0 : 0.0;
   __syncthreads();
   const int nvp = (nv + 1) & ~1;
   const int npairs = nvp / 2, rounds = nvp - 1;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepC
     for (int v = wid; v < nv; v += nw) {
       double a0 = 0.0;
 #pragma unroll
-      for (int m = 0; m < EPL; ++m) { const double x = B[v * W + lane + 32 * m]; a0 += x * x; }
+      for (int m = 0; m < EPL; ++m) { const double x = B[v * WL + lane + 32 * m]; a0 += x * x; }
       a0 = warp_sum(a0);
       sq[v] = a0;
     }
@@ -56,18 +57,20 @@ __global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepC
         int i, j;
         rr_pair(nvp, rd, q, i, j);
         if (j >= nv) continue;
-        double* bi = B + i * W + lane;
-        double* bj = B + j * W + lane;
-        double* ji = J + i * W + lane;
-        double* jj = J + j * W + lane;
-        double x[EPL], y[EPL], u_[EPL], v_[EPL];
+        double* bi = B + i * WL + lane;
+        double* bj = B + j * WL + lane;
+        double* ji = J + i * WR + lane;
+        double* jj = J + j * WR + lane;
+        double x[EPL], y[EPL], u_[JPL], v_[JPL];
 #pragma unroll
-        for (int m = 0; m < EPL; ++m) { x[m] = bi[32 * m]; y[m] = bj[32 * m]; u_[m] = ji[32 * m]; v_[m] = jj[32 * m]; }
+        for (int m = 0; m < EPL; ++m) { x[m] = bi[32 * m]; y[m] = bj[32 * m]; }
+#pragma unroll
+        for (int m = 0; m < JPL; ++m) { u_[m] = ji[32 * m]; v_[m] = jj[32 * m]; }
         const double al = sq[i], be = sq[j];
-        double g = 0.0;
+        double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-        for (int m = 0; m < EPL; ++m) g += x[m] * y[m];
-        const double ga = warp_sum(g);
+        for (int m = 0; m < EPL; ++m) { if (m & 1) g1 += x[m] * y[m]; else g0 += x[m] * y[m]; }
+        const double ga = warp_sum(g0 + g1);
         if (al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be) {
           // same rotation as jacobi_pair (sweep.cu): cos 2th = |da|/h, sin 2th = sign(da) b2/h
           const double da = be - al, b2 = 2.0 * ga;
@@ -87,6 +90,9 @@ __global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepC
           for (int m = 0; m < EPL; ++m) {
             bi[32 * m] = cs * x[m] - sn * y[m];
             bj[32 * m] = sn * x[m] + cs * y[m];
+          }
+#pragma unroll
+          for (int m = 0; m < JPL; ++m) {
             ji[32 * m] = cs * u_[m] - sn * v_[m];
             jj[32 * m] = sn * u_[m] + cs * v_[m];
           }
@@ -102,16 +108,16 @@ __global__ void __launch_bounds__(16 * W, W == 32 ? 2 : 1) k_jacobi_small(SweepC
     __syncthreads();
   }
   if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
-  jacobi_finish(c, s, b, B, W, nv, len, sig, srt);
+  jacobi_finish(c, s, b, B, WL, nv, len, sig, srt);
   double* Bg = c.Bv + (int64_t)b * c.bv_stride;
   double* Jg = c.Jv + (int64_t)b * c.jv_stride;
   for (int i = tid; i < nv * len; i += nt) {
     const int e = i % len, v = i / len;
-    Bg[(int64_t)v * c.ldv + e] = B[v * W + e];
+    Bg[(int64_t)v * c.ldv + e] = B[v * WL + e];
   }
   for (int i = tid; i < nv * nv; i += nt) {
     const int e = i % nv, v = i / nv;
-    Jg[(int64_t)v * c.ldj + e] = J[v * W + e];
+    Jg[(int64_t)v * c.ldj + e] = J[v * WR + e];
   }
 }
 

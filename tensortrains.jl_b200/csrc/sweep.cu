@@ -36,6 +36,7 @@ struct SweepCtx {
   double* logz;
   double* stat_err; int* stat_rank; double* spectrum;
   int* status;
+  int* hint;               // mapped pinned ring [kHintRing][batch]: retained rank of the step, for the host
 };
 
 struct StepDesc {
@@ -48,6 +49,7 @@ struct StepDesc {
   int last;                // absorb output goes to the neighbour's site storage
   int slot;                // maxabs ping-pong slot
   int next_site, next_nbr; // the step that follows in this sweep (-1: none): k_commit snapshots its dimensions
+  int hint_slot;           // ring slot k_commit reports the retained ranks into (-1: none)
   int jc_sd;               // > 0: both Jacobi paths are launched (host bounds cannot tell): trains whose ACTUAL
                            // 2 n_max + k (n + k) doubles fit jc_sd are done by k_jacobi, the others by the cluster
 };
@@ -789,6 +791,10 @@ __global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
   bond[s.bond_idx] = mp;
   if (s.bond_idx2 >= 0) bond[s.bond_idx2] = mp;
   if (s.next_site >= 0) snapshot_dims(c, b, s.dir, s.next_site, s.next_nbr, s.slot ^ 1);
+  if (s.hint_slot >= 0) {
+    c.hint[(int64_t)s.hint_slot * batch + b] = mp;
+    __threadfence_system();
+  }
 }
 
 __global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
@@ -830,7 +836,6 @@ __global__ void k_canon_resid(const double* site, int dl, int dr, int Q, int lef
 static const int kMaxSmem = 208 * 1024;
 static const int kCw = 4;
 static constexpr int kPanelNS = TTB_PANEL_NS;  // panel columns per warp (2 -> 16 warps, 4 -> 8 warps)
-static const int kRankHintEvery = 4;  // truncating sweeps: bond read-back period (launch sizing only)
 
 int ensure_sweep_ws(ttb_tt* h) {
   Workspace& w = h->ws;
@@ -867,7 +872,8 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(k_jacobi_small<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi_small<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_jacobi_small<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -904,6 +910,7 @@ static SweepCtx make_ctx(ttb_tt* h) {
   c.st = w.st; c.logz = h->d_logz;
   c.stat_err = w.stat_err; c.stat_rank = w.stat_rank; c.spectrum = h->record_spectrum ? w.spectrum : nullptr;
   c.status = h->d_status;
+  c.hint = h->hint_dev;
   return c;
 }
 
@@ -931,6 +938,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   bool side_pending = false;  // apply_q of the previous step may still be running on st2
   int side_slot = 0;
   const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
+  const bool feedback = !qr_only && getenv("TTB_NO_FEEDBACK") == nullptr;
   // Main-stream launches use programmatic dependent launch (common.cuh): the next grid is resident and
   // parked in griddepcontrol.wait while its predecessor drains.  A launch that follows an event wait (or
   // opens the sweep) is an ordinary one.
@@ -957,22 +965,33 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.next_site = si + 1 < steps.size() ? steps[si + 1].site : -1;
     s.next_nbr = si + 1 < steps.size() ? steps[si + 1].nbr : -1;
     s.jc_sd = 0;
+    s.hint_slot = feedback ? (int)(si % ttb_tt::kHintRing) : -1;
     SweepCtx c = cbase;
     c.T = cbase.T + (int64_t)slot * B * w.t_stride;
-    // Launch-sizing hint: every few truncating steps read back the bond array the device has already
-    // committed.  The rank DECISION never leaves the device; the host only learns that later grids can
-    // be smaller (and that whole QR phases can be skipped when p < n is certain).
-    if (!qr_only && si > 0 && kRankHintEvery > 0 && si % kRankHintEvery == 0) {
-      TTB_TRY(sync_bonds_to_host(h));
-      const int L1h = (int)h->L + 1;
-      for (int t = 0; t < L1h; ++t) {
-        int v = 0, lo = 1 << 30;
-        for (int64_t bb = 0; bb < h->batch; ++bb) {
-          v = std::max(v, h->h_bond[bb * L1h + t]);
-          lo = std::min(lo, h->h_bond[bb * L1h + t]);
-        }
-        ub[t] = v; lb[t] = lo;
+    // Launch-sizing feedback (never a blocking sync, and the rank DECISION never leaves the device): wait --
+    // by polling an event -- until the step two before this one has committed, then tighten the bounds
+    // with the ranks it reported.  Two steps of lead keep the GPU queue fed; bounds are at most two
+    // doublings above the truth, so later grids shrink, whole QR phases are skipped when p < n is certain
+    // and the Jacobi variant is picked for the real size.
+    if (feedback && si >= 2) {
+      const size_t done = si - 2;
+      const int rs = (int)(done % ttb_tt::kHintRing);
+      unsigned spins = 0;
+      while (cudaEventQuery(h->ev_hint[rs]) == cudaErrorNotReady) {
+        if (++spins > (1u << 30)) return fail(TTB_ECUDA, "rank feedback event never completed");
       }
+      const volatile int* hv = h->hint_host + (size_t)rs * B;
+      int v = 0, lo = 1 << 30;
+      for (int bb = 0; bb < B; ++bb) { const int r = hv[bb]; v = std::max(v, r); lo = std::min(lo, r); }
+      const HostStep& ds = steps[done];
+      ub[ds.bond_idx] = v; lb[ds.bond_idx] = lo;
+      if (ds.bond_idx2 >= 0) { ub[ds.bond_idx2] = v; lb[ds.bond_idx2] = lo; }
+      // the step in between was sized from the old bound of this bond: its own bound can be tightened too
+      const HostStep& ms = steps[done + 1];
+      const int pm = (dir == 0 ? ub[ms.site + 1] : ub[ms.site]) * Q, nm = dir == 0 ? ub[ms.site] : ub[ms.site + 1];
+      int capm = std::min(pm, nm);
+      if (tr->kind != TTB_TRUNC_THRESH) capm = (int)std::min<int64_t>(capm, tr->mprime);
+      if (capm < ub[ms.bond_idx]) { ub[ms.bond_idx] = capm; if (ms.bond_idx2 >= 0) ub[ms.bond_idx2] = capm; }
     }
     int p_ub, n_ub, N_ub, p_lb, n_lb;
     if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
@@ -1045,10 +1064,16 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         SW_LAUNCH("k_jacobi_finish", k_jacobi_finish, B, 1024, sizeof(double) * 2 * (size_t)w.n_max, c, s);
       } else if (nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
-        if (nv_ub <= 32 && len_ub <= 32)
-          SW_LAUNCH("k_jacobi", k_jacobi_small<32>, B, std::min(512, thr), sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
-        else
-          SW_LAUNCH("k_jacobi", k_jacobi_small<64>, B, thr, sizeof(double) * (2 * 64 + 2 * 64 * 64), c, s);
+        if (nv_ub <= 32 && len_ub <= 32) {
+          auto ks = k_jacobi_small<32, 32>;
+          SW_LAUNCH("k_jacobi", ks, B, std::min(512, thr), sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
+        } else {
+          auto ks = k_jacobi_small<64, 64>;
+          SW_LAUNCH("k_jacobi", ks, B, thr, sizeof(double) * (2 * 64 + 2 * 64 * 64), c, s);
+        }
+      } else if (nv_ub <= 32 && len_ub <= 256 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
+        auto ks = k_jacobi_small<32, 256>;
+        SW_LAUNCH("k_jacobi", ks, B, std::min(512, thr), sizeof(double) * (2 * 32 + 32 * 256 + 32 * 32), c, s);
       } else {
       auto kj = thr <= 512 ? (len_ub <= 64 ? k_jacobi<512, 2> : k_jacobi<512, 8>)
                            : (len_ub <= 64 ? k_jacobi<1024, 2> : k_jacobi<1024, 8>);
@@ -1089,6 +1114,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       dim3 g((unsigned)std::min<int64_t>((tot + 1023) / 1024, 1024), B);
       if (hs.last) SW_LAUNCH("k_rescale", k_rescale, g, 256, 0, c, s);
       SW_LAUNCH("k_commit", k_commit, (B + 127) / 128, 128, 0, c, s, B);
+      if (feedback) cudaEventRecord(h->ev_hint[s.hint_slot], st);
     }
     const int mp_lb = qr_only ? std::min(p_lb, n_lb) : 1;
     ub[hs.bond_idx] = mp_ub; lb[hs.bond_idx] = mp_lb;
