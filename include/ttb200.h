@@ -77,6 +77,15 @@ int ttb_upload_site(ttb_handle h, int64_t b, int64_t t, const double* host);
 int ttb_download_site(ttb_handle h, int64_t b, int64_t t, double* host);
 /* all sites of all trains, packed train-major then site-major, each at its current dims */
 int ttb_upload_all(ttb_handle h, const double* host);
+/* Asynchronous upload_all for a train at its original bond dimensions (fresh handle or after ttb_reset):
+ * returns when the copies are enqueued; `host` (pinned memory for a real overlap) must stay valid until the
+ * next call on the handle that returns results.  Sites travel last-to-first, so a following
+ * orthogonalize_right!/compress! (tensor_train.jl:151, abstract_tensor_train.jl:261) starts while the
+ * rest of the train is still on the bus.  Falls back to the synchronous copy for batches / shrunk bonds. */
+int ttb_upload_all_async(ttb_handle h, const double* host);
+/* bond dimensions back to the ones the handle was created with, z = 1: reuse the slab and the workspaces
+ * for the next train of the same shape */
+int ttb_reset(ttb_handle h);
 int ttb_download_all(ttb_handle h, double* host);
 int ttb_get_z(ttb_handle h, int64_t b, double* logabs, int* sign);
 int ttb_set_z(ttb_handle h, int64_t b, double logabs, int sign);

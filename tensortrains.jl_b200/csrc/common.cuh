@@ -88,6 +88,13 @@ struct ttb_tt {
   cudaEvent_t ev_hint[kHintRing] = {nullptr, nullptr, nullptr, nullptr};
   int* hint_host = nullptr;    // [kHintRing][batch], cudaHostAllocMapped
   int* hint_dev = nullptr;     // device alias of hint_host
+  // asynchronous upload (ttb_upload_all_async): chunks are copied on their own stream in REVERSE site order
+  // with one event each; a right sweep waits chunk by chunk (it starts at the last site), every other
+  // entry point joins all of them first
+  cudaStream_t stream_up = nullptr;
+  std::vector<cudaEvent_t> up_events;
+  std::vector<int> up_lo;      // lowest site present once chunk i has landed
+  int up_n = 0, up_waited = 0;
   int64_t L = 0, Q = 0, batch = 0;
   int periodic = 0;
   std::vector<int64_t> bond0;  // original (capacity) bonds, L+1
@@ -131,7 +138,9 @@ struct CallTimer {
   }
 };
 
-int check_handle(ttb_tt* h);
+int check_handle(ttb_tt* h);      // validates, selects the device, joins pending asynchronous uploads
+int check_handle_raw(ttb_tt* h);  // same without the join (sweeps that consume the upload chunk by chunk)
+int join_uploads(ttb_tt* h, int need_site);  // main stream waits for the chunks holding sites >= need_site (-1: all)
 void prof_pre(ttb_tt* h, const char* name);
 void prof_post(ttb_tt* h);
 // every kernel launch goes through this: counts the launch and, in profiling mode, brackets it with

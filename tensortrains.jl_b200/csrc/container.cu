@@ -20,10 +20,27 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-int check_handle(ttb_tt* h) {
+int check_handle_raw(ttb_tt* h) {
   if (!h) return fail(TTB_EINVAL, "null handle");
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return fail(TTB_ECUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+  return TTB_OK;
+}
+
+int join_uploads(ttb_tt* h, int need_site) {
+  while (h->up_waited < h->up_n &&
+         (need_site < 0 || h->up_waited == 0 || h->up_lo[h->up_waited - 1] > need_site)) {
+    cudaError_t e = cudaStreamWaitEvent(h->stream, h->up_events[h->up_waited], 0);
+    if (e != cudaSuccess) return fail(TTB_ECUDA, "upload join: %s", cudaGetErrorString(e));
+    ++h->up_waited;
+  }
+  if (h->up_waited == h->up_n) h->up_n = h->up_waited = 0;
+  return TTB_OK;
+}
+
+int check_handle(ttb_tt* h) {
+  TTB_TRY(check_handle_raw(h));
+  if (h->up_n) TTB_TRY(join_uploads(h, -1));
   return TTB_OK;
 }
 
@@ -129,6 +146,7 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
   if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  if ((e = cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&h->ev_qr[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->ev_aq[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -165,8 +183,11 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
 int ttb_destroy(ttb_handle h) {
   if (!h) return TTB_OK;
   cudaSetDevice(h->device);
+  if (h->stream_up) cudaStreamSynchronize(h->stream_up);
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (cudaEvent_t ev : h->up_events) cudaEventDestroy(ev);
+  if (h->stream_up) cudaStreamDestroy(h->stream_up);
   free_ws(h);
   cudaFree(h->slab); cudaFree(h->d_off); cudaFree(h->d_bond); cudaFree(h->d_logz); cudaFree(h->d_signz);
   cudaFree(h->d_status);
@@ -296,6 +317,65 @@ int ttb_upload_all(ttb_handle h, const double* host) {
   TTB_TRY(check_handle(h));
   if (!host) return fail(TTB_EINVAL, "null argument");
   return copy_all(h, const_cast<double*>(host), true);
+}
+
+// Asynchronous form of ttb_upload_all for a train at its ORIGINAL bond dimensions (fresh or ttb_reset):
+// returns once the copies are enqueued; `host` (pinned for a real overlap) must stay valid until the next
+// call on this handle that returns results.  Sites travel last-to-first in >= 16 MB chunks so that a right
+// sweep (orthogonalize_right!, compress!) starts as soon as its first sites have landed.
+int ttb_upload_all_async(ttb_handle h, const double* host) {
+  TTB_TRY(check_handle(h));
+  if (!host) return fail(TTB_EINVAL, "null argument");
+  TTB_TRY(sync_bonds_to_host(h));
+  const int L = (int)h->L, L1 = L + 1;
+  bool original = true;
+  for (int64_t b = 0; b < h->batch && original; ++b)
+    for (int t = 0; t < L1; ++t)
+      if (h->h_bond[b * L1 + t] != (int)h->bond0[t]) { original = false; break; }
+  if (!original || h->batch != 1) return copy_all(h, const_cast<double*>(host), true);
+  std::vector<int64_t> hoff(L1, 0);
+  for (int t = 0; t < L; ++t) hoff[t + 1] = hoff[t] + site_len(h, 0, t);
+  const int64_t chunk = int64_t(16) << 20;  // bytes
+  h->up_lo.clear(); h->up_n = 0; h->up_waited = 0;
+  int hi = L;
+  while (hi > 0) {
+    int lo = hi;
+    while (lo > 0 && (hoff[hi] - hoff[lo]) * 8 < chunk) --lo;
+    // one copy per run that is contiguous on the device (sites are 128-byte aligned there, packed on the host)
+    int t = lo;
+    while (t < hi) {
+      int u = t + 1;
+      while (u < hi && h->off[u] == h->off[u - 1] + site_len(h, 0, u - 1)) ++u;
+      TTB_CUDA(cudaMemcpyAsync(h->slab + h->off[t], host + hoff[t], sizeof(double) * (hoff[u] - hoff[t]),
+                               cudaMemcpyHostToDevice, h->stream_up));
+      t = u;
+    }
+    if ((int)h->up_events.size() <= h->up_n) {
+      cudaEvent_t ev;
+      TTB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      h->up_events.push_back(ev);
+    }
+    TTB_CUDA(cudaEventRecord(h->up_events[h->up_n], h->stream_up));
+    h->up_lo.push_back(lo);
+    ++h->up_n;
+    hi = lo;
+  }
+  return TTB_OK;
+}
+
+// Back to the original (capacity) bond dimensions and z = 1: the handle can take a new train of the same
+// shape without reallocating the slab or the workspaces.
+int ttb_reset(ttb_handle h) {
+  TTB_TRY(check_handle(h));
+  const int64_t L1 = h->L + 1;
+  for (int64_t b = 0; b < h->batch; ++b)
+    for (int64_t t = 0; t < L1; ++t) h->h_bond[b * L1 + t] = (int)h->bond0[t];
+  std::vector<int> ones(h->batch, 1);
+  TTB_CUDA(cudaMemcpyAsync(h->d_bond, h->h_bond.data(), sizeof(int) * h->h_bond.size(), cudaMemcpyHostToDevice, h->stream));
+  TTB_CUDA(cudaMemsetAsync(h->d_logz, 0, sizeof(double) * h->batch, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(h->d_signz, ones.data(), sizeof(int) * h->batch, cudaMemcpyHostToDevice, h->stream));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
 }
 
 int ttb_download_all(ttb_handle h, double* host) {

@@ -993,6 +993,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       if (tr->kind != TTB_TRUNC_THRESH) capm = (int)std::min<int64_t>(capm, tr->mprime);
       if (capm < ub[ms.bond_idx]) { ub[ms.bond_idx] = capm; if (ms.bond_idx2 >= 0) ub[ms.bond_idx2] = capm; }
     }
+    if (h->up_n) TTB_TRY(join_uploads(h, dir == 0 ? std::min(hs.site, hs.nbr) : -1));
     int p_ub, n_ub, N_ub, p_lb, n_lb;
     if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
     else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; p_lb = lb[hs.site] * Q; n_lb = lb[hs.site + 1]; }
@@ -1123,6 +1124,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   }
 #undef SW_LAUNCH
   if (side_pending && overlap) cudaStreamWaitEvent(st, h->ev_aq[side_slot], 0);  // join the side stream
+  if (h->up_n) TTB_TRY(join_uploads(h, -1));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TTB_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
   return TTB_OK;
@@ -1236,7 +1238,8 @@ int ttb_orthogonalize_two_site_center(ttb_handle h, const ttb_trunc* tr, int64_t
 }
 
 int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
-  TTB_TRY(check_handle(h));
+  TTB_TRY(check_handle_raw(h));   // a pending asynchronous upload is consumed chunk by chunk by the right sweep
+  if (is_orthogonal != TTB_ORTH_NONE && h->up_n) TTB_TRY(join_uploads(h, -1));
   TTB_TRY(check_trunc(tr));
   if (is_orthogonal == TTB_ORTH_LEFT) return ttb_orthogonalize_right(h, tr, 0, 0);
   if (is_orthogonal == TTB_ORTH_RIGHT) return ttb_orthogonalize_left(h, tr, 0, 0);

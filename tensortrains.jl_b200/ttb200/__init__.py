@@ -96,6 +96,8 @@ _sig("ttb_twovar_marginals", _h, _i64, _pd)
 _sig("ttb_evaluate", _h, _i64, C.POINTER(C.c_int32), _i64, _pd)
 _sig("ttb_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
 _sig("ttb_sample_stats", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
+_sig("ttb_upload_all_async", _h, _pd)
+_sig("ttb_reset", _h)
 _sig("ttb_dot", _h, _i64, _h, _i64, _pd, _pi)
 _sig("ttb_last_timing", _h, _pd, _pi64)
 _sig("ttb_profile", _h, C.c_int)
@@ -374,9 +376,20 @@ class AbstractTensorTrain:
             out[name] = (int(n), float(ms))
         return out
 
-    def upload_all(self, packed: np.ndarray):
-        """Raw packed upload (train-major, site-major, column-major sites at their current dims)."""
-        _ck(lib.ttb_upload_all(self._hd, _dp(packed)))
+    def upload_all(self, packed: np.ndarray, async_: bool = False):
+        """Raw packed upload (train-major, site-major, column-major sites at their current dims).
+        ``async_=True``: return once the copies are enqueued (``packed`` must stay alive, pinned for a real
+        overlap, until the next call that returns results); a following ``compress_`` starts on the sites
+        that have already landed."""
+        if async_:
+            self._keepalive = packed
+            _ck(lib.ttb_upload_all_async(self._hd, _dp(packed)))
+        else:
+            _ck(lib.ttb_upload_all(self._hd, _dp(packed)))
+
+    def reset(self):
+        """Back to the bond dimensions the train was created with, z = 1 (slab and workspaces are kept)."""
+        _ck(lib.ttb_reset(self._hd))
 
     def download_all(self, out: np.ndarray):
         _ck(lib.ttb_download_all(self._hd, _dp(out)))

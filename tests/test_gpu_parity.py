@@ -554,3 +554,32 @@ def test_large_bond_cluster_jacobi(case):
         for (t, lam_o, kept) in stats:
             assert spectra_close(A.spectrum(t), lam_o), t
         check_evals(A, Ao, X, 1e-6)
+
+
+def test_async_upload_and_reset_reuse_handle():
+    """ttb_reset + ttb_upload_all_async: a long-lived handle takes a stream of trains; the result is the one
+    a fresh handle gives, for the chunked path (single train) and the fallback (batch)."""
+    rng = RNG(900)
+    L, d, q = 40, 96, 2                       # 2.8 MB per bulk site: several 16 MB chunks
+    bonds = [1] + [d] * (L - 1) + [1]
+    H = T.TensorTrain.empty(bonds, (q,))
+    nd = sum(bonds[t] * bonds[t + 1] * q for t in range(L))
+    pin = T.PinnedBuffer(nd)
+    X = rng.integers(0, q, (5, L)).astype(np.int32)
+    for rep in range(3):
+        ts = [rng.random((bonds[t], bonds[t + 1], q)) for t in range(L)]
+        pin.array[:] = np.concatenate([a.reshape(-1, order="F") for a in ts])
+        F = T.TensorTrain(ts)
+        T.compress_(F, T.TruncThresh(1e-9))
+        H.reset()
+        assert T.bond_dims(H) == bonds[:L]
+        H.upload_all(pin.array, async_=True)
+        T.compress_(H, T.TruncThresh(1e-9))
+        assert T.bond_dims(H) == T.bond_dims(F)
+        assert np.allclose(T.evaluate(H, X), T.evaluate(F, X), rtol=1e-12, atol=0.0)
+        zh, zf = T.normalization(H), T.normalization(F)
+        assert zh.sign == zf.sign and close(zh.logabs, zf.logabs, 1e-12, 1e-12)
+    # async upload followed by something that is not a right sweep: joined before use
+    H.reset()
+    H.upload_all(pin.array, async_=True)
+    assert np.allclose(T.evaluate(H, X), T.evaluate(T.TensorTrain(ts), X), rtol=1e-13)
