@@ -86,6 +86,9 @@ int ttb_upload_all_async(ttb_handle h, const double* host);
 /* bond dimensions back to the ones the handle was created with, z = 1: reuse the slab and the workspaces
  * for the next train of the same shape */
 int ttb_reset(ttb_handle h);
+/* sample / twovar_marginals / dot keep their device scratch on the handle between calls (grow-only: a
+ * cudaFree of a few hundred MB costs up to hundreds of ms of wall clock); this releases it */
+int ttb_trim(ttb_handle h);
 int ttb_download_all(ttb_handle h, double* host);
 int ttb_get_z(ttb_handle h, int64_t b, double* logabs, int* sign);
 int ttb_set_z(ttb_handle h, int64_t b, double logabs, int sign);

@@ -40,7 +40,25 @@ struct StepState {
   int rot[2];                        // cluster Jacobi: rotations of the sweep in flight (ping-pong), all CTAs
 };
 
+// grow-only device scratch kept on the handle between calls (cudaFree of a few hundred MB costs up to
+// hundreds of ms of wall clock; the sampler needs the same buffers call after call)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct Workspace {
+  DevBuf samp[10];                    // sampler scratch (offsets, G, uniforms, x, p, hist, sum log p, packed A, packed G)
+  DevBuf scr[6];                      // twovar_marginals (pair offsets, out, scratch, GT, Tm) and dot scratch
   // sweep
   double* X[2] = {nullptr, nullptr};  // folded site / absorb output, p_max x n_max col-major
   int64_t x_stride = 0;

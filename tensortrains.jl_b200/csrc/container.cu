@@ -77,6 +77,8 @@ static void free_ws(ttb_tt* h) {
   cudaFree(w.X[0]); cudaFree(w.X[1]); cudaFree(w.T); cudaFree(w.Bv); cudaFree(w.Jv);
   cudaFree(w.perm); cudaFree(w.sigma); cudaFree(w.st); cudaFree(w.stat_err); cudaFree(w.stat_rank);
   cudaFree(w.spectrum); cudaFree(w.envL); cudaFree(w.envR); cudaFree(w.env_log); cudaFree(w.env_sign);
+  for (DevBuf& d : w.samp) d.release();
+  for (DevBuf& d : w.scr) d.release();
   w = Workspace();
 }
 
@@ -375,6 +377,15 @@ int ttb_reset(ttb_handle h) {
   TTB_CUDA(cudaMemsetAsync(h->d_logz, 0, sizeof(double) * h->batch, h->stream));
   TTB_CUDA(cudaMemcpyAsync(h->d_signz, ones.data(), sizeof(int) * h->batch, cudaMemcpyHostToDevice, h->stream));
   TTB_CUDA(cudaStreamSynchronize(h->stream));
+  return TTB_OK;
+}
+
+// release the grow-only scratch the sampler / twovar_marginals / dot keep on the handle between calls
+int ttb_trim(ttb_handle h) {
+  TTB_TRY(check_handle(h));
+  TTB_CUDA(cudaStreamSynchronize(h->stream));
+  for (DevBuf& d : h->ws.samp) d.release();
+  for (DevBuf& d : h->ws.scr) d.release();
   return TTB_OK;
 }
 

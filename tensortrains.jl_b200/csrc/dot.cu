@@ -176,10 +176,10 @@ extern "C" int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, doubl
   const int64_t S = (int64_t)ra * rb, capC = (int64_t)dA * dB;
   const int64_t need = S * capC * (2 + Q);
   if (need > (int64_t(1) << 31)) return fail(TTB_EUNSUPPORTED, "dot: boundary*bond product too large (%lld doubles of scratch)", (long long)need);
-  double* scratch = nullptr;
-  double* scal = nullptr;
-  TTB_CUDA(cudaMalloc(&scratch, sizeof(double) * need));
-  if (cudaMalloc(&scal, sizeof(double) * 8) != cudaSuccess) { cudaFree(scratch); return fail(TTB_ENOMEM, "dot scratch"); }
+  // scratch kept on handle `a` between calls (grow-only, ttb_trim releases it)
+  if (a->ws.scr[5].ensure(sizeof(double) * (need + 8)) != cudaSuccess) return fail(TTB_ENOMEM, "dot scratch");
+  double* scratch = static_cast<double*>(a->ws.scr[5].p);
+  double* scal = scratch + need;
   cudaStream_t s = a->stream;
   const double h_scal[8] = {1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   cudaMemcpyAsync(scal, h_scal, sizeof(h_scal), cudaMemcpyHostToDevice, s);
@@ -208,8 +208,6 @@ extern "C" int ttb_dot(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, doubl
   double h_out[2] = {0.0, 0.0};
   cudaMemcpyAsync(h_out, out_dev, sizeof(h_out), cudaMemcpyDeviceToHost, s);
   int rc = timer.finish();
-  cudaFree(scratch);
-  cudaFree(scal);
   if (rc != TTB_OK) return rc;
   *logabs = h_out[0];
   *sign = h_out[1] < 0.0 ? -1 : 1;

@@ -754,9 +754,12 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
   const int64_t scr_stride = 2 * ((Q * h->bond0[0] * h->dmax + 15) & ~int64_t(15));
   const size_t smem_need = sizeof(double) * (Q * Q + scr_stride);
   const bool scr_in_smem = smem_need <= 200 * 1024;
-  cudaError_t e = cudaMalloc(&d_poff, sizeof(int64_t) * L);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * h->batch * npairs * Q * Q);
-  if (e == cudaSuccess && !scr_in_smem) e = cudaMalloc(&d_scr, sizeof(double) * h->batch * (L - 1) * scr_stride);
+  // scratch is kept on the handle between calls (grow-only, ttb_trim releases it)
+  cudaError_t e = w.scr[0].ensure(sizeof(int64_t) * L);
+  if (e == cudaSuccess) e = w.scr[1].ensure(sizeof(double) * h->batch * npairs * Q * Q);
+  if (e == cudaSuccess && !scr_in_smem) e = w.scr[2].ensure(sizeof(double) * h->batch * (L - 1) * scr_stride);
+  d_poff = static_cast<int64_t*>(w.scr[0].p); d_out = static_cast<double*>(w.scr[1].p);
+  d_scr = scr_in_smem ? nullptr : static_cast<double*>(w.scr[2].p);
   int rc = TTB_OK;
   if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
   if (rc == TTB_OK) {
@@ -772,8 +775,9 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
     double *d_GT = nullptr, *d_Tm = nullptr;
     if (rc == TTB_OK && use_fast) {
       const int64_t gstride = (kcap + 15) & ~int64_t(15), tstride = (h->dmax * h->dmax + 15) & ~int64_t(15);
-      e = cudaMalloc(&d_GT, sizeof(double) * h->batch * L * Q * gstride);
-      if (e == cudaSuccess) e = cudaMalloc(&d_Tm, sizeof(double) * h->batch * L * tstride);
+      e = w.scr[3].ensure(sizeof(double) * h->batch * L * Q * gstride);
+      if (e == cudaSuccess) e = w.scr[4].ensure(sizeof(double) * h->batch * L * tstride);
+      d_GT = static_cast<double*>(w.scr[3].p); d_Tm = static_cast<double*>(w.scr[4].p);
       if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
       if (rc == TTB_OK) {
         TwoPre pc;
@@ -807,13 +811,11 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
       TTB_LAUNCH(h, "k_twovar", k_twovar<<<g, 256, scr_in_smem ? smem_need : sizeof(double) * Q * Q, h->stream>>>(c));
       rc = tm.finish();
     }
-    cudaFree(d_GT); cudaFree(d_Tm);
     if (rc == TTB_OK) {
       e = cudaMemcpy(out, d_out, sizeof(double) * h->batch * npairs * Q * Q, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = fail(TTB_ECUDA, "twovar copy: %s", cudaGetErrorString(e));
     }
   }
-  cudaFree(d_poff); cudaFree(d_out); cudaFree(d_scr);
   env_side_free(s);
   return rc;
 }

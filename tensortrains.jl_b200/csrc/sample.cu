@@ -285,15 +285,21 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
   uint8_t* d_x = nullptr;
   unsigned long long* d_hist = nullptr;
   cudaError_t e = cudaSuccess;
-  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  // scratch lives on the handle (grow-only): no cudaMalloc / cudaFree per call
+  int slot = 0;
+  auto A = [&](void** p, size_t bytes) {
+    DevBuf& d = w.samp[slot++];
+    if (e == cudaSuccess) e = d.ensure(bytes);
+    *p = d.p;
+  };
   A((void**)&d_eoff, sizeof(int64_t) * (L + 1));
   A((void**)&d_goff, sizeof(int64_t) * (L + 1));
   A((void**)&d_G, sizeof(double) * goff[L]);
-  if (uniforms) A((void**)&d_u, sizeof(double) * nsamples * L);
-  if (x_out) A((void**)&d_x, (size_t)nsamples * L);
-  if (p_out) A((void**)&d_p, sizeof(double) * nsamples);
-  if (hist) A((void**)&d_hist, sizeof(unsigned long long) * L * Q);
-  if (sum_logp) A((void**)&d_slp, sizeof(double));
+  if (uniforms) A((void**)&d_u, sizeof(double) * nsamples * L); else ++slot;
+  if (x_out) A((void**)&d_x, (size_t)nsamples * L); else ++slot;
+  if (p_out) A((void**)&d_p, sizeof(double) * nsamples); else ++slot;
+  if (hist) A((void**)&d_hist, sizeof(unsigned long long) * L * Q); else ++slot;
+  if (sum_logp) A((void**)&d_slp, sizeof(double)); else ++slot;
   int rc = TTB_OK;
   if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "sample buffers: %s", cudaGetErrorString(e));
   if (rc == TTB_OK) {
@@ -324,8 +330,9 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     CallTimer tm(h);
     if (tiled) {
       const size_t nAp = (size_t)L * DP * DP * Q, nGp = (size_t)L * DP * 8;
-      e = cudaMalloc(&d_Ap, sizeof(double) * nAp);
-      if (e == cudaSuccess) e = cudaMalloc(&d_Gp, sizeof(double) * nGp);
+      e = w.samp[8].ensure(sizeof(double) * nAp);
+      if (e == cudaSuccess) e = w.samp[9].ensure(sizeof(double) * nGp);
+      d_Ap = static_cast<double*>(w.samp[8].p); d_Gp = static_cast<double*>(w.samp[9].p);
       if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "sample pack buffers: %s", cudaGetErrorString(e));
       if (rc == TTB_OK) {
         cudaMemsetAsync(d_Gp, 0, sizeof(double) * nGp, h->stream);
@@ -360,7 +367,6 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
       }
     }
     if (rc == TTB_OK) rc = tm.finish();
-    cudaFree(d_Ap); cudaFree(d_Gp);
     h->last_ms += ms_acc; h->last_launches += l_acc;
   }
   if (rc == TTB_OK) {
@@ -374,8 +380,6 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     if (e == cudaSuccess && sum_logp) e = cudaMemcpy(sum_logp, d_slp, sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail(TTB_ECUDA, "sample copy: %s", cudaGetErrorString(e));
   }
-  cudaFree(d_eoff); cudaFree(d_goff); cudaFree(d_G); cudaFree(d_u); cudaFree(d_x); cudaFree(d_p); cudaFree(d_hist);
-  cudaFree(d_slp);
   if (rc == TTB_OK) {
     int st = 0;
     TTB_TRY(read_status(h, &st));

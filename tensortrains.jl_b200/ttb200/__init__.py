@@ -98,6 +98,7 @@ _sig("ttb_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_ui
 _sig("ttb_sample_stats", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
 _sig("ttb_upload_all_async", _h, _pd)
 _sig("ttb_reset", _h)
+_sig("ttb_trim", _h)
 _sig("ttb_dot", _h, _i64, _h, _i64, _pd, _pi)
 _sig("ttb_last_timing", _h, _pd, _pi64)
 _sig("ttb_profile", _h, C.c_int)
@@ -386,6 +387,10 @@ class AbstractTensorTrain:
             _ck(lib.ttb_upload_all_async(self._hd, _dp(packed)))
         else:
             _ck(lib.ttb_upload_all(self._hd, _dp(packed)))
+
+    def trim(self):
+        """Release the device scratch ``sample`` / ``twovar_marginals`` / ``dot`` keep between calls."""
+        _ck(lib.ttb_trim(self._hd))
 
     def reset(self):
         """Back to the bond dimensions the train was created with, z = 1 (slab and workspaces are kept)."""
