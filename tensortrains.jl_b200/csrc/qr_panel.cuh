@@ -125,11 +125,79 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
     double v[RPL];
     double tau = 0.0;
     if (wid == ow) {
-      // ---- owner: form reflector cc from its (fully updated) column, in place; publish for the others
+      // ---- owner: ONE reduction round per column.  The norm of the raw column x (rows > cc) and its dots
+      // with the warp's other columns ride the same butterfly; with v = (e_cc, x * scal) the products the
+      // reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing waits for the normalised v.
       double* vcol = vs + (size_t)cc * LDV;
+      double x[RPL];
 #pragma unroll
       for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 == os) tau = make_reflector<RPL>(a[s2], v, vcol, cc, lane);
+        if (s2 == os) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) x[i] = a[s2][i];
+        }
+      const double x0m = (lane > cc) ? x[0] : 0.0;   // rows <= cc of the first 32 do not belong to the reflector
+      double red[NS + 1];
+      {
+        double p0 = x0m * x0m, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+        for (int i = 1; i < RPL; ++i) {
+          if ((i & 3) == 0) p0 += x[i] * x[i];
+          else if ((i & 3) == 1) p1 += x[i] * x[i];
+          else if ((i & 3) == 2) p2 += x[i] * x[i];
+          else p3 += x[i] * x[i];
+        }
+        red[NS] = (p0 + p1) + (p2 + p3);
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        double d0 = x0m * a[s2][0], d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+        for (int i = 1; i < RPL; ++i) {
+          if ((i & 3) == 0) d0 += x[i] * a[s2][i];
+          else if ((i & 3) == 1) d1 += x[i] * a[s2][i];
+          else if ((i & 3) == 2) d2 += x[i] * a[s2][i];
+          else d3 += x[i] * a[s2][i];
+        }
+        red[s2] = (d0 + d1) + (d2 + d3);
+      }
+      double acc[NS];   // element at row cc of every own column (row cc lives in lane cc, i = 0)
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) acc[s2] = __shfl_sync(0xffffffffu, a[s2][0], cc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k <= NS; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], o);
+      }
+      const double xn2 = red[NS];
+      double alpha = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 == os) alpha = acc[s2];
+      double scal = 0.0, beta = alpha;
+      if (xn2 > 0.0) {
+        const double nn = alpha * alpha + xn2;
+        const double rs = rsqrt(nn);  // 1/||x||
+        const double nrm = nn * rs;
+        const double sg = alpha >= 0.0 ? 1.0 : -1.0;
+        beta = -sg * nrm;
+        const double den = alpha - beta;  // = sg*(|alpha| + nrm), no cancellation
+        scal = 1.0 / den;
+        tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
+      }
+      // v in registers and in shared memory; the column keeps (R_cc on the diagonal, v below)
+      {
+        double v0 = 0.0;
+        if (lane > cc) v0 = x[0] * scal;
+        else if (lane == cc) v0 = 1.0;
+        v[0] = v0;
+        vcol[lane] = v0;
+      }
+#pragma unroll
+      for (int i = 1; i < RPL; ++i) {
+        v[i] = x[i] * scal;
+        vcol[lane + 32 * i] = v[i];
+      }
       // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared
       // stores of one warp are performed in order and the flag is the last store instruction.
       sh_tau[cc] = tau;
@@ -138,6 +206,27 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
 #ifdef TTB_PANEL_STAMPS
       if (lane == 0) TTB_PANEL_STAMPS[8 + cc] = clock64();
 #endif
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        const int cs = wid * NS + s2;
+        if (cs >= bwc) continue;  // warp-uniform
+        if (s2 == os) {
+          // own column: R_cc on the diagonal, v below, untouched above
+          if (lane > cc) a[s2][0] = v[0];
+          else if (lane == cc) a[s2][0] = beta;
+#pragma unroll
+          for (int i = 1; i < RPL; ++i) a[s2][i] = v[i];
+        } else {
+          const double g = acc[s2] + scal * red[s2];   // v_cc^T a_cs
+          if (cs > cc) {
+            const double w = tau * g;
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+          } else {
+            G[cs + 32 * cc] = g;  // V_cs^T v_cc (same value from every lane)
+          }
+        }
+      }
     } else {
       // ---- consumer: every lane polls the same word (broadcast load, no divergence)
       unsigned it = 0;
@@ -148,27 +237,27 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
       const double* vcol = vs + (size_t)cc * LDV;
 #pragma unroll
       for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
-    }
-    // ---- apply reflector cc to all NS columns of this warp at once: independent dots, interleaved
-    //      butterfly reductions, then the rank-1 updates (finished columns only need the dot: V^T V)
-    double dot[NS];
+      // apply reflector cc to all NS columns of this warp at once: independent dots, interleaved
+      // butterfly reductions, then the rank-1 updates (finished columns only need the dot: V^T V)
+      double dot[NS];
 #pragma unroll
-    for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
+      for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) dot[s2] += __shfl_xor_sync(0xffffffffu, dot[s2], o);
-    }
+        for (int s2 = 0; s2 < NS; ++s2) dot[s2] += __shfl_xor_sync(0xffffffffu, dot[s2], o);
+      }
 #pragma unroll
-    for (int s2 = 0; s2 < NS; ++s2) {
-      const int cs = wid * NS + s2;
-      if (cs >= bwc || cs == cc) continue;  // warp-uniform
-      if (cs > cc) {
-        const double w = tau * dot[s2];
+      for (int s2 = 0; s2 < NS; ++s2) {
+        const int cs = wid * NS + s2;
+        if (cs >= bwc) continue;  // warp-uniform
+        if (cs > cc) {
+          const double w = tau * dot[s2];
 #pragma unroll
-        for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-      } else {
-        G[cs + 32 * cc] = dot[s2];  // V_cs^T v_cc (same value from every lane)
+          for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+        } else {
+          G[cs + 32 * cc] = dot[s2];  // V_cs^T v_cc (same value from every lane)
+        }
       }
     }
   }
