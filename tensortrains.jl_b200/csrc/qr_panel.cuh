@@ -36,49 +36,6 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
   return (d0 + d1) + (d2 + d3);
 }
 
-// Householder reflector of panel column `cc` (< 32) held as col[i] = row (lane + 32 i).  Overwrites the
-// column with (R_cc on the diagonal, v below), returns v in registers (unit diagonal, zeros above) and
-// publishes it to vcol.  Only the first 32 rows (i = 0) can lie on or above the diagonal.
-template <int RPL>
-__device__ __forceinline__ double make_reflector(double (&col)[RPL], double (&v)[RPL], double* vcol, int cc, int lane) {
-  double p0 = (lane > cc) ? col[0] * col[0] : 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-#pragma unroll
-  for (int i = 1; i < RPL; ++i) {
-    if ((i & 3) == 0) p0 += col[i] * col[i];
-    else if ((i & 3) == 1) p1 += col[i] * col[i];
-    else if ((i & 3) == 2) p2 += col[i] * col[i];
-    else p3 += col[i] * col[i];
-  }
-  const double xn2 = warp_sum((p0 + p1) + (p2 + p3));
-  const double alpha = __shfl_sync(0xffffffffu, col[0], cc);
-  double tau = 0.0, scal = 0.0, beta = alpha;
-  if (xn2 > 0.0) {
-    const double nn = alpha * alpha + xn2;
-    const double rs = rsqrt(nn);  // 1/||x||
-    const double nrm = nn * rs;
-    const double sg = alpha >= 0.0 ? 1.0 : -1.0;
-    beta = -sg * nrm;
-    const double den = alpha - beta;  // = sg*(|alpha| + nrm), no cancellation
-    scal = 1.0 / den;
-    tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
-  }
-  {
-    double v0 = 0.0;
-    if (lane > cc) { v0 = col[0] * scal; col[0] = v0; }
-    else if (lane == cc) { v0 = 1.0; col[0] = beta; }
-    v[0] = v0;
-    vcol[lane] = v0;
-  }
-#pragma unroll
-  for (int i = 1; i < RPL; ++i) {
-    const double vi = col[i] * scal;
-    col[i] = vi;
-    v[i] = vi;
-    vcol[lane + 32 * i] = vi;
-  }
-  return tau;
-}
-
 template <int RPL, int NS>
 __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
   pdl_enter();
@@ -229,8 +186,12 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
       }
     } else {
       // ---- consumer: every lane polls the same word (broadcast load, no divergence)
+      // warps that are not about to take over the chain back off between polls: their spinning would
+      // take issue slots from the owner on the same SM sub-partition
+      const bool relaxed = (wid != ow + 1 || os != NS - 1);
       unsigned it = 0;
       while (ld_flag(&ready[cc]) == 0) {
+        if (relaxed) __nanosleep(100);
         if (++it > (1u << 26)) __trap();
       }
       tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
