@@ -36,6 +36,139 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
   return (d0 + d1) + (d2 + d3);
 }
 
+// One link of the chain, executed by the warp that owns column cc = NS*wid + OS.  ONE reduction round: the
+// norm of the raw column x (rows > cc) and its dots with the warp's LATER columns ride the same butterfly;
+// with v = (e_cc, x * scal) the products the reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing
+// waits for the normalised v.  Publishes v / tau / the ready flag, updates the later own columns, leaves
+// (R_cc on the diagonal, v below) in the column.  Returns tau; v stays in registers.
+template <int RPL, int NS, int OS>
+__device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double (&v)[RPL], double* vcol, double* sh_tau,
+                                                   int* ready, int cc, int lane, int wid, int bwc) {
+  constexpr int NL = NS - 1 - OS;   // later own columns
+  double x[RPL];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) x[i] = a[OS][i];
+  const double x0m = (lane > cc) ? x[0] : 0.0;   // rows <= cc of the first 32 do not belong to the reflector
+  double red[NL + 1];
+  {
+    double p0 = x0m * x0m, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int i = 1; i < RPL; ++i) {
+      if ((i & 3) == 0) p0 += x[i] * x[i];
+      else if ((i & 3) == 1) p1 += x[i] * x[i];
+      else if ((i & 3) == 2) p2 += x[i] * x[i];
+      else p3 += x[i] * x[i];
+    }
+    red[NL] = (p0 + p1) + (p2 + p3);
+  }
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int s2 = OS + 1 + k;
+    double d0 = x0m * a[s2][0], d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+    for (int i = 1; i < RPL; ++i) {
+      if ((i & 3) == 0) d0 += x[i] * a[s2][i];
+      else if ((i & 3) == 1) d1 += x[i] * a[s2][i];
+      else if ((i & 3) == 2) d2 += x[i] * a[s2][i];
+      else d3 += x[i] * a[s2][i];
+    }
+    red[k] = (d0 + d1) + (d2 + d3);
+  }
+  double acc[NL + 1];   // element at row cc of this and the later own columns (row cc lives in lane cc, i = 0)
+#pragma unroll
+  for (int k = 0; k <= NL; ++k) acc[k] = __shfl_sync(0xffffffffu, a[OS + k][0], cc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k <= NL; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], o);
+  }
+  const double xn2 = red[NL];
+  const double alpha = acc[0];
+  double scal = 0.0, beta = alpha, tau = 0.0;
+  if (xn2 > 0.0) {
+    const double nn = alpha * alpha + xn2;
+    const double rs = rsqrt(nn);  // 1/||x||
+    const double nrm = nn * rs;
+    const double sg = alpha >= 0.0 ? 1.0 : -1.0;
+    beta = -sg * nrm;
+    const double den = alpha - beta;  // = sg*(|alpha| + nrm), no cancellation
+    scal = 1.0 / den;
+    tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
+  }
+  {
+    double v0 = 0.0;
+    if (lane > cc) v0 = x[0] * scal;
+    else if (lane == cc) v0 = 1.0;
+    v[0] = v0;
+    vcol[lane] = v0;
+  }
+#pragma unroll
+  for (int i = 1; i < RPL; ++i) {
+    v[i] = x[i] * scal;
+    vcol[lane + 32 * i] = v[i];
+  }
+  // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared stores of
+  // one warp are performed in order and the flag is the last store instruction.
+  sh_tau[cc] = tau;
+  __syncwarp();
+  *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
+  // own column: R_cc on the diagonal, v below, untouched above
+  if (lane > cc) a[OS][0] = v[0];
+  else if (lane == cc) a[OS][0] = beta;
+#pragma unroll
+  for (int i = 1; i < RPL; ++i) a[OS][i] = v[i];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int s2 = OS + 1 + k;
+    if (wid * NS + s2 < bwc) {   // warp-uniform
+      const double w = tau * (acc[k + 1] + scal * red[k]);   // tau * v_cc^T a_cs
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+    }
+  }
+  return tau;
+}
+
+// V^T V entries between the columns of ONE finished block (s1 < s2): G = v_s1[row cs2] + sum_{r > cs2} v_s1[r] v_s2[r].
+// Runs once per block after its last reflector has been published, i.e. off the chain.
+template <int RPL, int NS>
+__device__ __forceinline__ void panel_block_gram(const double (&a)[NS][RPL], double* G, int wid, int lane, int bwc) {
+  constexpr int NPAIR = NS * (NS - 1) / 2;
+  double red[NPAIR > 0 ? NPAIR : 1], diag[NPAIR > 0 ? NPAIR : 1];
+  int k = 0;
+#pragma unroll
+  for (int s2 = 1; s2 < NS; ++s2) {
+    const int cs2 = wid * NS + s2;
+#pragma unroll
+    for (int s1 = 0; s1 < s2; ++s1) {
+      double d0 = (lane > cs2) ? a[s1][0] * a[s2][0] : 0.0, d1 = 0.0;
+#pragma unroll
+      for (int i = 1; i < RPL; ++i) {
+        if (i & 1) d1 += a[s1][i] * a[s2][i];
+        else d0 += a[s1][i] * a[s2][i];
+      }
+      red[k] = d0 + d1;
+      diag[k] = __shfl_sync(0xffffffffu, a[s1][0], cs2 & 31);
+      ++k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) red[q] += __shfl_xor_sync(0xffffffffu, red[q], o);
+  }
+  k = 0;
+#pragma unroll
+  for (int s2 = 1; s2 < NS; ++s2) {
+    const int cs2 = wid * NS + s2;
+#pragma unroll
+    for (int s1 = 0; s1 < s2; ++s1) {
+      if (cs2 < bwc) G[(wid * NS + s1) + 32 * cs2] = diag[k] + red[k];   // same value from every lane
+      ++k;
+    }
+  }
+}
+
 template <int RPL, int NS>
 __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
   pdl_enter();
@@ -82,108 +215,15 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
     double v[RPL];
     double tau = 0.0;
     if (wid == ow) {
-      // ---- owner: ONE reduction round per column.  The norm of the raw column x (rows > cc) and its dots
-      // with the warp's other columns ride the same butterfly; with v = (e_cc, x * scal) the products the
-      // reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing waits for the normalised v.
-      double* vcol = vs + (size_t)cc * LDV;
-      double x[RPL];
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 == os) {
-#pragma unroll
-          for (int i = 0; i < RPL; ++i) x[i] = a[s2][i];
-        }
-      const double x0m = (lane > cc) ? x[0] : 0.0;   // rows <= cc of the first 32 do not belong to the reflector
-      double red[NS + 1];
-      {
-        double p0 = x0m * x0m, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-#pragma unroll
-        for (int i = 1; i < RPL; ++i) {
-          if ((i & 3) == 0) p0 += x[i] * x[i];
-          else if ((i & 3) == 1) p1 += x[i] * x[i];
-          else if ((i & 3) == 2) p2 += x[i] * x[i];
-          else p3 += x[i] * x[i];
-        }
-        red[NS] = (p0 + p1) + (p2 + p3);
+      // compile-time position inside the block: the dots with LATER own columns only (the Gram entries
+      // against the block's finished columns are formed once per block, off the chain)
+      switch (os) {
+        case 0: tau = panel_owner_step<RPL, NS, 0>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
+        case 1: tau = panel_owner_step<RPL, NS, (1 < NS ? 1 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
+        case 2: tau = panel_owner_step<RPL, NS, (2 < NS ? 2 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
+        default: tau = panel_owner_step<RPL, NS, (3 < NS ? 3 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
       }
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        double d0 = x0m * a[s2][0], d1 = 0.0, d2 = 0.0, d3 = 0.0;
-#pragma unroll
-        for (int i = 1; i < RPL; ++i) {
-          if ((i & 3) == 0) d0 += x[i] * a[s2][i];
-          else if ((i & 3) == 1) d1 += x[i] * a[s2][i];
-          else if ((i & 3) == 2) d2 += x[i] * a[s2][i];
-          else d3 += x[i] * a[s2][i];
-        }
-        red[s2] = (d0 + d1) + (d2 + d3);
-      }
-      double acc[NS];   // element at row cc of every own column (row cc lives in lane cc, i = 0)
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) acc[s2] = __shfl_sync(0xffffffffu, a[s2][0], cc);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k <= NS; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], o);
-      }
-      const double xn2 = red[NS];
-      double alpha = 0.0;
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2)
-        if (s2 == os) alpha = acc[s2];
-      double scal = 0.0, beta = alpha;
-      if (xn2 > 0.0) {
-        const double nn = alpha * alpha + xn2;
-        const double rs = rsqrt(nn);  // 1/||x||
-        const double nrm = nn * rs;
-        const double sg = alpha >= 0.0 ? 1.0 : -1.0;
-        beta = -sg * nrm;
-        const double den = alpha - beta;  // = sg*(|alpha| + nrm), no cancellation
-        scal = 1.0 / den;
-        tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
-      }
-      // v in registers and in shared memory; the column keeps (R_cc on the diagonal, v below)
-      {
-        double v0 = 0.0;
-        if (lane > cc) v0 = x[0] * scal;
-        else if (lane == cc) v0 = 1.0;
-        v[0] = v0;
-        vcol[lane] = v0;
-      }
-#pragma unroll
-      for (int i = 1; i < RPL; ++i) {
-        v[i] = x[i] * scal;
-        vcol[lane + 32 * i] = v[i];
-      }
-      // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared
-      // stores of one warp are performed in order and the flag is the last store instruction.
-      sh_tau[cc] = tau;
-      __syncwarp();
-      *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
-#ifdef TTB_PANEL_STAMPS
-      if (lane == 0) TTB_PANEL_STAMPS[8 + cc] = clock64();
-#endif
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        const int cs = wid * NS + s2;
-        if (cs >= bwc) continue;  // warp-uniform
-        if (s2 == os) {
-          // own column: R_cc on the diagonal, v below, untouched above
-          if (lane > cc) a[s2][0] = v[0];
-          else if (lane == cc) a[s2][0] = beta;
-#pragma unroll
-          for (int i = 1; i < RPL; ++i) a[s2][i] = v[i];
-        } else {
-          const double g = acc[s2] + scal * red[s2];   // v_cc^T a_cs
-          if (cs > cc) {
-            const double w = tau * g;
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-          } else {
-            G[cs + 32 * cc] = g;  // V_cs^T v_cc (same value from every lane)
-          }
-        }
-      }
+      if (os == NS - 1 || cc == bwc - 1) panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
     } else {
       // ---- consumer: every lane polls the same word (broadcast load, no divergence)
       // warps that are not about to take over the chain back off between polls: their spinning would
