@@ -335,7 +335,7 @@ def main():
         achieved = alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture
         # (profiles/r1_ncu_full_sweep_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum)
-        ncu_traffic = {"k_qr_panel_flag": 149504 + 0}
+        ncu_traffic = {"k_qr_panel_flag": 156672 + 0}
         line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": ncu_traffic.get(dom),
                             "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
