@@ -75,12 +75,16 @@ int main() {
     long long st[1024];
     cudaMemcpyFromSymbol(st, g_stamps, sizeof(st));
 #ifdef TTB_PANEL_FINE
-    printf("  col: flag->vload | dot+red+upd | (loop) | norm+red | rsqrt/rcp | v store | publish->next sees\n");
-    for (int cc = 2; cc < 31; cc += 6) {
-      long long* a = &st[64 + 16 * cc];        // stamps of reflector cc (next owner side: 0,1,2 ; owner side: 4..7)
-      long long* nx = &st[64 + 16 * (cc + 1)];
-      printf("  %2d: %5lld | %5lld | %5lld | %5lld | %5lld | %5lld | %5lld\n", cc, a[1] - a[0], a[2] - a[1], nx[4] - a[2],
-             nx[5] - nx[4], nx[6] - nx[5], nx[7] - nx[6], nx[0] - nx[7]);
+    printf("  col(OS): prev publish->entry | partial sums | butterfly | scalars | v + publish | own updates\n");
+    for (int cc = 8; cc < 16; ++cc) {
+      long long* a = &st[64 + 16 * cc];
+      printf("  %2d(%d): %5lld | %5lld | %5lld | %5lld | %5lld | %5lld\n", cc, cc % 4, a[0] - st[8 + cc - 1], a[1] - a[0], a[2] - a[1],
+             a[3] - a[2], a[4] - a[3], a[5] - a[4]);
+    }
+    printf("  next owner as consumer of reflector cc: publish->flag seen | apply | apply done -> its owner step entry\n");
+    for (int cc = 8; cc < 16; ++cc) {
+      long long* a = &st[64 + 16 * cc];
+      printf("  %2d: %5lld | %5lld | %5lld\n", cc, a[6] - st[8 + cc], a[7] - a[6], (cc % 4 == 3) ? st[64 + 16 * (cc + 1)] - a[7] : 0LL);
     }
 #endif
     printf("panel %d: kernel %.1f us (%s)  cycles: loop %lld  Tbuild %lld  store %lld\n", panel, best * 1e3,

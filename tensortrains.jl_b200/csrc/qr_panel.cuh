@@ -23,6 +23,37 @@ __device__ __forceinline__ int ld_flag(const int* p) {
   return v;
 }
 
+// NS (= 2 or 4) per-lane values -> lane l holds the warp total of value l / (32 / NS); every level of the
+// first log2(NS) sends the half of the values the partner lane keeps
+template <int NS>
+__device__ __forceinline__ double warp_reduce_ns(double (&a)[NS], int lane) {
+  static_assert(NS == 2 || NS == 4, "panel block size");
+  double r;
+  if (NS == 4) {
+    double b2[2];
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double send = hi ? a[k] : a[k + 2], keep = hi ? a[k + 2] : a[k];
+        b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    const bool hi = lane & 8;
+    const double send = hi ? b2[0] : b2[1], keep = hi ? b2[1] : b2[0];
+    r = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  } else {
+    const bool hi = lane & 16;
+    const double send = hi ? a[0] : a[NS - 1], keep = hi ? a[NS - 1] : a[0];
+    r = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+  }
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 template <int RPL>
 __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (&a)[RPL]) {
   double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -42,9 +73,13 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
 // waits for the normalised v.  Publishes v / tau / the ready flag, updates the later own columns, leaves
 // (R_cc on the diagonal, v below) in the column.  Returns tau; v stays in registers.
 template <int RPL, int NS, int OS>
-__device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double (&v)[RPL], double* vcol, double* sh_tau,
-                                                   int* ready, int cc, int lane, int wid, int bwc) {
+__device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* vcol, double* sh_tau, int* ready, int cc,
+                                                 int lane, int wid, int bwc) {
   constexpr int NL = NS - 1 - OS;   // later own columns
+  double v[RPL];
+#ifdef TTB_PANEL_FINE
+  if (lane == 0) TTB_PANEL_STAMPS[64 + 16 * cc + 0] = clock64();
+#endif
   double x[RPL];
 #pragma unroll
   for (int i = 0; i < RPL; ++i) x[i] = a[OS][i];
@@ -74,6 +109,9 @@ __device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double 
     }
     red[k] = (d0 + d1) + (d2 + d3);
   }
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && red[0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 1] = clock64();
+#endif
   double acc[NL + 1];   // element at row cc of this and the later own columns (row cc lives in lane cc, i = 0)
 #pragma unroll
   for (int k = 0; k <= NL; ++k) acc[k] = __shfl_sync(0xffffffffu, a[OS + k][0], cc);
@@ -83,6 +121,9 @@ __device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double 
     for (int k = 0; k <= NL; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], o);
   }
   const double xn2 = red[NL];
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && xn2 != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 2] = clock64();
+#endif
   const double alpha = acc[0];
   double scal = 0.0, beta = alpha, tau = 0.0;
   if (xn2 > 0.0) {
@@ -95,6 +136,9 @@ __device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double 
     scal = 1.0 / den;
     tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
   }
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && scal != 1.2345 && tau != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 3] = clock64();
+#endif
   {
     double v0 = 0.0;
     if (lane > cc) v0 = x[0] * scal;
@@ -112,6 +156,12 @@ __device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double 
   sh_tau[cc] = tau;
   __syncwarp();
   *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
+#ifdef TTB_PANEL_STAMPS
+  if (lane == 0) TTB_PANEL_STAMPS[8 + cc] = clock64();
+#endif
+#ifdef TTB_PANEL_FINE
+  if (lane == 0) TTB_PANEL_STAMPS[64 + 16 * cc + 4] = clock64();
+#endif
   // own column: R_cc on the diagonal, v below, untouched above
   if (lane > cc) a[OS][0] = v[0];
   else if (lane == cc) a[OS][0] = beta;
@@ -126,7 +176,9 @@ __device__ __forceinline__ double panel_owner_step(double (&a)[NS][RPL], double 
       for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
     }
   }
-  return tau;
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && a[NS - 1][0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 5] = clock64();
+#endif
 }
 
 // V^T V entries between the columns of ONE finished block (s1 < s2): G = v_s1[row cs2] + sum_{r > cs2} v_s1[r] v_s2[r].
@@ -208,57 +260,67 @@ __global__ void __launch_bounds__(1024 / NS, 1) k_qr_panel_flag(SweepCtx c, Step
   if (tid == 0) TTB_PANEL_STAMPS[0] = clock64();
 #endif
 
+  // One block of NS columns at a time.  The owner warp runs its NS chain links as straight-line code (no
+  // per-column dispatch: ~350 cycles of loop / switch / register shuffling per link in the previous
+  // form, and the rank-1 updates of one link overlap the partial sums of the next); every other warp
+  // consumes the block's reflectors as they are published.
 #pragma unroll 1
-  for (int cc = 0; cc < bwc; ++cc) {
-    const int ow = cc / NS;
-    const int os = cc % NS;
-    double v[RPL];
-    double tau = 0.0;
-    if (wid == ow) {
-      // compile-time position inside the block: the dots with LATER own columns only (the Gram entries
-      // against the block's finished columns are formed once per block, off the chain)
-      switch (os) {
-        case 0: tau = panel_owner_step<RPL, NS, 0>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
-        case 1: tau = panel_owner_step<RPL, NS, (1 < NS ? 1 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
-        case 2: tau = panel_owner_step<RPL, NS, (2 < NS ? 2 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
-        default: tau = panel_owner_step<RPL, NS, (3 < NS ? 3 : 0)>(a, v, vs + (size_t)cc * LDV, sh_tau, ready, cc, lane, wid, bwc); break;
-      }
-      if (os == NS - 1 || cc == bwc - 1) panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
+  for (int blk = 0; blk * NS < bwc; ++blk) {
+    const int c0 = blk * NS;
+    if (wid == blk) {
+      panel_owner_step<RPL, NS, 0>(a, vs + (size_t)c0 * LDV, sh_tau, ready, c0, lane, wid, bwc);
+      if (NS > 1 && c0 + 1 < bwc)
+        panel_owner_step<RPL, NS, (1 < NS ? 1 : 0)>(a, vs + (size_t)(c0 + 1) * LDV, sh_tau, ready, c0 + 1, lane, wid, bwc);
+      if (NS > 2 && c0 + 2 < bwc)
+        panel_owner_step<RPL, NS, (2 < NS ? 2 : 0)>(a, vs + (size_t)(c0 + 2) * LDV, sh_tau, ready, c0 + 2, lane, wid, bwc);
+      if (NS > 3 && c0 + 3 < bwc)
+        panel_owner_step<RPL, NS, (3 < NS ? 3 : 0)>(a, vs + (size_t)(c0 + 3) * LDV, sh_tau, ready, c0 + 3, lane, wid, bwc);
+      panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
     } else {
-      // ---- consumer: every lane polls the same word (broadcast load, no divergence)
-      // warps that are not about to take over the chain back off between polls: their spinning would
-      // take issue slots from the owner on the same SM sub-partition
-      const bool relaxed = (wid != ow + 1 || os != NS - 1);
-      unsigned it = 0;
-      while (ld_flag(&ready[cc]) == 0) {
-        if (relaxed) __nanosleep(100);
-        if (++it > (1u << 26)) __trap();
-      }
-      tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
-      const double* vcol = vs + (size_t)cc * LDV;
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
-      // apply reflector cc to all NS columns of this warp at once: independent dots, interleaved
-      // butterfly reductions, then the rank-1 updates (finished columns only need the dot: V^T V)
-      double dot[NS];
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2) dot[s2] += __shfl_xor_sync(0xffffffffu, dot[s2], o);
-      }
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        const int cs = wid * NS + s2;
-        if (cs >= bwc) continue;  // warp-uniform
-        if (cs > cc) {
-          const double w = tau * dot[s2];
-#pragma unroll
-          for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-        } else {
-          G[cs + 32 * cc] = dot[s2];  // V_cs^T v_cc (same value from every lane)
+      const int cend = min(c0 + NS, bwc);
+#pragma unroll 1
+      for (int cc = c0; cc < cend; ++cc) {
+        // ---- consumer: every lane polls the same word (broadcast load, no divergence).  Warps that are
+        // not about to take over the chain back off between polls: their spinning would take issue slots
+        // from the owner on the same SM sub-partition
+        const bool relaxed = (wid != blk + 1);
+        unsigned it = 0;
+        while (ld_flag(&ready[cc]) == 0) {
+          if (relaxed) __nanosleep(100);
+          if (++it > (1u << 26)) __trap();
         }
+#ifdef TTB_PANEL_FINE
+        if (lane == 0 && wid == blk + 1) TTB_PANEL_STAMPS[64 + 16 * cc + 6] = clock64();
+#endif
+        const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
+        const double* vcol = vs + (size_t)cc * LDV;
+        double v[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
+        // apply reflector cc to all NS columns of this warp at once: independent dots, ONE transpose
+        // butterfly (each level sends the half of the values the partner lane keeps: 6 shuffles for 4
+        // values instead of 20; lane l ends up with the total of value (l >> 3) & 3).  The consumer path is
+        // what the next owner must get through before it can take over the chain, so its instruction
+        // count is on the critical path at every hand-off.
+        double dot[NS];
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
+        const double tot = warp_reduce_ns<NS>(dot, lane);
+        if (wid > blk) {
+          // all own columns lie after cc (columns >= bwc are zero and stay zero): rank-1 updates
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) {
+            const double w = tau * __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+          }
+        } else {
+          // all own columns are finished reflectors: only the V^T V entries
+          if ((lane & (32 / NS - 1)) == 0) G[(wid * NS + lane / (32 / NS)) + 32 * cc] = tot;
+        }
+#ifdef TTB_PANEL_FINE
+        if (lane == 0 && wid == blk + 1 && a[0][0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 7] = clock64();
+#endif
       }
     }
   }
