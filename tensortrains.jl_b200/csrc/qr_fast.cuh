@@ -13,10 +13,16 @@ namespace ttb {
 __device__ __forceinline__ void stage_columns(double* dst, const double* src, int rows, int ncols, int64_t ld_g,
                                               uint64_t* bar, uint32_t& phase, bool aligned) {
   if (aligned) {
-    if (threadIdx.x == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(bar, (uint32_t)(rows * ncols * 8));
-      for (int cc = 0; cc < ncols; ++cc) bulk_g2s(dst + (size_t)rows * cc, src + ld_g * cc, (uint32_t)(rows * 8), bar);
+    if (threadIdx.x < 32) {
+      // one lane arms the barrier, then the copies are issued by the whole warp (one per lane) instead of
+      // one thread walking through up to 32 of them
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(rows * ncols * 8));
+      }
+      __syncwarp();
+      for (int cc = threadIdx.x; cc < ncols; cc += 32)
+        bulk_g2s(dst + (size_t)rows * cc, src + ld_g * cc, (uint32_t)(rows * 8), bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
@@ -187,13 +193,15 @@ __global__ void __launch_bounds__(256) k_qr_update_tma(SweepCtx c, StepDesc s, i
   const bool aligned = ((p & 1) == 0);
   // one barrier phase covers both the V panel and the chunk; the T factor is fetched while TMA runs
   if (aligned) {
-    if (tid == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&bar, (uint32_t)(rows * (bwc + cwc) * 8));
-      for (int cc = 0; cc < bwc; ++cc)
-        bulk_g2s(Vs + (size_t)rows * cc, X + j0 + p * (j0 + cc), (uint32_t)(rows * 8), &bar);
-      for (int cc = 0; cc < cwc; ++cc)
-        bulk_g2s(As + (size_t)rows * cc, X + j0 + p * (jc0 + cc), (uint32_t)(rows * 8), &bar);
+    if (tid < 32) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (uint32_t)(rows * (bwc + cwc) * 8));
+      }
+      __syncwarp();
+      // the whole warp issues the copies: lane cc one V column, lanes 0..cwc-1 also one chunk column
+      if (tid < bwc) bulk_g2s(Vs + (size_t)rows * tid, X + j0 + p * (j0 + tid), (uint32_t)(rows * 8), &bar);
+      if (tid < cwc) bulk_g2s(As + (size_t)rows * tid, X + j0 + p * (jc0 + tid), (uint32_t)(rows * 8), &bar);
     }
     {
       double t4[4];

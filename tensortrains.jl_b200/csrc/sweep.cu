@@ -49,6 +49,8 @@ struct StepDesc {
   int last;                // absorb output goes to the neighbour's site storage
   int slot;                // maxabs ping-pong slot
   int next_site, next_nbr; // the step that follows in this sweep (-1: none): k_commit snapshots its dimensions
+  int kp, kn, kN;          // >= 0: the step's dimensions are known exactly on the host (eps = 0 sweeps of a single
+                           // shape): kernels skip the dependent global loads of the device snapshot
   int hint_slot;           // ring slot k_commit reports the retained ranks into (-1: none)
   int jc_sd;               // > 0: both Jacobi paths are launched (host bounds cannot tell): trains whose ACTUAL
                            // 2 n_max + k (n + k) doubles fit jc_sd are done by k_jacobi, the others by the cluster
@@ -59,9 +61,12 @@ struct Dims { int p, n, k, mode, N; };  // mode 0 = QR, 1 = SVD tall (p>=n), 2 =
 // dimensions of the step in flight, from the snapshot k_snapshot took when the step started (the bond
 // array itself is rewritten by k_commit while side-stream kernels of the same step may still run)
 __device__ __forceinline__ Dims get_dims(const SweepCtx& c, const StepDesc& s, int b) {
-  const StepState& st = c.st[b];
   Dims d;
-  d.p = st.p[s.slot]; d.n = st.n[s.slot]; d.N = st.N[s.slot];
+  if (s.kp >= 0) { d.p = s.kp; d.n = s.kn; d.N = s.kN; }
+  else {
+    const StepState& st = c.st[b];
+    d.p = st.p[s.slot]; d.n = st.n[s.slot]; d.N = st.N[s.slot];
+  }
   d.k = min(d.p, d.n);
   d.mode = s.qr_only ? 0 : (d.p >= d.n ? 1 : 2);
   return d;
@@ -998,6 +1003,11 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     if (dir == 0) { p_ub = ub[hs.site + 1] * Q; n_ub = ub[hs.site]; N_ub = ub[hs.nbr]; p_lb = lb[hs.site + 1] * Q; n_lb = lb[hs.site]; }
     else { p_ub = ub[hs.site] * Q; n_ub = ub[hs.site + 1]; N_ub = ub[hs.nbr + 1]; p_lb = lb[hs.site] * Q; n_lb = lb[hs.site + 1]; }
     const int k_ub = std::min(p_ub, n_ub);
+    {
+      const int N_lb = dir == 0 ? lb[hs.nbr] : lb[hs.nbr + 1];
+      const bool exact = p_ub == p_lb && n_ub == n_lb && N_ub == N_lb;
+      s.kp = exact ? p_ub : -1; s.kn = exact ? n_ub : -1; s.kN = exact ? N_ub : -1;
+    }
     if (si == 0) SW_LAUNCH("k_snapshot", k_snapshot, (B + 127) / 128, 128, 0, c, s, B);
     if (si == 0) {
       const int64_t tot = (int64_t)p_ub * n_ub;
