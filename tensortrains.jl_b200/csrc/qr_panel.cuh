@@ -72,7 +72,8 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
 // with v = (e_cc, x * scal) the products the reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing
 // waits for the normalised v.  Publishes v / tau / the ready flag, updates the later own columns, leaves
 // (R_cc on the diagonal, v below) in the column.  Returns tau; v stays in registers.
-template <int RPL, int NS, int OS>
+// TAUPOS >= 0 (k_qr_stream): tau is also stored at vcol[TAUPOS], next to the reflector that gets shipped.
+template <int RPL, int NS, int OS, int TAUPOS = -1>
 __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* vcol, double* sh_tau, int* ready, int cc,
                                                  int lane, int wid, int bwc) {
   constexpr int NL = NS - 1 - OS;   // later own columns
@@ -154,6 +155,10 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
   // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared stores of
   // one warp are performed in order and the flag is the last store instruction.
   sh_tau[cc] = tau;
+  if (TAUPOS >= 0) {
+    vcol[TAUPOS] = tau;
+    fence_proxy_async();   // writer-side proxy fence: the reflector leaves through a bulk (async-proxy) copy
+  }
   __syncwarp();
   *reinterpret_cast<volatile int*>(&ready[cc]) = 1;
 #ifdef TTB_PANEL_STAMPS

@@ -1,0 +1,264 @@
+// qr_stream.cuh -- k_qr_stream: the blocked Householder QR of ONE site as a single thread-block CLUSTER.
+//
+// The panel/update chain of sweep.cu costs, per 32-column panel, one panel kernel (~27 us) plus one
+// trailing-update kernel that the next panel has to wait for (~10 us with its launch gap) -- and every
+// column block travels registers -> global -> registers between panels.  Here CTA k of the cluster OWNS
+// column block k (32 columns, all rows, in registers, for the whole factorisation):
+//   * while panels 0..k-1 are being factored in the other CTAs it CONSUMES their reflectors one by one as
+//     they arrive (rank-1 updates of its 4 columns per warp, the consumer path of qr_panel.cuh);
+//   * then it factors panel k with the register-resident chain of qr_panel.cuh;
+//   * then it stores R / V / the V^T V + tau block.
+// No trailing-update kernels, no launch gaps, no round trip through global memory between panels: the
+// critical path is the sum of the panel chains plus one push -> apply latency per hand-off.
+//
+// Transport of a reflector (distributed shared memory, no global staging, no polling of global memory):
+// the owner warp writes it to the factoring CTA's shared memory as before; warp 0 of that CTA PUSHES it
+// with bulk copies to every later CTA (cp.async.bulk shared::cta -> shared::cluster, lane r serves CTA r)
+// into slot g mod 8 of the destination's ring, completing on the DESTINATION's mbarrier.  Flow control is
+// credit based: ring slot w of a consumer CTA belongs to its warp w, which re-arms the slot's mbarrier
+// (expect_tx) as soon as every warp of the CTA is done with the previous occupant and then releases a
+// credit (one remote store) into the producing CTA; the pusher never blocks on credits except in its final
+// flush.  Slots are in ABSOLUTE row order (zeros above the producing panel, 8 doubles of header with tau),
+// so the consumer's register rotation turns into two contiguous runs with immediate offsets.
+//
+// Row mapping: CTA k keeps absolute row ((i + k) mod RPL) * 32 + lane in register i, so that in its own
+// factor phase register 0 holds the panel's diagonal rows -- the mapping qr_panel.cuh assumes.  Rows above
+// the panel are final when the factor phase starts: they are stored and zeroed at the transition.
+// Requirements (host-checked): dimensions exact on the host, p >= n, bw == 32, p <= 512, 2..8 column blocks.
+#pragma once
+
+namespace ttb {
+
+constexpr int kQsRing = 8;         // reflector slots per consumer CTA
+constexpr int kQsThreads = 256;    // 8 warps, 4 columns each
+constexpr int kQsMaxBlocks = 8;    // portable cluster size
+
+__host__ __device__ constexpr size_t qs_smem_bytes(int RPL) {
+  // vs[32][SL] + ring[RING][SL] + G[1024] + tau[32] doubles, ready[32] + done[8] + credit[8][RING] ints, RING mbarriers
+  return sizeof(double) * ((size_t)(32 + kQsRing) * (32 * RPL + 8) + 1024 + 32) + sizeof(int) * (40 + 8 * kQsRing) + 8 * kQsRing + 64;
+}
+
+// timeline stamps (globaltimer ns) of one traced site step: [CTA][0] start, [1 + j] consumed panel j,
+// [20] factor done, [21] all stored, [22 + blk] block done; written only when the step descriptor asks
+__device__ unsigned long long g_qs_trace[16 * 32];
+__device__ __forceinline__ unsigned long long qs_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  constexpr int NS = 4;
+  constexpr int LDV = 32 * RPL;
+  constexpr int SL = LDV + 8;           // slot stride; own panel: tau at [LDV]; ring: header [tau, .] at [0], rows at [8 ..)
+  const int b = blockIdx.y, kb = blockIdx.x;   // kb == rank in the cluster (cluster = one row of the grid)
+  const int nblk = gridDim.x;
+  const Dims d = get_dims(c, s, b);     // exact (host-known) dimensions
+  const int64_t p = d.p;
+  const int n = d.n;
+  const int j0 = 32 * kb;
+  const int bwc = min(32, n - j0);      // columns of this block (p >= n: all of them are factored)
+  const int nremote = j0;               // reflectors of the earlier panels
+  const int rows = d.p - j0;
+  double* Xa = xbuf(c, s.xin, b);
+  double* Xp = Xa + j0 + p * j0;        // panel origin
+  extern __shared__ __align__(16) double dyn[];
+  double* vs = dyn;                                  // [32][SL] reflectors of the own panel
+  double* ring = vs + 32 * SL;                       // [RING][SL] remote reflectors
+  double* G = ring + kQsRing * SL;                   // 32*32
+  double* sh_tau = G + 1024;                         // 32
+  int* ready = reinterpret_cast<int*>(sh_tau + 32);  // [32]
+  int* done = ready + 32;                            // [8] remote reflectors consumed per warp
+  int* credit = done + 8;                            // [8 consumer ranks][RING]: (global index + 1) of the reflector the slot is armed for
+  uint64_t* bars = reinterpret_cast<uint64_t*>(credit + 8 * kQsRing);  // [RING]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 1024; i += kQsThreads) G[i] = 0.0;
+  for (int i = tid; i < kQsRing * SL; i += kQsThreads) ring[i] = 0.0;   // rows above a producing panel must read as zero
+  if (tid < 40 + 8 * kQsRing) ready[tid] = 0;   // ready[32] + done[8] + credit[8][RING]
+  if (tid == 0)
+    for (int r = 0; r < kQsRing; ++r) mbar_init(&bars[r], 1);
+  __syncthreads();
+  cluster_sync_all();             // every CTA's barriers / credits exist before anybody pushes or releases credits
+  const bool trace = s.trace && b == 0 && tid == 0;
+  if (trace) g_qs_trace[kb * 32 + 0] = qs_now();
+
+  // columns 4*wid .. 4*wid+3 of the block, all rows, rotated row mapping
+  double a[NS][RPL];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid * NS + s2;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = ((i + kb) & (RPL - 1)) * 32 + lane;
+      a[s2][i] = (cs < bwc && r < d.p) ? Xa[r + p * (j0 + cs)] : 0.0;
+    }
+  }
+  // ---- consume the reflectors of the earlier panels; ring slot `wid` is armed by this warp
+  {
+    int my_next = wid;       // next reflector this warp arms its slot for (= wid mod 8)
+    auto try_arm = [&](int g_now) {
+      if (my_next >= nremote || g_now + (kQsRing - 1) < my_next) return;   // its slot cannot be free yet
+      if (my_next >= kQsRing) {   // slot free: every warp is done with reflector my_next - 8
+        int mc = lane < 8 ? *reinterpret_cast<volatile int*>(&done[lane]) : 0x7fffffff;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) mc = min(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mc = __shfl_sync(0xffffffffu, mc, 0);
+        if (mc < my_next - (kQsRing - 1)) return;
+      }
+      const int kprod = my_next >> 5;
+      double* slotp = ring + (size_t)wid * SL;
+      // first use of the slot for this producing panel: the previous panel's rows just above it become zeros
+      if (kprod > 0 && (my_next & 31) < kQsRing) slotp[8 + 32 * (kprod - 1) + lane] = 0.0;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&bars[wid], (uint32_t)((LDV - 32 * kprod) * 8 + 16));
+        st_remote_release_s32(mapa_u32(smem_u32(&credit[kb * kQsRing + wid]), (uint32_t)kprod), my_next + 1);
+      }
+      __syncwarp();
+      my_next += kQsRing;
+    };
+#pragma unroll 1
+    for (int g = 0; g < nremote; ++g) {
+      try_arm(g);
+      const int slot = g & (kQsRing - 1);
+      const uint32_t parity = (uint32_t)(g / kQsRing) & 1u;
+      for (uint32_t it = 0; !mbar_try_wait(&bars[slot], parity); ++it) {
+        try_arm(g);
+        if (it > (1u << 24)) __trap();
+      }
+      // register i holds row group (i + kb) mod RPL => two contiguous runs, immediate offsets
+      const double* vsl = ring + (size_t)slot * SL;
+      const double tau = vsl[0];
+      const double* pA = vsl + 8 + 32 * kb + lane;
+      const double* pB = pA - LDV;
+      double v[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) v[i] = (i < RPL - kb ? pA : pB)[32 * i];
+      double dot[NS];
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
+      const double tot = warp_reduce_ns<NS>(dot, lane);
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        const double w = tau * __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+      }
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(&done[wid]) = g + 1;
+      if (trace && (g & 31) == 31) g_qs_trace[kb * 32 + 1 + (g >> 5)] = qs_now();
+    }
+  }
+  // ---- transition: rows above the panel are final R entries; store them, zero the registers
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid * NS + s2;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      if (i >= RPL - kb) {   // wrapped register: absolute rows < j0
+        const int r = ((i + kb) & (RPL - 1)) * 32 + lane;
+        if (cs < bwc) Xa[r + p * (j0 + cs)] = a[s2][i];
+        a[s2][i] = 0.0;
+      }
+    }
+  }
+  if (kb == 0 && d.mode == 0 && tid == 0) c.st[b].mprime[s.slot] = d.k;
+  // ---- factor the own panel: the chain of qr_panel.cuh; warp 0 also pushes every reflector to the CTAs
+  //      that own later column blocks: lane r serves CTA r, as far as its credits allow, never blocking
+  // Warp 0 pushes: lane r serves CTA r (the CTAs after this one), as far as that CTA's credits allow, never
+  // blocking.  (Spreading the pushes over the warps was measured slower: every warp then carries the
+  // credit polling, and the warp about to take over the chain must not be delayed at all.)
+  const bool pusher = wid == 0 && lane > kb && lane < nblk;
+  int np = 0;   // own reflectors already pushed to CTA `lane`
+  const uint32_t ring_r = pusher ? mapa_u32(smem_u32(ring), (uint32_t)lane) : 0u;
+  const uint32_t bars_r = pusher ? mapa_u32(smem_u32(bars), (uint32_t)lane) : 0u;
+  auto pump = [&](int nready) {
+    if (pusher) {
+      while (np < nready) {
+        const int slot = (j0 + np) & (kQsRing - 1);
+        if (ld_acquire_cluster_s32(&credit[lane * kQsRing + slot]) <= j0 + np) break;   // slot not armed for it yet
+        const uint32_t bar_r = bars_r + (uint32_t)slot * 8u;
+        const uint32_t dst_r = ring_r + (uint32_t)(slot * SL * 8);
+        const double* src = vs + (size_t)np * SL;
+        bulk_s2remote(dst_r + (uint32_t)((8 + j0) * 8), src, (uint32_t)((LDV - j0) * 8), bar_r);   // rows j0.. of the slot
+        bulk_s2remote(dst_r, src + LDV, 16u, bar_r);                                                // header [tau, .]
+        ++np;
+      }
+    }
+    __syncwarp();
+  };
+#pragma unroll 1
+  for (int blk = 0; blk * NS < bwc; ++blk) {
+    const int c0 = blk * NS;
+    if (wid == blk) {
+      panel_owner_step<RPL, NS, 0, LDV>(a, vs + (size_t)c0 * SL, sh_tau, ready, c0, lane, wid, bwc);
+      if (c0 + 1 < bwc) panel_owner_step<RPL, NS, 1, LDV>(a, vs + (size_t)(c0 + 1) * SL, sh_tau, ready, c0 + 1, lane, wid, bwc);
+      if (c0 + 2 < bwc) panel_owner_step<RPL, NS, 2, LDV>(a, vs + (size_t)(c0 + 2) * SL, sh_tau, ready, c0 + 2, lane, wid, bwc);
+      if (c0 + 3 < bwc) panel_owner_step<RPL, NS, 3, LDV>(a, vs + (size_t)(c0 + 3) * SL, sh_tau, ready, c0 + 3, lane, wid, bwc);
+      if (s.trace && b == 0 && lane == 0) g_qs_trace[kb * 32 + 22 + blk] = qs_now();
+      if (wid == 0) pump(min(c0 + NS, bwc));   // warp 0's own block: its reflectors leave once the block is done
+      panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
+    } else {
+      const int cend = min(c0 + NS, bwc);
+#pragma unroll 1
+      for (int cc = c0; cc < cend; ++cc) {
+        const bool relaxed = (wid != blk + 1);
+        unsigned it = 0;
+        while (ld_flag(&ready[cc]) == 0) {
+          if (relaxed) __nanosleep(100);
+          if (++it > (1u << 26)) __trap();
+        }
+        if (wid == 0) pump(cc + 1);
+        const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
+        const double* vcol = vs + (size_t)cc * SL;
+        double v[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
+        double dot[NS];
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
+        const double tot = warp_reduce_ns<NS>(dot, lane);
+        if (wid > blk) {
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) {
+            const double w = tau * __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+          }
+        } else {
+          if ((lane & (32 / NS - 1)) == 0) G[(wid * NS + lane / (32 / NS)) + 32 * cc] = tot;
+        }
+      }
+    }
+  }
+  if (trace) g_qs_trace[kb * 32 + 20] = qs_now();
+  // flush: push what is left, now waiting for credits
+  if (wid == 0) {
+    for (unsigned it = 0;; ++it) {
+      pump(bwc);
+      if (!__any_sync(0xffffffffu, pusher && np < bwc)) break;
+      if (it > (1u << 24)) __trap();
+    }
+  }
+  __syncthreads();
+  if (tid < 32) G[tid + 32 * tid] = tid < bwc ? sh_tau[tid] : 0.0;
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid * NS + s2;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = lane + 32 * i;
+      if (cs < bwc && r < rows) Xp[r + p * cs] = a[s2][i];
+    }
+  }
+  __syncthreads();
+  double* Tg = c.T + (int64_t)b * c.t_stride + (int64_t)kb * 1024;
+  for (int i = tid; i < 1024; i += 256) Tg[i] = G[i];
+  if (trace) g_qs_trace[kb * 32 + 21] = qs_now();
+  // shared memory of this CTA is a copy source / credit target for the others until they are done
+  cluster_sync_all();
+}
+
+}  // namespace ttb

@@ -51,6 +51,7 @@ struct StepDesc {
   int next_site, next_nbr; // the step that follows in this sweep (-1: none): k_commit snapshots its dimensions
   int kp, kn, kN;          // >= 0: the step's dimensions are known exactly on the host (eps = 0 sweeps of a single
                            // shape): kernels skip the dependent global loads of the device snapshot
+  int trace;               // k_qr_stream: record the timeline of this step (TTB_QS_TRACE=<site>)
   int hint_slot;           // ring slot k_commit reports the retained ranks into (-1: none)
   int jc_sd;               // > 0: both Jacobi paths are launched (host bounds cannot tell): trains whose ACTUAL
                            // 2 n_max + k (n + k) doubles fit jc_sd are done by k_jacobi, the others by the cluster
@@ -371,6 +372,7 @@ __global__ void k_apply_q(SweepCtx c, StepDesc s, int cw) {
 #endif
 #include "qr_fast.cuh"
 #include "qr_panel.cuh"
+#include "qr_stream.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -876,6 +878,10 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_qr_stream<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi_small<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_jacobi_small<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -944,6 +950,9 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   int side_slot = 0;
   const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
   const bool feedback = !qr_only && getenv("TTB_NO_FEEDBACK") == nullptr;
+  const bool use_stream = getenv("TTB_NO_STREAM") == nullptr;
+  int sm_count = 0;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   // Main-stream launches use programmatic dependent launch (common.cuh): the next grid is resident and
   // parked in griddepcontrol.wait while its predecessor drains.  A launch that follows an event wait (or
   // opens the sweep) is an ordinary one.
@@ -970,6 +979,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.next_site = si + 1 < steps.size() ? steps[si + 1].site : -1;
     s.next_nbr = si + 1 < steps.size() ? steps[si + 1].nbr : -1;
     s.jc_sd = 0;
+    s.trace = 0;
     s.hint_slot = feedback ? (int)(si % ttb_tt::kHintRing) : -1;
     SweepCtx c = cbase;
     c.T = cbase.T + (int64_t)slot * B * w.t_stride;
@@ -1017,7 +1027,27 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     const bool maybe_qr = qr_only || !(p_ub < n_lb);  // p < n for every train => wide => Jacobi on X directly
     // register-panel / TMA kernels (they exchange V^T V + tau instead of an explicit T factor)
     const bool fast = (bw == 32 && p_ub <= 512);
-    if (maybe_qr) {
+    // One cooperative kernel for the whole site QR (qr_stream.cuh) when the dimensions are exact on the
+    // host, the matrix is tall, there are at least two panels and all column-block CTAs can be co-resident.
+    const int nblk = (n_ub + 31) / 32;
+    const bool stream_qr = maybe_qr && fast && use_stream && s.kp >= 0 && p_ub >= n_ub && nblk >= 2 &&
+                           nblk <= kQsMaxBlocks && (int64_t)nblk * B <= sm_count;
+    if (stream_qr) {
+      const int rpl = p_ub <= 64 ? 2 : (p_ub <= 128 ? 4 : (p_ub <= 256 ? 8 : 16));
+      static const char* trace_env = getenv("TTB_QS_TRACE");
+      s.trace = (trace_env && atoi(trace_env) == hs.site) ? 1 : 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nblk, B); cfg.blockDim = dim3(kQsThreads); cfg.dynamicSmemBytes = qs_smem_bytes(rpl); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (rpl == 2) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<2>, c, s));
+      else if (rpl == 4) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<4>, c, s));
+      else if (rpl == 8) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<8>, c, s));
+      else TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<16>, c, s));
+      hard_dep = false;
+    } else if (maybe_qr) {
       const int np = (k_ub + bw - 1) / bw;
       for (int panel = 0; panel < np; ++panel) {
         const int j0 = panel * bw;
@@ -1275,6 +1305,19 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
   if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, lb));
   if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_c);
   const int rc = finish_sweeps(h, tm);
+  if (getenv("TTB_QS_TRACE")) {
+    unsigned long long tr_h[16 * 32];
+    cudaMemcpyFromSymbol(tr_h, g_qs_trace, sizeof(tr_h));
+    const unsigned long long t0 = tr_h[0];
+    for (int kb = 0; kb < 8; ++kb) {
+      fprintf(stderr, "[qs trace] CTA %d: start %+6.1f us | consumed panels:", kb, ((double)tr_h[kb * 32] - (double)t0) * 1e-3);
+      for (int j = 0; j < kb; ++j) fprintf(stderr, " %6.1f", ((double)tr_h[kb * 32 + 1 + j] - (double)t0) * 1e-3);
+      fprintf(stderr, " | factor done %6.1f | stored %6.1f | blocks done:", ((double)tr_h[kb * 32 + 20] - (double)t0) * 1e-3,
+              ((double)tr_h[kb * 32 + 21] - (double)t0) * 1e-3);
+      for (int blk = 0; blk < 8; ++blk) fprintf(stderr, " %5.1f", ((double)tr_h[kb * 32 + 22 + blk] - (double)t0) * 1e-3);
+      fprintf(stderr, "\n");
+    }
+  }
   if (dbg) {
     clock_gettime(CLOCK_MONOTONIC, &t_d);
     auto ms = [](const timespec& x, const timespec& y) { return (y.tv_sec - x.tv_sec) * 1e3 + (y.tv_nsec - x.tv_nsec) * 1e-6; };

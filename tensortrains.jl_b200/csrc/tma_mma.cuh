@@ -22,6 +22,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// shared -> global bulk copy (bulk async-group completion); bytes and both addresses multiples of 16
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups are pending (their writes are then complete and visible)
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -51,4 +60,32 @@ __device__ __forceinline__ void dmma_16x8x8(double (&d)[4], const double (&a)[4]
       : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
+}  // namespace ttb
+
+namespace ttb {
+// ---- thread-block clusters: distributed shared memory ------------------------------------------------
+// shared::cta address of THIS CTA -> shared::cluster address of the same location in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// bulk copy from this CTA's shared memory into another CTA's; completion is counted on the REMOTE mbarrier
+__device__ __forceinline__ void bulk_s2remote(uint32_t dst_cluster, const void* src, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_remote_release_s32(uint32_t addr_cluster, int v) {
+  asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(addr_cluster), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cluster_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 }  // namespace ttb
