@@ -72,10 +72,11 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
 // with v = (e_cc, x * scal) the products the reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing
 // waits for the normalised v.  Publishes v / tau / the ready flag, updates the later own columns, leaves
 // (R_cc on the diagonal, v below) in the column.  Returns tau; v stays in registers.
-// TAUPOS >= 0 (k_qr_stream): tau is also stored at vcol[TAUPOS], next to the reflector that gets shipped.
-template <int RPL, int NS, int OS, int TAUPOS = -1>
+// STREAM (k_qr_stream): only the first `nvi` 32-row groups exist below the panel's first row; tau is stored
+// right behind them at vcol[tauoff] so that reflector + tau leave the CTA as ONE contiguous bulk copy.
+template <int RPL, int NS, int OS, bool STREAM = false>
 __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* vcol, double* sh_tau, int* ready, int cc,
-                                                 int lane, int wid, int bwc) {
+                                                 int lane, int wid, int bwc, int nvi = RPL, int tauoff = 0) {
   constexpr int NL = NS - 1 - OS;   // later own columns
   double v[RPL];
 #ifdef TTB_PANEL_FINE
@@ -150,13 +151,13 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
 #pragma unroll
   for (int i = 1; i < RPL; ++i) {
     v[i] = x[i] * scal;
-    vcol[lane + 32 * i] = v[i];
+    if (!STREAM || i < nvi) vcol[lane + 32 * i] = v[i];
   }
   // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared stores of
   // one warp are performed in order and the flag is the last store instruction.
   sh_tau[cc] = tau;
-  if (TAUPOS >= 0) {
-    vcol[TAUPOS] = tau;
+  if (STREAM) {
+    vcol[tauoff] = tau;
     fence_proxy_async();   // writer-side proxy fence: the reflector leaves through a bulk (async-proxy) copy
   }
   __syncwarp();

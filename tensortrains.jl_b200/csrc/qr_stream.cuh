@@ -18,8 +18,9 @@
 // credit based: ring slot w of a consumer CTA belongs to its warp w, which re-arms the slot's mbarrier
 // (expect_tx) as soon as every warp of the CTA is done with the previous occupant and then releases a
 // credit (one remote store) into the producing CTA; the pusher never blocks on credits except in its final
-// flush.  Slots are in ABSOLUTE row order (zeros above the producing panel, 8 doubles of header with tau),
-// so the consumer's register rotation turns into two contiguous runs with immediate offsets.
+// flush.  Slots are in ABSOLUTE row order (zeros above the producing panel, tau behind the last row), so
+// the consumer's register rotation turns into two contiguous runs with immediate offsets, and reflector
+// + tau are one contiguous copy on the producer's side.
 //
 // Row mapping: CTA k keeps absolute row ((i + k) mod RPL) * 32 + lane in register i, so that in its own
 // factor phase register 0 holds the panel's diagonal rows -- the mapping qr_panel.cuh assumes.  Rows above
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
   pdl_enter();
   constexpr int NS = 4;
   constexpr int LDV = 32 * RPL;
-  constexpr int SL = LDV + 8;           // slot stride; own panel: tau at [LDV]; ring: header [tau, .] at [0], rows at [8 ..)
+  constexpr int SL = LDV + 8;           // slot stride; own panel: relative rows, tau right behind the valid ones;
+                                        // ring: absolute rows (zeros above the producing panel), tau at [LDV]
   const int b = blockIdx.y, kb = blockIdx.x;   // kb == rank in the cluster (cluster = one row of the grid)
   const int nblk = gridDim.x;
   const Dims d = get_dims(c, s, b);     // exact (host-known) dimensions
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
   const int bwc = min(32, n - j0);      // columns of this block (p >= n: all of them are factored)
   const int nremote = j0;               // reflectors of the earlier panels
   const int rows = d.p - j0;
+  const int nvi = RPL - kb;             // 32-row groups at or below the panel's first row
   double* Xa = xbuf(c, s.xin, b);
   double* Xp = Xa + j0 + p * j0;        // panel origin
   extern __shared__ __align__(16) double dyn[];
@@ -110,10 +113,10 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       const int kprod = my_next >> 5;
       double* slotp = ring + (size_t)wid * SL;
       // first use of the slot for this producing panel: the previous panel's rows just above it become zeros
-      if (kprod > 0 && (my_next & 31) < kQsRing) slotp[8 + 32 * (kprod - 1) + lane] = 0.0;
+      if (kprod > 0 && (my_next & 31) < kQsRing) slotp[32 * (kprod - 1) + lane] = 0.0;
       __syncwarp();
       if (lane == 0) {
-        mbar_expect_tx(&bars[wid], (uint32_t)((LDV - 32 * kprod) * 8 + 16));
+        mbar_expect_tx(&bars[wid], (uint32_t)((LDV - 32 * kprod + 2) * 8));
         st_remote_release_s32(mapa_u32(smem_u32(&credit[kb * kQsRing + wid]), (uint32_t)kprod), my_next + 1);
       }
       __syncwarp();
@@ -130,8 +133,8 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       }
       // register i holds row group (i + kb) mod RPL => two contiguous runs, immediate offsets
       const double* vsl = ring + (size_t)slot * SL;
-      const double tau = vsl[0];
-      const double* pA = vsl + 8 + 32 * kb + lane;
+      const double tau = vsl[LDV];
+      const double* pA = vsl + 32 * kb + lane;
       const double* pB = pA - LDV;
       double v[RPL];
 #pragma unroll
@@ -182,8 +185,7 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
         const uint32_t bar_r = bars_r + (uint32_t)slot * 8u;
         const uint32_t dst_r = ring_r + (uint32_t)(slot * SL * 8);
         const double* src = vs + (size_t)np * SL;
-        bulk_s2remote(dst_r + (uint32_t)((8 + j0) * 8), src, (uint32_t)((LDV - j0) * 8), bar_r);   // rows j0.. of the slot
-        bulk_s2remote(dst_r, src + LDV, 16u, bar_r);                                                // header [tau, .]
+        bulk_s2remote(dst_r + (uint32_t)(j0 * 8), src, (uint32_t)((LDV - j0 + 2) * 8), bar_r);   // rows j0..LDV of the slot, then tau
         ++np;
       }
     }
@@ -193,10 +195,10 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
   for (int blk = 0; blk * NS < bwc; ++blk) {
     const int c0 = blk * NS;
     if (wid == blk) {
-      panel_owner_step<RPL, NS, 0, LDV>(a, vs + (size_t)c0 * SL, sh_tau, ready, c0, lane, wid, bwc);
-      if (c0 + 1 < bwc) panel_owner_step<RPL, NS, 1, LDV>(a, vs + (size_t)(c0 + 1) * SL, sh_tau, ready, c0 + 1, lane, wid, bwc);
-      if (c0 + 2 < bwc) panel_owner_step<RPL, NS, 2, LDV>(a, vs + (size_t)(c0 + 2) * SL, sh_tau, ready, c0 + 2, lane, wid, bwc);
-      if (c0 + 3 < bwc) panel_owner_step<RPL, NS, 3, LDV>(a, vs + (size_t)(c0 + 3) * SL, sh_tau, ready, c0 + 3, lane, wid, bwc);
+      panel_owner_step<RPL, NS, 0, true>(a, vs + (size_t)c0 * SL, sh_tau, ready, c0, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 1 < bwc) panel_owner_step<RPL, NS, 1, true>(a, vs + (size_t)(c0 + 1) * SL, sh_tau, ready, c0 + 1, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 2 < bwc) panel_owner_step<RPL, NS, 2, true>(a, vs + (size_t)(c0 + 2) * SL, sh_tau, ready, c0 + 2, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 3 < bwc) panel_owner_step<RPL, NS, 3, true>(a, vs + (size_t)(c0 + 3) * SL, sh_tau, ready, c0 + 3, lane, wid, bwc, nvi, LDV - j0);
       if (s.trace && b == 0 && lane == 0) g_qs_trace[kb * 32 + 22 + blk] = qs_now();
       if (wid == 0) pump(min(c0 + NS, bwc));   // warp 0's own block: its reflectors leave once the block is done
       panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
         const double* vcol = vs + (size_t)cc * SL;
         double v[RPL];
 #pragma unroll
-        for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
+        for (int i = 0; i < RPL; ++i) v[i] = i < nvi ? vcol[lane + 32 * i] : 0.0;   // behind the valid groups sits tau
         double dot[NS];
 #pragma unroll
         for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
