@@ -57,10 +57,22 @@ def qr_sweep_flops(bonds, Q, bw=32):
     Factor 2 m^2 (n - m/3) split into panel + trailing update, thin-Q formation, absorb 2 a m m' Q."""
     L = len(bonds) - 1
     b = list(bonds)
-    out = {"k_qr_panel": [0, 0.0], "k_qr_update": [0, 0.0], "k_apply_q": [0, 0.0], "k_absorb": [0, 0.0]}
+    out = {"k_qr_panel": [0, 0.0], "k_qr_update": [0, 0.0], "k_apply_q": [0, 0.0], "k_absorb": [0, 0.0],
+           "k_qr_stream": [0, 0.0]}
     for t in range(L - 1, 0, -1):
         p, n, a = b[t + 1] * Q, b[t], b[t - 1]
         k = min(p, n)
+        nblk = (n + 31) // 32
+        if p >= n and 2 <= nblk <= 8 and p <= 512:
+            # the whole site QR is ONE cluster kernel (qr_stream.cuh): panels + trailing updates
+            out["k_qr_stream"][0] += 1
+            out["k_qr_stream"][1] += 2.0 * k * k * (p - k / 3.0)
+            out["k_apply_q"][0] += 1
+            out["k_apply_q"][1] += 2.0 * k * k * (p - k / 3.0)
+            out["k_absorb"][0] += 1
+            out["k_absorb"][1] += 2.0 * a * n * k * Q
+            b[t] = k
+            continue
         for j0 in range(0, k, bw):
             bwc, rows = min(bw, k - j0), p - j0
             out["k_qr_panel"][0] += 1
@@ -335,7 +347,7 @@ def main():
         achieved = alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture
         # (profiles/r1_ncu_full_sweep_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum)
-        ncu_traffic = {"k_qr_panel_flag": 156672 + 0}
+        ncu_traffic = {"k_qr_panel_flag": 156672 + 0, "k_qr_stream": 1119232 + 0}
         line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": ncu_traffic.get(dom),
                             "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
@@ -343,9 +355,11 @@ def main():
                             "share_of_step": ms / tot_ms if tot_ms else None,
                             "flops_per_launch": per_launch, "launches": n_l, "working_launches": n_alg,
                             "ms_per_launch": ms / n_l,
-                            "note": "one CTA per panel: a chain of 32 dependent Householder columns, latency bound by "
-                                    "construction (profiles/r1_micro_panel.txt); achieved = algorithmic panel FLOPs / "
-                                    "CUDA-event time of all launches of the class",
+                            "note": "k_qr_stream = the whole Householder QR of one site (512 x 256) as one 8-CTA cluster: 256 "
+                                    "chained columns, dependency-latency bound by construction (profiles/r1_micro_panel.txt, "
+                                    "r1_ncu_panel_warpstates.txt); achieved = algorithmic QR FLOPs 2k^2(p-k/3) / CUDA-event "
+                                    "time of all launches of the class; traffic = dram bytes of one launch "
+                                    "(profiles/r1_ncu_full_qr_stream.csv: the 1.05 MB site read once, writes absorbed by L2)",
                             "kernels": {k: {"launches": v[0], "ms": v[1],
                                             "alg_gflop": fl.get(alias.get(k, k), [0, 0.0])[1] / 1e9}
                                         for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
