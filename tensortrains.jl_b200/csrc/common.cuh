@@ -38,6 +38,7 @@ struct StepState {
   int p[2], n[2], N[2];              // dimensions of the step, snapshotted from the bond array
   double scale_in[2];                // lazy rescale: factor the step applies to its input X (1/max|D| of the previous step)
   int rot[2];                        // cluster Jacobi: rotations of the sweep in flight (ping-pong), all CTAs
+  int ticket;                        // absorb: CTAs of the train that have finished (the last one commits the step)
 };
 
 // grow-only device scratch kept on the handle between calls (cudaFree of a few hundred MB costs up to

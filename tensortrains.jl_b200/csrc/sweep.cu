@@ -630,6 +630,29 @@ namespace ttb {
 // absorb: Xn[(a + m'x), j] = sum_l S(a,l) * Nbr_x(l,j)   (src/tensor_train.jl:168 / :207)
 // plus max|D| for the rescale (:169-173 / :208-212).  FP64 tile GEMM, 64x64 tile, 4x4 per thread.
 // ---------------------------------------------------------------------------------------------
+// commit the step for one train: z /= m, bond <- m', stats, reset the other maxabs slot, next step's
+// snapshot and pending scale, rank feedback for the host
+__device__ __forceinline__ void commit_train(const SweepCtx& c, const StepDesc& s, int b, int batch) {
+  int* bond = c.bond + (int64_t)b * c.L1;
+  const int mp = c.st[b].mprime[s.slot];
+  // L2 read: the other CTAs' atomicMax results; this CTA's L1 may hold the line from its dimension loads
+  const double m = __longlong_as_double((long long)__ldcg(&c.st[b].maxabs_bits[s.slot]));
+  const bool bad = (m != m) || isinf(m);
+  if (s.rescale && !bad && m != 0.0) c.logz[b] -= log(m);
+  if (s.rescale && bad) atomicOr(c.status, ST_NONFINITE);
+  c.st[b].maxabs_bits[s.slot ^ 1] = 0ull;
+  c.st[b].scale_in[s.slot ^ 1] = (s.rescale && !bad && m != 0.0 && !s.last) ? 1.0 / m : 1.0;
+  c.stat_rank[(int64_t)b * c.L1 + s.bond_idx] = mp;
+  if (s.qr_only) c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = 0.0;
+  bond[s.bond_idx] = mp;
+  if (s.bond_idx2 >= 0) bond[s.bond_idx2] = mp;
+  if (s.next_site >= 0) snapshot_dims(c, b, s.dir, s.next_site, s.next_nbr, s.slot ^ 1);
+  if (s.hint_slot >= 0) {
+    c.hint[(int64_t)s.hint_slot * batch + b] = mp;
+    __threadfence_system();
+  }
+}
+
 // DMMA variant: 32x32 output tile per CTA (4 warps, each 16x16 = two m16n8k8 FP64 tensor-core tiles),
 // K staged 32 at a time through shared memory with register prefetch of the next stage.
 #define AM_T 32
@@ -641,7 +664,7 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   const Dims d = get_dims(c, s, b);
   const int mprime = c.st[b].mprime[s.slot];
   const int i0 = blockIdx.x * AM_T, j0 = blockIdx.y * AM_T;
-  if (i0 >= mprime || j0 >= d.N) return;
+  const bool active = !(i0 >= mprime || j0 >= d.N);   // surplus CTAs still take a ticket below
   const int n = d.n, N = d.N;
   const int64_t p = d.p;
   const double* X = xbuf(c, s.xin, b);
@@ -655,94 +678,226 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = (wid & 1) * 16, wn = (wid >> 1) * 16;
-  double acc[2][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
-  double rs[8], rb[8];  // prefetch registers: 1024 elements / 128 threads
-  auto fetch = [&](int l0) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = tid + 128 * u;
-      int ii, ll;
-      if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
-      else { ll = i % AM_K; ii = i / AM_K; }
-      const int gi = i0 + ii, gl = l0 + ll;
+  if (active) {
+    double acc[2][4];
+  #pragma unroll
+    for (int a = 0; a < 2; ++a)
+  #pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
+    double rs[8], rb[8];  // prefetch registers: 1024 elements / 128 threads
+    auto fetch = [&](int l0) {
+  #pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + 128 * u;
+        int ii, ll;
+        if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
+        else { ll = i % AM_K; ii = i / AM_K; }
+        const int gi = i0 + ii, gl = l0 + ll;
+        double v = 0.0;
+        if (gi < mprime && gl < n) {
+          if (d.mode == 0) v = gi <= gl ? X[gi + p * gl] * scale_in : 0.0;
+          else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
+        }
+        rs[u] = v;
+        int l2, jj;
+        if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
+        else { jj = i % AM_T; l2 = i / AM_T; }
+        const int gl2 = l0 + l2, gj = j0 + jj;
+        double w = 0.0;
+        if (gl2 < n && gj < N)
+          w = s.dir == 1 ? nbr[gl2 + (int64_t)n * (gj + (int64_t)N * x)] : nbr[gj + (int64_t)N * (gl2 + (int64_t)n * x)];
+        rb[u] = w;
+      }
+    };
+    auto stash = [&]() {
+  #pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = tid + 128 * u;
+        int ii, ll;
+        if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
+        else { ll = i % AM_K; ii = i / AM_K; }
+        Ss[ll][ii] = rs[u];
+        int l2, jj;
+        if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
+        else { jj = i % AM_T; l2 = i / AM_T; }
+        Bs[l2][jj] = rb[u];
+      }
+    };
+    // mode 0: S is upper triangular -> K range starts at the tile's first row
+    const int lstart = (d.mode == 0) ? (i0 / AM_K) * AM_K : 0;
+    fetch(lstart);
+    for (int l0 = lstart; l0 < n; l0 += AM_K) {
+      __syncthreads();
+      stash();
+      __syncthreads();
+      if (l0 + AM_K < n) fetch(l0 + AM_K);
+  #pragma unroll
+      for (int kk = 0; kk < AM_K; kk += 8) {
+        double af[4];
+        af[0] = Ss[kk + t4][wm + g];
+        af[1] = Ss[kk + t4][wm + g + 8];
+        af[2] = Ss[kk + t4 + 4][wm + g];
+        af[3] = Ss[kk + t4 + 4][wm + g + 8];
+  #pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          double bf[2];
+          bf[0] = Bs[kk + t4][wn + nt * 8 + g];
+          bf[1] = Bs[kk + t4 + 4][wn + nt * 8 + g];
+          dmma_16x8x8(acc[nt], af, bf);
+        }
+      }
+    }
+    const int64_t ldo = (int64_t)mprime * c.Q;
+    double mx = 0.0;
+  #pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+  #pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gi = i0 + wm + g + ((e & 2) ? 8 : 0);
+        const int gj = j0 + wn + nt * 8 + t4 * 2 + (e & 1);
+        if (gi < mprime && gj < N) {
+          Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[nt][e];
+          mx = absmax_nan(mx, acc[nt][e]);
+        }
+      }
+    unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+  #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+      bits = other > bits ? other : bits;
+    }
+    if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
+  }
+  // the last CTA of the train to finish commits the step (z /= m, bond <- m', next step's snapshot and
+  // scale, rank feedback): one kernel launch and one dependent-launch gap less per site step
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int total = (int)(gridDim.x * gridDim.y) * c.Q;
+    if (atomicAdd(&c.st[b].ticket, 1) == total - 1) {
+      __threadfence();
+      c.st[b].ticket = 0;
+      commit_train(c, s, b, (int)gridDim.z / c.Q);
+    }
+  }
+}
+
+// Skinny absorb (m' <= 32 retained directions: every step of a truncating sweep once the bonds are small).
+// The tiled kernel above walks K in 8 synchronised stages per CTA and has only a handful of CTAs to run:
+// ~16 us of pure latency for 4 MFLOP.  Here one CTA owns 8 output columns, loads ALL of S (m' x n) and its
+// n x 8 neighbour tile in one shot (every load in flight at once), the four warps split K for the DMMAs and
+// are summed through shared memory.
+#define AS_TN 8
+__host__ __device__ inline int as_ld(int n) { return ((n + 15) & ~15) + 4; }   // = 4 (mod 16): conflict-free fragments
+__global__ void __launch_bounds__(128) k_absorb_skinny(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime[s.slot];   // host guarantees <= 32
+  const int j0 = blockIdx.y * AS_TN;
+  const bool active = j0 < d.N;
+  const int n = d.n, N = d.N;
+  const int64_t p = d.p;
+  const int ld = as_ld(n);
+  extern __shared__ double smk[];
+  double* Ss = smk;                 // [32][ld]
+  double* Bs = Ss + 32 * ld;        // [AS_TN][ld]
+  double* red = Bs + AS_TN * ld;    // [4 warps][2][32 lanes][4]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (active) {
+    const double* X = xbuf(c, s.xin, b);
+    const double* Bv = c.Bv + (int64_t)b * c.bv_stride;
+    const int* perm = c.perm + (int64_t)b * c.n_max;
+    const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+    const double scale_in = c.st[b].scale_in[s.slot];
+    const int mt_n = (mprime + 15) >> 4;   // 16-row tiles in use
+    for (int idx = tid; idx < 16 * mt_n * ld; idx += 128) {
+      const int i = idx / ld, l = idx - i * ld;
       double v = 0.0;
-      if (gi < mprime && gl < n) {
-        if (d.mode == 0) v = gi <= gl ? X[gi + p * gl] * scale_in : 0.0;
-        else v = Bv[(int64_t)perm[gi] * c.ldv + gl];
+      if (i < mprime && l < n) {
+        if (d.mode == 0) v = i <= l ? X[i + p * l] * scale_in : 0.0;
+        else v = Bv[(int64_t)perm[i] * c.ldv + l];
       }
-      rs[u] = v;
-      int l2, jj;
-      if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
-      else { jj = i % AM_T; l2 = i / AM_T; }
-      const int gl2 = l0 + l2, gj = j0 + jj;
-      double w = 0.0;
-      if (gl2 < n && gj < N)
-        w = s.dir == 1 ? nbr[gl2 + (int64_t)n * (gj + (int64_t)N * x)] : nbr[gj + (int64_t)N * (gl2 + (int64_t)n * x)];
-      rb[u] = w;
+      Ss[idx] = v;
     }
-  };
-  auto stash = [&]() {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = tid + 128 * u;
-      int ii, ll;
-      if (d.mode == 0) { ii = i % AM_T; ll = i / AM_T; }
-      else { ll = i % AM_K; ii = i / AM_K; }
-      Ss[ll][ii] = rs[u];
-      int l2, jj;
-      if (s.dir == 1) { l2 = i % AM_K; jj = i / AM_K; }
-      else { jj = i % AM_T; l2 = i / AM_T; }
-      Bs[l2][jj] = rb[u];
-    }
-  };
-  // mode 0: S is upper triangular -> K range starts at the tile's first row
-  const int lstart = (d.mode == 0) ? (i0 / AM_K) * AM_K : 0;
-  fetch(lstart);
-  for (int l0 = lstart; l0 < n; l0 += AM_K) {
-    __syncthreads();
-    stash();
-    __syncthreads();
-    if (l0 + AM_K < n) fetch(l0 + AM_K);
-#pragma unroll
-    for (int kk = 0; kk < AM_K; kk += 8) {
-      double af[4];
-      af[0] = Ss[kk + t4][wm + g];
-      af[1] = Ss[kk + t4][wm + g + 8];
-      af[2] = Ss[kk + t4 + 4][wm + g];
-      af[3] = Ss[kk + t4 + 4][wm + g + 8];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        double bf[2];
-        bf[0] = Bs[kk + t4][wn + nt * 8 + g];
-        bf[1] = Bs[kk + t4 + 4][wn + nt * 8 + g];
-        dmma_16x8x8(acc[nt], af, bf);
+    if (s.dir == 1) {
+      for (int idx = tid; idx < AS_TN * ld; idx += 128) {
+        const int jj = idx / ld, l = idx - jj * ld;
+        const int gj = j0 + jj;
+        Bs[idx] = (gj < N && l < n) ? nbr[l + (int64_t)n * (gj + (int64_t)N * x)] : 0.0;
       }
+    } else {
+      for (int idx = tid; idx < AS_TN * ld; idx += 128) {
+        const int jj = idx % AS_TN, l = idx / AS_TN;
+        const int gj = j0 + jj;
+        Bs[jj * ld + l] = (gj < N && l < n) ? nbr[gj + (int64_t)N * (l + (int64_t)n * x)] : 0.0;
+      }
+    }
+    __syncthreads();
+    const int g = lane >> 2, t4 = lane & 3;
+    double acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][e] = 0.0;
+    for (int kk = 8 * wid; kk < n; kk += 32) {
+      double bf[2];
+      bf[0] = Bs[g * ld + kk + t4];
+      bf[1] = Bs[g * ld + kk + t4 + 4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < mt_n) {
+          double af[4];
+          af[0] = Ss[(mt * 16 + g) * ld + kk + t4];
+          af[1] = Ss[(mt * 16 + g + 8) * ld + kk + t4];
+          af[2] = Ss[(mt * 16 + g) * ld + kk + t4 + 4];
+          af[3] = Ss[(mt * 16 + g + 8) * ld + kk + t4 + 4];
+          dmma_16x8x8(acc[mt], af, bf);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[((wid * 2 + mt) * 32 + lane) * 4 + e] = acc[mt][e];
+    __syncthreads();
+    if (wid == 0) {
+      double* Xn = xbuf(c, s.xin ^ 1, b);
+      const int64_t ldo = (int64_t)mprime * c.Q;
+      double mx = 0.0;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double v = 0.0;
+#pragma unroll
+          for (int w2 = 0; w2 < 4; ++w2) v += red[((w2 * 2 + mt) * 32 + lane) * 4 + e];
+          const int gi = mt * 16 + g + ((e & 2) ? 8 : 0);
+          const int gj = j0 + t4 * 2 + (e & 1);
+          if (gi < mprime && gj < N) {
+            Xn[(gi + (int64_t)mprime * x) + ldo * gj] = v;
+            mx = absmax_nan(mx, v);
+          }
+        }
+      unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+      }
+      if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
     }
   }
-  const int64_t ldo = (int64_t)mprime * c.Q;
-  double mx = 0.0;
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int gi = i0 + wm + g + ((e & 2) ? 8 : 0);
-      const int gj = j0 + wn + nt * 8 + t4 * 2 + (e & 1);
-      if (gi < mprime && gj < N) {
-        Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[nt][e];
-        mx = absmax_nan(mx, acc[nt][e]);
-      }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int total = (int)(gridDim.x * gridDim.y) * c.Q;
+    if (atomicAdd(&c.st[b].ticket, 1) == total - 1) {
+      __threadfence();
+      c.st[b].ticket = 0;
+      commit_train(c, s, b, (int)gridDim.z / c.Q);
     }
-  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
-    bits = other > bits ? other : bits;
   }
-  if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
 }
 
 // Rescale of the absorb output (src/tensor_train.jl:169-173 / :208-212).  Between steps it is LAZY: the
@@ -780,36 +935,13 @@ __global__ void k_rescale(SweepCtx c, StepDesc s) {
   }
 }
 
-// commit the step (one thread per train): z /= m, bond <- m', stats, reset the other maxabs slot
-__global__ void k_commit(SweepCtx c, StepDesc s, int batch) {
-  pdl_enter();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  int* bond = c.bond + (int64_t)b * c.L1;
-  const int mp = c.st[b].mprime[s.slot];
-  const double m = __longlong_as_double((long long)c.st[b].maxabs_bits[s.slot]);
-  const bool bad = (m != m) || isinf(m);
-  if (s.rescale && !bad && m != 0.0) c.logz[b] -= log(m);
-  if (s.rescale && bad) atomicOr(c.status, ST_NONFINITE);
-  c.st[b].maxabs_bits[s.slot ^ 1] = 0ull;
-  c.st[b].scale_in[s.slot ^ 1] = (s.rescale && !bad && m != 0.0 && !s.last) ? 1.0 / m : 1.0;
-  c.stat_rank[(int64_t)b * c.L1 + s.bond_idx] = mp;
-  if (s.qr_only) c.stat_err[(int64_t)b * c.L1 + s.bond_idx] = 0.0;
-  bond[s.bond_idx] = mp;
-  if (s.bond_idx2 >= 0) bond[s.bond_idx2] = mp;
-  if (s.next_site >= 0) snapshot_dims(c, b, s.dir, s.next_site, s.next_nbr, s.slot ^ 1);
-  if (s.hint_slot >= 0) {
-    c.hint[(int64_t)s.hint_slot * batch + b] = mp;
-    __threadfence_system();
-  }
-}
-
 __global__ void k_reset_state(StepState* st, double* stat_err, int* stat_rank, int batch, int L1) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch) {
     st[i].mprime[0] = st[i].mprime[1] = 1; st[i].maxabs_bits[0] = 0ull; st[i].maxabs_bits[1] = 0ull;
     st[i].scale_in[0] = st[i].scale_in[1] = 1.0;
+    st[i].ticket = 0;
   }
   if (i < batch * L1) { stat_err[i] = 0.0; stat_rank[i] = 0; }
 }
@@ -878,6 +1010,7 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(k_absorb_skinny, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1038,10 +1171,12 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       s.trace = (trace_env && atoi(trace_env) == hs.site) ? 1 : 0;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(nblk, B); cfg.blockDim = dim3(kQsThreads); cfg.dynamicSmemBytes = qs_smem_bytes(rpl); cfg.stream = st;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = nblk; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = (use_pdl && !hard_dep) ? 2 : 1;
       if (rpl == 2) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<2>, c, s));
       else if (rpl == 4) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<4>, c, s));
       else if (rpl == 8) TTB_LAUNCH(h, "k_qr_stream", cudaLaunchKernelEx(&cfg, k_qr_stream<8>, c, s));
@@ -1147,14 +1282,21 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       }
     }
     {
-      dim3 g((mp_ub + AM_T - 1) / AM_T, (N_ub + AM_T - 1) / AM_T, Q * B);
-      SW_LAUNCH("k_absorb_mma", k_absorb_mma, g, 128, 0, c, s);
+      const size_t sk_smem = sizeof(double) * ((size_t)(32 + AS_TN) * as_ld(n_ub) + 4 * 2 * 32 * 4);
+      // (a batch that already fills the GPU is better off with the small-footprint tiled kernel)
+      if (mp_ub <= 32 && sk_smem <= (size_t)200 * 1024 && (int64_t)B * Q * ((N_ub + AS_TN - 1) / AS_TN) <= 2 * (int64_t)sm_count &&
+          getenv("TTB_ABSORB_TILED") == nullptr) {
+        dim3 g(1, (N_ub + AS_TN - 1) / AS_TN, Q * B);
+        SW_LAUNCH("k_absorb_mma", k_absorb_skinny, g, 128, sk_smem, c, s);
+      } else {
+        dim3 g((mp_ub + AM_T - 1) / AM_T, (N_ub + AM_T - 1) / AM_T, Q * B);
+        SW_LAUNCH("k_absorb_mma", k_absorb_mma, g, 128, 0, c, s);
+      }
     }
     {
       const int64_t tot = (int64_t)mp_ub * Q * N_ub;
       dim3 g((unsigned)std::min<int64_t>((tot + 1023) / 1024, 1024), B);
       if (hs.last) SW_LAUNCH("k_rescale", k_rescale, g, 256, 0, c, s);
-      SW_LAUNCH("k_commit", k_commit, (B + 127) / 128, 128, 0, c, s, B);
       if (feedback) cudaEventRecord(h->ev_hint[s.hint_slot], st);
     }
     const int mp_lb = qr_only ? std::min(p_lb, n_lb) : 1;
