@@ -583,3 +583,27 @@ def test_async_upload_and_reset_reuse_handle():
     H.reset()
     H.upload_all(pin.array, async_=True)
     assert np.allclose(T.evaluate(H, X), T.evaluate(T.TensorTrain(ts), X), rtol=1e-13)
+
+
+@pytest.mark.parametrize("d,q", [(33, 2), (64, 2), (65, 3), (100, 2), (130, 3), (255, 2), (170, 3)])
+def test_eps0_sweeps_odd_sizes(d, q):
+    """eps = 0 sweeps over bond sizes that are not multiples of the 32-column panel / 32-row register group
+    (single-cluster QR with a partial last block, the panel/update path beyond 8 blocks or 512 rows, the
+    shared-memory fallbacks): gauge invariance, canonical form, exact bond dimensions."""
+    rng = RNG(1000 + d)
+    L = 6
+    bonds = [1, min(q, d), d, d, min(q * q, d), min(q, d), 1]
+    ts = rand_open(rng, bonds, (q,), "randn")
+    A, Ao = pair(ts)
+    X = rand_points(rng, Ao, 8)
+    e0 = np.array([o_eval_flat(Ao, X[i]) for i in range(X.shape[0])])
+    T.orthogonalize_right_(A, T.TruncThresh(0.0))
+    g = T.evaluate(A, X)
+    assert np.max(np.abs(g - e0)) <= 1e-10 * np.max(np.abs(e0))
+    assert all(T.is_right_canonical(A, t, atol=1e-10) for t in range(1, L))
+    O.orthogonalize_right(Ao, O.TruncThresh(0.0))
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    T.orthogonalize_left_(A, T.TruncThresh(0.0))
+    g = T.evaluate(A, X)
+    assert np.max(np.abs(g - e0)) <= 1e-10 * np.max(np.abs(e0))
+    assert all(T.is_left_canonical(A, t, atol=1e-10) for t in range(0, L - 1))
