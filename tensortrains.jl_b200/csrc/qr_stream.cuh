@@ -50,7 +50,6 @@ __device__ __forceinline__ unsigned long long qs_now() {
 
 template <int RPL>
 __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDesc s) {
-  pdl_enter();
   constexpr int NS = 4;
   constexpr int LDV = 32 * RPL;
   constexpr int SL = LDV + 8;           // slot stride; own panel: relative rows, tau right behind the valid ones;
@@ -84,6 +83,9 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
     for (int r = 0; r < kQsRing; ++r) mbar_init(&bars[r], 1);
   __syncthreads();
   cluster_sync_all();             // every CTA's barriers / credits exist before anybody pushes or releases credits
+  // everything above touched only this CTA's shared memory (the dimensions came with the launch): with
+  // programmatic dependent launch it overlaps the tail of the previous kernel; global memory from here on
+  pdl_enter();
   const bool trace = s.trace && b == 0 && tid == 0;
   if (trace) g_qs_trace[kb * 32 + 0] = qs_now();
 

@@ -323,7 +323,7 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     const int DP = dmax <= 32 ? 32 : (dmax <= 64 ? 64 : 128);
     const size_t tile_smem = sizeof(double) * ((size_t)(ST_SMAX + 1) * (DP + 4) + 2 * (size_t)Q * DP * 8 + (size_t)DP * 8 +
                                                ST_SMAX * 10) +
-                             sizeof(int) * (ST_SMAX + ST_MAXTILES * 17 + 4) + sizeof(unsigned) * (size_t)L * Q + 64;
+                             sizeof(int) * (ST_SMAX + ST_MAXTILES * 17 + 4 + 8 + ST_SMAX) + sizeof(unsigned) * (size_t)L * Q + 64;
     const bool tiled = !h->periodic && rmax == 1 && dmax <= 128 && Q <= 8 && nsamples >= 32 && tile_smem <= 200 * 1024 &&
                        getenv("TTB_SAMPLE_GENERIC") == nullptr;
     double *d_Ap = nullptr, *d_Gp = nullptr;

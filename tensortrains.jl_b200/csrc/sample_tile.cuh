@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_sample_tile(TileCtx c) {
   int* order = xsel + ST_SMAX;                       // MAXTILES*16 positions -> slot (or SMAX = zero row)
   int* tile_x = order + ST_MAXTILES * 16;            // MAXTILES
   int* misc = tile_x + ST_MAXTILES;                  // [0] = ntiles
-  unsigned int* hsm = reinterpret_cast<unsigned int*>(misc + 4);  // L*Q histogram (stats mode)
+  int* cnt_s = misc + 4;                             // [8] draws per value at this site
+  int* rank_s = cnt_s + 8;                           // SMAX: arrival rank of the slot inside its value group
+  unsigned int* hsm = reinterpret_cast<unsigned int*>(rank_s + ST_SMAX);  // L*Q histogram (stats mode)
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_sample_tile(TileCtx c) {
       Qs[i] = (k == 0 && r < nact) ? 1.0 : 0.0;
     }
     for (int i = tid; i < ST_SMAX; i += ST_THREADS) lp[i] = 0.0;
+    for (int i = tid; i < ST_MAXTILES * 16; i += ST_THREADS) order[i] = ST_SMAX;   // zero row
+    if (tid < 8) cnt_s[tid] = 0;
     __syncthreads();
 
     for (int t = 0; t < c.L; ++t) {
@@ -132,50 +136,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_sample_tile(TileCtx c) {
             lp[sl] += log(px / tot);
             if (c.x_out) c.x_out[(s0 + sl) * c.L + t] = (uint8_t)xs;
             if (c.hist) atomicAdd(&hsm[t * Q + xs], 1u);
+            rank_s[sl] = atomicAdd(&cnt_s[xs], 1);   // position inside the value group: any order will do
           }
           xsel[sl] = xs;
         }
       }
       __syncthreads();
-      // ---- counting sort by x into x-pure tiles of 16 positions (warp 0) ----
-      if (wid == 0) {
-        int cnt[8];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) cnt[x] = 0;
-        for (int pass = 0; pass < ST_SMAX / 32; ++pass) {
-          const int xv = xsel[pass * 32 + lane];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) cnt[x] += __popc(__ballot_sync(0xffffffffu, xv == x));
-        }
-        int start[8];
-        int pos = 0, nt_ = 0;
+      // ---- counting sort by x into x-pure tiles of 16 positions: the draw left the group sizes in cnt_s and
+      //      every slot's rank inside its group, so each thread places its slot itself (no serial pass) ----
+      int ntiles;
+      {
+        int start[8], pos = 0;
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
           start[x] = pos;
-          const int tl = (x < Q) ? (cnt[x] + 15) / 16 : 0;
-          for (int i = 0; i < tl; ++i) if (lane == 0) tile_x[nt_ + i] = x;
-          nt_ += tl;
-          pos += tl * 16;
+          pos += (x < Q) ? ((cnt_s[x] + 15) >> 4) << 4 : 0;
         }
-        for (int i = lane; i < ST_MAXTILES * 16; i += 32) order[i] = ST_SMAX;  // zero row
-        __syncwarp();
-        int base[8];
+        ntiles = pos >> 4;
+        if (tid < ST_SMAX) {
+          const int xv = xsel[tid];
+          if (xv < Q) {
+            int st = 0;
 #pragma unroll
-        for (int x = 0; x < 8; ++x) base[x] = start[x];
-        for (int pass = 0; pass < ST_SMAX / 32; ++pass) {
-          const int sl = pass * 32 + lane;
-          const int xv = xsel[sl];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            const unsigned m = __ballot_sync(0xffffffffu, xv == x);
-            if (xv == x) order[base[x] + __popc(m & ((1u << lane) - 1u))] = sl;
-            base[x] += __popc(m);
+            for (int x = 0; x < 8; ++x) st = (x == xv) ? start[x] : st;
+            order[st + rank_s[tid]] = tid;
           }
         }
-        if (lane == 0) misc[0] = nt_;
+        if (tid < ntiles) {
+          int tx = 0;
+#pragma unroll
+          for (int x = 1; x < 8; ++x) tx += (x < Q && tid * 16 >= start[x]) ? 1 : 0;   // start[] is non-decreasing
+          tile_x[tid] = tx;
+        }
       }
       __syncthreads();
-      const int ntiles = misc[0];
       const int rounds = (ntiles + 7) / 8;
       // ---- q_s <- q_s A_t(x_s) * scale_s : one x-pure 16 x DP tile per warp and round ----
       for (int rd = 0; rd < rounds; ++rd) {
@@ -242,6 +236,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_sample_tile(TileCtx c) {
         }
       }
       __syncthreads();
+      // next site's sort starts from an all-padding order and empty groups
+      for (int i = tid; i < ST_MAXTILES * 16; i += ST_THREADS) order[i] = ST_SMAX;
+      if (tid < 8) cnt_s[tid] = 0;
     }
     // ---- results of this batch ----
     for (int sl = tid; sl < nact; sl += ST_THREADS) {
