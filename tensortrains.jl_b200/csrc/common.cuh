@@ -60,6 +60,7 @@ struct DevBuf {
 struct Workspace {
   DevBuf samp[10];                    // sampler scratch (offsets, G, uniforms, x, p, hist, sum log p, packed A, packed G)
   DevBuf scr[6];                      // twovar_marginals (pair offsets, out, scratch, GT, Tm) and dot scratch
+  DevBuf scr_trace, scr_toff;         // two-phase environment pass: per-site traces and their offset table
   // sweep
   double* X[2] = {nullptr, nullptr};  // folded site / absorb output, p_max x n_max col-major
   int64_t x_stride = 0;

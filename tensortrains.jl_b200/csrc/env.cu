@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma_mma.cuh"
 
 namespace ttb {
 
@@ -525,11 +526,18 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
     const int L = (int)h->L;
     std::vector<int64_t> toff(L + 1, 0);
     for (int t = 0; t < L; ++t) toff[t + 1] = toff[t] + ((h->bond0[t] * h->bond0[t + 1] + 15) & ~int64_t(15));
-    cudaError_t e = cudaMallocAsync(&d_tr, sizeof(double) * h->batch * toff[L], h->stream);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_toff, sizeof(int64_t) * (L + 1), h->stream);
-    if (e != cudaSuccess) { if (d_tr) cudaFreeAsync(d_tr, h->stream); return fail(TTB_ENOMEM, "environment traces: %s", cudaGetErrorString(e)); }
-    cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * (L + 1), cudaMemcpyHostToDevice, h->stream);
-    cudaStreamSynchronize(h->stream);  // toff is a stack vector
+    // trace buffer and its offset table live on the handle (grow-only scratch; the offsets depend only on
+    // the creation-time bonds): no allocation, copy or synchronisation per call
+    cudaError_t e = w.scr_trace.ensure(sizeof(double) * h->batch * toff[L]);
+    if (e != cudaSuccess) return fail(TTB_ENOMEM, "environment traces: %s", cudaGetErrorString(e));
+    d_tr = static_cast<double*>(w.scr_trace.p);
+    if (!w.scr_toff.p) {
+      e = w.scr_toff.ensure(sizeof(int64_t) * (L + 1));
+      if (e != cudaSuccess) return fail(TTB_ENOMEM, "environment traces: %s", cudaGetErrorString(e));
+      cudaMemcpyAsync(w.scr_toff.p, toff.data(), sizeof(int64_t) * (L + 1), cudaMemcpyHostToDevice, h->stream);
+      cudaStreamSynchronize(h->stream);  // toff is a stack vector (first call only)
+    }
+    d_toff = static_cast<int64_t*>(w.scr_toff.p);
     const int64_t maxsite = h->dmax * h->dmax;
     const bool open_chain = !h->periodic && h->bond0[0] == 1 && h->bond0[L] == 1;
     if (open_chain) {
@@ -547,9 +555,21 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
       cc.T = d_tr; cc.t_stride = toff[L]; cc.toff = d_toff; cc.bond = h->d_bond; cc.L = L; cc.L1 = L + 1;
       cc.env = c.env; cc.env_stride = c.env_stride; cc.eoff = c.eoff; cc.log_out = c.log_out; cc.sign_out = c.sign_out;
       cc.normalize = normalize; cc.left = left ? 1 : 0; cc.dmax = (int)h->dmax;
-      TTB_LAUNCH(h, "k_chain_open", k_chain_open<<<(unsigned)h->batch, 1024, sizeof(double) * 2 * h->dmax, h->stream>>>(cc));
-      cudaFreeAsync(d_tr, h->stream);
-      cudaFreeAsync(d_toff, h->stream);
+      int sm_count = 0;
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+      if (h->dmax >= 64 && h->batch * kCcCluster <= sm_count && getenv("TTB_ENV_NOCLUSTER") == nullptr) {
+        // 8-CTA cluster per train: the per-site trace is read by 8 SMs instead of one
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kCcCluster, (unsigned)h->batch); cfg.blockDim = dim3(kCcThreads);
+        cfg.dynamicSmemBytes = sizeof(double) * (2 * (size_t)h->dmax + 2 * kCcCluster); cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kCcCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        TTB_LAUNCH(h, "k_chain_cluster", cudaLaunchKernelEx(&cfg, k_chain_cluster, cc));
+      } else {
+        TTB_LAUNCH(h, "k_chain_open", k_chain_open<<<(unsigned)h->batch, 1024, sizeof(double) * 2 * h->dmax, h->stream>>>(cc));
+      }
       return TTB_OK;
     }
     dim3 g((unsigned)std::min<int64_t>((maxsite + 255) / 256, 64), (unsigned)L, (unsigned)h->batch);
@@ -564,10 +584,6 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
     TTB_LAUNCH(h, "k_accumulate_R", k_accumulate_R<<<(unsigned)h->batch, thr, smem, h->stream>>>(c));
-  }
-  if (d_tr) {  // stream-ordered release: the chain kernel above is the last reader
-    cudaFreeAsync(d_tr, h->stream);
-    cudaFreeAsync(d_toff, h->stream);
   }
   return TTB_OK;
 }
