@@ -10,6 +10,8 @@
 // of the cyclic ordering, 8 SMs wide.  Blocks live at their home rows of the global workspace (L2 resident,
 // 0.5 MB) between block-rounds: store, __threadfence, hardware cluster barrier, load the next pair with
 // L1-bypassing loads.  Convergence is a cluster-wide rotation count exchanged through global memory.
+// Reference: `svd(M)` inside the truncating functors, src/svd_trunc.jl:37,73,97,129 (LAPACK gesdd there;
+// one-sided Jacobi here: same singular values to O(eps sigma_1), W orthonormal by construction).
 #pragma once
 #include <cooperative_groups.h>
 

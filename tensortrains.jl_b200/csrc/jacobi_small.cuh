@@ -7,6 +7,8 @@
 // Here rows are zero-padded to compile-time strides in shared memory -- no predicates, 32-bit offsets,
 // WL/32 row elements and WR/32 rotation elements per lane: ~120-180 instructions per pair.  With few warps
 // (config 3) the same leanness shortens the latency chain of a round, which one warp issues alone.
+// Reference: `svd(M)` inside the truncating functors, src/svd_trunc.jl:37,73,97,129; the rank rule that
+// follows (jacobi_finish -> rank_rule in sweep.cu) restates :38-47, :74, :98-100, :130-140 verbatim.
 #pragma once
 
 namespace ttb {

@@ -3,6 +3,8 @@
 //  * the panel factorisation itself is k_qr_panel_flag in qr_panel.cuh.
 //  * k_qr_update_tma / k_apply_q_tma : block-reflector application with the V panel staged in shared
 //    memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier), one copy per panel column.
+// Reference: trailing update and thin-Q formation of the same factorisation (src/tensor_train.jl:161-166:
+// C[t] = V' / :200-205: C[t] = U, the orthonormal factor that becomes the new site tensor).
 #pragma once
 
 namespace ttb {

@@ -13,6 +13,8 @@
 // Measured (profiles/micro_lat.cu, micro_panel2.cu, B200): dependent DFMA 8, shfl+DADD 35, rsqrt ~80,
 // 1/x ~80, LDS ~70 cycles; round-robin ownership cost ~2450 cycles per column of which ~600 were the
 // hand-off, block ownership removes it from NS-1 of NS links.
+// Reference: same call sites as qr_stream.cuh (src/tensor_train.jl:161-163, :200-202); this is the 32-column
+// panel of the blocked Householder QR that replaces the eps = 0 SVD and precedes the Jacobi SVD of tall steps.
 #pragma once
 
 namespace ttb {

@@ -26,6 +26,10 @@
 // factor phase register 0 holds the panel's diagonal rows -- the mapping qr_panel.cuh assumes.  Rows above
 // the panel are final when the factor phase starts: they are stored and zeroed at the transition.
 // Requirements (host-checked): dimensions exact on the host, p >= n, bw == 32, p <= 512, 2..8 column blocks.
+// Reference: the factorisation inside one step of orthogonalize_right! / orthogonalize_left! with
+// TruncThresh(0.0) -- `U, lambda, V = svd_trunc(M)` at src/tensor_train.jl:161-163 (right sweep, M = d_t x
+// d_{t+1}Q) and :200-202 (left sweep), src/periodic_tensor_train.jl:86,95,119,133; with eps = 0 every
+// direction is kept (src/svd_trunc.jl:38-47), so W S = Q R is gauge equivalent to U (lambda V').
 #pragma once
 
 namespace ttb {
