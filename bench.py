@@ -13,8 +13,8 @@ JSON line keys beyond the base contract:
                against an FP64 peak measured in this run (cuBLAS DGEMM through torch.matmul)
   cpu_baseline the CPU oracle (NumPy/SciPy-OpenBLAS gesdd restatement of the reference; Julia is not
                installed) on the same workload, host cores of this box
-  extra        the second half of the metric string: sample draws/s on config 4 (L=256,q=4,d=128), and
-               the randn fill of config 3
+  extra        the second half of the metric string: sample draws/s on config 4 (L=256,q=4,d=128), the
+               sharded 4096-train batch of config 5, and the randn fill of config 3
 `--impl reference` times the CPU oracle (the reference's algorithm; kind "port") on a bounded sample.
 """
 import argparse
@@ -326,6 +326,54 @@ def main():
                                "(L x Q int64) is the only result copied back"}
         del A4
 
+    # ---- config 5: 4096 periodic trains (64 sites, bond 32, q=2) sharded over the ranks by contiguous
+    #      train ranges (strong scaling of this leg); normalize! + twovar_marginals + compress!(1e-6);
+    #      collectives: all-gather of per-train log Z and bond dimensions ----
+    batch_info = None
+    if not args.no_extra:
+        import ctypes as C
+        from ttb200 import parallel as P
+        B5, L5, D5, Q5 = 4096, 64, 32, 2
+        lo5, hi5 = P.shard_range(B5, rank, world)
+        nb = hi5 - lo5
+        site5 = D5 * D5 * Q5
+        packed5 = np.empty(nb * L5 * site5)
+        for i, bg in enumerate(range(lo5, hi5, 256)):          # seeds by global chunk: shard-count independent
+            n_i = min(256, hi5 - bg)
+            packed5[i * 256 * L5 * site5:(i * 256 + n_i) * L5 * site5] = \
+                np.random.Generator(np.random.Philox(5000 + bg)).random(n_i * L5 * site5)
+        A5 = T.PeriodicTensorTrain.empty([D5] * (L5 + 1), (Q5,), batch=nb)
+        A5.upload_all(packed5)
+        npair = C.c_int64()
+        T._ck(T.lib.ttb_twovar_count(A5._hd, L5 - 1, C.byref(npair)))
+        out2 = np.zeros((nb, npair.value, Q5 * Q5))
+        def c5_pipeline(A):
+            ms = {}
+            lz = T.normalize_(A); ms["normalize"] = A.last_timing()[0]
+            T._ck(T.lib.ttb_twovar_marginals(A._hd, L5 - 1, T._dp(out2))); ms["twovar_marginals"] = A.last_timing()[0]
+            T.compress_(A, T.TruncThresh(1e-6)); ms["compress"] = A.last_timing()[0]
+            return lz, ms
+        c5_pipeline(A5.copy())                                   # warm-up (workspaces, scratch)
+        W5 = A5.copy()
+        barrier()
+        t0 = time.perf_counter()
+        lz5, ms5 = c5_pipeline(W5)
+        wall5 = max_over_ranks(time.perf_counter() - t0)
+        dev5 = max_over_ranks(sum(ms5.values()))
+        bonds5 = np.array([T.bond_dims(W5, b) for b in range(0, nb, max(nb // 64, 1))], dtype=np.float64)
+        lz_all = P.allgather(np.ascontiguousarray(lz5).reshape(-1, 1)) if B5 % world == 0 else lz5
+        assert np.all(np.isfinite(lz_all)) and abs(float(out2[0, 0].sum()) - 1.0) < 1e-9
+        batch_info = {"workload": "C5: 4096 PeriodicTensorTrains, 64 sites, bond 32, q=2, rand fill: normalize! + twovar_marginals "
+                                  "(2016 pairs per train) + compress!(TruncThresh(1e-6)); trains sharded over ranks, "
+                                  "all-gather of per-train log Z",
+                      "trains": B5, "trains_per_rank": nb, "device_ms": dev5, "device_ms_by_call_rank0": ms5,
+                      "trains_per_s": B5 / (dev5 * 1e-3), "e2e_wall_ms": wall5 * 1e3,
+                      "compress_site_steps_per_s": world * nb * 2 * L5 / (max_over_ranks(ms5["compress"]) * 1e-3),
+                      "max_bond_after": int(bonds5.max()), "logz_gathered": int(np.size(lz_all)),
+                      "note": "device_ms = sum of the three calls' CUDA-event times, max over ranks; e2e_wall_ms adds the "
+                              "D2H copy of all pair marginals (258 MB in total) and the host-side call overhead"}
+        del A5, W5, packed5, out2
+
     if rank == 0:
         # ---- roofline: per-kernel CUDA-event times of one more compress! (serial timeline) ----
         prof = base.copy()
@@ -375,6 +423,8 @@ def main():
                                        "ncu": "tensor pipe 64.9% active, DRAM traffic 34.1 MB per launch = the packed "
                                               "train read once (profiles/r1_ncu_full_sample_tile.csv)"}
             extra["sample"] = sample_info
+        if batch_info is not None:
+            extra["batch"] = batch_info
         if world == 1 and not args.no_extra:
             v, secs = cpu_compress_steps_per_s(L3, D3, Q3, 3)
             line["cpu_baseline"] = {"value": v, "unit": "site-steps/s", "cores": os.cpu_count(), "kind": "port",

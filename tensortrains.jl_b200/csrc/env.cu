@@ -447,7 +447,9 @@ __global__ void k_twovar(TwoCtx c) {
 
 }  // namespace ttb
 #include "twovar_fast.cuh"
+#include "twovar_mma.cuh"
 #include "env_fast.cuh"
+#include "env_small.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -510,7 +512,13 @@ static int env_threads(ttb_tt* h) {
   return d <= 64 ? 256 : 1024;
 }
 
-static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
+// small bonds with a matrix-valued boundary (periodic trains, config 5): the tensor-core kernels of
+// env_small.cuh, one CTA per train / per (site, train)
+static bool small_path(const ttb_tt* h) {
+  return h->dmax <= 32 && h->bond0[0] > 1 && getenv("TTB_ENV_NOSMALL") == nullptr;
+}
+
+static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s, int store = 1) {
   Workspace& w = h->ws;
   EnvCtx c;
   c.slab = h->slab; c.tt_stride = h->tt_stride; c.off = h->d_off; c.bond = h->d_bond;
@@ -518,6 +526,11 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s) {
   c.env = left ? w.envL : w.envR; c.env_stride = w.env_stride; c.eoff = left ? s.d_eoffL : s.d_eoffR;
   c.log_out = w.env_log + (left ? 0 : h->batch); c.sign_out = w.env_sign + (left ? 0 : h->batch);
   c.normalize = normalize;
+  if (small_path(h)) {
+    if (left) { TTB_LAUNCH(h, "k_env_small_L", k_env_small<true><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store)); }
+    else { TTB_LAUNCH(h, "k_env_small_R", k_env_small<false><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store)); }
+    return TTB_OK;
+  }
   const int thr = env_threads(h);
   // two-phase pass: parallel physical-index sum first (HBM streaming), then the chain on the traces
   double* d_tr = nullptr;
@@ -672,7 +685,7 @@ int ttb_normalize(ttb_handle h, double* logz_out) {
   EnvSide s; EnvOffsets eo;
   TTB_TRY(env_side(h, s, eo));
   CallTimer tm(h);
-  int rc = launch_acc(h, true, 1, s);
+  int rc = launch_acc(h, true, 1, s, /*store=*/0);
   if (rc == TTB_OK) {
     const int B = (int)h->batch;
     double* factor = w.env_log + 2 * h->batch;
@@ -728,6 +741,8 @@ int ttb_marginals(ttb_handle h, double* out) {
     c.envL = w.envL; c.envR = w.envR; c.env_stride = w.env_stride; c.eoffL = s.d_eoffL; c.eoffR = s.d_eoffR;
     c.out = d_out;
     dim3 g((unsigned)h->L, (unsigned)h->batch);
+    if (small_path(h) && h->Q <= 1024) { TTB_LAUNCH(h, "k_marginals_small", k_marginals_small<<<g, 128, sizeof(double) * 4 * h->Q, h->stream>>>(c)); }
+    else
     TTB_LAUNCH(h, "k_marginals", k_marginals<<<g, 256, sizeof(double) * h->Q, h->stream>>>(c));
     rc = tm.finish();
   }
@@ -801,6 +816,8 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
         pc.L = (int)L; pc.L1 = (int)L + 1; pc.Q = (int)Q;
         pc.envR = w.envR; pc.env_stride = w.env_stride; pc.eoffR = s.d_eoffR;
         pc.GT = d_GT; pc.Tm = d_Tm; pc.gstride = gstride; pc.tstride = tstride;
+        if (small_path(h)) { TTB_LAUNCH(h, "k_twovar_pre_small", k_twovar_pre_small<<<dim3((unsigned)L, (unsigned)h->batch), 128, 0, h->stream>>>(pc)); }
+        else
         TTB_LAUNCH(h, "k_twovar_pre", k_twovar_pre<<<dim3((unsigned)L, (unsigned)h->batch), 256, 0, h->stream>>>(pc));
         TwoFast fc;
         fc.slab = h->slab; fc.tt_stride = h->tt_stride; fc.off = h->d_off; fc.bond = h->d_bond;
@@ -811,6 +828,13 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
         fc.kcap = (int)kcap; fc.dmax = (int)h->dmax;
         static bool fattr = false;
         if (!fattr) { cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); fattr = true; }
+        // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh)
+        const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
+        const dim3 gm((unsigned)(L - 1), (unsigned)h->batch);
+        if (use_mma && Q == 2) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<2><<<gm, 256, 0, h->stream>>>(fc)); }
+        else if (use_mma && Q == 3) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<3><<<gm, 256, 0, h->stream>>>(fc)); }
+        else if (use_mma && Q == 4) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<4><<<gm, 256, 0, h->stream>>>(fc)); }
+        else
         TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<dim3((unsigned)(L - 1), (unsigned)h->batch), 256, fast_smem, h->stream>>>(fc));
         rc = tm.finish();
       }

@@ -311,6 +311,46 @@ def test_truncation_error_bound():
         assert O.norm2m(Ad, Bo) < (L * eps) ** 2 + 1e-13
 
 
+@pytest.mark.parametrize("d,q,L,B", [(32, (2,), 10, 3), (16, (4,), 7, 2), (21, (3,), 6, 2), (32, (2,), 5, 1)])
+def test_twovar_tensor_core_path_config5_shapes(d, q, L, B):
+    """twovar_mma.cuh (bonds <= 32, Q d_1 <= 64): full bonds, then the ragged bonds compress! leaves."""
+    rng = RNG(160 + d)
+    tsb = [rng.random((B, d, d) + q) for _ in range(L)]
+    A = T.PeriodicTensorTrain(tsb, batched=True) if B > 1 else T.PeriodicTensorTrain([a[0] for a in tsb])
+    for stage in range(2):
+        m2 = T.twovar_marginals(A)
+        m2 = m2 if B > 1 else [m2]
+        m3 = T.twovar_marginals(A, maxdist=3)
+        m3 = m3 if B > 1 else [m3]
+        envs = {(left, nrm): (T.accumulate_L if left else T.accumulate_R)(A, nrm) for left in (True, False) for nrm in (True, False)}
+        m1 = T.marginals(A)
+        m1 = m1 if B > 1 else [m1]
+        zs = T.normalization(A)
+        zs = zs if B > 1 else [zs]
+        for b in range(B):
+            zb = A.z[b] if B > 1 else A.z
+            Ao = O.PeriodicTensorTrain([a.copy() for a in A.tensors(b)], z=O.LogNum(logabs=zb.logabs, sign=zb.sign))
+            for (left, nrm), (e, z) in envs.items():
+                eo, zo = (O.accumulate_L if left else O.accumulate_R)(Ao, nrm)
+                e, z = (e[b], z[b]) if B > 1 else (e, z)
+                for a_, b_ in zip(e, eo):
+                    assert a_.shape == b_.shape and np.allclose(a_, b_, rtol=1e-10, atol=0), (stage, left, nrm)
+                assert close(z.logabs, zo.logabs, REL, 1e-12) and z.sign == zo.sign
+            zo = O.normalization(Ao)
+            assert close(zs[b].logabs, zo.logabs, REL, 1e-12) and zs[b].sign == zo.sign
+            for a_, b_ in zip(m1[b], O.marginals(Ao)):
+                assert np.allclose(a_, b_, rtol=1e-10, atol=0)
+            m2o = O.twovar_marginals(Ao)
+            assert set(m2[b]) == set(m2o)
+            for k in m2o:
+                assert np.allclose(m2[b][k], m2o[k], rtol=1e-10, atol=0), (stage, b, k)
+            m3o = O.twovar_marginals(Ao, maxdist=3)
+            assert set(m3[b]) == set(m3o)
+            for k in m3o:
+                assert np.allclose(m3[b][k], m3o[k], rtol=1e-10, atol=0), (stage, b, k)
+        T.compress_(A, T.TruncThresh(1e-4))
+
+
 def test_batched_periodic_matches_single():
     rng = RNG(150)
     B, bonds, q = 5, [4, 6, 3, 5], (2,)
