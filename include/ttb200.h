@@ -68,6 +68,11 @@ int ttb_host_free(void* p);
 int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_handle* out);
 int ttb_destroy(ttb_handle h);
 int ttb_clone(ttb_handle h, ttb_handle* out); /* deepcopy */
+/* A + B (sign = +1) / A - B (sign = -1): `_compose`, src/tensor_train.jl:240-261 (open: first site
+ * [za A, zb B], last site [A; B], block diagonal in between, z = min(|zA|, |zB|)),
+ * src/periodic_tensor_train.jl:62-78 (block diagonal everywhere, f on the first site's B block, z ignored
+ * like the reference); Base.:+ / Base.:- src/abstract_tensor_train.jl:315-322.  New handle, bonds add up. */
+int ttb_compose(ttb_handle a, ttb_handle b, int sign, ttb_handle* out);
 int ttb_info(ttb_handle h, int64_t* L, int64_t* Q, int* periodic, int64_t* batch);
 /* current bond dims of train b: L+1 entries (bond_dims(A) of the reference = the first L) */
 int ttb_get_bonds(ttb_handle h, int64_t b, int64_t* out);

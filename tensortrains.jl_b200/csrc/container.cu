@@ -229,6 +229,103 @@ int ttb_clone(ttb_handle h, ttb_handle* out) {
   return TTB_OK;
 }
 
+// ---- A + B / A - B (src/tensor_train.jl:240-261, src/periodic_tensor_train.jl:62-78,
+//      src/abstract_tensor_train.jl:315-322): block assembly on the device, a pure HBM copy -------------
+}  // extern "C"
+namespace ttb {
+struct ComposeSide { const double* slab; int64_t tt_stride; const int64_t* off; const int* bond; const double* logz; const int* signz; };
+struct ComposeCtx {
+  ComposeSide a, b;
+  double* slab; int64_t tt_stride; const int64_t* off; int* bond; double* logz; int* signz;
+  int L, L1, Q, periodic, sign;
+};
+
+// one CTA column per (site, train); the first CTA of a site also writes the site's bond entries and z
+__global__ void k_compose(ComposeCtx c) {
+  const int t = blockIdx.y, bt = blockIdx.z;
+  const int* ba = c.a.bond + (int64_t)bt * c.L1;
+  const int* bb = c.b.bond + (int64_t)bt * c.L1;
+  const int al = ba[t], ar = ba[t + 1], bl = bb[t], br = bb[t + 1];
+  const bool open = !c.periodic;
+  const bool first = open && t == 0, last = open && t == c.L - 1;
+  const int ol = first ? 1 : al + bl, orr = last ? 1 : ar + br;
+  // open trains: z = min(|zA|, |zB|), za = z / zA, zb = f(z / zB) scale the first site; periodic trains
+  // ignore z (the reference builds the sum with z = 1) and f acts on the first site's B block
+  double fa = 1.0, fb = 1.0;
+  if (open) {
+    const double la = c.a.logz[bt], lb = c.b.logz[bt], lz = fmin(la, lb);
+    if (t == 0) { fa = exp(lz - la) * c.a.signz[bt]; fb = exp(lz - lb) * c.b.signz[bt] * c.sign; }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && t == 0) { c.logz[bt] = lz; c.signz[bt] = 1; }
+  } else {
+    if (t == 0) fb = (double)c.sign;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && t == 0) { c.logz[bt] = 0.0; c.signz[bt] = 1; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int* bo = c.bond + (int64_t)bt * c.L1;
+    bo[t] = ol;
+    if (t == c.L - 1) bo[c.L] = orr;
+  }
+  const double* A = c.a.slab + (int64_t)bt * c.a.tt_stride + c.a.off[t];
+  const double* B = c.b.slab + (int64_t)bt * c.b.tt_stride + c.b.off[t];
+  double* O = c.slab + (int64_t)bt * c.tt_stride + c.off[t];
+  const int64_t n = (int64_t)ol * orr * c.Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % ol), cc = (int)((i / ol) % orr), x = (int)(i / ((int64_t)ol * orr));
+    // row / column inside the A block or the B block (the boundary sites of an open train concatenate)
+    const bool ra = first || r < al, ca = last || cc < ar;
+    const int rb = first ? 0 : r - al, cb = last ? 0 : cc - ar;
+    double v = 0.0;
+    if (first)      v = cc < ar ? fa * A[(int64_t)al * (cc + (int64_t)ar * x)] : fb * B[(int64_t)bl * (cb + (int64_t)br * x)];
+    else if (last)  v = r < al ? A[r + (int64_t)al * ((int64_t)ar * x)] : B[rb + (int64_t)bl * ((int64_t)br * x)];
+    else if (ra && ca)   v = fa * A[r + (int64_t)al * (cc + (int64_t)ar * x)];
+    else if (!ra && !ca) v = fb * B[rb + (int64_t)bl * (cb + (int64_t)br * x)];
+    O[i] = v;
+  }
+}
+}  // namespace ttb
+extern "C" {
+
+int ttb_compose(ttb_handle a, ttb_handle b, int sign, ttb_handle* out) {
+  TTB_TRY(check_handle(a));
+  TTB_TRY(check_handle(b));
+  if (!out || (sign != 1 && sign != -1)) return fail(TTB_EINVAL, "bad argument");
+  if (a->L != b->L) return fail(TTB_ESHAPE, "Tensor Trains must have the same length, got %lld and %lld", (long long)a->L, (long long)b->L);
+  if (a->Q != b->Q) return fail(TTB_ESHAPE, "Tensor Trains must have the same physical dimensions, got %lld and %lld", (long long)a->Q, (long long)b->Q);
+  if (a->periodic != b->periodic || a->batch != b->batch || a->device != b->device)
+    return fail(TTB_EINVAL, "trains of different kind, batch size or device");
+  const int64_t L = a->L, B = a->batch;
+  if (!a->periodic && L < 2) return fail(TTB_ESHAPE, "First matrix must have 1 row, last matrix must have 1 column");
+  // capacity = the largest sum over the batch; current dims = the per-train sums (written by the kernel)
+  std::vector<int64_t> cap(L + 1, 1);
+  std::vector<int> hb((size_t)B * (L + 1));
+  for (int64_t bt = 0; bt < B; ++bt)
+    for (int64_t t = 0; t <= L; ++t) {
+      const bool edge = !a->periodic && (t == 0 || t == L);
+      const int v = edge ? 1 : a->h_bond[bt * (L + 1) + t] + b->h_bond[bt * (L + 1) + t];
+      hb[bt * (L + 1) + t] = v;
+      cap[t] = std::max<int64_t>(cap[t], v);
+    }
+  ttb_handle c = nullptr;
+  TTB_TRY(ttb_create(L, cap.data(), a->Q, a->periodic, B, &c));
+  c->h_bond = hb;
+  ttb::ComposeCtx cc;
+  cc.a = {a->slab, a->tt_stride, a->d_off, a->d_bond, a->d_logz, a->d_signz};
+  cc.b = {b->slab, b->tt_stride, b->d_off, b->d_bond, b->d_logz, b->d_signz};
+  cc.slab = c->slab; cc.tt_stride = c->tt_stride; cc.off = c->d_off; cc.bond = c->d_bond; cc.logz = c->d_logz; cc.signz = c->d_signz;
+  cc.L = (int)L; cc.L1 = (int)L + 1; cc.Q = (int)a->Q; cc.periodic = a->periodic; cc.sign = sign;
+  cudaStreamSynchronize(a->stream);
+  cudaStreamSynchronize(b->stream);
+  int64_t maxsite = 0;
+  for (int64_t t = 0; t < L; ++t) maxsite = std::max(maxsite, cap[t] * cap[t + 1] * a->Q);
+  const dim3 g((unsigned)std::min<int64_t>((maxsite + 1023) / 1024, 256), (unsigned)L, (unsigned)B);
+  ttb::CallTimer tm(c);
+  TTB_LAUNCH(c, "k_compose", ttb::k_compose<<<g, 256, 0, c->stream>>>(cc));
+  int rc = tm.finish();
+  if (rc != TTB_OK) { ttb_destroy(c); return rc; }
+  *out = c;
+  return TTB_OK;
+}
+
 int ttb_info(ttb_handle h, int64_t* L, int64_t* Q, int* periodic, int64_t* batch) {
   if (!h) return fail(TTB_EINVAL, "null handle");
   if (L) *L = h->L;

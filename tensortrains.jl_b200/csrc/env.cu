@@ -831,9 +831,9 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
         // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh)
         const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
         const dim3 gm((unsigned)(L - 1), (unsigned)h->batch);
-        if (use_mma && Q == 2) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<2><<<gm, 256, 0, h->stream>>>(fc)); }
-        else if (use_mma && Q == 3) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<3><<<gm, 256, 0, h->stream>>>(fc)); }
-        else if (use_mma && Q == 4) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<4><<<gm, 256, 0, h->stream>>>(fc)); }
+        if (use_mma && Q == 2) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<2><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
+        else if (use_mma && Q == 3) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<3><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
+        else if (use_mma && Q == 4) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<4><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
         else
         TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<dim3((unsigned)(L - 1), (unsigned)h->batch), 256, fast_smem, h->stream>>>(fc));
         rc = tm.finish();

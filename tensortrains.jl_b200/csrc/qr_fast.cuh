@@ -294,4 +294,118 @@ __global__ void __launch_bounds__(256) k_apply_q_tma(SweepCtx c, StepDesc s) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// W = H_1 ... H_k E for a SMALL step (p <= 64 rows, one panel: k <= 32, m' <= 32 columns): one CTA forms
+// the whole orthonormal factor of its train instead of eight CTAs staging the same panel for four columns
+// each (a batch of config-5 trains launches 4096 of these per step).  Same algebra as block_reflect<false>
+// -- W = E - V (T (V^T E)), T applied as a back substitution on diag(1/tau) + striu(V^T V) -- but the two
+// products run on the FP64 tensor cores: operands in shared memory with leading dimensions 68 / 36
+// (= 4 mod 16, conflict-free m16n8k8 fragments in both orientations), zero padded to 64 x 32.
+// Reference: C[t] = V' / C[t] = U (src/tensor_train.jl:165-166, :204-205).
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kApplySmallSmem = sizeof(double) * (2 * 68 * 32 + 1024 + 36 * 32);
+__global__ void __launch_bounds__(256) k_apply_q_small(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  constexpr int LDV = 68, LDW = 36;
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime[s.slot];
+  const int p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  extern __shared__ __align__(16) double smq[];   // kApplySmallSmem bytes
+  double* Vs = smq;                 // (r, i)  at r + LDV i
+  double* Wc = Vs + LDV * 32;       // (r, cc) at r + LDV cc
+  double* Ts = Wc + LDV * 32;       // 32 x 32
+  double* W = Ts + 1024;            // (i, cc) at i + LDW cc
+  double* W2 = W;                   // the solve keeps its columns in registers: in place
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, tq = lane & 3;
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* Jv = c.Jv + (int64_t)b * c.jv_stride;
+  const int bwc = d.mode == 2 ? 0 : d.k;
+  for (int i = tid; i < 64 * 32; i += 256) {
+    const int r = i & 63, cc = i >> 6;
+    double v = 0.0, w = 0.0;
+    if (r < p && cc < mprime) {
+      if (d.mode == 0) v = (r == cc) ? 1.0 : 0.0;
+      else v = r < d.k ? Jv[(int64_t)perm[cc] * c.ldj + r] : 0.0;
+    }
+    if (r < p && cc < bwc) w = r < cc ? 0.0 : (r == cc ? 1.0 : X[r + (int64_t)p * cc]);  // explicit unit lower
+    Wc[r + LDV * cc] = v;
+    Vs[r + LDV * cc] = w;
+  }
+  if (d.mode != 2) {
+    const double* Tg = c.T + (int64_t)b * c.t_stride;
+    for (int i = tid; i < 1024; i += 256) Ts[i] = Tg[i];
+    __syncthreads();
+    {  // W (32 x 32) = V^T Wc, K = 64 rows: warp = one 16 x 8 tile
+      const int mt = wid & 1, nt = wid >> 1;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const double* pa = Vs + (mt * 16 + g) * LDV + (ks * 8 + tq);
+        const double af[4] = {pa[0], pa[8 * LDV], pa[4], pa[8 * LDV + 4]};
+        const double* pb = Wc + (ks * 8 + tq) + (nt * 8 + g) * LDV;
+        const double bf[2] = {pb[0], pb[4]};
+        dmma_16x8x8(acc, af, bf);
+      }
+      double* wo = W + (mt * 16 + g) + LDW * (nt * 8 + 2 * tq);
+      wo[0] = acc[0]; wo[LDW] = acc[1]; wo[8] = acc[2]; wo[8 + LDW] = acc[3];
+    }
+    __syncthreads();
+    {  // W2 = T W: four right-hand sides per warp, lane = row, interleaved for ILP
+      double w[4], y[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = (lane < bwc && wid + 8 * q < mprime) ? W[lane + LDW * (wid + 8 * q)] : 0.0;
+      for (int i = bwc - 1; i >= 0; --i) {
+        const double tau = Ts[i + 32 * i];
+        const double gi = lane < i ? Ts[lane + 32 * i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double yi = __shfl_sync(0xffffffffu, w[q], i) * tau;
+          w[q] -= gi * yi;
+          if (lane == i) y[q] = yi;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) W2[lane + LDW * (wid + 8 * q)] = y[q];
+    }
+    __syncthreads();
+    {  // Wc (64 x 32) -= V W2, K = 32: warp = 16 rows x 16 columns
+      const int mt = wid & 3, nt0 = (wid >> 2) * 2;
+      double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double* pa = Vs + (mt * 16 + g) + LDV * (ks * 8 + tq);
+        const double af[4] = {pa[0], pa[8], pa[4 * LDV], pa[8 + 4 * LDV]};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double* pb = W2 + (ks * 8 + tq) + LDW * ((nt0 + j) * 8 + g);
+          const double bf[2] = {pb[0], pb[4]};
+          dmma_16x8x8(acc[j], af, bf);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double* wo = Wc + (mt * 16 + g) + LDV * ((nt0 + j) * 8 + 2 * tq);
+        wo[0] -= acc[j][0]; wo[LDV] -= acc[j][1]; wo[8] -= acc[j][2]; wo[8 + LDV] -= acc[j][3];
+      }
+    }
+  }
+  __syncthreads();
+  double* site = c.slab + (int64_t)b * c.tt_stride + c.off[s.site];
+  if (s.dir == 0) {
+    for (int i = tid; i < p * mprime; i += 256) {
+      const int cc = i % mprime, r = i / mprime;
+      site[cc + (int64_t)mprime * r] = Wc[r + LDV * cc];
+    }
+  } else {
+    const int dl = p / c.Q;
+    for (int i = tid; i < p * mprime; i += 256) {
+      const int r = i % p, cc = i / p;
+      const int m = r % dl, x = r / dl;
+      site[m + (int64_t)dl * (cc + (int64_t)mprime * x)] = Wc[r + LDV * cc];
+    }
+  }
+}
+
 }  // namespace ttb

@@ -1265,7 +1265,12 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         cudaEventRecord(h->ev_qr[slot], st);
         cudaStreamWaitEvent(st2, h->ev_qr[slot], 0);
       }
-      if (fast) {
+      if (fast && p_ub <= 64 && k_ub <= 32 && getenv("TTB_APPLYQ_NOSMALL") == nullptr) {
+        // small step: one CTA forms the whole orthonormal factor of its train (tensor cores)
+        static bool aattr = false;
+        if (!aattr) { cudaFuncSetAttribute(k_apply_q_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmallSmem); aattr = true; }
+        TTB_LAUNCH(h, "k_apply_q_small", k_apply_q_small<<<B, 256, kApplySmallSmem, st2>>>(c, s));
+      } else if (fast) {
         size_t smem = sizeof(double) * ((size_t)1280 + (size_t)p_ub * 36);
         TTB_LAUNCH(h, "k_apply_q_tma", k_apply_q_tma<<<g, 256, smem, st2>>>(c, s));
       } else {

@@ -18,8 +18,9 @@
 namespace ttb {
 
 template <int Q>
-__global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
+__global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
   constexpr int LDK = 68, LDT = 36, QQ = Q * Q;
+  constexpr int EPT = (8 + Q - 1) / Q;   // Frobenius elements per thread: d_1 <= 64 / Q, so d_1 d_u <= 256 EPT
   const int t = blockIdx.x, b = blockIdx.y;
   if (t >= c.L - 1) return;
   const int* bond = c.bond + (int64_t)b * c.L1;
@@ -30,7 +31,10 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
   __shared__ double Ts[LDT * 32];
   __shared__ double red[2][8][QQ];
   __shared__ double redm[8];
+  extern __shared__ int sbond[];   // this train's bond dimensions (L + 1): keeps dependent global loads off the pair loop
   for (int i = tid; i < LDK * 32; i += 256) K[i] = 0.0;
+  for (int i = tid; i < c.L1; i += 256) sbond[i] = bond[i];
+  const int64_t out_base = ((int64_t)b * c.npairs + c.pair_off[t] - (t + 1)) * QQ;
   __syncthreads();
   // K_x = l[t-1] A_t(x)   (d_1 x d_{t+1}), stacked over x
   {
@@ -46,48 +50,51 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
     }
   }
   // this thread's four elements (a, cc) of the Frobenius products: i = tid + 256 m = a + r0 cc
-  int koff[4];
+  int koff[EPT];
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
+  for (int m = 0; m < EPT; ++m) {
     const int i = tid + 256 * m;
     koff[m] = (i % r0) + LDK * min(i / r0, 31);
   }
   const int uhi = min(c.L - 1, t + c.maxdist);
-  double gq[4][Q], tp[4];
-  auto prefetch = [&](int u) {
-    const int dl = bond[u], dr = bond[u + 1], nk = r0 * dl;
+  double gq[EPT][Q], tp[4];
+  auto prefetch_G = [&](int u) {
+    const int nk = r0 * sbond[u];
 #pragma unroll
     for (int x = 0; x < Q; ++x) {
       const double* GT = c.GT + (((int64_t)b * c.L + u) * Q + x) * c.gstride;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) { const int i = tid + 256 * m; gq[m][x] = i < nk ? GT[i] : 0.0; }
+      for (int m = 0; m < EPT; ++m) { const int i = tid + 256 * m; gq[m][x] = i < nk ? GT[i] : 0.0; }
     }
-    if (u < uhi) {
-      const double* Tm = c.Tm + ((int64_t)b * c.L + u) * c.tstride;
+  };
+  auto prefetch_T = [&](int u) {
+    const int dl = sbond[u], dr = sbond[u + 1];
+    const double* Tm = c.Tm + ((int64_t)b * c.L + u) * c.tstride;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int j = tid + 256 * m, cc = j & 31, e = j >> 5;
-        tp[m] = (cc < dl && e < dr) ? Tm[cc + dl * e] : 0.0;
-      }
+    for (int m = 0; m < 4; ++m) {
+      const int j = tid + 256 * m, cc = j & 31, e = j >> 5;
+      tp[m] = (cc < dl && e < dr) ? Tm[cc + dl * e] : 0.0;
     }
   };
   auto stage_T = [&]() {
 #pragma unroll
     for (int m = 0; m < 4; ++m) { const int j = tid + 256 * m; Ts[(j & 31) + LDT * (j >> 5)] = tp[m]; }
   };
-  prefetch(t + 1);
-  stage_T();
+  prefetch_G(t + 1);
+  if (t + 1 < uhi) { prefetch_T(t + 1); stage_T(); }
   __syncthreads();
   const int mt = wid & 3, nt0 = (wid >> 2) * 2;
   int par = 0;
   for (int u = t + 1; u <= uhi; ++u, par ^= 1) {
-    const int nk = r0 * bond[u];
+    const int nk = r0 * sbond[u];
+    const bool more = u < uhi;
+    if (more && u + 1 < uhi) prefetch_T(u + 1);   // the next pair's T travels while this pair is computed
     // b[x_t, x_u] partial sums
     double acc[QQ];
 #pragma unroll
     for (int i = 0; i < QQ; ++i) acc[i] = 0.0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < EPT; ++m) {
       if (tid + 256 * m < nk) {
 #pragma unroll
         for (int xt = 0; xt < Q; ++xt) {
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
       acc[i] = warp_sum(acc[i]);
       if (lane == 0) red[par][wid][i] = acc[i];
     }
-    const bool more = u < uhi;
+    if (more) prefetch_G(u + 1);                   // ... and its GT, consumed one full step from now
     double d[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
     if (more) {
       // K T_u on the tensor cores: warp = (16-row tile mt) x (two 8-column tiles nt0, nt0+1), K = 32
@@ -126,7 +133,6 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
         for (int i = 0; i < 4; ++i) mx = fmax(mx, fabs(d[j][i]));
       mx = warp_max(mx);
       if (lane == 0) redm[wid] = mx;
-      prefetch(u + 1);   // the next pair's GT (registers) and T (registers -> Ts after the barrier)
     }
     __syncthreads();
     if (wid == (u & 7)) {
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
         for (int w2 = 0; w2 < 8; ++w2) v += red[par][w2][lane];
       }
       const double tot = warp_sum(v);
-      if (lane < QQ) c.out[((int64_t)b * c.npairs + c.pair_off[t] + (u - t - 1)) * QQ + lane] = v / tot;
+      if (lane < QQ) c.out[out_base + (int64_t)u * QQ + lane] = v / tot;
     }
     if (more) {
       double m = 0.0;
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(256, 3) k_twovar_mma(TwoFast c) {
           ko[8] = d[j][2] * inv; ko[8 + LDK] = d[j][3] * inv;
         }
       }
-      stage_T();
+      if (u + 1 < uhi) stage_T();
     }
     __syncthreads();
   }
