@@ -262,6 +262,50 @@ class PeriodicTensorTrain(AbstractTensorTrain):
             raise ValueError("ArgumentError: Matrix indices for matrix product non compatible")
 
 
+def _compose(f, A, B):
+    """``A + B`` / ``A - B`` (``f`` = +1 / -1).  Open trains: ``src/tensor_train.jl:240-261`` -- first site
+    ``[za A, zb B]`` with ``z = min(|zA|, |zB|)``, ``za = z/zA``, ``zb = f(z/zB)``, last site ``[A; B]``,
+    block diagonal in between, ``C.z = z``.  Periodic trains: ``src/periodic_tensor_train.jl:62-78`` -- block
+    diagonal everywhere, ``f`` on the first site's B block, and ``z`` is ignored (the result has z = 1)."""
+    if type(A) is not type(B):
+        raise ValueError("ArgumentError: cannot compose trains of different kinds")
+    if len(A) != len(B):
+        raise ValueError(f"ArgumentError: Tensor Trains must have the same length, got {len(A)} and {len(B)}")
+    if A[0].shape[2:] != B[0].shape[2:]:
+        raise ValueError("ArgumentError: Tensor Trains must have the types of physical indices")
+    L = len(A)
+    out = []
+    if A.periodic:
+        za, zb, z = 1.0, float(f), LogNum(1.0)
+    else:
+        z = A.z if abs(A.z).logabs <= abs(B.z).logabs else B.z
+        z = abs(z)
+        za, zb = float(z / A.z), f * float(z / B.z)
+    for t in range(L):
+        At, Bt = _reshape1(A[t]), _reshape1(B[t])
+        (al, ar, Q), (bl, br, _) = At.shape, Bt.shape
+        if not A.periodic and t == 0:
+            C = np.concatenate([za * At, zb * Bt], axis=1)
+        elif not A.periodic and t == L - 1:
+            C = np.concatenate([At, Bt], axis=0)
+        else:
+            C = np.zeros((al + bl, ar + br, Q))
+            C[:al, :ar] = At
+            C[al:, ar:] = (zb * Bt) if (A.periodic and t == 0) else Bt
+        out.append(C.reshape(C.shape[:2] + A[t].shape[2:], order="F"))
+    return type(A)(out, z=z)
+
+
+def plus(A, B):
+    """``Base.:+`` (``src/abstract_tensor_train.jl:315``)"""
+    return _compose(1.0, A, B)
+
+
+def minus(A, B):
+    """``Base.:-`` (``src/abstract_tensor_train.jl:322``)"""
+    return _compose(-1.0, A, B)
+
+
 def bond_dims(A) -> List[int]:
     """Left bond of every site (``src/abstract_tensor_train.jl:23``)."""
     return [a.shape[0] for a in A]

@@ -66,6 +66,7 @@ _sig("ttb_host_free", C.c_void_p)
 _sig("ttb_create", _i64, _pi64, _i64, C.c_int, _i64, C.POINTER(_h))
 _sig("ttb_destroy", _h)
 _sig("ttb_clone", _h, C.POINTER(_h))
+_sig("ttb_compose", _h, _h, C.c_int, C.POINTER(_h))
 _sig("ttb_info", _h, _pi64, _pi64, _pi, _pi64)
 _sig("ttb_get_bonds", _h, _i64, _pi64)
 _sig("ttb_nparams", _h, _i64, _pi64)
@@ -351,6 +352,24 @@ class AbstractTensorTrain:
 
     def record_spectrum(self, on: bool = True):
         _ck(lib.ttb_record_spectrum(self._hd, int(on)))
+
+    def _compose(self, other, sign: int):
+        if type(self) is not type(other):
+            raise ValueError("ArgumentError: cannot compose trains of different kinds")
+        if tuple(self.q) != tuple(other.q):
+            raise ValueError("ArgumentError: Tensor Trains must have the types of physical indices")
+        nh = _h()
+        _ck(lib.ttb_compose(self._hd, other._hd, sign, C.byref(nh)))
+        return type(self)(None, batched=self.batched, _handle=nh, _q=self.q)
+
+    def __add__(self, other):
+        """``A + B`` (src/abstract_tensor_train.jl:315; `_compose` src/tensor_train.jl:240-261,
+        src/periodic_tensor_train.jl:62-78): bond dimensions add up, assembled on the device."""
+        return self._compose(other, 1)
+
+    def __sub__(self, other):
+        """``A - B`` (src/abstract_tensor_train.jl:322)"""
+        return self._compose(other, -1)
 
     def spectrum(self, bond_index: int, b: int = 0) -> np.ndarray:
         out = np.zeros(int(max(self.bonds(b).max(), 1)) * max(self.Q, 1) + 8)

@@ -647,3 +647,53 @@ def test_eps0_sweeps_odd_sizes(d, q):
     g = T.evaluate(A, X)
     assert np.max(np.abs(g - e0)) <= 1e-10 * np.max(np.abs(e0))
     assert all(T.is_left_canonical(A, t, atol=1e-10) for t in range(0, L - 1))
+
+
+# ---- A + B / A - B (section 8f rank 3): test/tensor_train.jl:302-345, test/periodic_tensor_train.jl:176-200
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("q", [(2,), (3, 2)])
+def test_sum_difference_then_compress(periodic, q):
+    rng = RNG(900 + len(q) + 2 * periodic)
+    L = 6
+    if periodic:
+        ba, bb = list(rng.integers(1, 7, L)), list(rng.integers(1, 7, L))
+        ta, tb = rand_per(rng, ba, q), rand_per(rng, bb, q)
+    else:
+        ba, bb = [1] + list(rng.integers(1, 8, L - 1)) + [1], [1] + list(rng.integers(1, 8, L - 1)) + [1]
+        ta, tb = rand_open(rng, ba, q), rand_open(rng, bb, q)
+    A, Ao = pair(ta, periodic=periodic, z=-0.6)
+    B, Bo = pair(tb, periodic=periodic, z=2.5)
+    for Cg, Co in ((A + B, O.plus(Ao, Bo)), (A - B, O.minus(Ao, Bo))):
+        assert T.bond_dims(Cg) == O.bond_dims(Co)
+        for g, o in zip(Cg.tensors(), Co.tensors):
+            assert g.shape == o.shape and np.allclose(g, o, rtol=1e-14, atol=0)
+        assert close(Cg.z.logabs, Co.z.logabs, 1e-14, 1e-15) and Cg.z.sign == Co.z.sign
+        X = rand_points(rng, Co, 8)
+        check_evals(Cg, Co, X, REL, signed=True)
+    # the canonical producer of over-sized bonds: A + A compresses back to the bonds of A
+    S, So = A + A, O.plus(Ao, Ao)
+    T.compress_(S, T.TruncThresh(1e-9))
+    O.compress(So, O.TruncThresh(1e-9))
+    assert T.bond_dims(S) == O.bond_dims(So)
+    check_evals(S, So, rand_points(rng, So, 8), 1e-8, signed=True)
+    with pytest.raises(ValueError):
+        A + T.TensorTrain(rand_open(rng, [1, 2, 1], q)) if not periodic else A + T.PeriodicTensorTrain(rand_per(rng, [2, 2], q))
+
+
+def test_sum_of_batched_trains_after_compress():
+    """ragged per-train bonds (after a truncating sweep) add up train by train"""
+    rng = RNG(930)
+    Bn, bonds, q = 4, [5, 6, 4, 5, 6], (2,)
+    n = len(bonds)
+    tsa = [rng.random((Bn, bonds[t], bonds[(t + 1) % n]) + q) for t in range(n)]
+    tsb = [rng.random((Bn, bonds[t], bonds[(t + 1) % n]) + q) for t in range(n)]
+    A, B = T.PeriodicTensorTrain(tsa, batched=True), T.PeriodicTensorTrain(tsb, batched=True)
+    T.compress_(A, T.TruncThresh(1e-3))
+    S = A + B
+    for b in range(Bn):
+        Ao = O.PeriodicTensorTrain([a.copy() for a in A.tensors(b)])
+        Bo = O.PeriodicTensorTrain([a[b].copy() for a in tsb])
+        So = O.plus(Ao, Bo)
+        assert T.bond_dims(S, b) == O.bond_dims(So)
+        for g, o in zip(S.tensors(b), So.tensors):
+            assert g.shape == o.shape and np.array_equal(g, o)

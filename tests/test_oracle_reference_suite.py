@@ -332,3 +332,31 @@ def test_philox_known_answer():
     assert [int(v) for v in r] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
     u = O.philox_uniform(4, np.arange(1000), 3)
     assert ((u >= 0) & (u < 1)).all() and abs(u.mean() - 0.5) < 0.05
+
+
+# ---- A + B / A - B: test/tensor_train.jl:302-345, test/periodic_tensor_train.jl:176-200 -----------
+@pytest.mark.parametrize("N,q", [(n, q) for n in (1, 2, 3) for q in (1, 2, 3)])
+def test_sum_and_difference_of_trains(N, q):
+    rng = RNG(700 + 10 * N + q)
+    L = 6
+    qs = (q,) * N
+    A = O.rand_tt(rng, [1] + list(rng.integers(1, 8, L - 1)) + [1], *qs)
+    B = O.rand_tt(rng, [1] + list(rng.integers(1, 8, L - 1)) + [1], *qs)
+    A.z, B.z = O.LogNum(-0.7), O.LogNum(3.1)
+    x = _rand_x(rng, A)
+    assert math.isclose(O.evaluate(A, x) + O.evaluate(B, x), O.evaluate(O.plus(A, B), x), rel_tol=1e-12)
+    assert math.isclose(O.evaluate(A, x) - O.evaluate(B, x), O.evaluate(O.minus(A, B), x), rel_tol=1e-12)
+    assert O.bond_dims(O.plus(A, B)) == [1] + [a + b for a, b in zip(O.bond_dims(A)[1:], O.bond_dims(B)[1:])]
+    A.z = O.LogNum(0.8)
+    assert O.isapprox(O.minus(O.plus(A, B), B), A, rtol=1e-4)       # (A + B) - B ~ A
+    C = A.copy()
+    C.z = C.z / 2
+    assert O.isapprox(C, O.plus(A, A))                              # A + A = A with z / 2
+    # periodic: block diagonal everywhere, z ignored (src/periodic_tensor_train.jl:62-78)
+    Ap = O.rand_periodic_tt(rng, list(rng.integers(1, 6, 4)), *qs)
+    Bp = O.rand_periodic_tt(rng, list(rng.integers(1, 6, 4)), *qs)
+    xp = _rand_x(rng, Ap)
+    assert math.isclose(O.evaluate(Ap, xp) + O.evaluate(Bp, xp), O.evaluate(O.plus(Ap, Bp), xp), rel_tol=1e-12)
+    assert math.isclose(O.evaluate(Ap, xp) - O.evaluate(Bp, xp), O.evaluate(O.minus(Ap, Bp), xp), rel_tol=1e-12)
+    with pytest.raises(ValueError):
+        O.plus(A, O.rand_tt(rng, [1, 2, 1], *qs))
