@@ -214,6 +214,8 @@ def main():
     T.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -360,6 +362,26 @@ def main():
         lz5, ms5 = c5_pipeline(W5)
         wall5 = max_over_ranks(time.perf_counter() - t0)
         dev5 = max_over_ranks(sum(ms5.values()))
+        # HBM roofline of the environment pass behind normalize! (k_env_small_L reads every site tensor once:
+        # algorithmic bytes = 8 * sum_t d_t d_{t+1} Q per train) and of the scaling pass (read + write)
+        P5 = A5.copy()
+        P5.profile(True)
+        T.normalize_(P5)
+        rep5 = P5.profile_report()
+        P5.profile(False)
+        del P5
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy figure)"
+        except Exception:
+            hbm_peak, hbm_src = 6545.9, "fallback: B200_PROFILING.md measured copy bandwidth"
+        slab_bytes = float(nb) * L5 * site5 * 8
+        roof5 = {}
+        for kname, nbytes_alg in (("k_env_small_L", slab_bytes), ("k_scale_trains", 2 * slab_bytes)):
+            if kname in rep5 and rep5[kname][1] > 0:
+                gbs = nbytes_alg / (rep5[kname][1] * 1e-3) / 1e9
+                roof5[kname] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "ms": rep5[kname][1], "alg_bytes": nbytes_alg}
         bonds5 = np.array([T.bond_dims(W5, b) for b in range(0, nb, max(nb // 64, 1))], dtype=np.float64)
         lz_all = P.allgather(np.ascontiguousarray(lz5).reshape(-1, 1)) if B5 % world == 0 else lz5
         assert np.all(np.isfinite(lz_all)) and abs(float(out2[0, 0].sum()) - 1.0) < 1e-9
@@ -370,6 +392,7 @@ def main():
                       "trains_per_s": B5 / (dev5 * 1e-3), "e2e_wall_ms": wall5 * 1e3,
                       "compress_site_steps_per_s": world * nb * 2 * L5 / (max_over_ranks(ms5["compress"]) * 1e-3),
                       "max_bond_after": int(bonds5.max()), "logz_gathered": int(np.size(lz_all)),
+                      "roofline_rank0": roof5, "hbm_peak_source": hbm_src,
                       "note": "device_ms = sum of the three calls' CUDA-event times, max over ranks; e2e_wall_ms adds the "
                               "D2H copy of all pair marginals (258 MB in total) and the host-side call overhead"}
         del A5, W5, packed5, out2
