@@ -132,6 +132,10 @@ int ttb_normalization(ttb_handle h, double* logabs, int* sign);
 /* normalize!(A): returns log(|Z|/z_old) per train (src/abstract_tensor_train.jl:184-197) */
 int ttb_normalize(ttb_handle h, double* logz_out);
 /* normalize_eachmatrix! (src/abstract_tensor_train.jl:165-176) */
+/* every site tensor of train b divided by divisor[b] (host array, one per train), z untouched: the rescaling
+ * step of normalize! (src/abstract_tensor_train.jl:189-193); the MPS wrapper's normalize!
+ * (src/MatrixProductStates/mps.jl:154-168) is ttb_dot(psi, psi) + this + ttb_set_z. */
+int ttb_scale_sites(ttb_handle h, const double* divisor);
 int ttb_normalize_eachmatrix(ttb_handle h);
 /* marginals (src/abstract_tensor_train.jl:208-220): out[b][t][x], batch*L*Q doubles */
 int ttb_marginals(ttb_handle h, double* out);

@@ -783,6 +783,121 @@ def isapprox(A, B, atol=0.0, rtol=1e-6) -> bool:
     return na ** 2 + nb ** 2 - 2 * dot(A, B) <= max(atol, rtol * max(na, nb)) ** 2
 
 
+
+# ----------------------------------------------------------------------------------------------
+# MPS Born-machine wrapper (src/MatrixProductStates/mps.jl), real Float64 (conj is a no-op)
+# ----------------------------------------------------------------------------------------------
+class MPS:
+    """``p(x) = |psi(x)|^2`` over a wrapped train ``psi`` (``mps.jl:19-21``)."""
+
+    def __init__(self, psi):
+        self.psi = psi
+
+    def __len__(self):
+        return len(self.psi)
+
+
+def _id4(d):
+    """``id4`` (``mps.jl:56``): ``[a == a1 && b == b1]`` indexed ``[a, a1, b, b1]``"""
+    e = np.eye(d)
+    return np.einsum("ac,bd->acbd", e, e)
+
+
+def mps_evaluate(p: MPS, X) -> float:
+    """``mps.jl:54``"""
+    return abs(evaluate(p.psi, X)) ** 2
+
+
+def mps_accumulate_L(p: MPS, normalize=True):
+    """``mps.jl:60-80``: ``Ll[a1, al, b1, bl]``, hermiticity restored after every step"""
+    psi = p.psi
+    Ll = _id4(psi[0].shape[0])
+    z = LogNum(1.0)
+    out = []
+    for Al in psi:
+        A = _reshape1(Al)
+        nl = np.max(np.abs(Ll))
+        if nl != 0 and normalize:
+            Ll /= nl
+            z = z * nl
+        Ll = np.einsum("acbd,cex,dfx->aebf", Ll, A, A, optimize=True)
+        Ll = (np.transpose(Ll, (2, 3, 0, 1)) + Ll) / 2
+        out.append(Ll)
+    z = z * float(np.einsum("aabb->", Ll))
+    return out, z
+
+
+def mps_accumulate_R(p: MPS, normalize=True):
+    """``mps.jl:82-103``: ``Rl[al, aL, bl, bL]``"""
+    psi = p.psi
+    Rl = _id4(psi[len(psi) - 1].shape[1])
+    z = LogNum(1.0)
+    out = []
+    for Al in reversed(psi.tensors):
+        A = _reshape1(Al)
+        nl = np.max(np.abs(Rl))
+        if nl != 0 and normalize:
+            Rl /= nl
+            z = z * nl
+        Rl = np.einsum("ecfd,aex,bfx->acbd", Rl, A, A, optimize=True)
+        Rl = (np.transpose(Rl, (2, 3, 0, 1)) + Rl) / 2
+        out.append(Rl)
+    z = z * float(np.einsum("aabb->", Rl))
+    return out[::-1], z
+
+
+def mps_normalization(p: MPS) -> LogNum:
+    """``mps.jl:139-146``: ``z / abs2(psi.z)``"""
+    _, z = mps_accumulate_L(p)
+    return z / (p.psi.z * p.psi.z)
+
+
+def mps_normalize(p: MPS) -> float:
+    """``normalize!`` (``mps.jl:154-168``): tensors divided by ``|Z|^(1/2L)``, ``psi.z = 1``, returns
+    ``log(|Z| / abs2(psi.z))``"""
+    Z = mps_accumulate_L(p)[1]
+    L = len(p)
+    x = math.exp(0.5 * Z.logabs / L)
+    if x != 0:
+        for a in p.psi.tensors:
+            a /= x
+    logz = Z.logabs - 2.0 * p.psi.z.logabs
+    p.psi.z = LogNum(1.0)
+    return logz
+
+
+def mps_marginals(p: MPS):
+    """``mps.jl:178-196``"""
+    psi = p.psi
+    l, _ = mps_accumulate_L(p)
+    r, _ = mps_accumulate_R(p)
+    d = psi[0].shape[0]
+    out = []
+    for t in range(len(psi)):
+        A = _reshape1(psi[t])
+        R = r[t + 1] if t + 1 < len(psi) else _id4(d)
+        Lm = l[t - 1] if t >= 1 else _id4(d)
+        pt = np.einsum("acbd,cex,dfx,eafb->x", Lm, A, A, R, optimize=True)
+        pt = pt / pt.sum()
+        out.append(pt.reshape(psi[t].shape[2:], order="F"))
+    return out
+
+
+def mps_exact_prob(p: MPS) -> np.ndarray:
+    """``test/exact.jl`` for an MPS: enumerate ``|psi(x)|^2``"""
+    return np.abs(_exact_values(p.psi)) ** 2
+
+
+def _exact_values(A) -> np.ndarray:
+    """all values ``tr(prod A_t(x_t)) / z`` as an array over the flattened configurations (site-major)"""
+    L = len(A)
+    Ts = [_reshape1(a) for a in A]
+    cur = np.moveaxis(Ts[0], 2, 0)  # (x, a, b)
+    for t in range(1, L):
+        nxt = np.moveaxis(Ts[t], 2, 0)
+        cur = np.einsum("kab,xbc->kxac", cur, nxt).reshape(-1, cur.shape[1], nxt.shape[2])
+    return np.einsum("kaa->k", cur) / float(A.z)
+
 # ----------------------------------------------------------------------------------------------
 # brute force  (test/exact.jl:1-50)
 # ----------------------------------------------------------------------------------------------

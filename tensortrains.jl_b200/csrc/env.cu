@@ -527,8 +527,18 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s, int
   c.log_out = w.env_log + (left ? 0 : h->batch); c.sign_out = w.env_sign + (left ? 0 : h->batch);
   c.normalize = normalize;
   if (small_path(h)) {
-    if (left) { TTB_LAUNCH(h, "k_env_small_L", k_env_small<true><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store)); }
-    else { TTB_LAUNCH(h, "k_env_small_R", k_env_small<false><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store)); }
+    const size_t raw = sizeof(double) * 1024 * (size_t)h->Q;
+    const bool pf = raw <= 64 * 1024 && getenv("TTB_ENV_NOPREFETCH") == nullptr;
+    static bool eattr = false;
+    if (!eattr) {
+      cudaFuncSetAttribute(k_env_small<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(k_env_small<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      eattr = true;
+    }
+    if (left && pf) { TTB_LAUNCH(h, "k_env_small_L", (k_env_small<true, true><<<(unsigned)h->batch, 128, raw, h->stream>>>(c, store))); }
+    else if (left) { TTB_LAUNCH(h, "k_env_small_L", (k_env_small<true, false><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store))); }
+    else if (pf) { TTB_LAUNCH(h, "k_env_small_R", (k_env_small<false, true><<<(unsigned)h->batch, 128, raw, h->stream>>>(c, store))); }
+    else { TTB_LAUNCH(h, "k_env_small_R", (k_env_small<false, false><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store))); }
     return TTB_OK;
   }
   const int thr = env_threads(h);
@@ -704,6 +714,22 @@ int ttb_normalize(ttb_handle h, double* logz_out) {
   TTB_TRY(read_status(h, &st));
   if (st & 8) return fail(TTB_EDOMAIN, "log of a negative number: normalize! on a train with negative z");
   return TTB_OK;
+}
+
+// every site tensor of train b divided by divisor[b] (z untouched): the rescaling step of normalize!
+// (src/abstract_tensor_train.jl:189-193) on its own, used by the MPS wrapper's normalize!
+// (src/MatrixProductStates/mps.jl:154-168), whose factor |Z|^(1/2L) comes from ttb_dot(psi, psi)
+int ttb_scale_sites(ttb_handle h, const double* divisor) {
+  TTB_TRY(check_handle(h));
+  if (!divisor) return fail(TTB_EINVAL, "null argument");
+  TTB_TRY(ensure_env_ws(h));
+  Workspace& w = h->ws;
+  double* factor = w.env_log + 2 * h->batch;
+  TTB_CUDA(cudaMemcpyAsync(factor, divisor, sizeof(double) * h->batch, cudaMemcpyHostToDevice, h->stream));
+  CallTimer tm(h);
+  dim3 g((unsigned)std::min<int64_t>((h->tt_stride + 1023) / 1024, 4096), (unsigned)h->batch);
+  TTB_LAUNCH(h, "k_scale_trains", k_scale_trains<<<g, 256, 0, h->stream>>>(h->slab, h->tt_stride, factor));
+  return tm.finish();
 }
 
 int ttb_normalize_eachmatrix(ttb_handle h) {

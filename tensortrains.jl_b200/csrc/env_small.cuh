@@ -18,48 +18,25 @@ namespace ttb {
 
 constexpr int kSmallLD = 36;
 
-// warp tile of a 32 x 32 x 32 product: rows 16 mt .. +16, columns 8 nt0 .. +16.
-// A(m, k) at Aop[m * ARS + k * ACS], B(k, n) at Bop[k * BKS + n * BNS]
-template <int ARS, int ACS, int BKS, int BNS>
-__device__ __forceinline__ void mma32_warp(double (&d)[2][4], const double* Aop, const double* Bop, int mt, int nt0, int g,
-                                           int tq) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const double* pa = Aop + (mt * 16 + g) * ARS + (ks * 8 + tq) * ACS;
-    const double af[4] = {pa[0], pa[8 * ARS], pa[4 * ACS], pa[8 * ARS + 4 * ACS]};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const double* pb = Bop + (ks * 8 + tq) * BKS + ((nt0 + j) * 8 + g) * BNS;
-      const double bf[2] = {pb[0], pb[4 * BKS]};
-      dmma_16x8x8(d[j], af, bf);
-    }
-  }
-}
-
-// block max over 4 warps of NaN-propagating max-abs values (ordered bits: NaN > inf > finite)
-__device__ __forceinline__ double block4_max_bits(double mx, double* red, int lane, int wid) {
-  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bits, o);
-    bits = ot > bits ? ot : bits;
-  }
-  if (lane == 0) red[wid] = __longlong_as_double((long long)bits);
-  __syncthreads();
-  unsigned long long bb = 0ull;
-#pragma unroll
-  for (int w2 = 0; w2 < 4; ++w2) {
-    const unsigned long long v = (unsigned long long)__double_as_longlong(red[w2]);
-    bb = v > bb ? v : bb;
-  }
-  return __longlong_as_double((long long)bb);
-}
-
 // l[t] = (l[t-1]/max|l[t-1]|) T_t  (LEFT)   /   r[t] = T_t (r[t+1]/max|r[t+1]|)  (RIGHT),  T_t = sum_x A_t(x).
 // The stored environments carry the reference's scaling (every stored matrix but the last one computed
 // has max-abs 1, :93-97), c.store == 0 skips the stores (normalize! only needs z).
-template <bool LEFT>
-__global__ void __launch_bounds__(128, 8) k_env_small(EnvCtx c, int store) {
+// PF: the raw site tensor travels global -> shared with cp.async (16-byte chunks, no registers) into a
+// staging buffer; the copy of site t+1 is issued as soon as site t has been summed into Ts and overlaps the
+// MMA, the max reduction and the stores of step t.  Without PF (Q too large for the staging buffer) the
+// loads are issued at the top of the step and only other CTAs hide their latency.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool LEFT, bool PF>
+__global__ void __launch_bounds__(128, PF ? 6 : 8) k_env_small(EnvCtx c, int store) {
   constexpr int LD = kSmallLD;
   const int b = blockIdx.x;
   const int* bond = c.bond + (int64_t)b * c.L1;
@@ -71,7 +48,15 @@ __global__ void __launch_bounds__(128, 8) k_env_small(EnvCtx c, int store) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, tq = lane & 3;
   const int mt = wid & 1, nt0 = (wid >> 1) * 2;
   const int r = LEFT ? bond[0] : bond[c.L];
+  extern __shared__ __align__(16) double raw[];   // PF: one site tensor at its current dims (<= 1024 Q doubles)
   for (int i = tid; i < LD * 32; i += 128) { E[i] = ((i % LD) == (i / LD) && (i / LD) < r) ? 1.0 : 0.0; Ts[i] = 0.0; }
+  auto issue = [&](int t) {
+    const double* A = tt + c.off[t];
+    const int tot = bond[t] * bond[t + 1] * c.Q;
+    for (int i = tid; i < (tot >> 1); i += 128) cp_async16(raw + 2 * i, A + 2 * i);
+    if ((tot & 1) && tid == 0) cp_async8(raw + tot - 1, A + tot - 1);
+  };
+  if (PF) issue(LEFT ? 0 : c.L - 1);
   double logz = 0.0;
   for (int s = 0; s < c.L; ++s) {
     const int t = LEFT ? s : c.L - 1 - s;
@@ -81,15 +66,28 @@ __global__ void __launch_bounds__(128, 8) k_env_small(EnvCtx c, int store) {
     double tv[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) tv[m] = 0.0;
-#pragma unroll 2
-    for (int x = 0; x < c.Q; ++x) {   // 8 independent loads per x in flight
+    if (PF) {
+      cp_async_wait_all();
+      __syncthreads();   // site t has landed (and the previous step's readers of Ts / writers of E are done)
+      for (int x = 0; x < c.Q; ++x) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int idx = tid + 128 * m, i = idx & 31, j = idx >> 5;
-        if (i < dl && j < dr) tv[m] += A[i + dl * j + nn * x];
+        for (int m = 0; m < 8; ++m) {
+          const int idx = tid + 128 * m, i = idx & 31, j = idx >> 5;
+          if (i < dl && j < dr) tv[m] += raw[i + dl * j + (int)nn * x];
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int x = 0; x < c.Q; ++x) {   // 8 independent loads per x in flight
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int idx = tid + 128 * m, i = idx & 31, j = idx >> 5;
+          if (i < dl && j < dr) tv[m] += A[i + dl * j + nn * x];
+        }
       }
     }
-    __syncthreads();  // the previous step's readers of Ts / writers of E are done
+    __syncthreads();  // the previous step's readers of Ts / writers of E are done; PF: every thread has read raw
+    if (PF && s + 1 < c.L) issue(LEFT ? s + 1 : c.L - 2 - s);
 #pragma unroll
     for (int m = 0; m < 8; ++m) { const int idx = tid + 128 * m; Ts[(idx & 31) + LD * (idx >> 5)] = tv[m]; }
     __syncthreads();

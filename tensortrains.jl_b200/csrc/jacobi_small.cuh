@@ -13,6 +13,82 @@
 
 namespace ttb {
 
+// Two pairs of one round in ONE warp, interleaved in source order (both pairs' loads, then both dots, one
+// combined butterfly, both rotations, both stores) and branch-free: a pair that needs no rotation gets
+// cs = 1, sn = 0.  In a batch the SM is full of warps that each walk one long dependent chain per pair;
+// with half the warps and two independent chains per warp the same issue slots hide twice the latency.
+template <int WL, int WR>
+__device__ __forceinline__ int jacobi_two_pairs(double* B, double* J, double* sq, int i0, int j0, int i1, int j1, double tol2,
+                                                int lane) {
+  constexpr int EPL = WL / 32, JPL = WR / 32;
+  double* bi[2] = {B + i0 * WL + lane, B + i1 * WL + lane};
+  double* bj[2] = {B + j0 * WL + lane, B + j1 * WL + lane};
+  double* ji[2] = {J + i0 * WR + lane, J + i1 * WR + lane};
+  double* jj[2] = {J + j0 * WR + lane, J + j1 * WR + lane};
+  const int ii[2] = {i0, i1}, jx[2] = {j0, j1};
+  double x[2][EPL], y[2][EPL], u_[2][JPL], v_[2][JPL], al[2], be[2], ga[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int m = 0; m < EPL; ++m) { x[k][m] = bi[k][32 * m]; y[k][m] = bj[k][32 * m]; }
+#pragma unroll
+    for (int m = 0; m < JPL; ++m) { u_[k][m] = ji[k][32 * m]; v_[k][m] = jj[k][32 * m]; }
+    al[k] = sq[ii[k]]; be[k] = sq[jx[k]];
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    double g0 = 0.0;
+#pragma unroll
+    for (int m = 0; m < EPL; ++m) g0 += x[k][m] * y[k][m];
+    ga[k] = g0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ga[0] += __shfl_xor_sync(0xffffffffu, ga[0], o);
+    ga[1] += __shfl_xor_sync(0xffffffffu, ga[1], o);
+  }
+  int rotated = 0;
+  double cs[2], sn[2], dsq[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool rot = al[k] > 0.0 && be[k] > 0.0 && ga[k] * ga[k] > tol2 * al[k] * be[k];
+    // same rotation as the single-pair path: cos 2th = |da|/h, sin 2th = sign(da) b2/h
+    const double da = be[k] - al[k], b2 = 2.0 * ga[k];
+    double h2 = da * da + b2 * b2, das = da, b2s = b2;
+    if (rot && !(h2 > 1e-280 && h2 < 1e280)) {   // rare: rescale before squaring
+      const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+      das = da * sc; b2s = b2 * sc;
+      h2 = das * das + b2s * b2s;
+    }
+    const double r = rsqrt_nr(rot ? h2 : 1.0);
+    const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+    const double uu = rot ? 0.5 + 0.5 * c2 : 1.0;
+    const double ic = rsqrt_nr(uu);
+    cs[k] = rot ? uu * ic : 1.0;
+    sn[k] = rot ? 0.5 * s2 * ic : 0.0;
+    dsq[k] = sn[k] * ic * ga[k];
+    rotated |= rot ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (sn[k] != 0.0 || cs[k] != 1.0) {
+#pragma unroll
+      for (int m = 0; m < EPL; ++m) {
+        bi[k][32 * m] = cs[k] * x[k][m] - sn[k] * y[k][m];
+        bj[k][32 * m] = sn[k] * x[k][m] + cs[k] * y[k][m];
+      }
+#pragma unroll
+      for (int m = 0; m < JPL; ++m) {
+        ji[k][32 * m] = cs[k] * u_[k][m] - sn[k] * v_[k][m];
+        jj[k][32 * m] = sn[k] * u_[k][m] + cs[k] * v_[k][m];
+      }
+      sq[ii[k]] = al[k] - dsq[k];
+      sq[jx[k]] = be[k] + dsq[k];
+    }
+  }
+  return rotated;
+}
+
 template <int WR, int WL>
 __global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jacobi_small(SweepCtx c, StepDesc s) {
   pdl_enter();
@@ -58,6 +134,15 @@ __global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jac
       for (int q = wid; q < npairs; q += nw) {
         int i, j;
         rr_pair(nvp, rd, q, i, j);
+        if constexpr (WR == 32 && WL == 32) if (q + nw < npairs) {   // fewer warps than pairs: this warp's next pair rides along (two chains interleaved)
+          int i2, j2;
+          rr_pair(nvp, rd, q + nw, i2, j2);
+          if (j < nv && j2 < nv) {
+            if (jacobi_two_pairs<WL, WR>(B, J, sq, i, j, i2, j2, tol2, lane)) rotated = 1;
+            q += nw;
+            continue;
+          }
+        }
         if (j >= nv) continue;
         double* bi = B + i * WL + lane;
         double* bj = B + j * WL + lane;

@@ -782,6 +782,85 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   }
 }
 
+// Small absorb (m', n, N <= 32: every step of a config-5 batch).  The tiled kernel above launches Q tiny CTAs
+// per train (168 registers each, a ticket and an atomic per CTA) and is bound by CTA turnover; here ONE CTA
+// per train stages S once, walks x, multiplies on the tensor cores out of zero-padded shared memory
+// (leading dimension 36: conflict-free fragments), takes the block max and commits the step itself.
+__global__ void __launch_bounds__(128, 8) k_absorb_small(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  constexpr int LD = 36;
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  const int mprime = c.st[b].mprime[s.slot];
+  const int n = d.n, N = d.N;
+  const int64_t p = d.p;
+  const double* X = xbuf(c, s.xin, b);
+  const double* Bv = c.Bv + (int64_t)b * c.bv_stride;
+  const int* perm = c.perm + (int64_t)b * c.n_max;
+  const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+  double* Xn = xbuf(c, s.xin ^ 1, b);
+  const double scale_in = c.st[b].scale_in[s.slot];
+  __shared__ double Ss[LD * 32];   // S(a, l)     at a + LD l
+  __shared__ double Ns[LD * 32];   // Nbr_x(l, j) at l + LD j
+  __shared__ double red[4];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, tq = lane & 3;
+  const int mt = wid & 1, nt0 = (wid >> 1) * 2;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int idx = tid + 128 * m;
+    int a, l;
+    if (d.mode == 0) { a = idx & 31; l = idx >> 5; } else { l = idx & 31; a = idx >> 5; }
+    double v = 0.0;
+    if (a < mprime && l < n) {
+      if (d.mode == 0) v = a <= l ? X[a + p * l] * scale_in : 0.0;
+      else v = Bv[(int64_t)perm[a] * c.ldv + l];
+    }
+    Ss[a + LD * l] = v;
+  }
+  const int64_t ldo = (int64_t)mprime * c.Q;
+  double mx = 0.0;
+  for (int x = 0; x < c.Q; ++x) {
+    double w[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int idx = tid + 128 * m;
+      int l, j;
+      if (s.dir == 1) { l = idx & 31; j = idx >> 5; } else { j = idx & 31; l = idx >> 5; }
+      w[m] = 0.0;
+      if (l < n && j < N) w[m] = s.dir == 1 ? nbr[l + (int64_t)n * (j + (int64_t)N * x)] : nbr[j + (int64_t)N * (l + (int64_t)n * x)];
+    }
+    if (x > 0) __syncthreads();   // the previous x's MMA has read Ns
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int idx = tid + 128 * m;
+      int l, j;
+      if (s.dir == 1) { l = idx & 31; j = idx >> 5; } else { j = idx & 31; l = idx >> 5; }
+      Ns[l + LD * j] = w[m];
+    }
+    __syncthreads();
+    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    mma32_warp<1, LD, 1, LD>(acc, Ss, Ns, mt, nt0, g, tq);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gi = mt * 16 + g + ((e & 2) ? 8 : 0);
+        const int gj = (nt0 + nt) * 8 + tq * 2 + (e & 1);
+        if (gi < mprime && gj < N) {
+          Xn[(gi + (int64_t)mprime * x) + ldo * gj] = acc[nt][e];
+          mx = absmax_nan(mx, acc[nt][e]);
+        }
+      }
+  }
+  __syncthreads();
+  const double m = block4_max_bits(mx, red, lane, wid);
+  if (tid == 0) {
+    atomicMax(&c.st[b].maxabs_bits[s.slot], (unsigned long long)__double_as_longlong(m));
+    __threadfence();
+    commit_train(c, s, b, (int)gridDim.x);
+  }
+}
+
 // Skinny absorb (m' <= 32 retained directions: every step of a truncating sweep once the bonds are small).
 // The tiled kernel above walks K in 8 synchronised stages per CTA and has only a handful of CTAs to run:
 // ~16 us of pure latency for 4 MFLOP.  Here one CTA owns 8 output columns, loads ALL of S (m' x n) and its
@@ -1242,7 +1321,9 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
         if (nv_ub <= 32 && len_ub <= 32) {
           auto ks = k_jacobi_small<32, 32>;
-          SW_LAUNCH("k_jacobi", ks, B, std::min(512, thr), sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
+          // a batch that fills the GPU runs half the warps with two interleaved pairs each (jacobi_two_pairs)
+          const int thr32 = (B >= 2 * sm_count && thr > 256 && getenv("TTB_JACOBI_NOILP") == nullptr) ? 256 : std::min(512, thr);
+          SW_LAUNCH("k_jacobi", ks, B, thr32, sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
         } else {
           auto ks = k_jacobi_small<64, 64>;
           SW_LAUNCH("k_jacobi", ks, B, thr, sizeof(double) * (2 * 64 + 2 * 64 * 64), c, s);
@@ -1289,7 +1370,9 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     {
       const size_t sk_smem = sizeof(double) * ((size_t)(32 + AS_TN) * as_ld(n_ub) + 4 * 2 * 32 * 4);
       // (a batch that already fills the GPU is better off with the small-footprint tiled kernel)
-      if (mp_ub <= 32 && sk_smem <= (size_t)200 * 1024 && (int64_t)B * Q * ((N_ub + AS_TN - 1) / AS_TN) <= 2 * (int64_t)sm_count &&
+      if (mp_ub <= 32 && n_ub <= 32 && N_ub <= 32 && (int64_t)B * Q >= 64 && getenv("TTB_ABSORB_NOSMALL") == nullptr) {
+        SW_LAUNCH("k_absorb_small", k_absorb_small, B, 128, 0, c, s);
+      } else if (mp_ub <= 32 && sk_smem <= (size_t)200 * 1024 && (int64_t)B * Q * ((N_ub + AS_TN - 1) / AS_TN) <= 2 * (int64_t)sm_count &&
           getenv("TTB_ABSORB_TILED") == nullptr) {
         dim3 g(1, (N_ub + AS_TN - 1) / AS_TN, Q * B);
         SW_LAUNCH("k_absorb_mma", k_absorb_skinny, g, 128, sk_smem, c, s);

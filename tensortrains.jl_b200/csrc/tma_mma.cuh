@@ -60,6 +60,44 @@ __device__ __forceinline__ void dmma_16x8x8(double (&d)[4], const double (&a)[4]
       : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
+// ---- 32 x 32 x 32 products of the small-bond kernels (env_small.cuh, twovar_mma.cuh, k_absorb_small) ----
+// warp tile of a 32 x 32 x 32 product: rows 16 mt .. +16, columns 8 nt0 .. +16.
+// A(m, k) at Aop[m * ARS + k * ACS], B(k, n) at Bop[k * BKS + n * BNS]
+template <int ARS, int ACS, int BKS, int BNS>
+__device__ __forceinline__ void mma32_warp(double (&d)[2][4], const double* Aop, const double* Bop, int mt, int nt0, int g,
+                                           int tq) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const double* pa = Aop + (mt * 16 + g) * ARS + (ks * 8 + tq) * ACS;
+    const double af[4] = {pa[0], pa[8 * ARS], pa[4 * ACS], pa[8 * ARS + 4 * ACS]};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double* pb = Bop + (ks * 8 + tq) * BKS + ((nt0 + j) * 8 + g) * BNS;
+      const double bf[2] = {pb[0], pb[4 * BKS]};
+      dmma_16x8x8(d[j], af, bf);
+    }
+  }
+}
+
+// block max over 4 warps of NaN-propagating max-abs values (ordered bits: NaN > inf > finite)
+__device__ __forceinline__ double block4_max_bits(double mx, double* red, int lane, int wid) {
+  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = ot > bits ? ot : bits;
+  }
+  if (lane == 0) red[wid] = __longlong_as_double((long long)bits);
+  __syncthreads();
+  unsigned long long bb = 0ull;
+#pragma unroll
+  for (int w2 = 0; w2 < 4; ++w2) {
+    const unsigned long long v = (unsigned long long)__double_as_longlong(red[w2]);
+    bb = v > bb ? v : bb;
+  }
+  return __longlong_as_double((long long)bb);
+}
+
 }  // namespace ttb
 
 namespace ttb {

@@ -91,6 +91,7 @@ _sig("ttb_accumulate_R", _h, C.c_int, _pd, _pd, _pi)
 _sig("ttb_normalization", _h, _pd, _pi)
 _sig("ttb_normalize", _h, _pd)
 _sig("ttb_normalize_eachmatrix", _h)
+_sig("ttb_scale_sites", _h, _pd)
 _sig("ttb_marginals", _h, _pd)
 _sig("ttb_twovar_count", _h, _i64, _pi64)
 _sig("ttb_twovar_marginals", _h, _i64, _pd)
@@ -791,3 +792,82 @@ def isapprox(A, B, atol: float = 0.0, rtol: float = 1e-6, ba: int = 0, bb: int =
 
 
 __all__ += ["dot", "dot_log", "norm", "norm2m", "isapprox"]
+
+
+# ---- MPS Born-machine wrapper (src/MatrixProductStates/mps.jl) ------------------
+class MPS:
+    """``p(x) = |psi(x)|^2`` over a device train ``psi`` (src/MatrixProductStates/mps.jl:19-25).
+
+    Built so far on the device: ``evaluate`` (:54), ``normalization`` (:139-146, the ``d^4`` environment
+    chain of ``accumulate_L`` is the ``dot(psi, psi)`` chain of ``dot.cu``), ``normalize_`` (:154-168) and the
+    sweeps, which the reference forwards to the wrapped train (:234-252).  ``marginals`` /
+    ``twovar_marginals`` / ``sample`` of an MPS need the stored ``d^4`` environments and are not built yet:
+    they raise ``NotImplementedError`` instead of falling back to the CPU."""
+
+    def __init__(self, psi: AbstractTensorTrain):
+        if getattr(psi, "batched", False):
+            raise NotImplementedError("MPS over a batched handle")
+        self.psi = psi
+
+    def __len__(self):
+        return self.psi.L
+
+    def copy(self):
+        return MPS(self.psi.copy())
+
+
+def mps_evaluate(p: MPS, X) -> float:
+    """``abs2(evaluate(p.psi, X...))`` (mps.jl:54)"""
+    v = evaluate(p.psi, X)
+    return v * v
+
+
+def mps_normalization(p: MPS) -> Logarithmic:
+    """``accumulate_L(p)[2] / abs2(psi.z)`` (mps.jl:139-146) = ``dot(psi, psi)``"""
+    return dot_log(p.psi, p.psi)
+
+
+def mps_normalize_(p: MPS) -> float:
+    """``normalize!(p::MPS)`` (mps.jl:154-168): tensors divided by ``|Z|^(1/2L)``, ``psi.z = 1``; returns
+    ``log(|Z| / abs2(psi.z))``"""
+    zn = dot_log(p.psi, p.psi)                     # = Z / z^2
+    zpsi = p.psi.z
+    raw = zn.logabs + 2.0 * zpsi.logabs            # log|Z| of the environment chain itself
+    x = math.exp(0.5 * raw / p.psi.L)
+    if x != 0.0 and math.isfinite(x):
+        _ck(lib.ttb_scale_sites(p.psi._hd, _dp(np.array([x], dtype=np.float64))))
+    _ck(lib.ttb_set_z(p.psi._hd, 0, 0.0, 1))
+    return zn.logabs
+
+
+def mps_compress_(p: MPS, svd_trunc=None, is_orthogonal: str = "none"):
+    """forwarded to the wrapped train (mps.jl:250-252)"""
+    compress_(p.psi, svd_trunc, is_orthogonal=is_orthogonal)
+    return p
+
+
+def mps_orthogonalize_left_(p: MPS, svd_trunc=None):
+    """mps.jl:238-240"""
+    orthogonalize_left_(p.psi, svd_trunc)
+    return p
+
+
+def mps_orthogonalize_right_(p: MPS, svd_trunc=None):
+    """mps.jl:234-236"""
+    orthogonalize_right_(p.psi, svd_trunc)
+    return p
+
+
+def _mps_not_built(name):
+    def f(p, *a, **k):
+        raise NotImplementedError(f"{name}(::MPS): the d^4 environments of mps.jl:60-126 are not built on the device yet")
+    f.__name__ = name
+    return f
+
+
+mps_marginals = _mps_not_built("marginals")
+mps_twovar_marginals = _mps_not_built("twovar_marginals")
+mps_sample = _mps_not_built("sample")
+
+__all__ += ["MPS", "mps_evaluate", "mps_normalization", "mps_normalize_", "mps_compress_", "mps_orthogonalize_left_",
+            "mps_orthogonalize_right_"]

@@ -127,3 +127,31 @@ def test_config5_batch_properties():
         e1 = T.evaluate(A, X, b=b)
         assert np.max(np.abs(e1 - e0[i]) / np.abs(e0[i])) <= 1e-3      # TruncThresh(1e-6) per bond, 64 bonds
         assert max(T.bond_dims(A, b)) < d
+
+
+def test_config5_large_batch_matches_oracle():
+    """A batch that fills the GPU (>= 2 trains per SM) takes the batch-tuned kernels -- two interleaved Jacobi
+    pairs per warp, one-CTA-per-train absorb / thin Q, three panel CTAs per SM: bond dimensions and values of
+    sampled trains against the oracle (C5 shape, shortened to 12 sites)."""
+    from oracle import tt_oracle as O
+    B, L, d, q = 320, 12, 32, 2
+    rng = RNG(55)
+    ts = [rng.random((B, d, d, q)) for _ in range(L)]
+    A = T.PeriodicTensorTrain(ts, batched=True)
+    lz = T.normalize_(A)
+    m2 = T.twovar_marginals(A)
+    T.compress_(A, T.TruncThresh(1e-6))
+    X = rng.integers(0, q, (6, L)).astype(np.int32)
+    for b in (0, 1, 159, 160, 318, 319):
+        Ao = O.PeriodicTensorTrain([a[b].copy() for a in ts])
+        lzo = O.normalize(Ao)
+        assert abs(lz[b] - lzo) <= 1e-10 * abs(lzo)
+        m2o = O.twovar_marginals(Ao)
+        for k in m2o:
+            assert np.allclose(m2[b][k], m2o[k], rtol=1e-10, atol=0), (b, k)
+        O.compress(Ao, O.TruncThresh(1e-6))
+        assert T.bond_dims(A, b) == O.bond_dims(Ao), (b, T.bond_dims(A, b), O.bond_dims(Ao))
+        g = T.evaluate(A, X, b=b)
+        for i in range(X.shape[0]):
+            o = O.evaluate(Ao, [(int(v),) for v in X[i]])
+            assert abs(g[i] - o) <= 1e-7 * abs(o), (b, i, g[i], o)

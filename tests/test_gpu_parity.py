@@ -697,3 +697,50 @@ def test_sum_of_batched_trains_after_compress():
         assert T.bond_dims(S, b) == O.bond_dims(So)
         for g, o in zip(S.tensors(b), So.tensors):
             assert g.shape == o.shape and np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_batched_small_step_kernels(periodic):
+    """batches with B*Q >= 64 take the one-CTA-per-train small-step kernels (k_absorb_small, k_apply_q_small)"""
+    rng = RNG(950 + periodic)
+    Bn, q = 36, (2,)
+    bonds = [4, 6, 3, 5, 7] if periodic else [1, 4, 7, 6, 3, 1]
+    n = len(bonds) if periodic else len(bonds) - 1
+    ts = [rng.random((Bn, bonds[t], bonds[(t + 1) % len(bonds)]) + q) for t in range(n)]
+    cls, ocls = (T.PeriodicTensorTrain, O.PeriodicTensorTrain) if periodic else (T.TensorTrain, O.TensorTrain)
+    for trunc, otrunc in ((T.TruncThresh(1e-5), O.TruncThresh(1e-5)), (T.TruncBond(3), O.TruncBond(3))):
+        A = cls(ts, batched=True)
+        T.compress_(A, trunc)
+        for b in range(0, Bn, 5):
+            Ao = ocls([a[b].copy() for a in ts])
+            O.compress(Ao, otrunc)
+            assert T.bond_dims(A, b) == O.bond_dims(Ao), (b, T.bond_dims(A, b), O.bond_dims(Ao))
+            X = rand_points(rng, Ao, 4)
+            gv = T.evaluate(A, X, b=b)
+            for i in range(4):
+                assert close(gv[i], o_eval_flat(Ao, X[i]), 1e-8)
+
+
+# ---- MPS wrapper (section 8f rank 2, the part that maps onto existing kernels): test/mps.jl:18-85 ------------
+@pytest.mark.parametrize("z", [1.0, 2.0, -0.5])
+def test_mps_wrapper_matches_oracle(z):
+    rng = RNG(960)
+    ts = [rng.standard_normal(s) for s in [(1, 5, 2, 2), (5, 4, 2, 2), (4, 10, 2, 2), (10, 1, 2, 2)]]
+    psi, psio = pair(ts, z=z)
+    p, po = T.MPS(psi), O.MPS(psio)
+    zn, zno = T.mps_normalization(p), O.mps_normalization(po)
+    assert zn.sign == zno.sign == 1 and close(zn.logabs, zno.logabs, REL, 1e-12)
+    X = [tuple(int(rng.integers(0, 2)) for _ in range(2)) for _ in range(4)]
+    assert close(T.mps_evaluate(p, X), O.mps_evaluate(po, X), REL)
+    px = T.mps_evaluate(p, X)
+    T.mps_orthogonalize_left_(p, T.TruncThresh(0.0))                      # test/mps.jl:71-75
+    assert close(T.mps_evaluate(p, X), px, 1e-9)
+    T.mps_orthogonalize_right_(p, T.TruncThresh(0.0))
+    assert close(T.mps_evaluate(p, X), px, 1e-9)
+    logz, logzo = T.mps_normalize_(p), O.mps_normalize(po)
+    assert close(logz, logzo, REL, 1e-12)
+    one = T.mps_normalization(p)
+    assert abs(one.logabs) <= 1e-12 and one.sign == 1
+    assert close(T.mps_evaluate(p, X), O.mps_evaluate(po, X), 1e-9)
+    with pytest.raises(NotImplementedError):
+        T.mps_marginals(p)

@@ -360,3 +360,30 @@ def test_sum_and_difference_of_trains(N, q):
     assert math.isclose(O.evaluate(Ap, xp) - O.evaluate(Bp, xp), O.evaluate(O.minus(Ap, Bp), xp), rel_tol=1e-12)
     with pytest.raises(ValueError):
         O.plus(A, O.rand_tt(rng, [1, 2, 1], *qs))
+
+
+# ---- MPS wrapper: test/mps.jl:18-67 (real Float64; the reference test uses ComplexF64) ----------------
+@pytest.mark.parametrize("z", [1.0, 2.0, -0.5])
+def test_mps_normalization_and_marginals_vs_brute_force(z):
+    rng = RNG(810)
+    psi = O.TensorTrain([rng.standard_normal(s) for s in [(1, 5, 2, 2), (5, 4, 2, 2), (4, 6, 2, 2), (6, 1, 2, 2)]], z=z)
+    p = O.MPS(psi)
+    q = O.mps_exact_prob(p)
+    zn = float(O.mps_normalization(p))
+    assert math.isclose(zn, q.sum(), rel_tol=1e-12)                       # z ~ sum(q)
+    assert math.isclose(zn, O.norm(psi) ** 2, rel_tol=1e-12)              # z ~ abs2(norm(psi))
+    (Lm, zL), (Rm, zR) = O.mps_accumulate_L(p, False), O.mps_accumulate_R(p, False)
+    assert math.isclose(float(zL), float(zR), rel_tol=1e-12)
+    assert math.isclose(float(np.einsum("aabb->", Lm[-1])), float(np.einsum("aabb->", Rm[0])), rel_tol=1e-12)
+    x = _rand_x(rng, psi)
+    assert math.isclose(O.mps_evaluate(p, x), O.evaluate(psi, x) ** 2, rel_tol=1e-14)
+    qq = q.reshape([4] * 4)
+    for t, mt in enumerate(O.mps_marginals(p)):                           # exact_marginals(p) ~ marginals(p)
+        pt = qq.sum(axis=tuple(i for i in range(4) if i != t))
+        assert np.allclose(pt / pt.sum(), mt.reshape(-1, order="F"), rtol=1e-11, atol=0)
+    pc = O.MPS(psi.copy())
+    logz = O.mps_normalize(pc)
+    assert math.isclose(float(O.mps_normalization(pc)), 1.0, rel_tol=1e-12)
+    assert math.isclose(math.exp(logz), zn, rel_tol=1e-12)
+    O.mps_normalize(pc)
+    assert math.isclose(float(O.mps_normalization(pc)), 1.0, rel_tol=1e-12)
