@@ -1321,8 +1321,11 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
         if (nv_ub <= 32 && len_ub <= 32) {
           auto ks = k_jacobi_small<32, 32>;
-          // a batch that fills the GPU runs half the warps with two interleaved pairs each (jacobi_two_pairs)
-          const int thr32 = (B >= 2 * sm_count && thr > 256 && getenv("TTB_JACOBI_NOILP") == nullptr) ? 256 : std::min(512, thr);
+          // TTB_JACOBI_ILP=1: half the warps with two interleaved pairs each (jacobi_two_pairs).  Measured on the
+          // 4096-train batch of config 5: 34.4 ms either way -- the round is bound by instruction issue, not by
+          // the latency of one warp's chain -- so it stays off by default.
+          static const bool ilp = getenv("TTB_JACOBI_ILP") != nullptr;
+          const int thr32 = (ilp && B >= 2 * sm_count && thr > 256) ? 256 : std::min(512, thr);
           SW_LAUNCH("k_jacobi", ks, B, thr32, sizeof(double) * (2 * 32 + 2 * 32 * 32), c, s);
         } else {
           auto ks = k_jacobi_small<64, 64>;
