@@ -104,10 +104,23 @@ __global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
         }
       }
     }
+    if constexpr (QQ == 4) {
+      // four totals with 6 shuffles instead of 20: every level sends the half the partner keeps; afterwards
+      // lanes 0, 8, 16, 24 hold the totals of values 0, 1, 2, 3
+      const bool h16 = lane & 16, h8 = lane & 8;
+      const double b0 = (h16 ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, h16 ? acc[0] : acc[2], 16);
+      const double b1 = (h16 ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, h16 ? acc[1] : acc[3], 16);
+      double cv = (h8 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, h8 ? b0 : b1, 8);
+      cv += __shfl_xor_sync(0xffffffffu, cv, 4);
+      cv += __shfl_xor_sync(0xffffffffu, cv, 2);
+      cv += __shfl_xor_sync(0xffffffffu, cv, 1);
+      if ((lane & 7) == 0) red[par][wid][lane >> 3] = cv;
+    } else {
 #pragma unroll
-    for (int i = 0; i < QQ; ++i) {
-      acc[i] = warp_sum(acc[i]);
-      if (lane == 0) red[par][wid][i] = acc[i];
+      for (int i = 0; i < QQ; ++i) {
+        acc[i] = warp_sum(acc[i]);
+        if (lane == 0) red[par][wid][i] = acc[i];
+      }
     }
     if (more) prefetch_G(u + 1);                   // ... and its GT, consumed one full step from now
     double d[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
