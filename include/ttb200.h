@@ -143,6 +143,10 @@ int ttb_marginals(ttb_handle h, double* out);
  * order, each Q*Q doubles column-major (x_t fastest); *npairs receives the count per train. */
 int ttb_twovar_count(ttb_handle h, int64_t maxdist, int64_t* npairs);
 int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out);
+/* the pairs (t, u) with t_lo <= t < t_hi only (0-based first site): a contiguous block of the full result
+ * (pairs are stored t-major); out holds batch x (pairs in the range) x Q*Q doubles.  This is the unit one
+ * rank computes when the pair marginals of ONE train are sharded over GPUs (third axis). */
+int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out);
 
 /* ---- evaluate (src/abstract_tensor_train.jl:80-83): X is n x L row-major int32 of 0-based flat
  *      physical indices; evaluates train b at n points; out = tr(prod A_t(x_t)) / z */

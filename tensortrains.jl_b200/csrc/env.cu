@@ -372,10 +372,11 @@ struct TwoCtx {
   int maxdist;
   double* out;                              // [batch][npairs][Q*Q]
   int64_t npairs;
+  int t0;                                   // first site of the range this launch covers (blockIdx.x = t - t0)
 };
 
 __global__ void k_twovar(TwoCtx c) {
-  const int t = blockIdx.x, b = blockIdx.y;
+  const int t = blockIdx.x + c.t0, b = blockIdx.y;
   if (t >= c.L - 1) return;
   const int* bond = c.bond + (int64_t)b * c.L1;
   const double* tt = c.slab + (int64_t)b * c.tt_stride;
@@ -799,13 +800,21 @@ int ttb_twovar_count(ttb_handle h, int64_t maxdist, int64_t* npairs) {
 }
 
 int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
+  if (!h) return fail(TTB_EINVAL, "null argument");
+  return ttb_twovar_marginals_range(h, maxdist, 0, h->L - 1, out);
+}
+
+// pairs (t, u) with t_lo <= t < t_hi only (0-based first site; pairs are stored t-major, so this is a contiguous
+// block of the full result): the unit one rank computes when the pairs of ONE train are sharded over GPUs
+int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out) {
   TTB_TRY(check_handle(h));
   if (!out) return fail(TTB_EINVAL, "null argument");
   const int64_t L = h->L, Q = h->Q;
+  if (t_lo < 0 || t_hi > L - 1 || t_lo > t_hi) return fail(TTB_EINVAL, "pair range [%lld, %lld) outside [0, %lld)", (long long)t_lo, (long long)t_hi, (long long)(L - 1));
   if (maxdist <= 0) maxdist = L - 1;
   int64_t npairs = 0;
   ttb_twovar_count(h, maxdist, &npairs);
-  if (npairs == 0) return TTB_OK;
+  if (npairs == 0 || t_lo == t_hi) return TTB_OK;
   if (Q * Q * sizeof(double) > 40 * 1024) return fail(TTB_EUNSUPPORTED, "twovar_marginals supports Q <= 71");
   TTB_TRY(ensure_env_ws(h));
   Workspace& w = h->ws;
@@ -858,17 +867,17 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
         fc.envL = w.envL; fc.env_stride = w.env_stride; fc.eoffL = s.d_eoffL;
         fc.GT = d_GT; fc.Tm = d_Tm; fc.gstride = gstride; fc.tstride = tstride;
         fc.pair_off = d_poff; fc.maxdist = (int)std::min<int64_t>(maxdist, L); fc.out = d_out; fc.npairs = npairs;
-        fc.kcap = (int)kcap; fc.dmax = (int)h->dmax;
+        fc.kcap = (int)kcap; fc.dmax = (int)h->dmax; fc.t0 = (int)t_lo;
         static bool fattr = false;
         if (!fattr) { cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); fattr = true; }
         // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh)
         const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
-        const dim3 gm((unsigned)(L - 1), (unsigned)h->batch);
+        const dim3 gm((unsigned)(t_hi - t_lo), (unsigned)h->batch);
         if (use_mma && Q == 2) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<2><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
         else if (use_mma && Q == 3) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<3><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
         else if (use_mma && Q == 4) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<4><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
         else
-        TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<dim3((unsigned)(L - 1), (unsigned)h->batch), 256, fast_smem, h->stream>>>(fc));
+        TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<gm, 256, fast_smem, h->stream>>>(fc));
         rc = tm.finish();
       }
     } else if (rc == TTB_OK) {
@@ -877,15 +886,18 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
       c.L = (int)L; c.L1 = (int)L + 1; c.Q = (int)Q;
       c.envL = w.envL; c.envR = w.envR; c.env_stride = w.env_stride; c.eoffL = s.d_eoffL; c.eoffR = s.d_eoffR;
       c.scratch = d_scr; c.scratch_stride = scr_stride; c.pair_off = d_poff; c.maxdist = (int)std::min<int64_t>(maxdist, L);
-      c.out = d_out; c.npairs = npairs;
-      dim3 g((unsigned)(L - 1), (unsigned)h->batch);
+      c.out = d_out; c.npairs = npairs; c.t0 = (int)t_lo;
+      dim3 g((unsigned)(t_hi - t_lo), (unsigned)h->batch);
       static bool attr = false;
       if (!attr) { cudaFuncSetAttribute(k_twovar, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
       TTB_LAUNCH(h, "k_twovar", k_twovar<<<g, 256, scr_in_smem ? smem_need : sizeof(double) * Q * Q, h->stream>>>(c));
       rc = tm.finish();
     }
     if (rc == TTB_OK) {
-      e = cudaMemcpy(out, d_out, sizeof(double) * h->batch * npairs * Q * Q, cudaMemcpyDeviceToHost);
+      // the range's pairs are the block [poff[t_lo], poff[t_hi]) of every train's result
+      const int64_t p_lo = poff[t_lo], p_hi = t_hi < L - 1 ? poff[t_hi] : npairs;
+      const size_t row = sizeof(double) * (size_t)(p_hi - p_lo) * Q * Q;
+      e = cudaMemcpy2D(out, row, d_out + p_lo * Q * Q, sizeof(double) * npairs * Q * Q, row, (size_t)h->batch, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = fail(TTB_ECUDA, "twovar copy: %s", cudaGetErrorString(e));
     }
   }

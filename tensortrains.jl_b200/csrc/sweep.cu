@@ -890,26 +890,25 @@ __global__ void __launch_bounds__(128) k_absorb_skinny(SweepCtx c, StepDesc s) {
     const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
     const double scale_in = c.st[b].scale_in[s.slot];
     const int mt_n = (mprime + 15) >> 4;   // 16-row tiles in use
-    for (int idx = tid; idx < 16 * mt_n * ld; idx += 128) {
-      const int i = idx / ld, l = idx - i * ld;
-      double v = 0.0;
-      if (i < mprime && l < n) {
-        if (d.mode == 0) v = i <= l ? X[i + p * l] * scale_in : 0.0;
-        else v = Bv[(int64_t)perm[i] * c.ldv + l];
+    // staging: thread = column l (coalesced over the warp), rows unrolled so that eight independent loads are
+    // in flight per thread and no index needs a division (the one-shot load IS this kernel's critical path)
+    for (int l = tid; l < ld; l += 128) {
+      const bool lin = l < n;
+      if (d.mode == 0) {
+#pragma unroll 8
+        for (int i = 0; i < 16 * mt_n; ++i) Ss[i * ld + l] = (lin && i < mprime && i <= l) ? X[i + p * l] * scale_in : 0.0;
+      } else {
+#pragma unroll 8
+        for (int i = 0; i < 16 * mt_n; ++i) Ss[i * ld + l] = (lin && i < mprime) ? Bv[(int64_t)perm[i] * c.ldv + l] : 0.0;
       }
-      Ss[idx] = v;
-    }
-    if (s.dir == 1) {
-      for (int idx = tid; idx < AS_TN * ld; idx += 128) {
-        const int jj = idx / ld, l = idx - jj * ld;
-        const int gj = j0 + jj;
-        Bs[idx] = (gj < N && l < n) ? nbr[l + (int64_t)n * (gj + (int64_t)N * x)] : 0.0;
-      }
-    } else {
-      for (int idx = tid; idx < AS_TN * ld; idx += 128) {
-        const int jj = idx % AS_TN, l = idx / AS_TN;
-        const int gj = j0 + jj;
-        Bs[jj * ld + l] = (gj < N && l < n) ? nbr[gj + (int64_t)N * (l + (int64_t)n * x)] : 0.0;
+      if (s.dir == 1) {
+#pragma unroll
+        for (int jj = 0; jj < AS_TN; ++jj)
+          Bs[jj * ld + l] = (lin && j0 + jj < N) ? nbr[l + (int64_t)n * (j0 + jj + (int64_t)N * x)] : 0.0;
+      } else {
+        const double* src = nbr + j0 + (int64_t)N * (l + (int64_t)n * x);   // AS_TN consecutive values
+#pragma unroll
+        for (int jj = 0; jj < AS_TN; ++jj) Bs[jj * ld + l] = (lin && j0 + jj < N) ? src[jj] : 0.0;
       }
     }
     __syncthreads();

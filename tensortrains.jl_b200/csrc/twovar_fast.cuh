@@ -53,11 +53,12 @@ struct TwoFast {
   double* out; int64_t npairs;
   int kcap;   // doubles reserved per K_x buffer (r0max * dmax)
   int dmax;
+  int t0;     // first site of the range this launch covers (blockIdx.x = t - t0)
 };
 
 // one CTA per (t, train): walks u = t+1 .. t+maxdist
 __global__ void __launch_bounds__(256) k_twovar_fast(TwoFast c) {
-  const int t = blockIdx.x, b = blockIdx.y;
+  const int t = blockIdx.x + c.t0, b = blockIdx.y;
   if (t >= c.L - 1) return;
   const int* bond = c.bond + (int64_t)b * c.L1;
   const double* tt = c.slab + (int64_t)b * c.tt_stride;

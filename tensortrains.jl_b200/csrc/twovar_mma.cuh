@@ -21,7 +21,7 @@ template <int Q>
 __global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
   constexpr int LDK = 68, LDT = 36, QQ = Q * Q;
   constexpr int EPT = (8 + Q - 1) / Q;   // Frobenius elements per thread: d_1 <= 64 / Q, so d_1 d_u <= 256 EPT
-  const int t = blockIdx.x, b = blockIdx.y;
+  const int t = blockIdx.x + c.t0, b = blockIdx.y;
   if (t >= c.L - 1) return;
   const int* bond = c.bond + (int64_t)b * c.L1;
   const double* tt = c.slab + (int64_t)b * c.tt_stride;

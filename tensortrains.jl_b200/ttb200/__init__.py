@@ -28,7 +28,7 @@ __all__ = [
     "TruncThresh", "TruncBond", "TruncBondMax", "TruncBondThresh",
     "flat_tt", "rand_tt", "randn_tt", "flat_periodic_tt", "rand_periodic_tt",
     "bond_dims", "nparams", "evaluate", "accumulate_L", "accumulate_R", "normalization", "lognormalization",
-    "normalize_", "normalize_eachmatrix_", "marginals", "twovar_marginals", "compress_",
+    "normalize_", "normalize_eachmatrix_", "marginals", "twovar_marginals", "twovar_marginals_block", "compress_",
     "orthogonalize_right_", "orthogonalize_left_", "orthogonalize_center_", "orthogonalize_two_site_center_",
     "is_left_canonical", "is_right_canonical", "is_canonical", "sample", "sample_stats", "lib", "TTBError",
 ]
@@ -92,6 +92,7 @@ _sig("ttb_normalization", _h, _pd, _pi)
 _sig("ttb_normalize", _h, _pd)
 _sig("ttb_normalize_eachmatrix", _h)
 _sig("ttb_scale_sites", _h, _pd)
+_sig("ttb_twovar_marginals_range", _h, _i64, _i64, _i64, _pd)
 _sig("ttb_marginals", _h, _pd)
 _sig("ttb_twovar_count", _h, _i64, _pi64)
 _sig("ttb_twovar_marginals", _h, _i64, _pd)
@@ -635,6 +636,18 @@ def twovar_marginals(A, maxdist: Optional[int] = None):
                 i += 1
         res.append(d)
     return res if A.batched else res[0]
+
+
+def twovar_marginals_block(A, t_lo: int, t_hi: int, maxdist: Optional[int] = None) -> np.ndarray:
+    """The pairs ``(t, u)`` with ``t_lo <= t < t_hi`` (0-based) of :func:`twovar_marginals` as one array
+    ``(batch, pairs in the range, Q*Q)``, t-major like the full result: the unit one rank computes when the
+    pair marginals of a train are sharded over GPUs (``ttb200.parallel.twovar_marginals_sharded``)."""
+    md = A.L - 1 if maxdist is None else int(maxdist)
+    n = sum(min(A.L - 1, t + md) - t for t in range(int(t_lo), int(t_hi)))
+    out = np.zeros((A.batch, n, A.Q * A.Q))
+    if n:
+        _ck(lib.ttb_twovar_marginals_range(A._hd, md, int(t_lo), int(t_hi), _dp(out)))
+    return out
 
 
 # ---- sweeps --------------------------------------------------------------------------------------

@@ -54,3 +54,61 @@ def max_over_ranks(x: float) -> float:
     t = torch.tensor([float(x)], dtype=torch.float64, device=_device(dist))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def pair_ranges(L: int, maxdist: int, world: int):
+    """Contiguous ranges [t_lo, t_hi) of first sites, one per rank, with (almost) equal numbers of pairs
+    (t, u), t < u <= t + maxdist -- the third sharding axis of SURVEY.md 8e: the pair marginals of ONE train.
+    The environments are recomputed on every rank (one streaming pass); only the O(L^2) pair loop is split."""
+    counts = [min(L - 1, t + maxdist) - t for t in range(L - 1)]
+    total = sum(counts)
+    bounds, acc, r = [0], 0, 1
+    for t, c in enumerate(counts):
+        acc += c
+        while r < world and acc * world >= total * r:
+            bounds.append(t + 1)
+            r += 1
+    while len(bounds) < world:
+        bounds.append(L - 1)
+    bounds.append(L - 1)
+    return [(bounds[k], bounds[k + 1]) for k in range(world)]
+
+
+def allgather_ragged(arr: np.ndarray, lengths) -> np.ndarray:
+    """Concatenate per-rank arrays whose axis-0 lengths differ (`lengths[k]` for rank k, known to all ranks):
+    pad to the longest, all-gather, trim."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return arr
+    m = max(int(n) for n in lengths)
+    pad = np.zeros((m,) + arr.shape[1:], dtype=arr.dtype)
+    pad[: arr.shape[0]] = arr
+    full = allgather(pad[None])                     # (world, m, ...)
+    return np.concatenate([full[k, : int(lengths[k])] for k in range(len(lengths))], axis=0)
+
+
+def twovar_marginals_sharded(A, maxdist=None, block=None):
+    """``twovar_marginals`` of one train with the pairs sharded over the ranks (every rank holds the train):
+    rank k computes the pairs whose first site lies in ``pair_ranges(...)[k]`` and the blocks are all-gathered
+    (NCCL on GPUs).  ``block(A, t_lo, t_hi, maxdist) -> (pairs, Q*Q) array`` defaults to the CUDA path; the
+    gloo test passes the oracle.  Returns the reference's dict ``(t, u) -> array``."""
+    import torch.distributed as dist
+    L = len(A)
+    md = L - 1 if maxdist is None else int(maxdist)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    ranges = pair_ranges(L, md, world)
+    if block is None:
+        import ttb200 as T
+        block = lambda A_, lo, hi, md_: T.twovar_marginals_block(A_, lo, hi, md_)[0]
+    lo, hi = ranges[rank]
+    mine = np.ascontiguousarray(block(A, lo, hi, md))
+    lengths = [sum(min(L - 1, t + md) - t for t in range(a, b)) for a, b in ranges]
+    full = allgather_ragged(mine, lengths)
+    q = tuple(A.q) if hasattr(A, "q") else tuple(A[0].shape[2:])
+    out, i = {}, 0
+    for t in range(L - 1):
+        for u in range(t + 1, min(L - 1, t + md) + 1):
+            out[(t, u)] = full[i].reshape(q + q, order="F")
+            i += 1
+    return out

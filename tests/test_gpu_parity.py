@@ -744,3 +744,30 @@ def test_mps_wrapper_matches_oracle(z):
     assert close(T.mps_evaluate(p, X), O.mps_evaluate(po, X), 1e-9)
     with pytest.raises(NotImplementedError):
         T.mps_marginals(p)
+
+
+@pytest.mark.parametrize("case", ["open_d40", "periodic_d20", "batched"])
+def test_twovar_marginals_block_is_a_slice_of_the_full_result(case):
+    """ttb_twovar_marginals_range: the unit of the pair-sharded multi-GPU path (all three kernels)"""
+    rng = RNG(970)
+    if case == "open_d40":
+        A = T.TensorTrain(rand_open(rng, [1, 40, 40, 33, 40, 12, 1], (2,)))       # k_twovar_fast
+    elif case == "periodic_d20":
+        A = T.PeriodicTensorTrain(rand_per(rng, [20, 16, 20, 9, 14], (2,)))       # k_twovar_mma
+    else:
+        bonds = [4, 6, 3, 5]
+        A = T.PeriodicTensorTrain([rng.random((3, bonds[t], bonds[(t + 1) % 4], 2)) for t in range(4)], batched=True)
+    L = A.L
+    for md in (None, 2):
+        full = T.twovar_marginals(A, md)
+        full = full if A.batched else [full]
+        mdv = L - 1 if md is None else md
+        for lo, hi in ((0, L - 1), (0, 1), (1, 3), (L - 2, L - 1), (2, 2)):
+            blk = T.twovar_marginals_block(A, lo, hi, md)
+            i = 0
+            for t in range(lo, hi):
+                for u in range(t + 1, min(L - 1, t + mdv) + 1):
+                    for b in range(A.batch):
+                        assert np.array_equal(blk[b, i], full[b][(t, u)].reshape(-1, order="F")), (case, md, lo, hi, t, u)
+                    i += 1
+            assert i == blk.shape[1]

@@ -93,3 +93,69 @@ def test_two_rank_sharding_and_collectives():
         assert np.array_equal(allr, np.array([[float(b), float(b) ** 2] for b in range(6)]))
         assert tmax == 2.0
     assert res[0][4] == (0, 32) and res[1][4] == (32, 64)
+
+
+def _oracle_block(A, lo, hi, md):
+    """the pairs with first site in [lo, hi) from the CPU oracle, t-major, flattened column-major"""
+    from oracle import tt_oracle as O
+    m2 = O.twovar_marginals(A, maxdist=md)
+    L = len(A)
+    rows = [m2[(t, u)].reshape(-1, order="F") for t in range(lo, hi) for u in range(t + 1, min(L - 1, t + md) + 1)]
+    Q = int(np.prod(A[0].shape[2:]))
+    return np.array(rows).reshape(len(rows), Q * Q)
+
+
+def _worker_pairs(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "tensortrains.jl_b200", "ttb200")):
+        sys.path.insert(0, p)
+    import parallel as P
+    from oracle import tt_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.Generator(np.random.Philox(19))
+        A = O.rand_tt(rng, [1, 3, 4, 2, 3, 2, 1], 2, 2)
+        res = {}
+        for md in (None, 2):
+            full = P.twovar_marginals_sharded(A, md, block=_oracle_block)
+            res[md] = {k: v.copy() for k, v in full.items()}
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pair_ranges_partition():
+    sys.path.insert(0, os.path.join(ROOT, "tensortrains.jl_b200", "ttb200"))
+    import parallel as P
+    for L, md, w in ((128, 127, 8), (64, 63, 3), (10, 3, 4), (5, 4, 8), (2, 1, 2), (7, 6, 1)):
+        r = P.pair_ranges(L, md, w)
+        assert len(r) == w and r[0][0] == 0 and r[-1][1] == L - 1
+        assert all(r[k][1] == r[k + 1][0] and r[k][0] <= r[k][1] for k in range(w - 1))
+        cnt = [sum(min(L - 1, t + md) - t for t in range(a, b)) for a, b in r]
+        per_t = max(min(L - 1, t + md) - t for t in range(L - 1))
+        assert max(cnt) - min(c for c in cnt) <= 2 * per_t or w > L - 1      # balanced up to one site's pairs
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_pair_marginals():
+    """the pair marginals of ONE train sharded over two ranks by first site, all-gathered (ragged blocks)"""
+    from oracle import tt_oracle as O
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_pairs, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.Generator(np.random.Philox(19))
+    A = O.rand_tt(rng, [1, 3, 4, 2, 3, 2, 1], 2, 2)
+    for md in (None, 2):
+        ref = O.twovar_marginals(A, maxdist=md)
+        for rank, got in res:
+            assert set(got[md]) == set(ref)
+            for k in ref:
+                assert np.array_equal(got[md][k], ref[k])
