@@ -782,6 +782,120 @@ __global__ void __launch_bounds__(128) k_absorb_mma(SweepCtx c, StepDesc s) {
   }
 }
 
+// Pipelined absorb for the large eps = 0 steps (mode 0, dimensions exact on the host and multiples of 32: every
+// bulk step of config 3's right sweep).  k_absorb_mma walks K in stages of 32 with ONE stage of register
+// prefetch: every stage pays a global-load round trip (~1 us) and two barriers, ~20 us for 67 MFLOP, on the
+// critical path between two site QRs.  Here both operand tiles travel global -> shared with cp.async
+// (16-byte chunks, no registers), three stages deep, so after the first round trip a stage costs its 8 DMMAs
+// per warp and one barrier; the lazy scale of R (scale_in) is applied to the accumulators (the product is
+// linear); the below-diagonal part of the diagonal K-block (Householder vectors sharing storage with R) is
+// masked in the fragments of that one stage.
+#define AP_STAGES 3
+__device__ __forceinline__ void ap_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(128) k_absorb_pipe(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  const int b = blockIdx.z / c.Q, x = blockIdx.z % c.Q;
+  const Dims d = get_dims(c, s, b);          // exact, host known
+  const int n = d.n, N = d.N, mprime = d.k;  // eps = 0: every direction is kept
+  const int64_t p = d.p;
+  const int i0 = blockIdx.x * AM_T, j0 = blockIdx.y * AM_T;
+  const double* X = xbuf(c, s.xin, b);
+  const double* nbr = c.slab + (int64_t)b * c.tt_stride + c.off[s.nbr];
+  double* Xn = xbuf(c, s.xin ^ 1, b);
+  const double scale_in = c.st[b].scale_in[s.slot];
+  extern __shared__ __align__(16) double apsm[];   // [AP_STAGES][2][32][AM_LD]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = (wid & 1) * 16, wn = (wid >> 1) * 16;
+  // stage = S tile [l][i] (rows l of R^T: 32 consecutive i per l) + neighbour tile ([l][j] for dir 0, [j][l] for dir 1)
+  auto issue = [&](int l0, int st) {
+    double* Ss = apsm + (size_t)st * 2 * 32 * AM_LD;
+    double* Bs = Ss + 32 * AM_LD;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ch = tid + 128 * u, row = ch >> 4, c2 = (ch & 15) * 2;   // 32 rows x 16 chunks of two doubles
+      ap_cp16(Ss + row * AM_LD + c2, X + (i0 + c2) + p * (l0 + row));
+      if (s.dir == 0) ap_cp16(Bs + row * AM_LD + c2, nbr + (j0 + c2) + (int64_t)N * ((l0 + row) + (int64_t)n * x));
+      else            ap_cp16(Bs + row * AM_LD + c2, nbr + (l0 + c2) + (int64_t)n * ((j0 + row) + (int64_t)N * x));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int lstart = i0;                 // R is upper triangular: K starts at the tile's first row
+  const int nst = (n - lstart) / AM_K;
+#pragma unroll
+  for (int q = 0; q < AP_STAGES - 1; ++q) {
+    if (q < nst) issue(lstart + q * AM_K, q);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+  for (int q = 0; q < nst; ++q) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(AP_STAGES - 2) : "memory");
+    __syncthreads();                     // stage q landed for everybody; stage q-1's readers are done
+    if (q + AP_STAGES - 1 < nst) issue(lstart + (q + AP_STAGES - 1) * AM_K, (q + AP_STAGES - 1) % AP_STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* Ss = apsm + (size_t)(q % AP_STAGES) * 2 * 32 * AM_LD;
+    const double* Bs = Ss + 32 * AM_LD;
+    const bool diag = (q == 0);          // l0 == i0: entries with l < i belong to the Householder vectors
+#pragma unroll
+    for (int kk = 0; kk < AM_K; kk += 8) {
+      double af[4];
+      af[0] = Ss[(kk + t4) * AM_LD + wm + g];
+      af[1] = Ss[(kk + t4) * AM_LD + wm + g + 8];
+      af[2] = Ss[(kk + t4 + 4) * AM_LD + wm + g];
+      af[3] = Ss[(kk + t4 + 4) * AM_LD + wm + g + 8];
+      if (diag) {
+        if (kk + t4 < wm + g) af[0] = 0.0;
+        if (kk + t4 < wm + g + 8) af[1] = 0.0;
+        if (kk + t4 + 4 < wm + g) af[2] = 0.0;
+        if (kk + t4 + 4 < wm + g + 8) af[3] = 0.0;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        double bf[2];
+        if (s.dir == 0) {
+          bf[0] = Bs[(kk + t4) * AM_LD + wn + nt * 8 + g];
+          bf[1] = Bs[(kk + t4 + 4) * AM_LD + wn + nt * 8 + g];
+        } else {
+          bf[0] = Bs[(wn + nt * 8 + g) * AM_LD + kk + t4];
+          bf[1] = Bs[(wn + nt * 8 + g) * AM_LD + kk + t4 + 4];
+        }
+        dmma_16x8x8(acc[nt], af, bf);
+      }
+    }
+  }
+  const int64_t ldo = (int64_t)mprime * c.Q;
+  double mx = 0.0;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gi = i0 + wm + g + ((e & 2) ? 8 : 0);
+      const int gj = j0 + wn + nt * 8 + t4 * 2 + (e & 1);
+      const double v = acc[nt][e] * scale_in;
+      Xn[(gi + (int64_t)mprime * x) + ldo * gj] = v;
+      mx = absmax_nan(mx, v);
+    }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = other > bits ? other : bits;
+  }
+  if (lane == 0) atomicMax(&c.st[b].maxabs_bits[s.slot], bits);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int total = (int)(gridDim.x * gridDim.y) * c.Q;
+    if (atomicAdd(&c.st[b].ticket, 1) == total - 1) {
+      __threadfence();
+      c.st[b].ticket = 0;
+      commit_train(c, s, b, (int)gridDim.z / c.Q);
+    }
+  }
+}
+
 // Small absorb (m', n, N <= 32: every step of a config-5 batch).  The tiled kernel above launches Q tiny CTAs
 // per train (168 registers each, a ticket and an atomic per CTA) and is bound by CTA turnover; here ONE CTA
 // per train stages S once, walks x, multiplies on the tensor cores out of zero-padded shared memory
@@ -1378,6 +1492,14 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
           getenv("TTB_ABSORB_TILED") == nullptr) {
         dim3 g(1, (N_ub + AS_TN - 1) / AS_TN, Q * B);
         SW_LAUNCH("k_absorb_mma", k_absorb_skinny, g, 128, sk_smem, c, s);
+      } else if (qr_only && s.kp >= 0 && p_ub >= n_ub && n_ub % 32 == 0 && N_ub % 32 == 0 && (p_ub & 1) == 0 &&
+                 getenv("TTB_ABSORB_NOPIPE") == nullptr) {
+        // exact, 32-aligned eps = 0 step: cp.async pipeline (k_absorb_pipe)
+        static bool pattr = false;
+        const size_t psm = sizeof(double) * AP_STAGES * 2 * 32 * AM_LD;
+        if (!pattr) { cudaFuncSetAttribute(k_absorb_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm); pattr = true; }
+        dim3 g(n_ub / AM_T, N_ub / AM_T, Q * B);
+        SW_LAUNCH("k_absorb_mma", k_absorb_pipe, g, 128, psm, c, s);
       } else {
         dim3 g((mp_ub + AM_T - 1) / AM_T, (N_ub + AM_T - 1) / AM_T, Q * B);
         SW_LAUNCH("k_absorb_mma", k_absorb_mma, g, 128, 0, c, s);
