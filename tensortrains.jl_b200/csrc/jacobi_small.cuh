@@ -208,4 +208,130 @@ __global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jac
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_jacobi_g8<W> -- SVDs with k, n <= W (W = 32: config-5 batches; W = 64: the truncating steps of config 2)
+// in the regime where a round is bound by INSTRUCTION ISSUE: thousands of trains filling every SM, or one
+// train whose 32 pair-warps crowd one SM.  In k_jacobi_small a warp spends ~175 instructions on ONE pair,
+// most of them the scalar rotation algebra that all 32 lanes execute redundantly.  Here a warp handles FOUR
+// pairs of the round at once: 8 lanes per pair, lane e of a group holds W/8 consecutive elements of both rows
+// (and of both rotation rows), the dot is a 3-level butterfly inside the group, and every instruction of the
+// rotation algebra serves four different pairs.  Branch-free: a pair that needs no rotation skips only its
+// stores.  4 W threads per train (W/2 pairs per round), row stride W + 4.  Same rotation, same convergence
+// test, same ordering as k_jacobi_small; jacobi_finish (sort + rank rule on the device) unchanged.
+// Reference: `svd(M)` inside the truncating functors, src/svd_trunc.jl:37,73,97,129.
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(4 * W, W == 32 ? 8 : 1) k_jacobi_g8(SweepCtx c, StepDesc s) {
+  pdl_enter();
+  constexpr int LD = W + 4, NT = 4 * W, EL = W / 8, E2 = EL / 2;
+  const int b = blockIdx.x;
+  const Dims d = get_dims(c, s, b);
+  if (d.mode == 0) return;
+  const int nv = d.k, len = d.n, p = d.p;   // host guarantees nv <= W, len <= W
+  const double* X = xbuf(c, s.xin, b);
+  const double scale_in = c.st[b].scale_in[s.slot];
+  extern __shared__ __align__(16) double jsm[];
+  double* B = jsm;                // [W][LD]
+  double* J = B + W * LD;         // [W][LD]
+  double* sig = J + W * LD;       // W
+  double* srt = sig + W;          // W
+  __shared__ int rotated;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < W * W; i += NT) {
+    const int r = i % W, j = i / W;   // coalesced read of column j of X
+    double v = 0.0;
+    if (r < nv && j < len && !(d.mode == 1 && r > j)) v = X[r + (int64_t)p * j] * scale_in;
+    B[r * LD + j] = v;
+    J[r * LD + j] = (r == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int nvp = (nv + 1) & ~1;
+  const int npairs = nvp / 2, rounds = nvp - 1;
+  const double tol2 = (double)max(len, 2) * 2.220446049250313e-16 * 2.220446049250313e-16;
+  double* sq = sig;
+  // lane e of a group holds the element pairs {16 m + 2 e, 16 m + 2 e + 1}, m < W/16: the eight 16-byte accesses
+  // of a group are contiguous (128 bytes, one conflict-free wavefront per quarter warp)
+  const int grp = lane >> 3, e0 = (lane & 7) * 2;    // pair slot inside the warp, first element of this lane
+  const int q = wid * 4 + grp;                       // pair index of the round handled by this lane group
+  bool conv = (nv < 2);
+  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+    if (tid < W) {   // cached squared norms, recomputed once per sweep (one row per thread, stride LD: conflict-free)
+      double a0 = 0.0;
+      if (tid < nv) {
+#pragma unroll 8
+        for (int m = 0; m < W; ++m) { const double xx = B[tid * LD + m]; a0 += xx * xx; }
+      }
+      sq[tid] = a0;
+    }
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int rd = 0; rd < rounds; ++rd) {
+      int i = 0, j = 0;
+      bool act = q < npairs;
+      if (act) { rr_pair(nvp, rd, q, i, j); act = j < nv; }
+      if (!act) { i = 0; j = 0; }       // idle group: harmless loads, no stores
+      double2* bi = reinterpret_cast<double2*>(B + i * LD + e0);
+      double2* bj = reinterpret_cast<double2*>(B + j * LD + e0);
+      double2* ji = reinterpret_cast<double2*>(J + i * LD + e0);
+      double2* jj = reinterpret_cast<double2*>(J + j * LD + e0);
+      double2 x[E2], y[E2], u[E2], v[E2];
+#pragma unroll
+      for (int m = 0; m < E2; ++m) { x[m] = bi[8 * m]; y[m] = bj[8 * m]; u[m] = ji[8 * m]; v[m] = jj[8 * m]; }
+      const double al = sq[i], be = sq[j];
+      double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < E2; ++m) { g0 += x[m].x * y[m].x; g1 += x[m].y * y[m].y; }
+      double ga = g0 + g1;
+      ga += __shfl_xor_sync(0xffffffffu, ga, 4);
+      ga += __shfl_xor_sync(0xffffffffu, ga, 2);
+      ga += __shfl_xor_sync(0xffffffffu, ga, 1);
+      const bool rot = act && al > 0.0 && be > 0.0 && ga * ga > tol2 * al * be;
+      // same rotation as k_jacobi_small: cos 2th = |da|/h, sin 2th = sign(da) b2/h
+      const double da = be - al, b2 = 2.0 * ga;
+      double h2 = da * da + b2 * b2, das = da, b2s = b2;
+      if (rot && !(h2 > 1e-280 && h2 < 1e280)) {   // rare: rescale before squaring
+        const double sc = 1.0 / fmax(fabs(da), fabs(b2));
+        das = da * sc; b2s = b2 * sc;
+        h2 = das * das + b2s * b2s;
+      }
+      const double r = rsqrt_nr(rot ? h2 : 1.0);
+      const double c2 = fabs(das) * r, s2 = (da < 0.0 ? -b2s : b2s) * r;
+      const double uu = rot ? 0.5 + 0.5 * c2 : 1.0;
+      const double ic = rsqrt_nr(uu);
+      const double cs = uu * ic, sn = 0.5 * s2 * ic;
+      if (rot) {
+#pragma unroll
+        for (int m = 0; m < E2; ++m) {
+          bi[8 * m] = make_double2(cs * x[m].x - sn * y[m].x, cs * x[m].y - sn * y[m].y);
+          bj[8 * m] = make_double2(sn * x[m].x + cs * y[m].x, sn * x[m].y + cs * y[m].y);
+          ji[8 * m] = make_double2(cs * u[m].x - sn * v[m].x, cs * u[m].y - sn * v[m].y);
+          jj[8 * m] = make_double2(sn * u[m].x + cs * v[m].x, sn * u[m].y + cs * v[m].y);
+        }
+        if ((lane & 7) == 0) {
+          const double t = sn * ic;
+          sq[i] = al - t * ga;
+          sq[j] = be + t * ga;
+          rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    conv = (rotated == 0);
+    __syncthreads();
+  }
+  if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
+  jacobi_finish(c, s, b, B, LD, nv, len, sig, srt);
+  double* Bg = c.Bv + (int64_t)b * c.bv_stride;
+  double* Jg = c.Jv + (int64_t)b * c.jv_stride;
+  for (int i = tid; i < nv * len; i += NT) {
+    const int e = i % len, v2 = i / len;
+    Bg[(int64_t)v2 * c.ldv + e] = B[v2 * LD + e];
+  }
+  for (int i = tid; i < nv * nv; i += NT) {
+    const int e = i % nv, v2 = i / nv;
+    Jg[(int64_t)v2 * c.ldj + e] = J[v2 * LD + e];
+  }
+}
+__host__ __device__ constexpr size_t jg8_smem(int W) { return sizeof(double) * (2 * (size_t)W * (W + 4) + 2 * W); }
+
 }  // namespace ttb

@@ -1432,7 +1432,18 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         SW_LAUNCH("k_jacobi_finish", k_jacobi_finish, B, 1024, sizeof(double) * 2 * (size_t)w.n_max, c, s);
       } else if (nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
-        if (nv_ub <= 32 && len_ub <= 32) {
+        static const bool no_g8 = getenv("TTB_JACOBI_NOG8") != nullptr;
+        static bool g8attr = false;
+        if (!g8attr) { cudaFuncSetAttribute(k_jacobi_g8<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jg8_smem(64)); g8attr = true; }
+        if (nv_ub <= 32 && len_ub <= 32 && B >= sm_count && !no_g8) {
+          // a batch that fills the GPU is issue-bound: four pairs per warp (k_jacobi_g8)
+          auto kg = k_jacobi_g8<32>;
+          SW_LAUNCH("k_jacobi", kg, B, 128, jg8_smem(32), c, s);
+        } else if (!(nv_ub <= 32 && len_ub <= 32) && !no_g8) {
+          // k, n <= 64: 32 pair-warps of one train crowd one SM (issue-bound as well): 8 warps, four pairs each
+          auto kg = k_jacobi_g8<64>;
+          SW_LAUNCH("k_jacobi", kg, B, 256, jg8_smem(64), c, s);
+        } else if (nv_ub <= 32 && len_ub <= 32) {
           auto ks = k_jacobi_small<32, 32>;
           // TTB_JACOBI_ILP=1: half the warps with two interleaved pairs each (jacobi_two_pairs).  Measured on the
           // 4096-train batch of config 5: 34.4 ms either way -- the round is bound by instruction issue, not by
