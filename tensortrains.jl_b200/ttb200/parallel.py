@@ -87,28 +87,34 @@ def allgather_ragged(arr: np.ndarray, lengths) -> np.ndarray:
     return np.concatenate([full[k, : int(lengths[k])] for k in range(len(lengths))], axis=0)
 
 
-def twovar_marginals_sharded(A, maxdist=None, block=None):
-    """``twovar_marginals`` of one train with the pairs sharded over the ranks (every rank holds the train):
-    rank k computes the pairs whose first site lies in ``pair_ranges(...)[k]`` and the blocks are all-gathered
-    (NCCL on GPUs).  ``block(A, t_lo, t_hi, maxdist) -> (pairs, Q*Q) array`` defaults to the CUDA path; the
-    gloo test passes the oracle.  Returns the reference's dict ``(t, u) -> array``."""
+def gather_pair_blocks(L: int, q, maxdist: int, mine: np.ndarray):
+    """All-gather the per-rank blocks of pair marginals (rank k holds the pairs whose first site lies in
+    ``pair_ranges(L, maxdist, world)[k]``, t-major, one row of Q*Q values per pair) and return the reference's
+    dict ``(t, u) -> array`` shaped ``q + q``."""
     import torch.distributed as dist
-    L = len(A)
-    md = L - 1 if maxdist is None else int(maxdist)
     world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    ranges = pair_ranges(L, md, world)
-    if block is None:
-        import ttb200 as T
-        block = lambda A_, lo, hi, md_: T.twovar_marginals_block(A_, lo, hi, md_)[0]
-    lo, hi = ranges[rank]
-    mine = np.ascontiguousarray(block(A, lo, hi, md))
-    lengths = [sum(min(L - 1, t + md) - t for t in range(a, b)) for a, b in ranges]
-    full = allgather_ragged(mine, lengths)
-    q = tuple(A.q) if hasattr(A, "q") else tuple(A[0].shape[2:])
+    ranges = pair_ranges(L, maxdist, world)
+    lengths = [sum(min(L - 1, t + maxdist) - t for t in range(a, b)) for a, b in ranges]
+    full = allgather_ragged(np.ascontiguousarray(mine), lengths)
+    q = tuple(q)
     out, i = {}, 0
     for t in range(L - 1):
-        for u in range(t + 1, min(L - 1, t + md) + 1):
+        for u in range(t + 1, min(L - 1, t + maxdist) + 1):
             out[(t, u)] = full[i].reshape(q + q, order="F")
             i += 1
     return out
+
+
+def twovar_marginals_sharded(A, maxdist=None):
+    """``twovar_marginals`` of one device train with the pairs sharded over the ranks (every rank holds the
+    train): rank k computes the pairs whose first site lies in ``pair_ranges(...)[k]`` on its GPU
+    (``ttb_twovar_marginals_range``) and the ragged blocks are all-gathered (NCCL)."""
+    import torch.distributed as dist
+    import ttb200 as T
+    L = A.L
+    md = L - 1 if maxdist is None else int(maxdist)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = pair_ranges(L, md, world)[rank]
+    mine = T.twovar_marginals_block(A, lo, hi, md)[0]
+    return gather_pair_blocks(L, A.q, md, mine)

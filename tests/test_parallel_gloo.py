@@ -117,8 +117,11 @@ def _worker_pairs(rank, world, port, q):
         rng = np.random.Generator(np.random.Philox(19))
         A = O.rand_tt(rng, [1, 3, 4, 2, 3, 2, 1], 2, 2)
         res = {}
+        L = len(A)
         for md in (None, 2):
-            full = P.twovar_marginals_sharded(A, md, block=_oracle_block)
+            mdv = L - 1 if md is None else md
+            lo, hi = P.pair_ranges(L, mdv, world)[rank]
+            full = P.gather_pair_blocks(L, A[0].shape[2:], mdv, _oracle_block(A, lo, hi, mdv))
             res[md] = {k: v.copy() for k, v in full.items()}
         q.put((rank, res))
     finally:
