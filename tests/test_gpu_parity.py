@@ -311,7 +311,8 @@ def test_truncation_error_bound():
         assert O.norm2m(Ad, Bo) < (L * eps) ** 2 + 1e-13
 
 
-@pytest.mark.parametrize("d,q,L,B", [(32, (2,), 10, 3), (16, (4,), 7, 2), (21, (3,), 6, 2), (32, (2,), 5, 1)])
+@pytest.mark.parametrize("d,q,L,B", [(32, (2,), 10, 3), (16, (4,), 7, 2), (21, (3,), 6, 2), (32, (2,), 5, 1),
+                                     (6, (3, 4), 4, 2)])   # Q = 12: no cp.async staging buffer, scalar pair kernel
 def test_twovar_tensor_core_path_config5_shapes(d, q, L, B):
     """twovar_mma.cuh (bonds <= 32, Q d_1 <= 64): full bonds, then the ragged bonds compress! leaves."""
     rng = RNG(160 + d)
