@@ -522,7 +522,13 @@ def main():
                                         "sample": f"the full C3 compress! once in-process ({secs:.1f} s; subprocess failed: {ex!r}): "
                                                   "NumPy/SciPy-OpenBLAS gesdd restatement of the reference, not Julia/MKL"}
             try:
+                try:   # same BLAS thread count as the compress baseline picked
+                    from threadpoolctl import threadpool_limits
+                    _lim = threadpool_limits(limits=int(line["cpu_baseline"].get("cores", os.cpu_count())))
+                except Exception:
+                    _lim = None
                 extra["sample"]["cpu_draws_per_s"] = cpu_sample_draws_per_s(L4, D4, Q4, 4, 20)
+                extra["sample"]["cpu_blas_threads"] = int(line["cpu_baseline"].get("cores", 0))
                 # randn fill of config 3 (both sweeps full rank): reduced length
                 Lr = 48
                 br, tsr = make_open(3, Lr, D3, Q3, "randn")
