@@ -772,3 +772,16 @@ def test_twovar_marginals_block_is_a_slice_of_the_full_result(case):
                         assert np.array_equal(blk[b, i], full[b][(t, u)].reshape(-1, order="F")), (case, md, lo, hi, t, u)
                     i += 1
             assert i == blk.shape[1]
+
+
+def test_sharded_pair_marginals_single_process_path():
+    """parallel.twovar_marginals_sharded without a process group = one rank owning every pair (the N > 1 logic is
+    covered by the gloo test; the per-rank block by test_twovar_marginals_block_is_a_slice_of_the_full_result)"""
+    from ttb200 import parallel as P
+    rng = RNG(980)
+    A = T.TensorTrain(rand_open(rng, [1, 6, 9, 7, 5, 1], (3,)))
+    for md in (None, 2):
+        full, sh = T.twovar_marginals(A, md), P.twovar_marginals_sharded(A, md)
+        assert set(full) == set(sh)
+        for k in full:
+            assert np.array_equal(full[k], sh[k])
