@@ -847,7 +847,12 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
     const bool use_fast = fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr;
     double *d_GT = nullptr, *d_Tm = nullptr;
     if (rc == TTB_OK && use_fast) {
-      const int64_t gstride = (kcap + 15) & ~int64_t(15), tstride = (h->dmax * h->dmax + 15) & ~int64_t(15);
+      // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh); with the
+      // small-path precompute its operands are stored zero padded (no per-pair dimension handling)
+      const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
+      const bool padded = use_mma && small_path(h) && getenv("TTB_TWOVAR_NOPAD") == nullptr;
+      const int64_t gstride = padded ? ((h->bond0[0] * 32 + 15) & ~int64_t(15)) : ((kcap + 15) & ~int64_t(15));
+      const int64_t tstride = padded ? 1024 : ((h->dmax * h->dmax + 15) & ~int64_t(15));
       e = w.scr[3].ensure(sizeof(double) * h->batch * L * Q * gstride);
       if (e == cudaSuccess) e = w.scr[4].ensure(sizeof(double) * h->batch * L * tstride);
       d_GT = static_cast<double*>(w.scr[3].p); d_Tm = static_cast<double*>(w.scr[4].p);
@@ -857,7 +862,7 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
         pc.slab = h->slab; pc.tt_stride = h->tt_stride; pc.off = h->d_off; pc.bond = h->d_bond;
         pc.L = (int)L; pc.L1 = (int)L + 1; pc.Q = (int)Q;
         pc.envR = w.envR; pc.env_stride = w.env_stride; pc.eoffR = s.d_eoffR;
-        pc.GT = d_GT; pc.Tm = d_Tm; pc.gstride = gstride; pc.tstride = tstride;
+        pc.GT = d_GT; pc.Tm = d_Tm; pc.gstride = gstride; pc.tstride = tstride; pc.padded = padded ? 1 : 0;
         if (small_path(h)) { TTB_LAUNCH(h, "k_twovar_pre_small", k_twovar_pre_small<<<dim3((unsigned)L, (unsigned)h->batch), 128, 0, h->stream>>>(pc)); }
         else
         TTB_LAUNCH(h, "k_twovar_pre", k_twovar_pre<<<dim3((unsigned)L, (unsigned)h->batch), 256, 0, h->stream>>>(pc));
@@ -870,14 +875,19 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
         fc.kcap = (int)kcap; fc.dmax = (int)h->dmax; fc.t0 = (int)t_lo;
         static bool fattr = false;
         if (!fattr) { cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); fattr = true; }
-        // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh)
-        const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
         const dim3 gm((unsigned)(t_hi - t_lo), (unsigned)h->batch);
-        if (use_mma && Q == 2) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<2><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
-        else if (use_mma && Q == 3) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<3><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
-        else if (use_mma && Q == 4) { TTB_LAUNCH(h, "k_twovar_mma", k_twovar_mma<4><<<gm, 256, sizeof(int) * (L + 1), h->stream>>>(fc)); }
+        const size_t bsm = sizeof(int) * (L + 1);
+#define TTB_TV(Q_)                                                                                                        \
+  do {                                                                                                                    \
+    if (padded) { TTB_LAUNCH(h, "k_twovar_mma", (k_twovar_mma<Q_, true><<<gm, 256, bsm, h->stream>>>(fc))); }              \
+    else { TTB_LAUNCH(h, "k_twovar_mma", (k_twovar_mma<Q_, false><<<gm, 256, bsm, h->stream>>>(fc))); }                    \
+  } while (0)
+        if (use_mma && Q == 2) TTB_TV(2);
+        else if (use_mma && Q == 3) TTB_TV(3);
+        else if (use_mma && Q == 4) TTB_TV(4);
         else
         TTB_LAUNCH(h, "k_twovar_fast", k_twovar_fast<<<gm, 256, fast_smem, h->stream>>>(fc));
+#undef TTB_TV
         rc = tm.finish();
       }
     } else if (rc == TTB_OK) {

@@ -239,16 +239,18 @@ __global__ void __launch_bounds__(128, 6) k_twovar_pre_small(TwoPre c) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int a = mt * 16 + g, cc = (nt0 + j) * 8 + 2 * tq;
-      if (a < r0 && cc < dl) GT[a + r0 * cc] = d[j][0];
-      if (a < r0 && cc + 1 < dl) GT[a + r0 * (cc + 1)] = d[j][1];
-      if (a + 8 < r0 && cc < dl) GT[a + 8 + r0 * cc] = d[j][2];
-      if (a + 8 < r0 && cc + 1 < dl) GT[a + 8 + r0 * (cc + 1)] = d[j][3];
+      const int ccmax = c.padded ? 32 : dl;   // padded: columns >= dl are written as the zeros the MMA produced
+      if (a < r0 && cc < ccmax) GT[a + r0 * cc] = d[j][0];
+      if (a < r0 && cc + 1 < ccmax) GT[a + r0 * (cc + 1)] = d[j][1];
+      if (a + 8 < r0 && cc < ccmax) GT[a + 8 + r0 * cc] = d[j][2];
+      if (a + 8 < r0 && cc + 1 < ccmax) GT[a + 8 + r0 * (cc + 1)] = d[j][3];
     }
   }
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int idx = tid + 128 * m, i = idx & 31, j = idx >> 5;
-    if (i < dl && j < dr) Tm[i + dl * j] = Tsum[i + LD * j];
+    if (c.padded) Tm[i + 32 * j] = Tsum[i + LD * j];
+    else if (i < dl && j < dr) Tm[i + dl * j] = Tsum[i + LD * j];
   }
 }
 

@@ -17,6 +17,7 @@ struct TwoPre {
   const double* envR; int64_t env_stride; const int64_t* eoffR;
   double* GT; double* Tm;          // [batch][L][Q][gstride], [batch][L][tstride]
   int64_t gstride, tstride;
+  int padded;   // k_twovar_pre_small only: T_u as a zero-padded 32 x 32 (ld 32), GT_u(x) zero-padded to 32 columns
 };
 
 // one CTA per (site u, train): T_u and GT_u(x) for every x

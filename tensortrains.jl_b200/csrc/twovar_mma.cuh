@@ -17,7 +17,11 @@
 
 namespace ttb {
 
-template <int Q>
+// PAD: k_twovar_pre_small wrote T_u as a zero-padded 32 x 32 and GT_u(x) zero-padded to 32 columns, so the pair
+// loop needs no dimension lookups, no predicates that change from pair to pair and no address arithmetic beyond
+// two running pointers (ncu on the unpadded version: ~750 warp instructions per warp and pair, 384 of the
+// kernel's 1760 SASS instructions were IMADs of address math).
+template <int Q, bool PAD>
 __global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
   constexpr int LDK = 68, LDT = 36, QQ = Q * Q;
   constexpr int EPT = (8 + Q - 1) / Q;   // Frobenius elements per thread: d_1 <= 64 / Q, so d_1 d_u <= 256 EPT
@@ -58,22 +62,31 @@ __global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
   }
   const int uhi = min(c.L - 1, t + c.maxdist);
   double gq[EPT][Q], tp[4];
+  const double* gbase = c.GT + (int64_t)b * c.L * Q * c.gstride + tid;
+  const double* tbase = c.Tm + (int64_t)b * c.L * c.tstride + tid;
+  const int gs = (int)c.gstride, tsd = (int)c.tstride, nkp = r0 * 32;
   auto prefetch_G = [&](int u) {
-    const int nk = r0 * sbond[u];
+    const int nk = PAD ? nkp : r0 * sbond[u];
+    const double* GT = gbase + (int64_t)u * Q * gs;
 #pragma unroll
     for (int x = 0; x < Q; ++x) {
-      const double* GT = c.GT + (((int64_t)b * c.L + u) * Q + x) * c.gstride;
 #pragma unroll
-      for (int m = 0; m < EPT; ++m) { const int i = tid + 256 * m; gq[m][x] = i < nk ? GT[i] : 0.0; }
+      for (int m = 0; m < EPT; ++m) gq[m][x] = (tid + 256 * m < nk) ? GT[x * gs + 256 * m] : 0.0;
     }
   };
   auto prefetch_T = [&](int u) {
-    const int dl = sbond[u], dr = sbond[u + 1];
-    const double* Tm = c.Tm + ((int64_t)b * c.L + u) * c.tstride;
+    if (PAD) {
+      const double* Tm = tbase + (int64_t)u * tsd;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int j = tid + 256 * m, cc = j & 31, e = j >> 5;
-      tp[m] = (cc < dl && e < dr) ? Tm[cc + dl * e] : 0.0;
+      for (int m = 0; m < 4; ++m) tp[m] = Tm[256 * m];
+    } else {
+      const int dl = sbond[u], dr = sbond[u + 1];
+      const double* Tm = tbase - tid + (int64_t)u * tsd;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = tid + 256 * m, cc = j & 31, e = j >> 5;
+        tp[m] = (cc < dl && e < dr) ? Tm[cc + dl * e] : 0.0;
+      }
     }
   };
   auto stage_T = [&]() {
@@ -86,7 +99,7 @@ __global__ void __launch_bounds__(256, 4) k_twovar_mma(TwoFast c) {
   const int mt = wid & 3, nt0 = (wid >> 2) * 2;
   int par = 0;
   for (int u = t + 1; u <= uhi; ++u, par ^= 1) {
-    const int nk = r0 * sbond[u];
+    const int nk = PAD ? nkp : r0 * sbond[u];
     const bool more = u < uhi;
     if (more && u + 1 < uhi) prefetch_T(u + 1);   // the next pair's T travels while this pair is computed
     // b[x_t, x_u] partial sums
