@@ -230,7 +230,7 @@ __device__ __forceinline__ void panel_block_gram(const double (&a)[NS][RPL], dou
 }
 
 template <int RPL, int NS>
-__global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 3 : 1)) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
+__global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag(SweepCtx c, StepDesc s, int panel) {
   pdl_enter();
   constexpr int NW = 32 / NS;
   constexpr int NT = 32 * NW;

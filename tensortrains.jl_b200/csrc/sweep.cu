@@ -1395,7 +1395,9 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
           size_t smem = sizeof(double) * ((size_t)2 * bw * bw + 2 * bw + 40 + (size_t)rows_ub * bw);
           SW_LAUNCH("k_qr_panel", k_qr_panel, B, thr, smem, c, s, panel);
         }
-        const int trail = n_ub - j0 - 1;
+        // columns behind the panel: when every train is certainly tall (k = n) the panel covers min(32, n - j0)
+        // columns and a single-panel step has nothing to update (it used to launch a grid of early exits)
+        const int trail = (p_lb >= n_ub) ? n_ub - j0 - bw : n_ub - j0 - 1;
         if (trail > 0) {
           dim3 g((trail + kCw - 1) / kCw, B);
           if (fast) {
