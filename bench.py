@@ -402,55 +402,13 @@ def main():
             T._ck(T.lib.ttb_twovar_marginals(A._hd, L5 - 1, T._dp(out2))); ms["twovar_marginals"] = A.last_timing()[0]
             T.compress_(A, T.TruncThresh(1e-6)); ms["compress"] = A.last_timing()[0]
             return lz, ms
-        # A rank that holds only a slice of the batch (N > 1) no longer fills its GPU: 128 sequential sweep steps of
-        # a few hundred CTAs are latency-bound.  The slice is then split into sub-batches, one handle (= one CUDA
-        # stream) and one host thread each, whose pipelines overlap on the device -- what a caller with several
-        # independent batches does.  device_ms is the CUDA-event sum for one sub-batch, the wall clock of the
-        # concurrent region otherwise.
-        nsub = 1 if nb >= 2048 or os.environ.get("TTB_BENCH_NOSUB") else (2 if nb >= 1024 else 4)
-        if nsub == 1:
-            c5_pipeline(A5.copy())                               # warm-up (workspaces, scratch)
-            W5 = A5.copy()
-            barrier()
-            t0 = time.perf_counter()
-            lz5, ms5 = c5_pipeline(W5)
-            wall5 = max_over_ranks(time.perf_counter() - t0)
-            dev5 = max_over_ranks(sum(ms5.values()))
-        else:
-            cuts = [P.shard_range(nb, k, nsub) for k in range(nsub)]
-            per = L5 * site5
-            def make_sub():
-                hs = []
-                for a_, b_ in cuts:
-                    hsub = T.PeriodicTensorTrain.empty([D5] * (L5 + 1), (Q5,), batch=b_ - a_)
-                    hsub.upload_all(packed5[a_ * per:b_ * per])
-                    hs.append(hsub)
-                return hs
-            outs = [np.zeros((b_ - a_, npair.value, Q5 * Q5)) for a_, b_ in cuts]
-            def sub_pipeline(hsub, o, res, k):
-                m_ = {}
-                lz_ = T.normalize_(hsub); m_["normalize"] = hsub.last_timing()[0]
-                T._ck(T.lib.ttb_twovar_marginals(hsub._hd, L5 - 1, T._dp(o))); m_["twovar_marginals"] = hsub.last_timing()[0]
-                T.compress_(hsub, T.TruncThresh(1e-6)); m_["compress"] = hsub.last_timing()[0]
-                res[k] = (np.atleast_1d(lz_), m_)
-            def run_all(hs):
-                res = [None] * nsub
-                th = [threading.Thread(target=sub_pipeline, args=(hs[k], outs[k], res, k)) for k in range(nsub)]
-                for t_ in th: t_.start()
-                for t_ in th: t_.join()
-                return res
-            run_all(make_sub())                                  # warm-up
-            subs = make_sub()
-            barrier()
-            t0 = time.perf_counter()
-            res5 = run_all(subs)
-            torch.cuda.synchronize()
-            wall5 = max_over_ranks(time.perf_counter() - t0)
-            dev5 = wall5 * 1e3
-            lz5 = np.concatenate([r[0] for r in res5])
-            ms5 = {k_: max(r[1][k_] for r in res5) for k_ in res5[0][1]}
-            out2[:outs[0].shape[0]] = outs[0]
-            W5 = subs[0]
+        c5_pipeline(A5.copy())                                   # warm-up (workspaces, scratch)
+        W5 = A5.copy()
+        barrier()
+        t0 = time.perf_counter()
+        lz5, ms5 = c5_pipeline(W5)
+        wall5 = max_over_ranks(time.perf_counter() - t0)
+        dev5 = max_over_ranks(sum(ms5.values()))
         # HBM roofline of the environment pass behind normalize! (k_env_small_L reads every site tensor once:
         # algorithmic bytes = 8 * sum_t d_t d_{t+1} Q per train) and of the scaling pass (read + write)
         P5 = A5.copy()
@@ -480,22 +438,19 @@ def main():
             fl5 = float(nb) * ((npr - (L5 - 1)) * 2.0 * Q5 * D5 * D5 * D5 + npr * 2.0 * Q5 * Q5 * D5 * D5)
             roof5["k_twovar_mma"] = {"bound": "tensor", "achieved": fl5 / (rep5b["k_twovar_mma"][1] * 1e-3) / 1e12, "unit": "TFLOP/s",
                                      "ms": rep5b["k_twovar_mma"][1], "alg_flops": fl5}
-        bonds5 = np.array([T.bond_dims(W5, b) for b in range(0, W5.batch, max(W5.batch // 64, 1))], dtype=np.float64)
+        bonds5 = np.array([T.bond_dims(W5, b) for b in range(0, nb, max(nb // 64, 1))], dtype=np.float64)
         lz_all = P.allgather(np.ascontiguousarray(lz5).reshape(-1, 1)) if B5 % world == 0 else lz5
         assert np.all(np.isfinite(lz_all)) and abs(float(out2[0, 0].sum()) - 1.0) < 1e-9
         batch_info = {"workload": "C5: 4096 PeriodicTensorTrains, 64 sites, bond 32, q=2, rand fill: normalize! + twovar_marginals "
                                   "(2016 pairs per train) + compress!(TruncThresh(1e-6)); trains sharded over ranks, "
                                   "all-gather of per-train log Z",
-                      "trains": B5, "trains_per_rank": nb, "sub_batches_per_rank": nsub,
-                      "device_ms": dev5, "device_ms_by_call_rank0": ms5,
+                      "trains": B5, "trains_per_rank": nb, "device_ms": dev5, "device_ms_by_call_rank0": ms5,
                       "trains_per_s": B5 / (dev5 * 1e-3), "e2e_wall_ms": wall5 * 1e3,
                       "compress_site_steps_per_s": world * nb * 2 * L5 / (max_over_ranks(ms5["compress"]) * 1e-3),
                       "max_bond_after": int(bonds5.max()), "logz_gathered": int(np.size(lz_all)),
                       "roofline_rank0": roof5, "hbm_peak_source": hbm_src,
-                      "note": "one sub-batch: device_ms = sum of the three calls' CUDA-event times, max over ranks, and "
-                              "e2e_wall_ms adds the D2H copy of all pair marginals (258 MB in total) and the host-side call "
-                              "overhead; several sub-batches (N > 1): the sub-batches' pipelines run concurrently on their "
-                              "own streams / host threads and device_ms = e2e_wall_ms = wall clock of that region"}
+                      "note": "device_ms = sum of the three calls' CUDA-event times, max over ranks; e2e_wall_ms adds the "
+                              "D2H copy of all pair marginals (258 MB in total) and the host-side call overhead"}
         del A5, W5, packed5, out2
 
     if rank == 0:
