@@ -643,6 +643,8 @@ def twovar_marginals_block(A, t_lo: int, t_hi: int, maxdist: Optional[int] = Non
     ``(batch, pairs in the range, Q*Q)``, t-major like the full result: the unit one rank computes when the
     pair marginals of a train are sharded over GPUs (``ttb200.parallel.twovar_marginals_sharded``)."""
     md = A.L - 1 if maxdist is None else int(maxdist)
+    if not (0 <= int(t_lo) <= int(t_hi) <= A.L - 1):
+        raise ValueError(f"ArgumentError: pair range [{t_lo}, {t_hi}) outside [0, {A.L - 1})")
     n = sum(min(A.L - 1, t + md) - t for t in range(int(t_lo), int(t_hi)))
     out = np.zeros((A.batch, n, A.Q * A.Q))
     if n:

@@ -785,3 +785,39 @@ def test_sharded_pair_marginals_single_process_path():
         assert set(full) == set(sh)
         for k in full:
             assert np.array_equal(full[k], sh[k])
+
+
+def test_edge_cases_of_the_round_1b_entries():
+    """shortest trains, argument errors and empty ranges of ttb_compose / ttb_twovar_marginals_range /
+    ttb_scale_sites (the reference's ArgumentError paths: src/tensor_train.jl:241-242,
+    src/periodic_tensor_train.jl:63-64)"""
+    rng = RNG(990)
+    # L = 2 open trains: first site [za A, zb B], last site [A; B], nothing in between
+    ta, tb = rand_open(rng, [1, 3, 1], (2,)), rand_open(rng, [1, 5, 1], (2,))
+    A, Ao = pair(ta, z=0.5)
+    B, Bo = pair(tb, z=-3.0)
+    for Cg, Co in ((A + B, O.plus(Ao, Bo)), (A - B, O.minus(Ao, Bo))):
+        assert T.bond_dims(Cg) == O.bond_dims(Co) == [1, 8]
+        check_evals(Cg, Co, rand_points(rng, Co, 4), REL, signed=True)
+    # L = 1 periodic train (a single matrix-valued site): block diagonal, trace adds up
+    pa, pb = rand_per(rng, [3], (2,)), rand_per(rng, [2], (2,))
+    P1, P1o = pair(pa, periodic=True)
+    P2, P2o = pair(pb, periodic=True)
+    check_evals(P1 + P2, O.plus(P1o, P2o), rand_points(rng, P1o, 2), REL, signed=True)
+    # mismatched physical dimensions / kinds
+    with pytest.raises(ValueError):
+        A + T.TensorTrain(rand_open(rng, [1, 3, 1], (3,)))
+    with pytest.raises(ValueError):
+        A + P1
+    # pair ranges: empty and out-of-range
+    C4 = T.TensorTrain(rand_open(rng, [1, 3, 4, 3, 1], (2,)))
+    assert T.twovar_marginals_block(C4, 2, 2).shape == (1, 0, 4)
+    with pytest.raises(ValueError):
+        T.twovar_marginals_block(C4, 0, 4)          # first sites run over [0, L-1)
+    with pytest.raises(ValueError):
+        T.twovar_marginals_block(C4, 3, 1)
+    # scale_sites: every tensor divided by the factor, z untouched, evaluate scales by factor^-L
+    X = rand_points(rng, O.TensorTrain(C4.tensors()), 1)
+    e0, z0 = float(T.evaluate(C4, X)[0]), C4.z
+    T._ck(T.lib.ttb_scale_sites(C4._hd, T._dp(np.array([2.0]))))
+    assert close(float(T.evaluate(C4, X)[0]), e0 / 2.0 ** 4, 1e-14) and C4.z.logabs == z0.logabs
