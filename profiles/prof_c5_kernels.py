@@ -1,12 +1,11 @@
 """Config 5 at batch B (default 4096): per-kernel CUDA-event times of normalize!, marginals,
 twovar_marginals and compress!(TruncThresh(1e-6)) on a batch of periodic trains (64 sites, bond 32, q=2).
-Packed upload (no per-train Python objects); a few trains are checked against the oracle."""
+Packed upload (no per-train Python objects).  Timing only: parity lives in tests/."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tensortrains.jl_b200")]
 import numpy as np
 import ttb200 as T
-from oracle import tt_oracle as O
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 L, d, q = 64, 32, 2
@@ -55,9 +54,3 @@ def raw_twovar(W):
     return out
 _, _ = run("twovar_marginals", raw_twovar)
 _, _ = run("compress!", lambda W: T.compress_(W, T.TruncThresh(1e-6)))
-
-for b in (0, B // 2, B - 1):
-    ts = [packed[(b * L + t) * site:(b * L + t + 1) * site].reshape((d, d, q), order="F") for t in range(L)]
-    Ao = O.PeriodicTensorTrain([a.copy() for a in ts])
-    lzo = O.normalize(Ao)
-    print(f"  train {b}: |dlogZ| = {abs(lz[b]-lzo):.2e}")
