@@ -36,7 +36,8 @@ enum {
   TTB_ECUDA = 5,        /* CUDA runtime error (message has the CUDA string)                          */
   TTB_ENOMEM = 6,
   TTB_EUNSUPPORTED = 7, /* shape outside what the kernels cover (message says which limit)          */
-  TTB_EDOMAIN = 8       /* DomainError: log of a negative normalization                              */
+  TTB_EDOMAIN = 8,      /* DomainError: log of a negative normalization                              */
+  TTB_ENOCONV = 9       /* LAPACKException of svd (src/svd_trunc.jl:37): the Jacobi SVD did not converge */
 };
 
 /* SVD truncation policy: src/svd_trunc.jl:33-50 (THRESH), :69-77 (BOND), :91-103 (BONDMAX),
@@ -115,8 +116,10 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal);
 int ttb_sweep_stats(ttb_handle h, int64_t b, int64_t* rank, double* err);
 /* keep every singular-value vector of truncating sweeps (test/diagnostic aid; costs L*dmax doubles) */
 int ttb_record_spectrum(ttb_handle h, int on);
-/* singular values (descending, BEFORE truncation) seen at bond i in the last truncating sweep */
-int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t* n);
+/* singular values (descending, BEFORE truncation) seen at bond i in the last truncating sweep; `out` holds
+ * `cap` doubles, *n receives the count (0 for a bond that sweep did not touch; TTB_EINVAL with *n set when
+ * cap is too small; the largest ORIGINAL bond dimension always suffices) */
+int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t cap, int64_t* n);
 /* is_left_canonical / is_right_canonical residual max|A'A - I| (src/tensor_train.jl:263-273) */
 int ttb_canonical_residual(ttb_handle h, int64_t b, int64_t t, int left, double* resid);
 

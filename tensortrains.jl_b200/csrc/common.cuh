@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,7 @@ struct ttb_tt {
   int* d_status = nullptr;     // [1]
   ttb::Workspace ws;
   bool record_spectrum = false;
+  bool keep_stats = false;     // second sweep of orthogonalize_center!: per-bond stats / spectra of the first one stay
   double last_ms = 0.0;
   int64_t last_launches = 0;
   int64_t launches = 0;        // running counter inside a call
@@ -173,6 +175,22 @@ void prof_post(ttb_tt* h);
     (h)->launches++;                 \
   } while (0)
 int sync_bonds_to_host(ttb_tt* h);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a process-wide once-flag leaves the second
+// device of a process without it ("invalid argument" at launch).  True exactly once per (device, slot),
+// under a lock held while the caller's attribute calls run (see TTB_ONCE_PER_DEVICE).
+struct OnceGuard {
+  std::unique_lock<std::mutex> lk;
+  bool first;
+  OnceGuard(int dev, int slot) : lk(mu()), first(false) {
+    static unsigned seen[64] = {};
+    const unsigned bit = 1u << slot;
+    unsigned& w = seen[dev & 63];
+    first = !(w & bit);
+    w |= bit;
+  }
+  static std::mutex& mu() { static std::mutex m; return m; }
+};
+#define TTB_ONCE_PER_DEVICE(h, slot) if (ttb::OnceGuard og__((h)->device, (slot)); og__.first)
 int ensure_sweep_ws(ttb_tt* h);
 int ensure_env_ws(ttb_tt* h);
 int read_status(ttb_tt* h, int* st);  // reads and clears the device status word

@@ -537,11 +537,9 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s, int
   if (small_path(h)) {
     const size_t raw = sizeof(double) * 1024 * (size_t)h->Q;
     const bool pf = raw <= 64 * 1024 && getenv("TTB_ENV_NOPREFETCH") == nullptr;
-    static bool eattr = false;
-    if (!eattr) {
+    TTB_ONCE_PER_DEVICE(h, 0) {
       cudaFuncSetAttribute(k_env_small<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
       cudaFuncSetAttribute(k_env_small<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      eattr = true;
     }
     if (left && pf) { TTB_LAUNCH(h, "k_env_small_L", (k_env_small<true, true><<<(unsigned)h->batch, 128, raw, h->stream>>>(c, store))); }
     else if (left) { TTB_LAUNCH(h, "k_env_small_L", (k_env_small<true, false><<<(unsigned)h->batch, 128, 0, h->stream>>>(c, store))); }
@@ -612,8 +610,7 @@ static int launch_acc(ttb_tt* h, bool left, int normalize, const EnvSide& s, int
     TTB_LAUNCH(h, "k_accumulate_L", k_accumulate_L<<<(unsigned)h->batch, thr, 0, h->stream>>>(c));
   } else {
     const size_t smem = sizeof(double) * (size_t)thr * ENV_AC;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
+    TTB_ONCE_PER_DEVICE(h, 1) cudaFuncSetAttribute(k_accumulate_R, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     TTB_LAUNCH(h, "k_accumulate_R", k_accumulate_R<<<(unsigned)h->batch, thr, smem, h->stream>>>(c));
   }
   return TTB_OK;
@@ -873,8 +870,7 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
         fc.GT = d_GT; fc.Tm = d_Tm; fc.gstride = gstride; fc.tstride = tstride;
         fc.pair_off = d_poff; fc.maxdist = (int)std::min<int64_t>(maxdist, L); fc.out = d_out; fc.npairs = npairs;
         fc.kcap = (int)kcap; fc.dmax = (int)h->dmax; fc.t0 = (int)t_lo;
-        static bool fattr = false;
-        if (!fattr) { cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); fattr = true; }
+        TTB_ONCE_PER_DEVICE(h, 2) cudaFuncSetAttribute(k_twovar_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
         const dim3 gm((unsigned)(t_hi - t_lo), (unsigned)h->batch);
         const size_t bsm = sizeof(int) * (L + 1);
 #define TTB_TV(Q_)                                                                                                        \
@@ -898,8 +894,7 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
       c.scratch = d_scr; c.scratch_stride = scr_stride; c.pair_off = d_poff; c.maxdist = (int)std::min<int64_t>(maxdist, L);
       c.out = d_out; c.npairs = npairs; c.t0 = (int)t_lo;
       dim3 g((unsigned)(t_hi - t_lo), (unsigned)h->batch);
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_twovar, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
+      TTB_ONCE_PER_DEVICE(h, 3) cudaFuncSetAttribute(k_twovar, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
       TTB_LAUNCH(h, "k_twovar", k_twovar<<<g, 256, scr_in_smem ? smem_need : sizeof(double) * Q * Q, h->stream>>>(c));
       rc = tm.finish();
     }

@@ -171,7 +171,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
   int* rot = c.st[b].rot;
   bool conv = (nv < 2);
   int sweep = 0;
-  for (; sweep < 60 && !conv; ++sweep) {
+  for (; sweep < s.max_sweeps && !conv; ++sweep) {
     if (tid == 0) rotated = 0;
     for (int kr = 0; kr < kJcBlocks - 1; ++kr) {
       int bi, bj;

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jac
   const double tol2 = (double)max(len, 2) * 2.220446049250313e-16 * 2.220446049250313e-16;
   double* sq = sig;
   bool conv = (nv < 2);
-  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+  for (int sweep = 0; sweep < s.max_sweeps && !conv; ++sweep) {
     for (int v = wid; v < nv; v += nw) {
       double a0 = 0.0;
 #pragma unroll
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(4 * W, W == 32 ? 8 : 1) k_jacobi_g8(SweepCtx c
   const int grp = lane >> 3, e0 = (lane & 7) * 2;    // pair slot inside the warp, first element of this lane
   const int q = wid * 4 + grp;                       // pair index of the round handled by this lane group
   bool conv = (nv < 2);
-  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+  for (int sweep = 0; sweep < s.max_sweeps && !conv; ++sweep) {
     if (tid < W) {   // cached squared norms, recomputed once per sweep (one row per thread, stride LD: conflict-free)
       double a0 = 0.0;
       if (tid < nv) {

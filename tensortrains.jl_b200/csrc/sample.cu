@@ -316,8 +316,7 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
     c.b = (int)b; c.dmax = (int)dmax; c.rmax = (int)rmax;
     c.uniforms = d_u; c.seed = seed; c.first = first;
     c.x_out = d_x; c.p_out = d_p; c.hist = d_hist; c.sum_logp = d_slp; c.status = h->d_status; c.nsamples = nsamples;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); attr = true; }
+    TTB_ONCE_PER_DEVICE(h, 4) cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     // Tiled tensor-core sampler for open trains whose state fits (d <= 128); the generic one-CTA-per-draw
     // kernel covers periodic trains, larger bonds and tiny requests.
     const int DP = dmax <= 32 ? 32 : (dmax <= 64 ? 64 : 128);
@@ -347,12 +346,10 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
         const int64_t nb = (nsamples + ST_SMAX - 1) / ST_SMAX;
         const unsigned g = (unsigned)std::min<int64_t>(nb, nsm);
-        static bool tattr = false;
-        if (!tattr) {
+        TTB_ONCE_PER_DEVICE(h, 5) {
           cudaFuncSetAttribute(k_sample_tile<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
           cudaFuncSetAttribute(k_sample_tile<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
           cudaFuncSetAttribute(k_sample_tile<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-          tattr = true;
         }
         if (DP == 32) TTB_LAUNCH(h, "k_sample_tile", k_sample_tile<32><<<g, ST_THREADS, tile_smem, h->stream>>>(tc));
         else if (DP == 64) TTB_LAUNCH(h, "k_sample_tile", k_sample_tile<64><<<g, ST_THREADS, tile_smem, h->stream>>>(tc));

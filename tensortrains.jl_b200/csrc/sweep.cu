@@ -53,6 +53,7 @@ struct StepDesc {
                            // shape): kernels skip the dependent global loads of the device snapshot
   int trace;               // k_qr_stream: record the timeline of this step (TTB_QS_TRACE=<site>)
   int hint_slot;           // ring slot k_commit reports the retained ranks into (-1: none)
+  int max_sweeps;          // Jacobi sweep cap (60; TTB_JACOBI_MAXSWEEPS lowers it so tests can force ST_NOCONV)
   int jc_sd;               // > 0: both Jacobi paths are launched (host bounds cannot tell): trains whose ACTUAL
                            // 2 n_max + k (n + k) doubles fit jc_sd are done by k_jacobi, the others by the cluster
 };
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
   const double tol2 = tol * tol;
   double* sq = sig;  // cached squared norms live in the sigma scratch until the end
   bool conv = (nv < 2);
-  for (int sweep = 0; sweep < 60 && !conv; ++sweep) {
+  for (int sweep = 0; sweep < s.max_sweeps && !conv; ++sweep) {
     for (int v = wid; v < nv; v += nw) {
       const double* bi = B + (size_t)v * ldb;
       double a0 = 0.0, a1 = 0.0;
@@ -1195,8 +1196,7 @@ int ensure_sweep_ws(ttb_tt* h) {
   A((void**)&w.stat_err, sizeof(double) * B * (h->L + 1));
   A((void**)&w.stat_rank, sizeof(int) * B * (h->L + 1));
   if (e != cudaSuccess) return fail(TTB_ENOMEM, "sweep workspace: %s", cudaGetErrorString(e));
-  static bool attr_done = false;
-  if (!attr_done) {
+  TTB_ONCE_PER_DEVICE(h, 6) {
     cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_apply_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -1218,7 +1218,6 @@ int ensure_sweep_ws(ttb_tt* h) {
     cudaFuncSetAttribute(k_qr_panel_flag<4, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_panel_flag<8, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaFuncSetAttribute(k_qr_panel_flag<16, kPanelNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    attr_done = true;
   }
   w.sweep_ready = true;
   return TTB_OK;
@@ -1230,6 +1229,8 @@ static int ensure_spectrum(ttb_tt* h) {
   if (!w.spectrum) {
     const size_t n = (size_t)h->batch * (h->L + 1) * w.n_max;
     TTB_CUDA(cudaMalloc(&w.spectrum, sizeof(double) * n));
+    // all bits set = a negative NaN: fails the `>= 0` scan of ttb_get_spectrum, i.e. "bond not touched"
+    TTB_CUDA(cudaMemsetAsync(w.spectrum, 0xff, sizeof(double) * n, h->stream));
   }
   return TTB_OK;
 }
@@ -1276,6 +1277,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   const bool qr_only = (tr->kind == TTB_TRUNC_THRESH && tr->eps == 0.0);
   const bool feedback = !qr_only && getenv("TTB_NO_FEEDBACK") == nullptr;
   const bool use_stream = getenv("TTB_NO_STREAM") == nullptr;
+  const int max_sweeps = getenv("TTB_JACOBI_MAXSWEEPS") ? std::max(1, atoi(getenv("TTB_JACOBI_MAXSWEEPS"))) : 60;
   int sm_count = 0;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   // Main-stream launches use programmatic dependent launch (common.cuh): the next grid is resident and
@@ -1291,7 +1293,10 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
   } while (0)
   {
     const int n = std::max(B, B * L1);
-    SW_LAUNCH("k_reset_state", k_reset_state, (n + 255) / 256, 256, 0, w.st, w.stat_err, w.stat_rank, B, L1);
+    // per-bond stats and spectra describe the last CALL: the second sweep of orthogonalize_center! keeps the first one's
+    SW_LAUNCH("k_reset_state", k_reset_state, (n + 255) / 256, 256, 0, w.st, w.stat_err, w.stat_rank, B, h->keep_stats ? 0 : L1);
+    if (cbase.spectrum && !h->keep_stats)
+      cudaMemsetAsync(w.spectrum, 0xff, sizeof(double) * (size_t)B * L1 * w.n_max, st);   // "bond not touched"
   }
   int xin = 0, slot = 0;
   for (size_t si = 0; si < steps.size(); ++si) {
@@ -1304,6 +1309,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
     s.next_site = si + 1 < steps.size() ? steps[si + 1].site : -1;
     s.next_nbr = si + 1 < steps.size() ? steps[si + 1].nbr : -1;
     s.jc_sd = 0;
+    s.max_sweeps = max_sweeps;
     s.trace = 0;
     s.hint_slot = feedback ? (int)(si % ttb_tt::kHintRing) : -1;
     SweepCtx c = cbase;
@@ -1435,8 +1441,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       } else if (nv_ub <= 64 && len_ub <= 64 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
         static const bool no_g8 = getenv("TTB_JACOBI_NOG8") != nullptr;
-        static bool g8attr = false;
-        if (!g8attr) { cudaFuncSetAttribute(k_jacobi_g8<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jg8_smem(64)); g8attr = true; }
+        TTB_ONCE_PER_DEVICE(h, 7) cudaFuncSetAttribute(k_jacobi_g8<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jg8_smem(64));
         if (nv_ub <= 32 && len_ub <= 32 && B >= sm_count && !no_g8) {
           // a batch that fills the GPU is issue-bound: four pairs per warp (k_jacobi_g8)
           auto kg = k_jacobi_g8<32>;
@@ -1477,8 +1482,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       }
       if (fast && p_ub <= 64 && k_ub <= 32 && getenv("TTB_APPLYQ_NOSMALL") == nullptr) {
         // small step: one CTA forms the whole orthonormal factor of its train (tensor cores)
-        static bool aattr = false;
-        if (!aattr) { cudaFuncSetAttribute(k_apply_q_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmallSmem); aattr = true; }
+        TTB_ONCE_PER_DEVICE(h, 8) cudaFuncSetAttribute(k_apply_q_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmallSmem);
         TTB_LAUNCH(h, "k_apply_q_small", k_apply_q_small<<<B, 256, kApplySmallSmem, st2>>>(c, s));
       } else if (fast) {
         size_t smem = sizeof(double) * ((size_t)1280 + (size_t)p_ub * 36);
@@ -1508,9 +1512,8 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
       } else if (qr_only && s.kp >= 0 && p_ub >= n_ub && n_ub % 32 == 0 && N_ub % 32 == 0 && (p_ub & 1) == 0 &&
                  getenv("TTB_ABSORB_NOPIPE") == nullptr) {
         // exact, 32-aligned eps = 0 step: cp.async pipeline (k_absorb_pipe)
-        static bool pattr = false;
         const size_t psm = sizeof(double) * AP_STAGES * 2 * 32 * AM_LD;
-        if (!pattr) { cudaFuncSetAttribute(k_absorb_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm); pattr = true; }
+        TTB_ONCE_PER_DEVICE(h, 9) cudaFuncSetAttribute(k_absorb_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
         dim3 g(n_ub / AM_T, N_ub / AM_T, Q * B);
         SW_LAUNCH("k_absorb_mma", k_absorb_pipe, g, 128, psm, c, s);
       } else {
@@ -1589,6 +1592,9 @@ static int finish_sweeps(ttb_tt* h, CallTimer& tm) {
   int st = 0;
   TTB_TRY(read_status(h, &st));
   if (st & ST_NONFINITE) return fail(TTB_ENONFINITE, "non-finite values met during the sweep");
+  // the reference's LAPACK svd throws when it does not converge; a non-converged Jacobi step has wrong singular
+  // values, a wrong rank decision and non-orthogonal factors, so the call must not report success
+  if (st & ST_NOCONV) return fail(TTB_ENOCONV, "one-sided Jacobi SVD did not converge within the sweep cap");
   return TTB_OK;
 }
 
@@ -1631,8 +1637,13 @@ int ttb_orthogonalize_center(ttb_handle h, const ttb_trunc* tr, int64_t l) {
   if (h->periodic) return fail(TTB_EINVAL, "orthogonalize_center! is defined for TensorTrain only");
   if (l < 1 || l > h->L) return fail(TTB_EINVAL, "center %lld out of range", (long long)l);
   if (l - 1 >= 1) TTB_TRY(ttb_orthogonalize_left(h, tr, 1, l - 1));
-  if (l + 1 <= h->L) TTB_TRY(ttb_orthogonalize_right(h, tr, l + 1, h->L));
-  return TTB_OK;
+  int rc = TTB_OK;
+  if (l + 1 <= h->L) {
+    h->keep_stats = (l - 1 >= 1);   // svd_trunc.jl:98-100 updates maxerr on every SVD of BOTH sweeps
+    rc = ttb_orthogonalize_right(h, tr, l + 1, h->L);
+    h->keep_stats = false;
+  }
+  return rc;
 }
 
 int ttb_orthogonalize_two_site_center(ttb_handle h, const ttb_trunc* tr, int64_t k) {
@@ -1640,8 +1651,13 @@ int ttb_orthogonalize_two_site_center(ttb_handle h, const ttb_trunc* tr, int64_t
   if (h->periodic) return fail(TTB_EINVAL, "orthogonalize_two_site_center! is defined for TensorTrain only");
   if (k < 1 || k >= h->L) return fail(TTB_EINVAL, "k must be between 1 and length(C)-1 for two-site update");
   if (k - 1 >= 1) TTB_TRY(ttb_orthogonalize_left(h, tr, 1, k - 1));
-  if (k + 2 <= h->L) TTB_TRY(ttb_orthogonalize_right(h, tr, k + 2, h->L));
-  return TTB_OK;
+  int rc = TTB_OK;
+  if (k + 2 <= h->L) {
+    h->keep_stats = (k - 1 >= 1);
+    rc = ttb_orthogonalize_right(h, tr, k + 2, h->L);
+    h->keep_stats = false;
+  }
+  return rc;
 }
 
 int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
@@ -1716,7 +1732,7 @@ int ttb_sweep_stats(ttb_handle h, int64_t b, int64_t* rank, double* err) {
   return TTB_OK;
 }
 
-int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t* n) {
+int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, int64_t cap, int64_t* n) {
   TTB_TRY(check_handle(h));
   if (!h->ws.spectrum) return fail(TTB_EINVAL, "spectrum recording is off (ttb_record_spectrum)");
   if (b < 0 || b >= h->batch || bond_index < 0 || bond_index > h->L) return fail(TTB_EINVAL, "index out of range");
@@ -1726,8 +1742,10 @@ int ttb_get_spectrum(ttb_handle h, int64_t b, int64_t bond_index, double* out, i
                            cudaMemcpyDeviceToHost, h->stream));
   TTB_CUDA(cudaStreamSynchronize(h->stream));
   int64_t cnt = 0;
-  while (cnt < nm && tmp[cnt] >= 0.0) { out[cnt] = tmp[cnt]; ++cnt; }
-  *n = cnt;
+  while (cnt < nm && tmp[cnt] >= 0.0) ++cnt;
+  *n = cnt;   // the caller learns the length even when `out` is too small
+  if (cnt > cap) return fail(TTB_EINVAL, "spectrum has %lld values, out holds %lld", (long long)cnt, (long long)cap);
+  for (int64_t i = 0; i < cnt; ++i) out[i] = tmp[i];
   return TTB_OK;
 }
 

@@ -83,7 +83,7 @@ _sig("ttb_orthogonalize_two_site_center", _h, C.POINTER(_Trunc), _i64)
 _sig("ttb_compress", _h, C.POINTER(_Trunc), C.c_int)
 _sig("ttb_sweep_stats", _h, _i64, _pi64, _pd)
 _sig("ttb_record_spectrum", _h, C.c_int)
-_sig("ttb_get_spectrum", _h, _i64, _i64, _pd, _pi64)
+_sig("ttb_get_spectrum", _h, _i64, _i64, _pd, _i64, _pi64)
 _sig("ttb_canonical_residual", _h, _i64, _i64, C.c_int, _pd)
 _sig("ttb_env_size", _h, _i64, C.c_int, _pi64)
 _sig("ttb_accumulate_L", _h, C.c_int, _pd, _pd, _pi)
@@ -120,7 +120,11 @@ class NegativeValuesError(TTBError):
     (src/abstract_tensor_train.jl:371)."""
 
 
-_EINVAL, _ESHAPE, _ENEGATIVE, _ENONFINITE, _ECUDA, _ENOMEM, _EUNSUPPORTED, _EDOMAIN = 1, 2, 3, 4, 5, 6, 7, 8
+_EINVAL, _ESHAPE, _ENEGATIVE, _ENONFINITE, _ECUDA, _ENOMEM, _EUNSUPPORTED, _EDOMAIN, _ENOCONV = 1, 2, 3, 4, 5, 6, 7, 8, 9
+
+
+class SVDNotConvergedError(TTBError):
+    """LAPACKException thrown by ``svd`` (src/svd_trunc.jl:37) when it fails to converge."""
 
 
 def _ck(rc):
@@ -133,6 +137,8 @@ def _ck(rc):
         raise ValueError("DomainError: " + msg)
     if rc == _ENEGATIVE:
         raise NegativeValuesError(rc, msg)
+    if rc == _ENOCONV:
+        raise SVDNotConvergedError(rc, msg)
     if rc == _ENOMEM:
         raise MemoryError(msg)
     if rc == _EUNSUPPORTED:
@@ -374,9 +380,12 @@ class AbstractTensorTrain:
         return self._compose(other, -1)
 
     def spectrum(self, bond_index: int, b: int = 0) -> np.ndarray:
-        out = np.zeros(int(max(self.bonds(b).max(), 1)) * max(self.Q, 1) + 8)
-        n = _i64()
-        _ck(lib.ttb_get_spectrum(self._hd, b, bond_index, _dp(out), C.byref(n)))
+        out, n = np.zeros(64), _i64()
+        rc = lib.ttb_get_spectrum(self._hd, b, bond_index, _dp(out), out.size, C.byref(n))
+        if rc != 0 and n.value > out.size:      # *n is filled in even when `out` was too small
+            out = np.zeros(n.value)
+            rc = lib.ttb_get_spectrum(self._hd, b, bond_index, _dp(out), out.size, C.byref(n))
+        _ck(rc)
         return out[: n.value].copy()
 
     def last_timing(self):

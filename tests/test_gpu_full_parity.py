@@ -1,0 +1,162 @@
+"""GPU parity against the CPU oracle at BASELINE.json's FULL sizes: the oracle runs
+on the GPU box's host cores next to the CUDA path, on the same seeded input -- retained bond dimensions
+identical, singular values per bond to 1e-8 of sigma_1, evaluate / log Z to 1e-8 after truncation -- for
+C3 (L=256, q=2, d=256) with both fills, C5 trains of the bench's own batch (64 sites, seeds 5000+), and C4
+(L=256, q=4, d=128: injected-uniform draws bit-equal, two-site chi-square on >= 200 site pairs)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1500)]
+
+from oracle import tt_oracle as O
+
+T = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global T
+    import ttb200
+    T = ttb200
+    T.set_device(0)
+    yield
+
+
+RNG = lambda s: np.random.Generator(np.random.Philox(s))
+
+
+def make_open(seed, L, d, q, fill="rand"):
+    """bench.py's generator for configs 3 and 4 (same seeds, same order of draws)."""
+    rng = RNG(seed)
+    bonds = [1] + [d] * (L - 1) + [1]
+    if fill == "rand":
+        return [rng.random((bonds[t], bonds[t + 1], q)) for t in range(L)]
+    s = 1.0 / math.sqrt(d)
+    return [s * rng.standard_normal((bonds[t], bonds[t + 1], q)) for t in range(L)]
+
+
+def spectra_close(lam_g, lam_o, tol=1e-8):
+    return len(lam_g) == len(lam_o) and np.max(np.abs(lam_g / lam_g[0] - lam_o / lam_o[0])) <= tol
+
+
+def oracle_threads():
+    """256 x 512 gesdd with all host threads is several times slower than with 4-8 (OpenBLAS oversubscription)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=8)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+@pytest.mark.parametrize("fill", ["rand", "randn"])
+def test_config3_full_length_against_oracle(fill):
+    """C3 at L=256: compress!(TruncThresh(1e-10)) on bench.py's own input (seed 3)."""
+    L, d, q = 256, 256, 2
+    ts = make_open(3, L, d, q, fill)
+    A = T.TensorTrain(ts)
+    Ao = O.TensorTrain([a.copy() for a in ts])
+    del ts
+    A.record_spectrum(True)
+    stats = []
+    T.compress_(A, T.TruncThresh(1e-10))
+    with oracle_threads():
+        O.compress(Ao, O.TruncThresh(1e-10), stats=stats)
+    bg, bo = T.bond_dims(A), O.bond_dims(Ao)
+    assert bg == bo, [(t, g, o) for t, (g, o) in enumerate(zip(bg, bo)) if g != o]
+    assert len(stats) == L - 1
+    worst = 0.0
+    for (t, lam_o, kept) in stats:
+        lam_g = A.spectrum(t)
+        assert spectra_close(lam_g, lam_o), (t, lam_g[:12], lam_o[:12])
+        worst = max(worst, float(np.max(np.abs(lam_g / lam_g[0] - lam_o / lam_o[0]))))
+    print(f"[C3 {fill}] bonds identical (max {max(bg)}), worst |d sigma_k|/sigma_1 = {worst:.2e}")
+    # values: both results are rescaled by their own z, so compare the evaluated numbers themselves
+    rng = RNG(31)
+    X = rng.integers(0, q, (16, L)).astype(np.int32)
+    zg, zo = T.normalization(A), O.normalization(Ao)
+    if fill == "rand":
+        # a 256-site rand chain over/underflows a plain evaluate: compare log|Z| and the ratios p(x) = f(x)/Z
+        assert zg.sign == zo.sign and abs(zg.logabs - zo.logabs) <= 1e-8 * abs(zo.logabs)
+        lg, lo = T.normalize_(A), O.normalize(Ao)
+        g = T.evaluate(A, X)
+        e = np.array([O.evaluate(Ao, [(int(v),) for v in X[i]]) for i in range(X.shape[0])])
+        assert np.all(e > 0) and np.max(np.abs(g - e) / e) <= 1e-8, (g, e)
+    else:
+        g = T.evaluate(A, X)
+        e = np.array([O.evaluate(Ao, [(int(v),) for v in X[i]]) for i in range(X.shape[0])])
+        assert np.max(np.abs(g - e)) <= 1e-8 * np.max(np.abs(e)), (g, e)
+
+
+def test_config5_bench_trains_against_oracle():
+    """C5 at full length (64 sites, bond 32, q=2): the first 8 trains of bench.py's chunks 0 and 3840 (seeds
+    5000 + chunk start): normalize! + twovar_marginals + compress!(TruncThresh(1e-6)) against the oracle."""
+    L, d, q = 64, 32, 2
+    site = d * d * q
+    packed, ids = [], []
+    for bg in (0, 3840):
+        v = RNG(5000 + bg).random(256 * L * site)
+        packed.append(v[: 8 * L * site]); ids += list(range(bg, bg + 8))
+    packed = np.concatenate(packed)
+    nb = len(ids)
+    A = T.PeriodicTensorTrain.empty([d] * (L + 1), (q,), batch=nb)
+    A.upload_all(packed)
+    lz = T.normalize_(A)
+    m2 = T.twovar_marginals(A)
+    A.record_spectrum(True)
+    T.compress_(A, T.TruncThresh(1e-6))
+    X = RNG(51).integers(0, q, (6, L)).astype(np.int32)
+    for b in range(nb):
+        ts = [packed[(b * L + t) * site:(b * L + t + 1) * site].reshape((d, d, q), order="F") for t in range(L)]
+        Ao = O.PeriodicTensorTrain(ts)
+        lzo = O.normalize(Ao)
+        assert abs(lz[b] - lzo) <= 1e-10 * abs(lzo), (ids[b], lz[b], lzo)
+        m2o = O.twovar_marginals(Ao)
+        assert len(m2o) == L * (L - 1) // 2
+        for k in m2o:
+            assert np.allclose(m2[b][k], m2o[k], rtol=1e-9, atol=1e-13), (ids[b], k)
+        stats = []
+        O.compress(Ao, O.TruncThresh(1e-6), stats=stats)
+        assert T.bond_dims(A, b) == O.bond_dims(Ao), (ids[b], T.bond_dims(A, b), O.bond_dims(Ao))
+        for (t, lam_o, kept) in stats:
+            assert spectra_close(A.spectrum(t, b), lam_o), (ids[b], t)
+        g = T.evaluate(A, X, b=b)
+        e = np.array([O.evaluate(Ao, [(int(v),) for v in X[i]]) for i in range(X.shape[0])])
+        assert np.max(np.abs(g - e) / np.abs(e)) <= 1e-7, (ids[b], g, e)
+
+
+def test_config4_full_length_sampling_against_oracle():
+    """C4 at L=256: 64 injected-uniform draws bit-equal to the oracle's sample!, and a two-site chi-square of 2e5
+    Philox draws against twovar_marginals on 255 neighbouring + 64 distant site pairs."""
+    L, d, q = 256, 128, 4
+    ts = make_open(4, L, d, q)
+    A = T.TensorTrain(ts)
+    Ao = O.TensorTrain([a.copy() for a in ts])
+    del ts
+    lg, lo = T.normalize_(A), O.normalize(Ao)
+    assert abs(lg - lo) <= 1e-10 * abs(lo)
+    n = 64
+    us = RNG(41).random((n, L))
+    X, p = T.sample(A, n, uniforms=us)
+    rz = O.accumulate_R(Ao)
+    for i in range(n):
+        xo, po = O.sample(lambda t: us[i, t], Ao, rz=rz)
+        assert list(X[i]) == xo, (i, [t for t in range(L) if X[i][t] != xo[t]][:5])
+        assert abs(p[i] - po) <= 1e-8 * po
+    # two-site statistics of the Philox stream
+    nd = 200_000
+    Xs, _ = T.sample(A, nd, seed=77, first_index=0)
+    Xs = Xs.astype(np.int64)
+    m2 = T.twovar_marginals(A, maxdist=40)
+    pairs = [(t, t + 1) for t in range(L - 1)] + [(t, t + 40) for t in range(0, L - 40, 4)][:64]
+    assert len(pairs) >= 200
+    worst = 0.0
+    for (t, u) in pairs:
+        cnt = np.bincount(Xs[:, t] + q * Xs[:, u], minlength=q * q).astype(np.float64)
+        ex = nd * m2[(t, u)].reshape(-1, order="F")
+        chi = float(np.sum((cnt - ex) ** 2 / ex))
+        worst = max(worst, chi)
+    # dof 15; P(chi2_15 > 60) ~ 2e-7 per pair, 319 pairs
+    assert worst < 60.0, worst

@@ -821,3 +821,58 @@ def test_edge_cases_of_the_round_1b_entries():
     e0, z0 = float(T.evaluate(C4, X)[0]), C4.z
     T._ck(T.lib.ttb_scale_sites(C4._hd, T._dp(np.array([2.0]))))
     assert close(float(T.evaluate(C4, X)[0]), e0 / 2.0 ** 4, 1e-14) and C4.z.logabs == z0.logabs
+
+
+# ---- round-2 boundary fixes ------------------------------------------------------------------------------
+def test_jacobi_non_convergence_is_an_error(monkeypatch):
+    """The reference's LAPACK svd throws when it does not converge (src/svd_trunc.jl:37); a Jacobi SVD that hits
+    its sweep cap must not return TTB_OK.  TTB_JACOBI_MAXSWEEPS=1 forces the cap on every Jacobi variant."""
+    rng = RNG(900)
+    cases = [([1, 8, 8, 8, 1], (2,), 1),        # k_jacobi_small / g8 sized steps
+             ([1, 48, 48, 1], (2,), 1),         # k_jacobi_g8<64> / k_jacobi_small<64,64>
+             ([1, 160, 160, 1], (2,), 1)]       # cluster Jacobi
+    for bonds, q, _ in cases:
+        ts = rand_open(rng, bonds, q, "randn")
+        A = T.TensorTrain(ts)
+        monkeypatch.setenv("TTB_JACOBI_MAXSWEEPS", "1")
+        with pytest.raises(T.SVDNotConvergedError):
+            T.compress_(A, T.TruncThresh(1e-12))
+        monkeypatch.delenv("TTB_JACOBI_MAXSWEEPS")
+        B = T.TensorTrain(ts)
+        T.compress_(B, T.TruncThresh(1e-12))     # the status word was cleared: the next call is clean
+        assert T.bond_dims(B)[0] == 1
+
+
+def test_truncbondmax_maxerr_covers_both_sweeps_of_center_calls():
+    """src/svd_trunc.jl:98-100 updates maxerr on every SVD: orthogonalize_center! runs a left AND a right sweep."""
+    rng = RNG(901)
+    ts = rand_open(rng, [1, 6, 9, 9, 9, 6, 1], (3,), "randn")
+    for l, two in ((3, False), (4, False), (3, True)):
+        A, Ao = pair(ts)
+        tg, to = T.TruncBondMax(2), O.TruncBondMax(2)
+        if two:
+            T.orthogonalize_two_site_center_(A, l, tg); O.orthogonalize_two_site_center(Ao, l, to)
+        else:
+            T.orthogonalize_center_(A, l, tg); O.orthogonalize_center(Ao, l, to)
+        assert T.bond_dims(A) == O.bond_dims(Ao)
+        assert close(tg.maxerr[0], to.maxerr[0], 1e-6), (l, two, tg.maxerr, to.maxerr)
+        # the errors of the left half must be in it: the left sweep alone already gives a non-zero error
+        Bo, tl = O.TensorTrain([a.copy() for a in ts]), O.TruncBondMax(2)
+        O.orthogonalize_left(Bo, tl, range(1, l))
+        assert tl.maxerr[0] > 0 and tg.maxerr[0] >= tl.maxerr[0] * (1 - 1e-6)
+
+
+def test_spectrum_of_untouched_bonds_is_empty_and_capacity_checked():
+    import ctypes as C
+    rng = RNG(902)
+    ts = rand_open(rng, [1, 12, 12, 12, 1], (2,))
+    A = T.TensorTrain(ts)
+    A.record_spectrum(True)
+    T.orthogonalize_left_(A, T.TruncThresh(1e-9), indices=range(1, 3))     # touches bonds 1 and 2 only
+    assert len(A.spectrum(1)) == 2 and len(A.spectrum(2)) > 2
+    assert len(A.spectrum(3)) == 0 and len(A.spectrum(0)) == 0 and len(A.spectrum(4)) == 0
+    out, n = np.zeros(1), C.c_int64()
+    rc = T.lib.ttb_get_spectrum(A._hd, 0, 2, T._dp(out), 1, C.byref(n))     # too small: error, length reported
+    assert rc == 1 and n.value == len(A.spectrum(2))
+    T.orthogonalize_right_(A, T.TruncThresh(0.0))                           # eps = 0 sweep records nothing
+    assert all(len(A.spectrum(i)) == 0 for i in range(5))
