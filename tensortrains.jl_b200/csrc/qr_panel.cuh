@@ -69,18 +69,36 @@ __device__ __forceinline__ double dot_rpl(const double (&v)[RPL], const double (
   return (d0 + d1) + (d2 + d3);
 }
 
-// One link of the chain, executed by the warp that owns column cc = NS*wid + OS.  ONE reduction round: the
-// norm of the raw column x (rows > cc) and its dots with the warp's LATER columns ride the same butterfly;
-// with v = (e_cc, x * scal) the products the reflector needs are v^T a = a[cc] + scal * (x^T a), so nothing
-// waits for the normalised v.  Publishes v / tau / the ready flag, updates the later own columns, leaves
-// (R_cc on the diagonal, v below) in the column.  Returns tau; v stays in registers.
-// STREAM (k_qr_stream): only the first `nvi` 32-row groups exist below the panel's first row; tau is stored
-// right behind them at vcol[tauoff] so that reflector + tau leave the CTA as ONE contiguous bulk copy.
+// 1/a for a normal, positive double: MUFU.RCP64H seed + two Newton iterations (the library division carries
+// ~20 instructions of special-case handling; callers range-check).
+__device__ __forceinline__ double rcp_nr(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// One link of the chain, executed by the warp that owns column cc = NS*wid + OS.
+//
+// UN-NORMALISED reflectors inside the factorisation: v' = (den, x) with x the raw column below the diagonal and
+// den = alpha + sign(alpha) ||(alpha, x)||, H = I - tau' v' v'^T, tau' = 1 / (||.|| |den|).  Nothing on the chain
+// waits for a scaled copy of the column: the raw x goes to shared memory BEFORE the reduction (raw[cc] is raised,
+// consumers start their dot products while the owner is still in its butterfly and scalar arithmetic), and what
+// follows the reduction is one rsqrt, one reciprocal (both MUFU seed + two Newton steps) and three stores
+// (den into row cc of the published column, tau', the ready flag).  ONE reduction round per column: the norm of
+// x and its dots with the warp's LATER columns ride the same butterfly; v'^T a = den a[cc] + x^T a.
+// The LAPACK form (v_cc = 1, tau = tau' den^2) that the kernels downstream read is produced once per column in
+// the store epilogue, off the chain (panel_normalise).
+// STREAM (k_qr_stream): only the first `nvi` 32-row groups exist below the panel's first row; tau' is stored
+// right behind them at vcol[tauoff] so that reflector + tau' leave the CTA as ONE contiguous bulk copy.
 template <int RPL, int NS, int OS, bool STREAM = false>
-__device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* vcol, double* sh_tau, int* ready, int cc,
-                                                 int lane, int wid, int bwc, int nvi = RPL, int tauoff = 0) {
+__device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* vcol, double* sh_tau, double* sh_den,
+                                                 int* ready, int* raw, int cc, int lane, int wid, int bwc, int nvi = RPL,
+                                                 int tauoff = 0) {
   constexpr int NL = NS - 1 - OS;   // later own columns
-  double v[RPL];
 #ifdef TTB_PANEL_FINE
   if (lane == 0) TTB_PANEL_STAMPS[64 + 16 * cc + 0] = clock64();
 #endif
@@ -119,47 +137,58 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
   double acc[NL + 1];   // element at row cc of this and the later own columns (row cc lives in lane cc, i = 0)
 #pragma unroll
   for (int k = 0; k <= NL; ++k) acc[k] = __shfl_sync(0xffffffffu, a[OS + k][0], cc);
+  // the raw column goes to shared memory in the latency bubbles of the butterfly (a quarter of it per level):
+  // consumers start their dots on it while the owner is in its scalar arithmetic
+  constexpr int SPL = (RPL + 3) / 4;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int lv = 0; lv < 5; ++lv) {
+    const int o = 16 >> lv;
+    double got[NL + 1];
 #pragma unroll
-    for (int k = 0; k <= NL; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], o);
+    for (int k = 0; k <= NL; ++k) got[k] = __shfl_xor_sync(0xffffffffu, red[k], o);
+#pragma unroll
+    for (int i = lv * SPL; i < (lv + 1) * SPL; ++i) {
+      if (i < RPL && (!STREAM || i < nvi)) vcol[lane + 32 * i] = i == 0 ? x0m : x[i];
+    }
+#pragma unroll
+    for (int k = 0; k <= NL; ++k) red[k] += got[k];
   }
+  __syncwarp();
+  *reinterpret_cast<volatile int*>(&raw[cc]) = 1;
   const double xn2 = red[NL];
 #ifdef TTB_PANEL_FINE
   if (lane == 0 && xn2 != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 2] = clock64();
 #endif
   const double alpha = acc[0];
-  double scal = 0.0, beta = alpha, tau = 0.0;
-  if (xn2 > 0.0) {
-    const double nn = alpha * alpha + xn2;
-    const double rs = rsqrt(nn);  // 1/||x||
-    const double nrm = nn * rs;
-    const double sg = alpha >= 0.0 ? 1.0 : -1.0;
-    beta = -sg * nrm;
-    const double den = alpha - beta;  // = sg*(|alpha| + nrm), no cancellation
-    scal = 1.0 / den;
-    tau = den * sg * rs;  // (beta-alpha)/beta = den/(sg*nrm)
+  double den = 1.0, beta = alpha, taup = 0.0;
+  if (xn2 > 0.0) {   // warp-uniform
+    const double nn = fma(alpha, alpha, xn2);
+    if (nn > 1e-280 && nn < 1e280) {
+      const double rs = rsqrt_nr(nn);        // 1 / ||(alpha, x)||
+      const double nrm = nn * rs;
+      const double aa = fabs(alpha);
+      const double ad = aa + nrm;            // |den|: no cancellation
+      den = alpha >= 0.0 ? ad : -ad;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      taup = rs * rcp_nr(ad);                // 2 / (v'^T v') = 1 / (nrm |den|)
+    } else {                                  // far outside the normal range (rare): library arithmetic
+      const double nrm = sqrt(nn);
+      const double ad = fabs(alpha) + nrm;
+      den = alpha >= 0.0 ? ad : -ad;
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      taup = (1.0 / nrm) / ad;
+    }
   }
 #ifdef TTB_PANEL_FINE
-  if (lane == 0 && scal != 1.2345 && tau != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 3] = clock64();
+  if (lane == 0 && den != 1.2345 && taup != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 3] = clock64();
 #endif
-  {
-    double v0 = 0.0;
-    if (lane > cc) v0 = x[0] * scal;
-    else if (lane == cc) v0 = 1.0;
-    v[0] = v0;
-    vcol[lane] = v0;
-  }
-#pragma unroll
-  for (int i = 1; i < RPL; ++i) {
-    v[i] = x[i] * scal;
-    if (!STREAM || i < nvi) vcol[lane + 32 * i] = v[i];
-  }
-  // every lane stores the same tau / flag (no divergent region on the chain).  No MEMBAR: shared stores of
-  // one warp are performed in order and the flag is the last store instruction.
-  sh_tau[cc] = tau;
+  // publish: every lane stores the same values (no divergent region on the chain).  No MEMBAR: shared stores
+  // of one warp are performed in order and the flag is the last store instruction.
+  vcol[cc] = den;
+  sh_tau[cc] = taup;
+  sh_den[cc] = den;
   if (STREAM) {
-    vcol[tauoff] = tau;
+    vcol[tauoff] = taup;
     fence_proxy_async();   // writer-side proxy fence: the reflector leaves through a bulk (async-proxy) copy
   }
   __syncwarp();
@@ -170,18 +199,17 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
 #ifdef TTB_PANEL_FINE
   if (lane == 0) TTB_PANEL_STAMPS[64 + 16 * cc + 4] = clock64();
 #endif
-  // own column: R_cc on the diagonal, v below, untouched above
-  if (lane > cc) a[OS][0] = v[0];
-  else if (lane == cc) a[OS][0] = beta;
-#pragma unroll
-  for (int i = 1; i < RPL; ++i) a[OS][i] = v[i];
+  // own column: R_cc on the diagonal, the raw x stays below (normalised in the epilogue), untouched above
+  const double v0 = lane > cc ? x[0] : (lane == cc ? den : 0.0);
+  if (lane == cc) a[OS][0] = beta;
 #pragma unroll
   for (int k = 0; k < NL; ++k) {
     const int s2 = OS + 1 + k;
     if (wid * NS + s2 < bwc) {   // warp-uniform
-      const double w = tau * (acc[k + 1] + scal * red[k]);   // tau * v_cc^T a_cs
+      const double w = taup * fma(den, acc[k + 1], red[k]);   // tau' * v'^T a_cs
+      a[s2][0] -= v0 * w;
 #pragma unroll
-      for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
+      for (int i = 1; i < RPL; ++i) a[s2][i] -= x[i] * w;
     }
   }
 #ifdef TTB_PANEL_FINE
@@ -189,43 +217,106 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
 #endif
 }
 
-// V^T V entries between the columns of ONE finished block (s1 < s2): G = v_s1[row cs2] + sum_{r > cs2} v_s1[r] v_s2[r].
-// Runs once per block after its last reflector has been published, i.e. off the chain.
+// A warp that owns LATER columns applies reflector cc of the block in flight to all NS of them at once.  Two
+// flags: raw[cc] says the raw column x is in shared memory -- the dots x^T a and their transpose butterfly (6
+// shuffles for 4 values; lane l ends up with the total of value l / (32 / NS)) run while the owner is still
+// reducing -- and ready[cc] says den / tau' are there: what is left on the hand-off is two broadcast loads, one
+// FMA per column and the rank-1 update.
 template <int RPL, int NS>
-__device__ __forceinline__ void panel_block_gram(const double (&a)[NS][RPL], double* G, int wid, int lane, int bwc) {
-  constexpr int NPAIR = NS * (NS - 1) / 2;
-  double red[NPAIR > 0 ? NPAIR : 1], diag[NPAIR > 0 ? NPAIR : 1];
-  int k = 0;
+__device__ __forceinline__ void panel_consume_later(double (&a)[NS][RPL], const double* vcol, const double* sh_tau,
+                                                    const int* ready, const int* raw, int cc, int lane, bool relaxed,
+                                                    int nvi = RPL) {
+  unsigned it = 0;
+  while (ld_flag(&raw[cc]) == 0) {
+    if (relaxed) __nanosleep(100);
+    if (++it > (1u << 26)) __trap();
+  }
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && !relaxed) TTB_PANEL_STAMPS[64 + 16 * cc + 6] = clock64();
+#endif
+  double v[RPL];
+  v[0] = lane > cc ? vcol[lane] : 0.0;    // row cc will hold den: it enters through acc below, never through v
 #pragma unroll
-  for (int s2 = 1; s2 < NS; ++s2) {
-    const int cs2 = wid * NS + s2;
+  for (int i = 1; i < RPL; ++i) v[i] = i < nvi ? vcol[lane + 32 * i] : 0.0;   // (stream: tau' sits behind the valid groups)
+  double dot[NS], acc[NS];
 #pragma unroll
-    for (int s1 = 0; s1 < s2; ++s1) {
-      double d0 = (lane > cs2) ? a[s1][0] * a[s2][0] : 0.0, d1 = 0.0;
+  for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
 #pragma unroll
-      for (int i = 1; i < RPL; ++i) {
-        if (i & 1) d1 += a[s1][i] * a[s2][i];
-        else d0 += a[s1][i] * a[s2][i];
-      }
-      red[k] = d0 + d1;
-      diag[k] = __shfl_sync(0xffffffffu, a[s1][0], cs2 & 31);
-      ++k;
-    }
+  for (int s2 = 0; s2 < NS; ++s2) acc[s2] = __shfl_sync(0xffffffffu, a[s2][0], cc);
+  const double tot = warp_reduce_ns<NS>(dot, lane);
+  double ts[NS];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) ts[s2] = __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && !relaxed && ts[0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 7] = clock64();
+#endif
+  it = 0;
+  while (ld_flag(&ready[cc]) == 0) {
+    if (++it > (1u << 26)) __trap();
+  }
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && !relaxed) TTB_PANEL_STAMPS[64 + 16 * cc + 8] = clock64();
+#endif
+  const double den = *reinterpret_cast<const volatile double*>(&vcol[cc]);
+  const double taup = *reinterpret_cast<const volatile double*>(&sh_tau[cc]);
+  const double v0 = lane == cc ? den : v[0];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const double w = taup * fma(den, acc[s2], ts[s2]);
+    a[s2][0] -= v0 * w;
+#pragma unroll
+    for (int i = 1; i < RPL; ++i) a[s2][i] -= v[i] * w;
+  }
+#ifdef TTB_PANEL_FINE
+  if (lane == 0 && !relaxed && a[0][0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 9] = clock64();
+#endif
+}
+
+// V'^T V' of the whole panel on the FP64 tensor cores, once, off the chain: G[i + 32 j] = sum_r v'_i[r] v'_j[r] for
+// i < j < bwc from the published reflectors (shared memory, column stride SL, rows 0 .. krows-1 valid, zeros above
+// each diagonal and den on it).  While the chain runs, warps whose columns are finished do NOTHING -- their dots
+// used to take FP64 issue slots from the owner and the next owner on the same SM sub-partition.  Eight 16 x 8
+// tiles of mma.sync.m16n8k8.f64, one per warp (warps 0..7), K = krows.  Call between two block barriers.
+__device__ __forceinline__ void panel_gram_mma(const double* vs, int SL, int krows, double* G, int wid, int lane, int bwc) {
+  if (wid >= 8) return;
+  const int mt = wid & 1, nt = wid >> 1;         // rows 16 mt .., columns 8 nt ..
+  if (16 * mt >= 8 * nt + 8) return;             // tile entirely on or below the diagonal
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa = vs + (size_t)(16 * mt + g) * SL + t;
+  const double* pb = vs + (size_t)(8 * nt + g) * SL + t;
+  double d[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < krows; k0 += 8) {
+    const double af[4] = {pa[k0], pa[k0 + 8 * (size_t)SL], pa[k0 + 4], pa[k0 + 8 * (size_t)SL + 4]};
+    const double bf[2] = {pb[k0], pb[k0 + 4]};
+    dmma_16x8x8(d, af, bf);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int q = 0; q < NPAIR; ++q) red[q] += __shfl_xor_sync(0xffffffffu, red[q], o);
+  for (int e = 0; e < 4; ++e) {
+    const int i = 16 * mt + g + ((e & 2) ? 8 : 0), j = 8 * nt + 2 * t + (e & 1);
+    if (i < j && j < bwc) G[i + 32 * j] = d[e];
   }
-  k = 0;
+}
+
+// Store epilogue, off the chain: LAPACK form of the panel.  Column cs of the warp: rows below the diagonal are
+// divided by den_cs; G (strict upper part = V'^T V') is scaled by 1/(den_i den_j), its diagonal receives
+// tau_i = tau'_i den_i^2.  Call after a block barrier (all reflectors and G entries are in shared memory).
+template <int RPL, int NS>
+__device__ __forceinline__ void panel_normalise(double (&a)[NS][RPL], double* G, const double* sh_tau, const double* sh_den,
+                                                int tid, int nthreads, int wid, int lane, int bwc) {
 #pragma unroll
-  for (int s2 = 1; s2 < NS; ++s2) {
-    const int cs2 = wid * NS + s2;
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int cs = wid * NS + s2;
+    if (cs < bwc) {
+      const double scal = 1.0 / sh_den[cs];
+      if (lane > cs) a[s2][0] *= scal;
 #pragma unroll
-    for (int s1 = 0; s1 < s2; ++s1) {
-      if (cs2 < bwc) G[(wid * NS + s1) + 32 * cs2] = diag[k] + red[k];   // same value from every lane
-      ++k;
+      for (int i = 1; i < RPL; ++i) a[s2][i] *= scal;
     }
+  }
+  for (int i = tid; i < 1024; i += nthreads) {
+    const int r = i & 31, cj = i >> 5;
+    if (r < cj && cj < bwc) G[i] = G[i] / (sh_den[r] * sh_den[cj]);
+    else if (r == cj) G[i] = cj < bwc ? sh_tau[cj] * sh_den[cj] * sh_den[cj] : 0.0;
   }
 }
 
@@ -248,8 +339,10 @@ __global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag
   extern __shared__ __align__(16) double dyn[];
   double* vs = dyn;                       // [32][32*RPL] all reflectors of the panel
   double* G = vs + 32 * LDV;              // 32*32: striu = V^T V, diagonal = tau
-  double* sh_tau = G + 1024;              // 32
-  int* ready = reinterpret_cast<int*>(sh_tau + 32);  // 32 flags
+  double* sh_tau = G + 1024;              // 32  tau' of the un-normalised reflectors
+  double* sh_den = sh_tau + 32;           // 32  their diagonal elements
+  int* ready = reinterpret_cast<int*>(sh_den + 32);  // 32 flags: den / tau' published
+  int* raw = ready + 32;                  // 32 flags: raw column in shared memory
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double a[NS][RPL];
 #pragma unroll
@@ -262,7 +355,8 @@ __global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag
     }
   }
   for (int i = tid; i < 1024; i += NT) G[i] = 0.0;
-  if (tid < 32) ready[tid] = 0;
+  if (tid < 64) ready[tid] = 0;   // ready[32] + raw[32]
+  if (tid < 32) sh_den[tid] = 1.0;
   __syncthreads();
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[0] = clock64();
@@ -276,67 +370,35 @@ __global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag
   for (int blk = 0; blk * NS < bwc; ++blk) {
     const int c0 = blk * NS;
     if (wid == blk) {
-      panel_owner_step<RPL, NS, 0>(a, vs + (size_t)c0 * LDV, sh_tau, ready, c0, lane, wid, bwc);
+      panel_owner_step<RPL, NS, 0>(a, vs + (size_t)c0 * LDV, sh_tau, sh_den, ready, raw, c0, lane, wid, bwc);
       if (NS > 1 && c0 + 1 < bwc)
-        panel_owner_step<RPL, NS, (1 < NS ? 1 : 0)>(a, vs + (size_t)(c0 + 1) * LDV, sh_tau, ready, c0 + 1, lane, wid, bwc);
+        panel_owner_step<RPL, NS, (1 < NS ? 1 : 0)>(a, vs + (size_t)(c0 + 1) * LDV, sh_tau, sh_den, ready, raw, c0 + 1, lane, wid, bwc);
       if (NS > 2 && c0 + 2 < bwc)
-        panel_owner_step<RPL, NS, (2 < NS ? 2 : 0)>(a, vs + (size_t)(c0 + 2) * LDV, sh_tau, ready, c0 + 2, lane, wid, bwc);
+        panel_owner_step<RPL, NS, (2 < NS ? 2 : 0)>(a, vs + (size_t)(c0 + 2) * LDV, sh_tau, sh_den, ready, raw, c0 + 2, lane, wid, bwc);
       if (NS > 3 && c0 + 3 < bwc)
-        panel_owner_step<RPL, NS, (3 < NS ? 3 : 0)>(a, vs + (size_t)(c0 + 3) * LDV, sh_tau, ready, c0 + 3, lane, wid, bwc);
-      panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
-    } else {
+        panel_owner_step<RPL, NS, (3 < NS ? 3 : 0)>(a, vs + (size_t)(c0 + 3) * LDV, sh_tau, sh_den, ready, raw, c0 + 3, lane, wid, bwc);
+    } else if (wid * NS >= bwc) {
+      // no column of this warp exists in a narrow panel: nothing to update, nothing to contribute to G
+    } else if (wid > blk) {
+      // all own columns lie after the block (columns >= bwc are zero and stay zero): rank-1 updates, started on
+      // the raw column while the owner is still reducing.  Warps that are not about to take over the chain back
+      // off between polls: their spinning would take issue slots from the owner on the same SM sub-partition
       const int cend = min(c0 + NS, bwc);
 #pragma unroll 1
-      for (int cc = c0; cc < cend; ++cc) {
-        // ---- consumer: every lane polls the same word (broadcast load, no divergence).  Warps that are
-        // not about to take over the chain back off between polls: their spinning would take issue slots
-        // from the owner on the same SM sub-partition
-        const bool relaxed = (wid != blk + 1);
-        unsigned it = 0;
-        while (ld_flag(&ready[cc]) == 0) {
-          if (relaxed) __nanosleep(100);
-          if (++it > (1u << 26)) __trap();
-        }
-#ifdef TTB_PANEL_FINE
-        if (lane == 0 && wid == blk + 1) TTB_PANEL_STAMPS[64 + 16 * cc + 6] = clock64();
-#endif
-        const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
-        const double* vcol = vs + (size_t)cc * LDV;
-        double v[RPL];
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) v[i] = vcol[lane + 32 * i];
-        // apply reflector cc to all NS columns of this warp at once: independent dots, ONE transpose
-        // butterfly (each level sends the half of the values the partner lane keeps: 6 shuffles for 4
-        // values instead of 20; lane l ends up with the total of value (l >> 3) & 3).  The consumer path is
-        // what the next owner must get through before it can take over the chain, so its instruction
-        // count is on the critical path at every hand-off.
-        double dot[NS];
-#pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
-        const double tot = warp_reduce_ns<NS>(dot, lane);
-        if (wid > blk) {
-          // all own columns lie after cc (columns >= bwc are zero and stay zero): rank-1 updates
-#pragma unroll
-          for (int s2 = 0; s2 < NS; ++s2) {
-            const double w = tau * __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-          }
-        } else {
-          // all own columns are finished reflectors: only the V^T V entries
-          if ((lane & (32 / NS - 1)) == 0) G[(wid * NS + lane / (32 / NS)) + 32 * cc] = tot;
-        }
-#ifdef TTB_PANEL_FINE
-        if (lane == 0 && wid == blk + 1 && a[0][0] != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 7] = clock64();
-#endif
-      }
+      for (int cc = c0; cc < cend; ++cc)
+        panel_consume_later<RPL, NS>(a, vs + (size_t)cc * LDV, sh_tau, ready, raw, cc, lane, wid != blk + 1);
     }
+    // (warps whose columns are finished reflectors have nothing to do: V'^T V' is formed after the chain)
   }
   __syncthreads();
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[1] = clock64();
 #endif
-  if (tid < 32) G[tid + 32 * tid] = tid < bwc ? sh_tau[tid] : 0.0;
+  for (int i = bwc * LDV + tid; i < 32 * LDV; i += NT) vs[i] = 0.0;   // columns a narrow panel never published
+  __syncthreads();
+  panel_gram_mma(vs, LDV, LDV, G, wid, lane, bwc);
+  __syncthreads();
+  panel_normalise<RPL, NS>(a, G, sh_tau, sh_den, tid, NT, wid, lane, bwc);
 #ifdef TTB_PANEL_STAMPS
   if (tid == 0) TTB_PANEL_STAMPS[2] = clock64();
 #endif

@@ -39,8 +39,9 @@ constexpr int kQsThreads = 256;    // 8 warps, 4 columns each
 constexpr int kQsMaxBlocks = 8;    // portable cluster size
 
 __host__ __device__ constexpr size_t qs_smem_bytes(int RPL) {
-  // vs[32][SL] + ring[RING][SL] + G[1024] + tau[32] doubles, ready[32] + done[8] + credit[8][RING] ints, RING mbarriers
-  return sizeof(double) * ((size_t)(32 + kQsRing) * (32 * RPL + 8) + 1024 + 32) + sizeof(int) * (40 + 8 * kQsRing) + 8 * kQsRing + 64;
+  // vs[32][SL] + ring[RING][SL] + G[1024] + tau'[32] + den[32] doubles, ready[32] + raw[32] + done[8] + credit[8][RING] ints,
+  // RING mbarriers
+  return sizeof(double) * ((size_t)(32 + kQsRing) * (32 * RPL + 8) + 1024 + 64) + sizeof(int) * (72 + 8 * kQsRing) + 8 * kQsRing + 64;
 }
 
 // timeline stamps (globaltimer ns) of one traced site step: [CTA][0] start, [1 + j] consumed panel j,
@@ -74,15 +75,18 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
   double* vs = dyn;                                  // [32][SL] reflectors of the own panel
   double* ring = vs + 32 * SL;                       // [RING][SL] remote reflectors
   double* G = ring + kQsRing * SL;                   // 32*32
-  double* sh_tau = G + 1024;                         // 32
-  int* ready = reinterpret_cast<int*>(sh_tau + 32);  // [32]
-  int* done = ready + 32;                            // [8] remote reflectors consumed per warp
+  double* sh_tau = G + 1024;                         // 32  tau' of the un-normalised reflectors (qr_panel.cuh)
+  double* sh_den = sh_tau + 32;                      // 32  their diagonal elements
+  int* ready = reinterpret_cast<int*>(sh_den + 32);  // [32] den / tau' published
+  int* raw = ready + 32;                             // [32] raw column in shared memory
+  int* done = raw + 32;                              // [8] remote reflectors consumed per warp
   int* credit = done + 8;                            // [8 consumer ranks][RING]: (global index + 1) of the reflector the slot is armed for
   uint64_t* bars = reinterpret_cast<uint64_t*>(credit + 8 * kQsRing);  // [RING]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < 1024; i += kQsThreads) G[i] = 0.0;
   for (int i = tid; i < kQsRing * SL; i += kQsThreads) ring[i] = 0.0;   // rows above a producing panel must read as zero
-  if (tid < 40 + 8 * kQsRing) ready[tid] = 0;   // ready[32] + done[8] + credit[8][RING]
+  if (tid < 72 + 8 * kQsRing) ready[tid] = 0;   // ready[32] + raw[32] + done[8] + credit[8][RING]
+  if (tid < 32) sh_den[tid] = 1.0;
   if (tid == 0)
     for (int r = 0; r < kQsRing; ++r) mbar_init(&bars[r], 1);
   __syncthreads();
@@ -201,43 +205,29 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
   for (int blk = 0; blk * NS < bwc; ++blk) {
     const int c0 = blk * NS;
     if (wid == blk) {
-      panel_owner_step<RPL, NS, 0, true>(a, vs + (size_t)c0 * SL, sh_tau, ready, c0, lane, wid, bwc, nvi, LDV - j0);
-      if (c0 + 1 < bwc) panel_owner_step<RPL, NS, 1, true>(a, vs + (size_t)(c0 + 1) * SL, sh_tau, ready, c0 + 1, lane, wid, bwc, nvi, LDV - j0);
-      if (c0 + 2 < bwc) panel_owner_step<RPL, NS, 2, true>(a, vs + (size_t)(c0 + 2) * SL, sh_tau, ready, c0 + 2, lane, wid, bwc, nvi, LDV - j0);
-      if (c0 + 3 < bwc) panel_owner_step<RPL, NS, 3, true>(a, vs + (size_t)(c0 + 3) * SL, sh_tau, ready, c0 + 3, lane, wid, bwc, nvi, LDV - j0);
+      panel_owner_step<RPL, NS, 0, true>(a, vs + (size_t)c0 * SL, sh_tau, sh_den, ready, raw, c0, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 1 < bwc) panel_owner_step<RPL, NS, 1, true>(a, vs + (size_t)(c0 + 1) * SL, sh_tau, sh_den, ready, raw, c0 + 1, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 2 < bwc) panel_owner_step<RPL, NS, 2, true>(a, vs + (size_t)(c0 + 2) * SL, sh_tau, sh_den, ready, raw, c0 + 2, lane, wid, bwc, nvi, LDV - j0);
+      if (c0 + 3 < bwc) panel_owner_step<RPL, NS, 3, true>(a, vs + (size_t)(c0 + 3) * SL, sh_tau, sh_den, ready, raw, c0 + 3, lane, wid, bwc, nvi, LDV - j0);
       if (s.trace && b == 0 && lane == 0) g_qs_trace[kb * 32 + 22 + blk] = qs_now();
       if (wid == 0) pump(min(c0 + NS, bwc));   // warp 0's own block: its reflectors leave once the block is done
-      panel_block_gram<RPL, NS>(a, G, wid, lane, bwc);
-    } else {
+    } else if (wid > blk) {
+      const int cend = min(c0 + NS, bwc);
+#pragma unroll 1
+      for (int cc = c0; cc < cend; ++cc)
+        panel_consume_later<RPL, NS>(a, vs + (size_t)cc * SL, sh_tau, ready, raw, cc, lane, wid != blk + 1, nvi);
+    } else if (wid == 0) {
+      // warp 0 owns finished columns from the second block on: it only keeps the pushes going (V'^T V' is formed
+      // after the chain, panel_gram_mma)
       const int cend = min(c0 + NS, bwc);
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc) {
-        const bool relaxed = (wid != blk + 1);
         unsigned it = 0;
         while (ld_flag(&ready[cc]) == 0) {
-          if (relaxed) __nanosleep(100);
+          __nanosleep(100);
           if (++it > (1u << 26)) __trap();
         }
-        if (wid == 0) pump(cc + 1);
-        const double tau = *reinterpret_cast<volatile double*>(&sh_tau[cc]);
-        const double* vcol = vs + (size_t)cc * SL;
-        double v[RPL];
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) v[i] = i < nvi ? vcol[lane + 32 * i] : 0.0;   // behind the valid groups sits tau
-        double dot[NS];
-#pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2) dot[s2] = dot_rpl<RPL>(v, a[s2]);
-        const double tot = warp_reduce_ns<NS>(dot, lane);
-        if (wid > blk) {
-#pragma unroll
-          for (int s2 = 0; s2 < NS; ++s2) {
-            const double w = tau * __shfl_sync(0xffffffffu, tot, s2 * (32 / NS));
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) a[s2][i] -= v[i] * w;
-          }
-        } else {
-          if ((lane & (32 / NS - 1)) == 0) G[(wid * NS + lane / (32 / NS)) + 32 * cc] = tot;
-        }
+        pump(cc + 1);
       }
     }
   }
@@ -251,7 +241,13 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
     }
   }
   __syncthreads();
-  if (tid < 32) G[tid + 32 * tid] = tid < bwc ? sh_tau[tid] : 0.0;
+  // K range of the Gram product = the 32 nvi valid rows: tau' sits right behind them and must stay intact (a bulk
+  // push may still be reading it); columns a narrow panel never published are cleared (they are never pushed)
+  for (int i = bwc * SL + tid; i < 32 * SL; i += kQsThreads) vs[i] = 0.0;
+  __syncthreads();
+  panel_gram_mma(vs, SL, 32 * nvi, G, wid, lane, bwc);
+  __syncthreads();
+  panel_normalise<RPL, NS>(a, G, sh_tau, sh_den, tid, kQsThreads, wid, lane, bwc);   // LAPACK form for the kernels downstream
 #pragma unroll
   for (int s2 = 0; s2 < NS; ++s2) {
     const int cs = wid * NS + s2;

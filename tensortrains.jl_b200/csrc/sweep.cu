@@ -1389,7 +1389,7 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
 #define TTB_PANEL(RPL_)                                                                            \
   do {                                                                                             \
     auto kp = k_qr_panel_flag<RPL_, kPanelNS>;                                                     \
-    SW_LAUNCH("k_qr_panel_flag", kp, B, 1024 / kPanelNS, sizeof(double) * (1024 * RPL_ + 1056) + 128, c, s, panel); \
+    SW_LAUNCH("k_qr_panel_flag", kp, B, 1024 / kPanelNS, sizeof(double) * (1024 * RPL_ + 1088) + 256, c, s, panel); \
   } while (0)
           if (rows_ub <= 64) TTB_PANEL(2);
           else if (rows_ub <= 128) TTB_PANEL(4);
