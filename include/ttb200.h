@@ -26,6 +26,7 @@ extern "C" {
 #endif
 
 typedef struct ttb_tt* ttb_handle;
+typedef struct ttb_env* ttb_env_handle; /* a stored accumulate_L / accumulate_R result (see "environment handles") */
 
 enum {
   TTB_OK = 0,
@@ -151,6 +152,31 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out);
  * rank computes when the pair marginals of ONE train are sharded over GPUs (third axis). */
 int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out);
 
+/* ---- environment handles: the keyword arguments l=, r= of marginals / twovar_marginals
+ *      (src/abstract_tensor_train.jl:208-209, 231-233) and rz= of sample / sample! (:335-336, :355-356) let a
+ *      caller pay accumulate_L / accumulate_R once and reuse it.  ttb_env_create runs the accumulate pass
+ *      (left != 0: accumulate_L, else accumulate_R) and keeps the result on the device; the *_env entry points
+ *      take NULL for "compute it" (the reference's default keyword).  An environment only fits the train it was
+ *      computed on AS IT WAS THEN: a call whose train has other shapes / bond dimensions fails with TTB_EINVAL. */
+int ttb_env_create(ttb_handle h, int left, int normalize, ttb_env_handle* out);
+int ttb_env_destroy(ttb_env_handle e);
+/* the Logarithmic z returned next to the environments (accumulate_L(A)[2]), one entry per train */
+int ttb_env_z(ttb_env_handle e, double* logabs, int* sign);
+int ttb_marginals_env(ttb_handle h, ttb_env_handle l, ttb_env_handle r, double* out);
+int ttb_twovar_marginals_env(ttb_handle h, ttb_env_handle l, ttb_env_handle r, int64_t maxdist, int64_t t_lo,
+                             int64_t t_hi, double* out);
+/* accumulate_M (src/abstract_tensor_train.jl:119-137) of train b: the matrices M[t,u], t < u (0-based), packed in
+ * lexicographic (t,u) order, each d_{t+1} x d_u column-major, M[u-1,u] = I.  twovar_marginals streams this table
+ * and never stores it (63 GiB at config 5); the entry serves callers of the reference API (M= keyword) and tests. */
+int ttb_accumulate_M_size(ttb_handle h, int64_t b, int64_t* n_doubles);
+int ttb_accumulate_M(ttb_handle h, int64_t b, int normalize, double* out);
+
+/* ---- is_in_domain (src/abstract_tensor_train.jl:59-64): X is n x L flat 0-based indices; *ok = all inside 0:Q-1.
+ *      == (src/abstract_tensor_train.jl:85): isequal of the site tensors (z is NOT compared, like the reference;
+ *      NaN equals NaN, -0.0 differs from 0.0); trains of different kind / length / shape are unequal. */
+int ttb_is_in_domain(ttb_handle h, const int32_t* X, int64_t n, int* ok);
+int ttb_equal(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, int* equal);
+
 /* ---- evaluate (src/abstract_tensor_train.jl:80-83): X is n x L row-major int32 of 0-based flat
  *      physical indices; evaluates train b at n points; out = tr(prod A_t(x_t)) / z */
 int ttb_evaluate(ttb_handle h, int64_t b, const int32_t* X, int64_t n, double* out);
@@ -165,6 +191,12 @@ int ttb_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_
  * (L*Q int64, accumulated) come back.  hist may be NULL. */
 int ttb_sample_stats(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
                      int64_t* hist, double* sum_logp);
+
+/* sample / sample_stats with rz= (an accumulate_R environment handle; NULL = recompute like the default keyword) */
+int ttb_sample_env(ttb_handle h, ttb_env_handle rz, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
+                   const double* uniforms, uint8_t* x_out, double* p_out);
+int ttb_sample_stats_env(ttb_handle h, ttb_env_handle rz, int64_t b, int64_t nsamples, uint64_t seed,
+                         uint64_t first_index, int64_t* hist, double* sum_logp);
 
 /* ---- dot (src/abstract_tensor_train.jl:395-408) of train ba of `a` with train bb of `b` (same length and
  * physical dimension, same device; open or periodic, bonds may differ).  The value is returned as

@@ -883,6 +883,82 @@ def mps_marginals(p: MPS):
     return out
 
 
+def mps_marginals_env(p: MPS, l=None, r=None):
+    """``marginals(p; l, r)`` with caller-supplied environments (``mps.jl:176-177``)"""
+    psi = p.psi
+    l = mps_accumulate_L(p)[0] if l is None else l
+    r = mps_accumulate_R(p)[0] if r is None else r
+    d = psi[0].shape[0]
+    out = []
+    for t in range(len(psi)):
+        A = _reshape1(psi[t])
+        R = r[t + 1] if t + 1 < len(psi) else _id4(d)
+        Lm = l[t - 1] if t >= 1 else _id4(d)
+        pt = np.einsum("acbd,cex,dfx,eafb->x", Lm, A, A, R, optimize=True)
+        out.append((pt / pt.sum()).reshape(psi[t].shape[2:], order="F"))
+    return out
+
+
+def mps_accumulate_M(p: MPS):
+    """``mps.jl:104-126``: ``M[t,u][a_{t+1}, a_u, b_{t+1}, b_u]`` (0-based keys ``(t,u)``, ``t < u``), no rescaling,
+    hermiticity restored after every step, ``M[u-1,u] = id4(d_u)``"""
+    L = len(p)
+    M = {}
+    for u in range(1, L):
+        Au = _reshape1(p.psi[u - 1])
+        for t in range(0, u - 1):
+            Mu = np.einsum("acbd,cex,dfx->aebf", M[(t, u - 1)], Au, Au, optimize=True)
+            M[(t, u)] = (np.transpose(Mu, (2, 3, 0, 1)) + Mu) / 2
+        M[(u - 1, u)] = _id4(p.psi[u].shape[0])
+    return M
+
+
+def mps_twovar_marginals(p: MPS, l=None, r=None, M=None, maxdist=None):
+    """``mps.jl:206-232`` (open trains): dict ``(t,u) -> b[x_t..., x_u...]``"""
+    psi = p.psi
+    L = len(psi)
+    l = mps_accumulate_L(p)[0] if l is None else l
+    r = mps_accumulate_R(p)[0] if r is None else r
+    M = mps_accumulate_M(p) if M is None else M
+    maxdist = L - 1 if maxdist is None else maxdist
+    d = psi[0].shape[0]
+    qs = tuple(psi[0].shape[2:])
+    out = {}
+    for t in range(L - 1):
+        lt = _id4(d) if t == 0 else l[t - 1]
+        At = _reshape1(psi[t])
+        for u in range(t + 1, min(L - 1, t + maxdist) + 1):
+            ru = _id4(d) if u == L - 1 else r[u + 1]
+            Au = _reshape1(psi[u])
+            lAAM = np.einsum("acbd,cex,dfx,egfh->abghx", lt, At, At, M[(t, u)], optimize=True)
+            AAr = np.einsum("gky,hly,kalb->abghy", Au, Au, ru, optimize=True)
+            btu = np.einsum("abghx,abghy->xy", lAAM, AAr, optimize=True)
+            btu = btu / btu.sum()
+            out[(t, u)] = btu.reshape(qs + qs, order="F")
+    return out
+
+
+def mps_sample(uniform: Callable[[int], float], p: MPS, rz=None):
+    """``sample!`` for an MPS (``mps.jl:264-290``): ``uniform(t)`` supplies the one ``rand`` of site ``t``.
+    Returns ``(x, q)`` with ``x`` 0-based multi-indices and ``q = |tr Q|^2 / z``."""
+    psi = p.psi
+    r, z = mps_accumulate_R(p) if rz is None else rz
+    L = len(psi)
+    d = psi[L - 1].shape[1]
+    Qm = np.eye(d)
+    x = []
+    for t in range(L):
+        rl = _id4(d) if t == L - 1 else r[t + 1]
+        A = _reshape1(psi[t])
+        QA = np.einsum("km,mnx->knx", Qm, A)
+        q = np.einsum("acx,cadb,bdx->x", QA, rl, QA, optimize=True)
+        q = q / q.sum()
+        xt = sample_noalloc(uniform(t), q)
+        x.append(tuple(int(v) for v in np.unravel_index(xt, psi[t].shape[2:], order="F")))
+        Qm = QA[:, :, xt]
+    return x, float(np.trace(Qm) ** 2 / float(z))
+
+
 def mps_exact_prob(p: MPS) -> np.ndarray:
     """``test/exact.jl`` for an MPS: enumerate ``|psi(x)|^2``"""
     return np.abs(_exact_values(p.psi)) ** 2
@@ -989,3 +1065,25 @@ def philox_uniform(seed: int, sample_index, site) -> np.ndarray:
                                  np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
     bits = (r0.astype(np.uint64) << np.uint64(21)) ^ (r1.astype(np.uint64) >> np.uint64(11))
     return bits.astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# is_in_domain, ==  (src/abstract_tensor_train.jl:59-64, :85)
+# ----------------------------------------------------------------------------------------------
+def is_in_domain(A, X) -> bool:
+    """``src/abstract_tensor_train.jl:59-64`` with 0-based indices: ``X`` is a list over sites of index tuples."""
+    return all(all(0 <= int(xi) < Ax.shape[i + 2] for i, xi in enumerate(np.atleast_1d(x))) for Ax, x in zip(A, X))
+
+
+def equal(A, B) -> bool:
+    """``==`` (``src/abstract_tensor_train.jl:85``): ``isequal(A.tensors, B.tensors)`` for trains of the same type --
+    elementwise ``isequal`` (NaN equals NaN, -0.0 differs from 0.0); ``z`` is not compared."""
+    if type(A) is not type(B) or len(A) != len(B):
+        return False
+    for a, b in zip(A, B):
+        if a.shape != b.shape:
+            return False
+        same = (np.isnan(a) & np.isnan(b)) | (a.view(np.int64) == b.view(np.int64)) if a.size else np.array([True])
+        if not bool(np.all(same)):
+            return False
+    return True

@@ -137,6 +137,20 @@ struct ttb_tt {
   int64_t launches = 0;        // running counter inside a call
 };
 
+// accumulate_L / accumulate_R result kept on the device for the l= / r= / rz= keyword arguments of marginals,
+// twovar_marginals and sample (src/abstract_tensor_train.jl:208-209, 231-233, 335-336)
+struct ttb_env {
+  int device = 0;
+  int left = 0, normalize = 1;
+  int64_t L = 0, Q = 0, batch = 0, env_stride = 0;
+  int periodic = 0;
+  std::vector<int64_t> bond0;   // capacity bonds of the train it was computed on (they fix the slot offsets)
+  std::vector<int> bonds;       // current bonds of every train at that time
+  double* env = nullptr;        // [batch][env_stride], laid out like Workspace::envL / envR
+  double* logabs = nullptr;     // [batch]
+  int* sign = nullptr;          // [batch]
+};
+
 namespace ttb {
 
 // RAII-ish timing bracket used by every entry point that launches kernels

@@ -1,6 +1,7 @@
 // container.cu -- device container behind TensorTrain / PeriodicTensorTrain
 // (reference: src/tensor_train.jl:8-24, src/periodic_tensor_train.jl:8-27,
 //  check_bond_dims src/abstract_tensor_train.jl:40-52).
+#include <algorithm>
 #include <stdarg.h>
 #include <string.h>
 
@@ -511,6 +512,74 @@ int ttb_set_z(ttb_handle h, int64_t b, double logabs, int sign) {
   TTB_CUDA(cudaMemcpyAsync(h->d_signz + b, &s, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   TTB_CUDA(cudaStreamSynchronize(h->stream));
   return TTB_OK;
+}
+
+// ---- is_in_domain (src/abstract_tensor_train.jl:59-64) and == (:85) --------------------------------------
+int ttb_is_in_domain(ttb_handle h, const int32_t* X, int64_t n, int* ok) {
+  TTB_TRY(check_handle_raw(h));
+  if (!X || !ok || n < 0) return fail(TTB_EINVAL, "bad argument");
+  *ok = 1;
+  for (int64_t i = 0; i < n * h->L; ++i)
+    if (X[i] < 0 || X[i] >= h->Q) { *ok = 0; break; }
+  return TTB_OK;
+}
+
+}  // extern "C"
+
+namespace ttb {
+// isequal on doubles: NaN equals NaN, -0.0 differs from 0.0 (Julia's isequal, used by == on the tensor vectors)
+__global__ void k_equal(const double* a, const double* b, int64_t n, int* differ) {
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a[i], y = b[i];
+    const bool same = (x != x && y != y) || __double_as_longlong(x) == __double_as_longlong(y);
+    bad |= !same;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(differ, 1);
+}
+}  // namespace ttb
+
+extern "C" {
+
+int ttb_equal(ttb_handle a, int64_t ba, ttb_handle b, int64_t bb, int* equal) {
+  TTB_TRY(check_handle(a));
+  TTB_TRY(check_handle(b));
+  if (!equal) return fail(TTB_EINVAL, "null argument");
+  if (ba < 0 || ba >= a->batch || bb < 0 || bb >= b->batch) return fail(TTB_EINVAL, "train index out of range");
+  if (a->device != b->device) return fail(TTB_EINVAL, "== needs both trains on the same device");
+  *equal = 0;
+  // different types / lengths / shapes are simply not equal (isequal of the tensor vectors)
+  if (a->periodic != b->periodic || a->L != b->L || a->Q != b->Q) return TTB_OK;
+  const int L = (int)a->L;
+  const int* da = &a->h_bond[ba * (L + 1)];
+  const int* db = &b->h_bond[bb * (L + 1)];
+  for (int t = 0; t <= L; ++t)
+    if (da[t] != db[t]) return TTB_OK;
+  int* d_flag = nullptr;
+  TTB_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+  cudaMemsetAsync(d_flag, 0, sizeof(int), a->stream);
+  // b's stream may still be writing its slab: order this stream after it
+  cudaEvent_t ev;
+  cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  cudaEventRecord(ev, b->stream);
+  cudaStreamWaitEvent(a->stream, ev, 0);
+  cudaEventDestroy(ev);
+  CallTimer tm(a);
+  for (int t = 0; t < L; ++t) {
+    const int64_t n = (int64_t)da[t] * da[t + 1] * a->Q;
+    const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, 1184);
+    TTB_LAUNCH(a, "k_equal", k_equal<<<g, 256, 0, a->stream>>>(a->slab + ba * a->tt_stride + a->off[t],
+                                                               b->slab + bb * b->tt_stride + b->off[t], n, d_flag));
+  }
+  int rc = tm.finish();
+  int differ = 1;
+  if (rc == TTB_OK) {
+    cudaError_t e = cudaMemcpy(&differ, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(TTB_ECUDA, "==: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_flag);
+  if (rc == TTB_OK) *equal = differ ? 0 : 1;
+  return rc;
 }
 
 int ttb_record_spectrum(ttb_handle h, int on) {

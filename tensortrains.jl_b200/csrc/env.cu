@@ -654,11 +654,196 @@ static int accumulate(ttb_tt* h, bool left, int normalize, double* env_out, doub
   return TTB_OK;
 }
 
+// l= / r= / rz=: a caller-supplied environment replaces the accumulate pass (it is copied into the workspace slot
+// the kernels read: a few hundred KB device to device against one streaming pass over the whole train)
+static int env_check(ttb_tt* h, const ttb_env* e, bool left) {
+  if (!e) return TTB_OK;
+  if (e->device != h->device) return fail(TTB_EINVAL, "environment lives on another device");
+  if ((e->left != 0) != left) return fail(TTB_EINVAL, left ? "l= needs an accumulate_L environment" : "r= / rz= needs an accumulate_R environment");
+  if (e->L != h->L || e->Q != h->Q || e->batch != h->batch || e->periodic != h->periodic || e->bond0 != h->bond0 ||
+      e->bonds != h->h_bond)
+    return fail(TTB_EINVAL, "environment does not match the train (length, physical dimension or bond dimensions differ)");
+  return TTB_OK;
+}
+
+int provide_env(ttb_tt* h, bool left, const ttb_env* e, const int64_t* d_eoffL, const int64_t* d_eoffR) {
+  if (!e) {
+    EnvSide s;
+    s.d_eoffL = const_cast<int64_t*>(d_eoffL); s.d_eoffR = const_cast<int64_t*>(d_eoffR);
+    return launch_acc(h, left, 1, s);
+  }
+  Workspace& w = h->ws;
+  TTB_CUDA(cudaMemcpyAsync(left ? w.envL : w.envR, e->env, sizeof(double) * h->batch * w.env_stride, cudaMemcpyDeviceToDevice, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(w.env_log + (left ? 0 : h->batch), e->logabs, sizeof(double) * h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  TTB_CUDA(cudaMemcpyAsync(w.env_sign + (left ? 0 : h->batch), e->sign, sizeof(int) * h->batch, cudaMemcpyDeviceToDevice, h->stream));
+  return TTB_OK;
+}
+
+// used by sample.cu (rz=)
+int provide_env_R(ttb_tt* h, const ttb_env* rz) {
+  TTB_TRY(ensure_env_ws(h));
+  TTB_TRY(env_check(h, rz, false));
+  CallTimer tm(h);
+  TTB_TRY(provide_env(h, false, rz, nullptr, nullptr));
+  return tm.finish();
+}
+
+// accumulate_M (src/abstract_tensor_train.jl:119-137): row t of the table, M[t,t+1] = I, M[t,u] = M[t,u-1] T_{u-1}
+// max-abs rescaled; T_s = sum_x A_s(x) precomputed by k_site_trace.  One CTA per t; the running matrix ping-pongs
+// in global memory.  (The product path -- twovar_marginals -- streams this table and never stores it; this entry
+// exists for callers of the reference API and for parity tests.)
+struct AccM {
+  const double* T; const int64_t* toff; const int* bond; int L;
+  double* out; const int64_t* moff;   // moff[t]: offset of M[t, t+1] in out; the row's matrices follow each other
+  double* scratch; int64_t sstride;   // [L][2][dmax*dmax]
+  int normalize;
+};
+__global__ void k_accumulate_M(AccM c) {
+  const int t = blockIdx.x;                  // 0-based row: pairs (t, u), u = t+1 .. L-1
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double red[40];
+  const int dr = c.bond[t + 1];              // rows of every M[t, u]
+  double* o = c.out + c.moff[t];
+  for (int i = tid; i < dr * dr; i += nt) o[i] = (i % dr == i / dr) ? 1.0 : 0.0;   // M[t, t+1] = I (d_{t+1} x d_{t+1})
+  const double* prev = o;
+  int dc = dr;
+  o += (int64_t)dr * dr;
+  __syncthreads();
+  for (int u = t + 2; u < c.L; ++u) {
+    const double* Tm = c.T + c.toff[u - 1];  // trace of site u-1: d_{u-1} x d_u, column-major
+    const int dn = c.bond[u];
+    double mx = 0.0;
+    for (int i = tid; i < dr * dn; i += nt) {
+      const int r = i % dr, cc = i / dr;
+      double acc = 0.0;
+      for (int k = 0; k < dc; ++k) acc += prev[r + (int64_t)dr * k] * Tm[k + (int64_t)dc * cc];
+      o[i] = acc;
+      mx = fmax(mx, fabs(acc));
+    }
+    mx = block_max(mx, red);
+    if (c.normalize && mx != 0.0)
+      for (int i = tid; i < dr * dn; i += nt) o[i] /= mx;
+    __syncthreads();
+    prev = o; dc = dn;
+    o += (int64_t)dr * dn;
+  }
+}
+
+static int marginals_impl(ttb_tt* h, const ttb_env* l, const ttb_env* r, double* out);
+static int twovar_impl(ttb_tt* h, const ttb_env* l, const ttb_env* r, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out);
+
 }  // namespace ttb
 
 using namespace ttb;
 
 extern "C" {
+
+int ttb_env_create(ttb_handle h, int left, int normalize, ttb_env_handle* out) {
+  TTB_TRY(check_handle(h));
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  TTB_TRY(accumulate(h, left != 0, normalize, nullptr, nullptr, nullptr));
+  Workspace& w = h->ws;
+  ttb_env* e = new ttb_env();
+  e->device = h->device; e->left = left ? 1 : 0; e->normalize = normalize;
+  e->L = h->L; e->Q = h->Q; e->batch = h->batch; e->periodic = h->periodic; e->env_stride = w.env_stride;
+  e->bond0 = h->bond0; e->bonds = h->h_bond;
+  cudaError_t ce = cudaMalloc(&e->env, sizeof(double) * h->batch * w.env_stride);
+  if (ce == cudaSuccess) ce = cudaMalloc(&e->logabs, sizeof(double) * h->batch);
+  if (ce == cudaSuccess) ce = cudaMalloc(&e->sign, sizeof(int) * h->batch);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->env, left ? w.envL : w.envR, sizeof(double) * h->batch * w.env_stride, cudaMemcpyDeviceToDevice, h->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->logabs, w.env_log + (left ? 0 : h->batch), sizeof(double) * h->batch, cudaMemcpyDeviceToDevice, h->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->sign, w.env_sign + (left ? 0 : h->batch), sizeof(int) * h->batch, cudaMemcpyDeviceToDevice, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  if (ce != cudaSuccess) {
+    cudaFree(e->env); cudaFree(e->logabs); cudaFree(e->sign);
+    delete e;
+    return fail(TTB_ENOMEM, "environment handle: %s", cudaGetErrorString(ce));
+  }
+  *out = e;
+  return TTB_OK;
+}
+
+int ttb_env_destroy(ttb_env_handle e) {
+  if (!e) return TTB_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->env); cudaFree(e->logabs); cudaFree(e->sign);
+  delete e;
+  return TTB_OK;
+}
+
+int ttb_env_z(ttb_env_handle e, double* logabs, int* sign) {
+  if (!e) return fail(TTB_EINVAL, "null environment");
+  cudaSetDevice(e->device);
+  if (logabs) TTB_CUDA(cudaMemcpy(logabs, e->logabs, sizeof(double) * e->batch, cudaMemcpyDeviceToHost));
+  if (sign) TTB_CUDA(cudaMemcpy(sign, e->sign, sizeof(int) * e->batch, cudaMemcpyDeviceToHost));
+  return TTB_OK;
+}
+
+int ttb_marginals_env(ttb_handle h, ttb_env_handle l, ttb_env_handle r, double* out) { return marginals_impl(h, l, r, out); }
+
+int ttb_twovar_marginals_env(ttb_handle h, ttb_env_handle l, ttb_env_handle r, int64_t maxdist, int64_t t_lo, int64_t t_hi,
+                             double* out) {
+  if (!h) return fail(TTB_EINVAL, "null argument");
+  return twovar_impl(h, l, r, maxdist, t_lo, t_hi, out);
+}
+
+int ttb_accumulate_M_size(ttb_handle h, int64_t b, int64_t* n_doubles) {
+  TTB_TRY(check_handle(h));
+  if (b < 0 || b >= h->batch || !n_doubles) return fail(TTB_EINVAL, "bad argument");
+  const int L = (int)h->L;
+  const int* bd = &h->h_bond[b * (L + 1)];
+  int64_t n = 0;
+  for (int t = 0; t + 1 < L; ++t)
+    for (int u = t + 1; u < L; ++u) n += (int64_t)bd[t + 1] * bd[u];
+  *n_doubles = n;
+  return TTB_OK;
+}
+
+int ttb_accumulate_M(ttb_handle h, int64_t b, int normalize, double* out) {
+  TTB_TRY(check_handle(h));
+  if (b < 0 || b >= h->batch || !out) return fail(TTB_EINVAL, "bad argument");
+  const int L = (int)h->L;
+  if (L < 2) return TTB_OK;
+  const int* bd = &h->h_bond[b * (L + 1)];
+  std::vector<int64_t> toff(L + 1, 0), moff(L, 0);
+  for (int t = 0; t < L; ++t) toff[t + 1] = toff[t] + (((int64_t)h->bond0[t] * h->bond0[t + 1] + 15) & ~int64_t(15));
+  for (int t = 0; t + 1 < L; ++t) {
+    int64_t n = 0;
+    for (int u = t + 1; u < L; ++u) n += (int64_t)bd[t + 1] * bd[u];
+    moff[t + 1] = moff[t] + n;
+  }
+  const int64_t total = moff[L - 1];
+  double *d_tr = nullptr, *d_out = nullptr;
+  int64_t *d_toff = nullptr, *d_moff = nullptr;
+  cudaError_t e = cudaMalloc(&d_tr, sizeof(double) * toff[L]);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * std::max<int64_t>(total, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_toff, sizeof(int64_t) * (L + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_moff, sizeof(int64_t) * L);
+  int rc = TTB_OK;
+  if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "accumulate_M: %s", cudaGetErrorString(e));
+  if (rc == TTB_OK) {
+    cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * (L + 1), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_moff, moff.data(), sizeof(int64_t) * L, cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    CallTimer tm(h);
+    const int64_t maxsite = h->dmax * h->dmax;
+    dim3 g((unsigned)std::min<int64_t>((maxsite + 255) / 256, 64), (unsigned)L, 1);
+    // traces of train b only: the kernel indexes trains by blockIdx.z, so hand it this train's slab / bonds
+    TTB_LAUNCH(h, "k_site_trace", k_site_trace<<<g, 256, 0, h->stream>>>(h->slab + b * h->tt_stride, h->tt_stride, h->d_off,
+                                                                   h->d_bond + b * (L + 1), L + 1, (int)h->Q, d_tr, toff[L], d_toff));
+    AccM c;
+    c.T = d_tr; c.toff = d_toff; c.bond = h->d_bond + b * (L + 1); c.L = L; c.out = d_out; c.moff = d_moff;
+    c.scratch = nullptr; c.sstride = 0; c.normalize = normalize;
+    TTB_LAUNCH(h, "k_accumulate_M", k_accumulate_M<<<(unsigned)(L - 1), 256, 0, h->stream>>>(c));
+    rc = tm.finish();
+    if (rc == TTB_OK && total > 0) {
+      e = cudaMemcpy(out, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = fail(TTB_ECUDA, "accumulate_M copy: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaFree(d_tr); cudaFree(d_out); cudaFree(d_toff); cudaFree(d_moff);
+  return rc;
+}
 
 int ttb_env_size(ttb_handle h, int64_t b, int left, int64_t* n_doubles) {
   TTB_TRY(check_handle(h));
@@ -751,10 +936,17 @@ int ttb_normalize_eachmatrix(ttb_handle h) {
   return rc;
 }
 
-int ttb_marginals(ttb_handle h, double* out) {
+int ttb_marginals(ttb_handle h, double* out) { return marginals_impl(h, nullptr, nullptr, out); }
+
+}  // extern "C"
+
+namespace ttb {
+static int marginals_impl(ttb_tt* h, const ttb_env* l, const ttb_env* r, double* out) {
   TTB_TRY(check_handle(h));
   if (!out) return fail(TTB_EINVAL, "null argument");
   TTB_TRY(ensure_env_ws(h));
+  TTB_TRY(env_check(h, l, true));
+  TTB_TRY(env_check(h, r, false));
   Workspace& w = h->ws;
   EnvSide s; EnvOffsets eo;
   TTB_TRY(env_side(h, s, eo));
@@ -763,8 +955,8 @@ int ttb_marginals(ttb_handle h, double* out) {
   cudaError_t e = cudaMalloc(&d_out, sizeof(double) * n);
   if (e != cudaSuccess) { env_side_free(s); return fail(TTB_ENOMEM, "marginals: %s", cudaGetErrorString(e)); }
   CallTimer tm(h);
-  int rc = launch_acc(h, true, 1, s);
-  if (rc == TTB_OK) rc = launch_acc(h, false, 1, s);
+  int rc = provide_env(h, true, l, s.d_eoffL, s.d_eoffR);
+  if (rc == TTB_OK) rc = provide_env(h, false, r, s.d_eoffL, s.d_eoffR);
   if (rc == TTB_OK) {
     MargCtx c;
     c.slab = h->slab; c.tt_stride = h->tt_stride; c.off = h->d_off; c.bond = h->d_bond;
@@ -785,6 +977,9 @@ int ttb_marginals(ttb_handle h, double* out) {
   env_side_free(s);
   return rc;
 }
+}  // namespace ttb
+
+extern "C" {
 
 int ttb_twovar_count(ttb_handle h, int64_t maxdist, int64_t* npairs) {
   if (!h || !npairs) return fail(TTB_EINVAL, "null argument");
@@ -804,8 +999,17 @@ int ttb_twovar_marginals(ttb_handle h, int64_t maxdist, double* out) {
 // pairs (t, u) with t_lo <= t < t_hi only (0-based first site; pairs are stored t-major, so this is a contiguous
 // block of the full result): the unit one rank computes when the pairs of ONE train are sharded over GPUs
 int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out) {
+  return twovar_impl(h, nullptr, nullptr, maxdist, t_lo, t_hi, out);
+}
+
+}  // extern "C"
+
+namespace ttb {
+static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int64_t maxdist, int64_t t_lo, int64_t t_hi, double* out) {
   TTB_TRY(check_handle(h));
   if (!out) return fail(TTB_EINVAL, "null argument");
+  TTB_TRY(env_check(h, lenv, true));
+  TTB_TRY(env_check(h, renv, false));
   const int64_t L = h->L, Q = h->Q;
   if (t_lo < 0 || t_hi > L - 1 || t_lo > t_hi) return fail(TTB_EINVAL, "pair range [%lld, %lld) outside [0, %lld)", (long long)t_lo, (long long)t_hi, (long long)(L - 1));
   if (maxdist <= 0) maxdist = L - 1;
@@ -836,8 +1040,8 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
     cudaMemcpyAsync(d_poff, poff.data(), sizeof(int64_t) * L, cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
     CallTimer tm(h);
-    rc = launch_acc(h, true, 1, s);
-    if (rc == TTB_OK) rc = launch_acc(h, false, 1, s);
+    rc = provide_env(h, true, lenv, s.d_eoffL, s.d_eoffR);
+    if (rc == TTB_OK) rc = provide_env(h, false, renv, s.d_eoffL, s.d_eoffR);
     // fast path: GT_u(x), T_u once per call, then Frobenius products + one small GEMM per pair
     const int64_t kcap = h->bond0[0] * h->dmax;
     const size_t fast_smem = sizeof(double) * (3 * (size_t)Q * kcap + (size_t)h->dmax * h->dmax + 8 * (Q * Q + 1) + Q * Q);
@@ -909,5 +1113,4 @@ int ttb_twovar_marginals_range(ttb_handle h, int64_t maxdist, int64_t t_lo, int6
   env_side_free(s);
   return rc;
 }
-
-}  // extern "C"
+}  // namespace ttb

@@ -259,9 +259,10 @@ using namespace ttb;
 extern "C" int ttb_accumulate_R(ttb_handle h, int normalize, double* r_out, double* logabs, int* sign);
 
 namespace ttb {
+int provide_env_R(ttb_tt* h, const ttb_env* rz);   // env.cu
 
 static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first, const double* uniforms,
-                       uint8_t* x_out, double* p_out, int64_t* hist, double* sum_logp) {
+                       uint8_t* x_out, double* p_out, int64_t* hist, double* sum_logp, const ttb_env* rz = nullptr) {
   TTB_TRY(check_handle(h));
   if (b < 0 || b >= h->batch) return fail(TTB_EINVAL, "train index out of range");
   if (nsamples < 0) return fail(TTB_EINVAL, "nsamples must be >= 0");
@@ -271,8 +272,10 @@ static int sample_impl(ttb_tt* h, int64_t b, int64_t nsamples, uint64_t seed, ui
   const int64_t rmax = h->bond0[0], dmax = h->dmax;
   const size_t smem = sizeof(double) * (2 * (size_t)rmax * dmax + Q);
   if (smem > 200 * 1024) return fail(TTB_EUNSUPPORTED, "sample: periodic state d_1*d_max too large for shared memory");
-  // r = accumulate_R(A)  (recomputed per call like the reference's default keyword, :336)
-  TTB_TRY(ttb_accumulate_R(h, 1, nullptr, nullptr, nullptr));
+  // r = accumulate_R(A): recomputed per call like the reference's default keyword (:336) unless the caller
+  // passes rz= (an environment handle: the streaming pass over the train is paid once for many calls)
+  if (rz) TTB_TRY(provide_env_R(h, rz));
+  else TTB_TRY(ttb_accumulate_R(h, 1, nullptr, nullptr, nullptr));
   double ms_acc = h->last_ms; int64_t l_acc = h->last_launches;
   Workspace& w = h->ws;
   std::vector<int64_t> eoffR(L + 1, 0), goff(L + 1, 0);
@@ -431,6 +434,17 @@ int ttb_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_
 int ttb_sample_stats(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index, int64_t* hist,
                      double* sum_logp) {
   return sample_impl(h, b, nsamples, seed, first_index, nullptr, nullptr, nullptr, hist, sum_logp);
+}
+
+int ttb_sample_env(ttb_handle h, ttb_env_handle rz, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
+                   const double* uniforms, uint8_t* x_out, double* p_out) {
+  if (!x_out) return fail(TTB_EINVAL, "null x_out");
+  return sample_impl(h, b, nsamples, seed, first_index, uniforms, x_out, p_out, nullptr, nullptr, rz);
+}
+
+int ttb_sample_stats_env(ttb_handle h, ttb_env_handle rz, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index,
+                         int64_t* hist, double* sum_logp) {
+  return sample_impl(h, b, nsamples, seed, first_index, nullptr, nullptr, nullptr, hist, sum_logp, rz);
 }
 
 }  // extern "C"

@@ -31,6 +31,7 @@ __all__ = [
     "normalize_", "normalize_eachmatrix_", "marginals", "twovar_marginals", "twovar_marginals_block", "compress_",
     "orthogonalize_right_", "orthogonalize_left_", "orthogonalize_center_", "orthogonalize_two_site_center_",
     "is_left_canonical", "is_right_canonical", "is_canonical", "sample", "sample_stats", "lib", "TTBError",
+    "Environment", "accumulate_M", "is_in_domain",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -85,6 +86,17 @@ _sig("ttb_sweep_stats", _h, _i64, _pi64, _pd)
 _sig("ttb_record_spectrum", _h, C.c_int)
 _sig("ttb_get_spectrum", _h, _i64, _i64, _pd, _i64, _pi64)
 _sig("ttb_canonical_residual", _h, _i64, _i64, C.c_int, _pd)
+_sig("ttb_env_create", _h, C.c_int, C.c_int, C.POINTER(_h))
+_sig("ttb_env_destroy", _h)
+_sig("ttb_env_z", _h, _pd, _pi)
+_sig("ttb_marginals_env", _h, _h, _h, _pd)
+_sig("ttb_twovar_marginals_env", _h, _h, _h, _i64, _i64, _i64, _pd)
+_sig("ttb_accumulate_M_size", _h, _i64, _pi64)
+_sig("ttb_accumulate_M", _h, _i64, C.c_int, _pd)
+_sig("ttb_is_in_domain", _h, C.POINTER(C.c_int32), _i64, _pi)
+_sig("ttb_equal", _h, _i64, _h, _i64, _pi)
+_sig("ttb_sample_env", _h, _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
+_sig("ttb_sample_stats_env", _h, _h, _i64, _i64, C.c_uint64, C.c_uint64, _pi64, _pd)
 _sig("ttb_env_size", _h, _i64, C.c_int, _pi64)
 _sig("ttb_accumulate_L", _h, C.c_int, _pd, _pd, _pi)
 _sig("ttb_accumulate_R", _h, C.c_int, _pd, _pd, _pi)
@@ -379,6 +391,20 @@ class AbstractTensorTrain:
         """``A - B`` (src/abstract_tensor_train.jl:322)"""
         return self._compose(other, -1)
 
+    def __eq__(self, other):
+        """``==`` (src/abstract_tensor_train.jl:85): ``isequal`` of the site tensors; ``z`` is not compared."""
+        if not isinstance(other, AbstractTensorTrain) or type(self) is not type(other) or self.batch != other.batch \
+                or self.q != other.q:
+            return False
+        eq = C.c_int(0)
+        for b in range(self.batch):
+            _ck(lib.ttb_equal(self._hd, b, other._hd, b, C.byref(eq)))
+            if not eq.value:
+                return False
+        return True
+
+    __hash__ = None
+
     def spectrum(self, bond_index: int, b: int = 0) -> np.ndarray:
         out, n = np.zeros(64), _i64()
         rc = lib.ttb_get_spectrum(self._hd, b, bond_index, _dp(out), out.size, C.byref(n))
@@ -578,14 +604,100 @@ def _accumulate(A, left: bool, normalize: bool):
     return (envs, zs) if A.batched else (envs[0], zs[0])
 
 
-def accumulate_L(A, normalize: bool = True):
-    """src/abstract_tensor_train.jl:89-102 -> ``(l, z)``"""
+class Environment:
+    """A stored ``accumulate_L`` / ``accumulate_R`` result kept on the device: what the reference's ``l=`` / ``r=``
+    keywords of ``marginals`` / ``twovar_marginals`` (src/abstract_tensor_train.jl:208-209, 231-233) and ``rz=`` of
+    ``sample`` (:335-336) take.  Only valid for the train it was computed on, as it was then."""
+
+    def __init__(self, A, left: bool, normalize: bool = True):
+        self._hd = _h()
+        self.left, self.batch, self.batched = bool(left), A.batch, A.batched
+        _ck(lib.ttb_env_create(A._hd, int(left), int(normalize), C.byref(self._hd)))
+
+    @property
+    def z(self):
+        la = np.zeros(self.batch)
+        sg = np.zeros(self.batch, dtype=np.int32)
+        _ck(lib.ttb_env_z(self._hd, _dp(la), sg.ctypes.data_as(_pi)))
+        zs = [Logarithmic(logabs=la[b], sign=int(sg[b])) for b in range(self.batch)]
+        return zs if self.batched else zs[0]
+
+    def __del__(self):
+        try:
+            if self._hd:
+                lib.ttb_env_destroy(self._hd)
+                self._hd = _h()
+        except Exception:
+            pass
+
+
+def _env_arg(e, left: bool, name: str):
+    if e is None:
+        return None
+    if isinstance(e, tuple) and len(e) == 2 and isinstance(e[0], Environment):   # the (env, z) pair of accumulate_*
+        e = e[0]
+    if not isinstance(e, Environment):
+        raise TypeError(f"{name}= takes the device-resident result of accumulate_{'L' if left else 'R'}(A, keep=True)")
+    if e.left != left:
+        raise ValueError(f"ArgumentError: {name}= needs an accumulate_{'L' if left else 'R'} environment")
+    return e._hd
+
+
+def accumulate_L(A, normalize: bool = True, keep: bool = False):
+    """src/abstract_tensor_train.jl:89-102 -> ``(l, z)``.  ``keep=True`` leaves ``l`` on the device
+    (an :class:`Environment`, to be passed as ``l=``) instead of copying the matrices to the host."""
+    if keep:
+        e = Environment(A, True, normalize)
+        return e, e.z
     return _accumulate(A, True, normalize)
 
 
-def accumulate_R(A, normalize: bool = True):
-    """src/abstract_tensor_train.jl:104-117 -> ``(r, z)``"""
+def accumulate_R(A, normalize: bool = True, keep: bool = False):
+    """src/abstract_tensor_train.jl:104-117 -> ``(r, z)``; ``keep=True``: device-resident, for ``r=`` / ``rz=``."""
+    if keep:
+        e = Environment(A, False, normalize)
+        return e, e.z
     return _accumulate(A, False, normalize)
+
+
+def accumulate_M(A, normalize: bool = True, b: int = 0):
+    """src/abstract_tensor_train.jl:119-137: the ``L x L`` table ``M[t][u]`` (0-based) of matrices
+    ``d_{t+1} x d_u`` for ``t < u``, ``M[u-1][u] = I``; the other entries are empty ``0 x 0`` arrays like the
+    reference's.  (``twovar_marginals`` streams this table on the device and never stores it.)"""
+    n = _i64()
+    _ck(lib.ttb_accumulate_M_size(A._hd, b, C.byref(n)))
+    buf = np.zeros(max(n.value, 1))
+    _ck(lib.ttb_accumulate_M(A._hd, b, int(normalize), _dp(buf)))
+    bd = A.bonds(b)
+    M = [[np.zeros((0, 0)) for _ in range(A.L)] for _ in range(A.L)]
+    o = 0
+    for t in range(A.L - 1):
+        for u in range(t + 1, A.L):
+            shp = (int(bd[t + 1]), int(bd[u]))
+            M[t][u] = buf[o:o + shp[0] * shp[1]].reshape(shp, order="F").copy()
+            o += shp[0] * shp[1]
+    return M
+
+
+def is_in_domain(A, X) -> bool:
+    """src/abstract_tensor_train.jl:59-64: every index of every point of ``X`` lies inside the physical dimensions
+    (0-based here).  ``X``: one point (list over sites of indices / multi-indices) or an ``(n, L)`` array."""
+    Xa = X if isinstance(X, np.ndarray) else None
+    if Xa is None:
+        try:
+            pts = [tuple(np.atleast_1d(x)) for x in X]
+        except TypeError:
+            return False
+        if len(pts) != A.L:
+            return False
+        for x in pts:
+            if len(x) != len(A.q) or any(int(xi) < 0 or int(xi) >= qi for xi, qi in zip(x, A.q)):
+                return False
+        return True
+    Xa = np.ascontiguousarray(Xa, dtype=np.int32).reshape(-1, A.L)
+    ok = C.c_int(0)
+    _ck(lib.ttb_is_in_domain(A._hd, Xa.ctypes.data_as(C.POINTER(C.c_int32)), Xa.shape[0], C.byref(ok)))
+    return bool(ok.value)
 
 
 def normalization(A):
@@ -619,23 +731,26 @@ def normalize_eachmatrix_(A):
     _ck(lib.ttb_normalize_eachmatrix(A._hd))
 
 
-def marginals(A):
-    """src/abstract_tensor_train.jl:208-220: list over sites of arrays shaped ``q``"""
+def marginals(A, l=None, r=None):
+    """src/abstract_tensor_train.jl:208-220: list over sites of arrays shaped ``q``.  ``l`` / ``r``: environments
+    from ``accumulate_L(A, keep=True)`` / ``accumulate_R(A, keep=True)`` (default: computed here, like the
+    reference's default keywords)."""
     out = np.zeros((A.batch, A.L, A.Q))
-    _ck(lib.ttb_marginals(A._hd, _dp(out)))
+    _ck(lib.ttb_marginals_env(A._hd, _env_arg(l, True, "l"), _env_arg(r, False, "r"), _dp(out)))
     res = [[out[b, t].reshape(A.q, order="F") for t in range(A.L)] for b in range(A.batch)]
     return res if A.batched else res[0]
 
 
-def twovar_marginals(A, maxdist: Optional[int] = None):
+def twovar_marginals(A, maxdist: Optional[int] = None, l=None, r=None, M=None):
     """src/abstract_tensor_train.jl:231-254: dict ``(t,u) -> (q..., q...)`` array, 0-based t<u<=t+maxdist
-    (the reference's other entries are empty arrays)."""
+    (the reference's other entries are empty arrays).  ``l`` / ``r`` as in :func:`marginals`.  ``M`` (the table of
+    :func:`accumulate_M`) is accepted for signature parity and not read: the kernels stream ``M[t,u]`` along ``u``."""
     md = A.L - 1 if maxdist is None else int(maxdist)
     n = _i64()
     _ck(lib.ttb_twovar_count(A._hd, md, C.byref(n)))
     out = np.zeros((A.batch, n.value, A.Q * A.Q))
     if n.value:
-        _ck(lib.ttb_twovar_marginals(A._hd, md, _dp(out)))
+        _ck(lib.ttb_twovar_marginals_env(A._hd, _env_arg(l, True, "l"), _env_arg(r, False, "r"), md, 0, A.L - 1, _dp(out)))
     res = []
     for b in range(A.batch):
         d, i = {}, 0
@@ -755,11 +870,12 @@ def is_canonical(A, central_idx: int, atol: float = 1e-10, b: int = 0) -> bool:
 
 
 # ---- sampling ------------------------------------------------------------------------------------
-def sample(A, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None, b: int = 0):
+def sample(A, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None, b: int = 0, rz=None):
     """``sample`` (src/abstract_tensor_train.jl:335-384).  Without ``nsamples`` returns one draw
     ``(x, p)`` like the reference (x = list over sites of 0-based multi-indices); with ``nsamples``
     returns ``(X, p)`` with ``X`` an ``(nsamples, L)`` uint8 array of flat 0-based indices.
-    ``uniforms`` (``(nsamples, L)`` doubles) replaces the Philox stream (one ``rand`` per site)."""
+    ``uniforms`` (``(nsamples, L)`` doubles) replaces the Philox stream (one ``rand`` per site).
+    ``rz``: ``accumulate_R(A, keep=True)`` computed once for many calls (the reference's ``rz`` keyword, :336)."""
     n = 1 if nsamples is None else int(nsamples)
     up = None
     if uniforms is not None:
@@ -767,21 +883,21 @@ def sample(A, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 
         up = _dp(u)
     X = np.zeros((n, A.L), dtype=np.uint8)
     p = np.zeros(n)
-    _ck(lib.ttb_sample(A._hd, b, n, C.c_uint64(seed), C.c_uint64(first_index), up,
-                       X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(p)))
+    _ck(lib.ttb_sample_env(A._hd, _env_arg(rz, False, "rz"), b, n, C.c_uint64(seed), C.c_uint64(first_index), up,
+                           X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(p)))
     if nsamples is None:
         x = [list(np.unravel_index(int(xi), A.q, order="F")) for xi in X[0]]
         return x, float(p[0])
     return X, p
 
 
-def sample_stats(A, nsamples: int, seed: int = 0, first_index: int = 0, b: int = 0):
+def sample_stats(A, nsamples: int, seed: int = 0, first_index: int = 0, b: int = 0, rz=None):
     """Throughput variant: draws stay on the device; returns the ``(L, Q)`` histogram of the drawn
     values and the sum of log-probabilities."""
     hist = np.zeros((A.L, A.Q), dtype=np.int64)
     slp = C.c_double(0.0)
-    _ck(lib.ttb_sample_stats(A._hd, b, int(nsamples), C.c_uint64(seed), C.c_uint64(first_index),
-                             hist.ctypes.data_as(_pi64), C.byref(slp)))
+    _ck(lib.ttb_sample_stats_env(A._hd, _env_arg(rz, False, "rz"), b, int(nsamples), C.c_uint64(seed), C.c_uint64(first_index),
+                                 hist.ctypes.data_as(_pi64), C.byref(slp)))
     return hist, slp.value
 
 

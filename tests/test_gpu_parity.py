@@ -876,3 +876,105 @@ def test_spectrum_of_untouched_bonds_is_empty_and_capacity_checked():
     assert rc == 1 and n.value == len(A.spectrum(2))
     T.orthogonalize_right_(A, T.TruncThresh(0.0))                           # eps = 0 sweep records nothing
     assert all(len(A.spectrum(i)) == 0 for i in range(5))
+
+
+# ---- environment handles (l=, r=, rz=), accumulate_M, is_in_domain, == ---------------------------------------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_environment_keywords_reuse_accumulate(periodic):
+    """marginals / twovar_marginals with l=, r= and sample with rz= (src/abstract_tensor_train.jl:208-209, 231-233,
+    335-336): same results as the default keywords, the accumulate pass paid once."""
+    rng = RNG(910 + periodic)
+    q = (2, 3)
+    ts = rand_per(rng, [3, 5, 4, 2, 6], q) if periodic else rand_open(rng, [1, 4, 6, 5, 3, 1], q)
+    A, Ao = pair(ts, periodic=periodic)
+    T.normalize_(A); O.normalize(Ao)
+    l, zl = T.accumulate_L(A, keep=True)
+    r, zr = T.accumulate_R(A, keep=True)
+    _, zo = O.accumulate_L(Ao)
+    assert zl.sign == zo.sign and close(zl.logabs, zo.logabs, 1e-10, 1e-12)
+    assert zr.sign == zo.sign and close(zr.logabs, zo.logabs, 1e-10, 1e-12)
+    m0, m1 = T.marginals(A), T.marginals(A, l=l, r=r)
+    for a, b, c in zip(m0, m1, O.marginals(Ao)):
+        assert np.array_equal(a, b) and np.allclose(a, c, rtol=1e-10, atol=1e-14)
+    m1 = T.marginals(A, l=l)            # one of the two given
+    assert all(np.array_equal(a, b) for a, b in zip(m0, m1))
+    p0, p1 = T.twovar_marginals(A), T.twovar_marginals(A, l=l, r=r, M=T.accumulate_M(A))
+    po = O.twovar_marginals(Ao)
+    for k in po:
+        assert np.array_equal(p0[k], p1[k]) and np.allclose(p0[k], po[k], rtol=1e-10, atol=1e-14)
+    us = rng.random((40, len(ts)))
+    X0, q0 = T.sample(A, 40, uniforms=us)
+    X1, q1 = T.sample(A, 40, uniforms=us, rz=r)
+    assert np.array_equal(X0, X1) and np.array_equal(q0, q1)
+    h0, s0 = T.sample_stats(A, 500, seed=3)
+    h1, s1 = T.sample_stats(A, 500, seed=3, rz=(r, zr))      # the (env, z) pair itself is accepted too
+    assert np.array_equal(h0, h1) and close(s0, s1, 1e-12, 0.0)   # sum of log p: atomics, order may differ
+    # wrong side / stale environment
+    with pytest.raises(ValueError):
+        T.marginals(A, l=r)
+    with pytest.raises(TypeError):
+        T.marginals(A, l=[np.eye(3)])
+    T.compress_(A, T.TruncBond(2))
+    with pytest.raises(ValueError):
+        T.marginals(A, l=l, r=r)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_accumulate_M_matches_oracle(periodic):
+    """src/abstract_tensor_train.jl:119-137: the table itself, and l[0] M[0,L-1] r[L-1] == Z for open trains
+    (test/tensor_train.jl:185-196)."""
+    rng = RNG(920 + periodic)
+    ts = rand_per(rng, [3, 5, 4, 2, 6, 3], (2, 2)) if periodic else rand_open(rng, [1, 4, 6, 5, 3, 2, 1], (3,))
+    A, Ao = pair(ts, periodic=periodic)
+    L = len(ts)
+    for normalize in (True, False):
+        M, Mo = T.accumulate_M(A, normalize=normalize), O.accumulate_M(Ao, normalize=normalize)
+        for t in range(L):
+            for u in range(L):
+                if t < u:
+                    assert M[t][u].shape == Mo[(t, u)].shape
+                    assert np.allclose(M[t][u], Mo[(t, u)], rtol=1e-12, atol=1e-300), (t, u)
+                else:
+                    assert M[t][u].shape == (0, 0)
+    if not periodic:
+        M = T.accumulate_M(A, normalize=False)
+        l, z = T.accumulate_L(A, normalize=False)
+        r, _ = T.accumulate_R(A, normalize=False)
+        assert close((l[0] @ M[0][L - 1] @ r[L - 1]).item(), float(z), 1e-10)
+
+
+def test_is_in_domain_and_equality():
+    """src/abstract_tensor_train.jl:59-64, :85."""
+    rng = RNG(930)
+    ts = rand_open(rng, [1, 3, 4, 1], (2, 3))
+    A, Ao = pair(ts)
+    good = [(1, 2), (0, 0), (1, 1)]
+    bad = [(1, 3), (0, 0), (1, 1)]
+    assert T.is_in_domain(A, good) and O.is_in_domain(Ao, good)
+    assert not T.is_in_domain(A, bad) and not O.is_in_domain(Ao, bad)
+    assert not T.is_in_domain(A, [(2, 0), (0, 0), (0, 0)]) and not T.is_in_domain(A, good[:2])
+    assert T.is_in_domain(A, np.array([[5, 0, 3], [0, 1, 2]])) and not T.is_in_domain(A, np.array([[6, 0, 0]]))
+    B = A.copy()
+    assert A == B and O.equal(Ao, Ao.copy())
+    B.z = 3.0                                   # z is not part of == (isequal of the tensors only)
+    assert A == B
+    s1 = ts[1].copy(); s1[2, 1, 0, 2] = np.nextafter(s1[2, 1, 0, 2], 1.0)
+    B.set_site(1, s1)
+    Bo = Ao.copy(); Bo[1] = s1
+    assert not (A == B) and A != B and not O.equal(Ao, Bo)
+    # isequal semantics: NaN equals NaN, -0.0 differs from 0.0
+    n1 = ts[1].copy(); n1[0, 0, 0, 0] = np.nan
+    Cn, Dn = T.TensorTrain([ts[0], n1, ts[2]]), T.TensorTrain([ts[0], n1.copy(), ts[2]])
+    assert Cn == Dn and not (Cn == A)
+    z0, z1 = ts[1].copy(), ts[1].copy()
+    z0[0, 0, 0, 0], z1[0, 0, 0, 0] = 0.0, -0.0
+    assert not (T.TensorTrain([ts[0], z0, ts[2]]) == T.TensorTrain([ts[0], z1, ts[2]]))
+    assert not O.equal(O.TensorTrain([ts[0], z0, ts[2]]), O.TensorTrain([ts[0], z1, ts[2]]))
+    # other shapes / kinds are simply unequal
+    assert not (A == T.TensorTrain(rand_open(rng, [1, 3, 5, 1], (2, 3))))
+    P = T.PeriodicTensorTrain(rand_per(rng, [2, 3, 2], (2, 3)))
+    assert not (A == P) and P == P.copy()
+    # after a sweep the comparison runs on the CURRENT dims
+    C1, C2 = A.copy(), A.copy()
+    T.compress_(C1, T.TruncBond(2)); T.compress_(C2, T.TruncBond(2))
+    assert C1 == C2 and not (C1 == A)
