@@ -15,7 +15,10 @@ JSON line keys beyond the base contract:
                installed) on the same workload, host cores of this box
   extra        the second half of the metric string: sample draws/s on config 4 (L=256,q=4,d=128), the
                sharded 4096-train batch of config 5, and the randn fill of config 3
-`--impl reference` times the CPU oracle (the reference's algorithm; kind "port") on a bounded sample.
+`--impl reference` times the CPU oracle (the reference's algorithm; kind "port") on a bounded sample
+(`--fill randn` = the full-rank fill of config 3, reported as extra.randn_fill of the main arm); when the sample
+is the full chain its line carries the retained bond dimensions, and the main arm asserts the CUDA path's are
+identical (outside the timed region).
 """
 import argparse
 import json
@@ -138,15 +141,20 @@ def measure_fp64_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_compress_steps_per_s(L, d, q, seed, reps=1):
+LAST_CPU_BONDS = None
+
+
+def cpu_compress_steps_per_s(L, d, q, seed, reps=1, fill="rand"):
+    global LAST_CPU_BONDS
     from oracle import tt_oracle as O
-    _, ts = make_open(seed, L, d, q)
+    _, ts = make_open(seed, L, d, q, fill)
     best = 1e99
     for _ in range(reps):
         A = O.TensorTrain([a.copy() for a in ts])
         t0 = time.perf_counter()
         O.compress(A, O.TruncThresh(EPS3))
         best = min(best, time.perf_counter() - t0)
+        LAST_CPU_BONDS = [int(x) for x in O.bond_dims(A)]
     return 2 * (L - 1) / best, best
 
 
@@ -173,6 +181,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    fill = args.fill
     # BLAS thread count: all host threads is NOT the fastest setting for 256 x 512 gesdd calls (measured: 8 of 8
     # threads 4.5x slower than 4 in this image); probe the L=32 slice at 1, 2, 4, ... threads and keep the best
     ncpu = os.cpu_count() or 1
@@ -187,9 +196,9 @@ def reference_arm(args):
         t0 = time.perf_counter()
         if ctx:
             with ctx:
-                cpu_compress_steps_per_s(32, D3, Q3, 3)
+                cpu_compress_steps_per_s(32, D3, Q3, 3, fill=fill)
         else:
-            cpu_compress_steps_per_s(32, D3, Q3, 3)
+            cpu_compress_steps_per_s(32, D3, Q3, 3, fill=fill)
         probes[n] = time.perf_counter() - t0
     nthr = min(probes, key=probes.get)
     probe = probes[nthr]
@@ -204,10 +213,10 @@ def reference_arm(args):
     else:
         Ls = 32
     for _ in range(args.warmup):
-        cpu_compress_steps_per_s(Ls, D3, Q3, 3)
+        cpu_compress_steps_per_s(Ls, D3, Q3, 3, fill=fill)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_compress_steps_per_s(Ls, D3, Q3, 3)
+        cpu_compress_steps_per_s(Ls, D3, Q3, 3, fill=fill)
     dt = time.perf_counter() - t0
     # the timed region includes input generation (~5%); subtract nothing, say so
     val = args.steps * 2 * (Ls - 1) / dt
@@ -217,7 +226,8 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "compress_site_steps_per_s", "value": val, "unit": "site-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 single TT q=2 d=256 rand_tt compress!(TruncThresh(1e-10))", "sample": what,
+            "config": {"workload": f"C3 single TT q=2 d=256 {fill}_tt compress!(TruncThresh(1e-10))", "sample": what, "fill": fill,
+                       "bonds_after": LAST_CPU_BONDS if Ls == L3 else None, "seed": 3,
                        "probe_L32_s": probe, "blas_threads": nthr, "host_cores": ncpu,
                        "probe_L32_s_by_threads": {str(k): round(v, 3) for k, v in probes.items()}},
             "cpu_baseline": {"value": val, "unit": "site-steps/s", "cores": nthr, "kind": "port",
@@ -234,6 +244,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-extra", action="store_true", help="skip the sampling / randn / cpu legs")
+    ap.add_argument("--fill", default="rand", choices=["rand", "randn"], help="--impl reference only: fill of the C3 train")
+    ap.add_argument("--draws", type=int, default=int(os.environ.get("TTB_BENCH_DRAWS", "100000000")),
+                    help="total draws of the config-4 leg (BASELINE.json: 10^8), sharded over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -347,8 +360,20 @@ def main():
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk)}
 
-    # ---- sampling half of the metric (config 4): the train is replicated, the draws are sharded by
-    #      global draw index (Philox key), the only collective is the all-reduce of the histogram ----
+    def alone_on_rank0(fn):
+        """At N > 1: rank 0 repeats a leg ALONE on the whole workload (the other ranks wait at the barrier), so the
+        line carries the 1-GPU figure measured in the same job and speedup_vs_1gpu is arithmetic on two numbers of
+        this run.  Returns fn()'s result on rank 0, None elsewhere."""
+        res = None
+        barrier()
+        if rank == 0:
+            res = fn()
+        barrier()
+        return res
+
+    # ---- sampling half of the metric (config 4): the train is replicated, the --draws (10^8) draws are sharded by
+    #      global draw index (Philox counter) over the ranks = STRONG scaling; chunked launches, histograms stay on
+    #      the device per chunk, the only collective is the all-reduce of the L x Q histogram ----
     sample_info = None
     if not args.no_extra:
         from ttb200 import parallel as P
@@ -356,69 +381,133 @@ def main():
         A4 = T.TensorTrain(t4)
         del t4
         T.normalize_(A4)
-        nd = 1_000_000                                   # draws per rank
-        T.sample_stats(A4, 20000, seed=1, first_index=0)  # warm-up
+        rz4 = T.accumulate_R(A4, keep=True)[0]            # rz= keyword: the environment pass is paid once, not per chunk
+        ND = int(args.draws)
+        CH = 10_000_000
+
+        def draw_range(lo, hi):
+            hist = np.zeros((L4, Q4), dtype=np.int64)
+            ms, slp = 0.0, 0.0
+            t0 = time.perf_counter()
+            for a in range(lo, hi, CH):
+                h, s_ = T.sample_stats(A4, min(CH, hi - a), seed=1, first_index=a, rz=rz4)
+                hist += h; slp += s_
+                ms += A4.last_timing()[0]
+            return hist, slp, ms, time.perf_counter() - t0
+
+        T.sample_stats(A4, 20000, seed=1, first_index=0, rz=rz4)   # warm-up (pack buffers, attributes)
+        lo4, hi4 = P.shard_range(ND, rank, world)
         barrier()
-        t0 = time.perf_counter()
-        hist, slp = T.sample_stats(A4, nd, seed=1, first_index=rank * nd)
-        wall4 = time.perf_counter() - t0
-        ms4, _ = A4.last_timing()
+        hist, slp, ms4, wall4 = draw_range(lo4, hi4)
         ms4 = max_over_ranks(ms4)
         wall4 = max_over_ranks(wall4)
         hist_tot = P.allreduce_sum(hist)
-        assert int(hist_tot.sum()) == world * nd * L4
-        sample_info = {"workload": "C4: TensorTrain L=256 q=4 d=128 rand_tt, normalize! then sample; draws sharded over ranks",
-                       "draws": world * nd, "draws_per_s": world * nd / (ms4 * 1e-3),
-                       "e2e_draws_per_s": world * nd / wall4,
-                       "alg_mflop_per_draw": 8.65,
-                       "note": "device time of ttb_sample_stats (accumulate_R + pack + tiled DMMA sampler); histogram "
-                               "(L x Q int64) is the only result copied back"}
-        del A4
+        assert int(hist_tot.sum()) == ND * L4
+        sample_info = {"workload": f"C4: TensorTrain L=256 q=4 d=128 rand_tt, normalize! then {ND:.0e} draws in all (BASELINE.json "
+                                   "configs[3]), sharded over the ranks by global draw index (strong scaling), chunks of 1e7",
+                       "draws": ND, "draws_per_rank": hi4 - lo4, "draws_per_s": ND / (ms4 * 1e-3), "device_ms": ms4,
+                       "e2e_draws_per_s": ND / wall4, "alg_mflop_per_draw": 8.65,
+                       "hist_checksum": int((hist_tot * np.arange(1, Q4 + 1)).sum()),
+                       "note": "device time of ttb_sample_stats (pack + tiled DMMA sampler; accumulate_R passed as rz=); the "
+                               "histogram (L x Q int64) is the only result copied back; hist_checksum is independent of N "
+                               "(Philox counter = global draw index)"}
+        if world > 1:
+            one = alone_on_rank0(lambda: draw_range(0, ND))
+            if rank == 0:
+                h1, _, ms1, wall1 = one
+                assert np.array_equal(h1, hist_tot), "histogram of the sharded run differs from the one-GPU run"
+                sample_info["one_gpu"] = {"draws_per_s": ND / (ms1 * 1e-3), "e2e_draws_per_s": ND / wall1, "device_ms": ms1}
+                sample_info["speedup_vs_1gpu"] = {"device": ms1 / ms4, "e2e": wall1 / wall4,
+                                                  "histogram_identical_to_one_gpu_run": True}
+        del A4, rz4
 
     # ---- config 5: 4096 periodic trains (64 sites, bond 32, q=2) sharded over the ranks by contiguous
     #      train ranges (strong scaling of this leg); normalize! + twovar_marginals + compress!(1e-6);
-    #      collectives: all-gather of per-train log Z and bond dimensions ----
+    #      collectives (NCCL): all-gather of per-train log Z, bond dimensions and of the pair marginals, the
+    #      latter between DEVICE buffers (258 MiB in all), then one copy into a pinned host buffer ----
     batch_info = None
     if not args.no_extra:
         import ctypes as C
         from ttb200 import parallel as P
         B5, L5, D5, Q5 = 4096, 64, 32, 2
+        site5 = D5 * D5 * Q5
+        npair = C.c_int64()
+
+        def gen5(lo, hi):
+            packed = np.empty((hi - lo) * L5 * site5)
+            for bg in range(lo - lo % 256, hi, 256):            # seeds by global chunk of 256 trains: shard-count independent
+                chunk = np.random.Generator(np.random.Philox(5000 + bg)).random(256 * L5 * site5)
+                a, b_ = max(bg, lo), min(bg + 256, hi)
+                packed[(a - lo) * L5 * site5:(b_ - lo) * L5 * site5] = chunk[(a - bg) * L5 * site5:(b_ - bg) * L5 * site5]
+            return packed
+
+        def c5_run(lo, hi, gather):
+            """normalize! + pair marginals + compress! of trains [lo, hi) on this GPU; returns timings and results.
+            The pair marginals are written to a DEVICE tensor (no pageable staging)."""
+            nb_ = hi - lo
+            A = T.PeriodicTensorTrain.empty([D5] * (L5 + 1), (Q5,), batch=nb_)
+            A.upload_all(gen5(lo, hi))
+            T._ck(T.lib.ttb_twovar_count(A._hd, L5 - 1, C.byref(npair)))
+            npr = int(npair.value)
+            dev_out = torch.empty((nb_, npr, Q5 * Q5), dtype=torch.float64, device=dev)
+            def pipeline(X):
+                ms = {}
+                lz = T.normalize_(X); ms["normalize"] = X.last_timing()[0]
+                T.twovar_marginals_block(X, 0, L5 - 1, L5 - 1, out=dev_out); ms["twovar_marginals"] = X.last_timing()[0]
+                T.compress_(X, T.TruncThresh(1e-6)); ms["compress"] = X.last_timing()[0]
+                return lz, ms
+            Wm = A.copy()
+            pipeline(Wm)                                       # warm-up on the SAME handle (workspaces, scratch)
+            Wm.reset(); Wm.upload_all(gen5(lo, hi))            # fresh input in the warmed handle
+            if gather:
+                barrier()
+            else:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lz, ms = pipeline(Wm)
+            full_dev = dev_out
+            if gather and world > 1 and B5 % world == 0:
+                full_dev = torch.empty((B5, npr, Q5 * Q5), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(full_dev, dev_out)
+            host = pin_pairs(full_dev.shape)
+            host.copy_(full_dev, non_blocking=True)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            bonds = np.array([Wm.bonds(b) for b in range(nb_)], dtype=np.int64)
+            return {"A": A, "W": Wm, "lz": np.asarray(lz, dtype=np.float64), "ms": ms, "wall": wall, "pairs_host": host,
+                    "bonds": bonds, "npr": npr}
+
+        _pin = {}
+        def pin_pairs(shape):
+            key = tuple(shape)
+            if key not in _pin:
+                _pin.clear()
+                _pin[key] = torch.empty(key, dtype=torch.float64, pin_memory=True)
+            return _pin[key]
+
         lo5, hi5 = P.shard_range(B5, rank, world)
         nb = hi5 - lo5
-        site5 = D5 * D5 * Q5
-        packed5 = np.empty(nb * L5 * site5)
-        for i, bg in enumerate(range(lo5, hi5, 256)):          # seeds by global chunk: shard-count independent
-            n_i = min(256, hi5 - bg)
-            packed5[i * 256 * L5 * site5:(i * 256 + n_i) * L5 * site5] = \
-                np.random.Generator(np.random.Philox(5000 + bg)).random(n_i * L5 * site5)
-        A5 = T.PeriodicTensorTrain.empty([D5] * (L5 + 1), (Q5,), batch=nb)
-        A5.upload_all(packed5)
-        npair = C.c_int64()
-        T._ck(T.lib.ttb_twovar_count(A5._hd, L5 - 1, C.byref(npair)))
-        out2 = np.zeros((nb, npair.value, Q5 * Q5))
-        def c5_pipeline(A):
-            ms = {}
-            lz = T.normalize_(A); ms["normalize"] = A.last_timing()[0]
-            T._ck(T.lib.ttb_twovar_marginals(A._hd, L5 - 1, T._dp(out2))); ms["twovar_marginals"] = A.last_timing()[0]
-            T.compress_(A, T.TruncThresh(1e-6)); ms["compress"] = A.last_timing()[0]
-            return lz, ms
-        c5_pipeline(A5.copy())                                   # warm-up (workspaces, scratch)
-        W5 = A5.copy()
-        barrier()
-        t0 = time.perf_counter()
-        lz5, ms5 = c5_pipeline(W5)
-        wall5 = max_over_ranks(time.perf_counter() - t0)
+        r5 = c5_run(lo5, hi5, gather=True)
+        wall5 = max_over_ranks(r5["wall"])
+        ms5 = r5["ms"]
         dev5 = max_over_ranks(sum(ms5.values()))
+        ms5_max = {k: max_over_ranks(v) for k, v in ms5.items()}
+        lz_all = P.allgather(np.ascontiguousarray(r5["lz"]).reshape(-1, 1)).reshape(-1) if (world > 1 and B5 % world == 0) else r5["lz"]
+        bonds_all = P.allgather(r5["bonds"]) if (world > 1 and B5 % world == 0) else r5["bonds"]
+        pairs_all = r5["pairs_host"].numpy()
         # HBM roofline of the environment pass behind normalize! (k_env_small_L reads every site tensor once:
         # algorithmic bytes = 8 * sum_t d_t d_{t+1} Q per train) and of the scaling pass (read + write)
-        P5 = A5.copy()
+        P5 = r5["A"].copy()
         P5.profile(True)
         T.normalize_(P5)
         rep5 = P5.profile_report()
-        T._ck(T.lib.ttb_twovar_marginals(P5._hd, L5 - 1, T._dp(out2)))
+        scratch_dev = torch.empty((nb, r5["npr"], Q5 * Q5), dtype=torch.float64, device=dev)
+        T.twovar_marginals_block(P5, 0, L5 - 1, L5 - 1, out=scratch_dev)
         rep5b = P5.profile_report()
+        T.compress_(P5, T.TruncThresh(1e-6))
+        rep5c = P5.profile_report()
         P5.profile(False)
-        del P5
+        del P5, scratch_dev
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
             hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy figure)"
@@ -434,24 +523,76 @@ def main():
         # FP64-tensor roofline of the pair-marginal chain: per pair one stacked (Q d_1) x d x d update (the last
         # pair of every first site needs none) and the Q^2 Frobenius products; peak is filled in by rank 0 below
         if "k_twovar_mma" in rep5b and rep5b["k_twovar_mma"][1] > 0:
-            npr = int(npair.value)
+            npr = r5["npr"]
             fl5 = float(nb) * ((npr - (L5 - 1)) * 2.0 * Q5 * D5 * D5 * D5 + npr * 2.0 * Q5 * Q5 * D5 * D5)
             roof5["k_twovar_mma"] = {"bound": "tensor", "achieved": fl5 / (rep5b["k_twovar_mma"][1] * 1e-3) / 1e12, "unit": "TFLOP/s",
                                      "ms": rep5b["k_twovar_mma"][1], "alg_flops": fl5}
-        bonds5 = np.array([T.bond_dims(W5, b) for b in range(0, nb, max(nb // 64, 1))], dtype=np.float64)
-        lz_all = P.allgather(np.ascontiguousarray(lz5).reshape(-1, 1)) if B5 % world == 0 else lz5
-        assert np.all(np.isfinite(lz_all)) and abs(float(out2[0, 0].sum()) - 1.0) < 1e-9
+        compress_kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(rep5c.items(), key=lambda kv: -kv[1][1])
+                            if k not in rep5b}
+        assert np.all(np.isfinite(lz_all))
         batch_info = {"workload": "C5: 4096 PeriodicTensorTrains, 64 sites, bond 32, q=2, rand fill: normalize! + twovar_marginals "
-                                  "(2016 pairs per train) + compress!(TruncThresh(1e-6)); trains sharded over ranks, "
-                                  "all-gather of per-train log Z",
+                                  "(2016 pairs per train) + compress!(TruncThresh(1e-6)); trains sharded over ranks (strong scaling); "
+                                  "all-gather (NCCL) of per-train log Z, bond dimensions and of the pair marginals between device "
+                                  "buffers, then device -> pinned host",
                       "trains": B5, "trains_per_rank": nb, "device_ms": dev5, "device_ms_by_call_rank0": ms5,
-                      "trains_per_s": B5 / (dev5 * 1e-3), "e2e_wall_ms": wall5 * 1e3,
-                      "compress_site_steps_per_s": world * nb * 2 * L5 / (max_over_ranks(ms5["compress"]) * 1e-3),
-                      "max_bond_after": int(bonds5.max()), "logz_gathered": int(np.size(lz_all)),
-                      "roofline_rank0": roof5, "hbm_peak_source": hbm_src,
-                      "note": "device_ms = sum of the three calls' CUDA-event times, max over ranks; e2e_wall_ms adds the "
-                              "D2H copy of all pair marginals (258 MB in total) and the host-side call overhead"}
-        del A5, W5, packed5, out2
+                      "device_ms_by_call_max": ms5_max,
+                      "trains_per_s": B5 / (dev5 * 1e-3), "e2e_wall_ms": wall5 * 1e3, "e2e_trains_per_s": B5 / wall5,
+                      "compress_site_steps_per_s": B5 * 2 * L5 / (ms5_max["compress"] * 1e-3),
+                      "logz_gathered": int(np.size(lz_all)), "pair_marginals_gathered_bytes": int(pairs_all.nbytes),
+                      "roofline_rank0": roof5, "hbm_peak_source": hbm_src, "compress_kernels_rank0": compress_kernels,
+                      "note": "device_ms = sum of the three calls' CUDA-event times, max over ranks; e2e_wall_ms = the three calls + "
+                              "the all-gather of the pair marginals (device buffers) + their copy into pinned host memory"}
+        c5_check = {"lz": lz_all, "bonds": bonds_all, "pairs": pairs_all.copy() if world > 1 else pairs_all}
+        del r5
+        if world > 1:
+            one = alone_on_rank0(lambda: c5_run(0, B5, gather=False))
+            if rank == 0:
+                ms1 = sum(one["ms"].values())
+                same = (np.array_equal(one["bonds"], c5_check["bonds"]) and
+                        np.allclose(one["pairs_host"].numpy(), c5_check["pairs"], rtol=1e-12, atol=0) and
+                        np.allclose(one["lz"], c5_check["lz"], rtol=1e-12, atol=0))
+                assert same, "sharded C5 results differ from the one-GPU run"
+                batch_info["one_gpu"] = {"device_ms": ms1, "device_ms_by_call": one["ms"], "e2e_wall_ms": one["wall"] * 1e3,
+                                         "trains_per_s": B5 / (ms1 * 1e-3)}
+                batch_info["speedup_vs_1gpu"] = {"device": ms1 / dev5, "e2e": one["wall"] / wall5,
+                                                 "by_call": {k: one["ms"][k] / ms5_max[k] for k in ms5_max},
+                                                 "results_identical_to_one_gpu_run": True}
+            del one
+        _pin.clear()
+
+    # ---- third sharding axis: the pair marginals of ONE train (config-2 size: L=128, d=64, q=2,
+    #      8128 pairs) sharded over the ranks by first site, ragged all-gather between device buffers ----
+    pairs_info = None
+    if not args.no_extra:
+        from ttb200 import parallel as P
+        L2, D2, Q2 = 128, 64, 2
+        _, t2 = make_open(2, L2, D2, Q2)
+        A2 = T.TensorTrain(t2)
+        T.normalize_(A2)
+        P.twovar_marginals_sharded(A2, as_dict=False)                 # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        full2 = P.twovar_marginals_sharded(A2, as_dict=False)
+        wall2 = max_over_ranks(time.perf_counter() - t0)
+        ms2 = max_over_ranks(A2.last_timing()[0])
+        npairs2 = L2 * (L2 - 1) // 2
+        assert full2.shape == (npairs2, Q2 * Q2) and np.allclose(full2.sum(axis=1), 1.0, rtol=0, atol=1e-9)
+        pairs_info = {"workload": "pair marginals of ONE TensorTrain L=128 q=2 d=64 (rand_tt, normalized), all 8128 pairs, first sites "
+                                  "sharded over the ranks (parallel.pair_ranges), ragged NCCL all-gather of the blocks from device buffers",
+                      "pairs": npairs2, "device_ms": ms2, "wall_ms": wall2 * 1e3, "pairs_per_s": npairs2 / (ms2 * 1e-3),
+                      "e2e_pairs_per_s": npairs2 / wall2}
+        if world > 1:
+            def one2():
+                T.twovar_marginals_block(A2, 0, L2 - 1)
+                t0_ = time.perf_counter()
+                o = T.twovar_marginals_block(A2, 0, L2 - 1)
+                return o[0], A2.last_timing()[0], time.perf_counter() - t0_
+            one = alone_on_rank0(one2)
+            if rank == 0:
+                assert np.allclose(one[0], full2, rtol=1e-12, atol=0)
+                pairs_info["one_gpu"] = {"device_ms": one[1], "wall_ms": one[2] * 1e3}
+                pairs_info["speedup_vs_1gpu"] = {"device": one[1] / ms2, "e2e": one[2] / wall2}
+        del A2, t2
 
     if rank == 0:
         # ---- roofline: per-kernel CUDA-event times of one more compress! (serial timeline) ----
@@ -472,11 +613,18 @@ def main():
         n_alg, alg = fl.get(alias.get(dom, dom), [n_l, 0.0])
         per_launch = alg / max(n_alg, 1)
         achieved = alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture
-        # (profiles/r1_ncu_full_sweep_kernels.csv: dram__bytes_read.sum + dram__bytes_write.sum)
-        ncu_traffic = {"k_qr_panel_flag": 156672 + 0, "k_qr_stream": 1119232 + 0}
+        # DRAM traffic per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+        # `ncu --set full` capture, read from profiles/ncu_traffic.json (profiles/make_ncu_traffic.py writes it from the
+        # per-round summaries); null when the kernel has no capture
+        try:
+            ncu_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            ncu_tab = {}
+        ncu_traffic = {k: int(v["dram_bytes_per_launch"]) for k, v in ncu_tab.items()}
+        ncu_src = {k: v.get("source") for k, v in ncu_tab.items()}
         line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak if peak else None, "traffic": ncu_traffic.get(dom),
+                            "traffic_source": ncu_src.get(dom),
                             "peak_source": "measured in this run: torch.matmul float64 4096^3 (cuBLAS DGEMM, best of 8); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
                             "share_of_step": ms / tot_ms if tot_ms else None,
@@ -485,14 +633,15 @@ def main():
                             "note": "k_qr_stream = the whole Householder QR of one site (512 x 256) as one 8-CTA cluster: 256 "
                                     "chained columns, dependency-latency bound by construction (profiles/r1_micro_panel.txt, "
                                     "r1_ncu_panel_warpstates.txt); achieved = algorithmic QR FLOPs 2k^2(p-k/3) / CUDA-event "
-                                    "time of all launches of the class; traffic = dram bytes of one launch "
-                                    "(profiles/r1_ncu_full_qr_stream.csv: the 1.05 MB site read once, writes absorbed by L2)",
+                                    "time of all launches of the class; traffic = dram bytes of one launch under ncu --set full "
+                                    "(the 1.05 MB site read once, writes absorbed by L2)",
                             "kernels": {k: {"launches": v[0], "ms": v[1],
                                             "alg_gflop": fl.get(alias.get(k, k), [0, 0.0])[1] / 1e9}
                                         for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])},
                             "whole_step": {"alg_gflop": sum(v[1] for v in fl.values()) / 1e9,
                                            "tflops": sum(v[1] for v in fl.values()) / (dev_ms / K * 1e-3) / 1e12}}
         extra = {}
+        parity_fail = False
         if sample_info is not None:
             sample_info["tflops_minimal_algorithm"] = sample_info["draws_per_s"] * 8.65e6 / 1e12
             sample_info["frac_of_fp64_peak"] = sample_info["tflops_minimal_algorithm"] / (peak * world) if peak else None
@@ -508,9 +657,38 @@ def main():
                 tw["peak"] = peak
                 tw["frac"] = tw["achieved"] / peak
             extra["batch"] = batch_info
+        if pairs_info is not None:
+            extra["pairs_of_one_train"] = pairs_info
+        if not args.no_extra:
+            # ---- config 2 (BASELINE.json configs[1]): single TT L=128 q=2 d=64: orthogonalize_right! + compress!(TruncBond(32))
+            #      + normalize! + all single-site marginals, device time of the four calls ----
+            try:
+                L2, D2, Q2 = 128, 64, 2
+                _, t2 = make_open(2, L2, D2, Q2)
+                def c2_pipeline(A):
+                    ms = {}
+                    T.orthogonalize_right_(A, T.TruncThresh(0.0)); ms["orthogonalize_right"] = A.last_timing()[0]
+                    T.compress_(A, T.TruncBond(32), is_orthogonal="right"); ms["compress_TruncBond32"] = A.last_timing()[0]
+                    lz = T.normalize_(A); ms["normalize"] = A.last_timing()[0]
+                    m = T.marginals(A); ms["marginals"] = A.last_timing()[0]
+                    return ms, lz, m
+                A2 = T.TensorTrain(t2)
+                c2_pipeline(A2.copy())
+                w0_ = time.perf_counter()
+                ms2, lz2, m2 = c2_pipeline(A2)
+                wall2_ = time.perf_counter() - w0_
+                c2 = {"workload": "C2: single TensorTrain L=128 q=2 d=64 rand_tt: orthogonalize_right!(TruncThresh(0.0)) + "
+                                  "compress!(TruncBond(32), is_orthogonal=:right) + normalize! + marginals (254 site-steps)",
+                      "device_ms": sum(ms2.values()), "device_ms_by_call": ms2, "wall_ms": wall2_ * 1e3,
+                      "site_steps_per_s": 2 * (L2 - 1) / ((ms2["orthogonalize_right"] + ms2["compress_TruncBond32"]) * 1e-3),
+                      "bonds_after_max": int(max(T.bond_dims(A2)))}
+                extra["config2"] = c2
+            except Exception as ex:
+                extra["config2_error"] = repr(ex)
         if world == 1 and not args.no_extra:
             # in a clean process (this one holds a CUDA context, pinned buffers and sampler threads, which was
             # measured to slow the host BLAS several-fold): exactly what `--impl reference` times
+            refl = None
             try:
                 cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                                     capture_output=True, text=True, timeout=900)
@@ -521,6 +699,16 @@ def main():
                 line["cpu_baseline"] = {"value": v, "unit": "site-steps/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"the full C3 compress! once in-process ({secs:.1f} s; subprocess failed: {ex!r}): "
                                                   "NumPy/SciPy-OpenBLAS gesdd restatement of the reference, not Julia/MKL"}
+                refl = {"config": {"bonds_after": LAST_CPU_BONDS}}
+            # parity of the TIMED run against the CPU arm, outside the timed region: retained bond dimensions of the
+            # last timed compress! (same seed-3 input) must be identical to the oracle's
+            cpu_bonds = (refl or {}).get("config", {}).get("bonds_after")
+            if cpu_bonds is not None:
+                same = [int(x) for x in bonds_after] == [int(x) for x in cpu_bonds]
+                line["parity_in_run"] = {"bonds_identical_to_cpu_arm": bool(same), "bonds_after": [int(x) for x in bonds_after],
+                                         "what": "retained bond dimensions of the last timed compress! vs the oracle's on the same input "
+                                                 "(the CPU arm's own run)"}
+                parity_fail = parity_fail or not same
             try:
                 try:   # same BLAS thread count as the compress baseline picked
                     from threadpoolctl import threadpool_limits
@@ -529,21 +717,89 @@ def main():
                     _lim = None
                 extra["sample"]["cpu_draws_per_s"] = cpu_sample_draws_per_s(L4, D4, Q4, 4, 20)
                 extra["sample"]["cpu_blas_threads"] = int(line["cpu_baseline"].get("cores", 0))
-                # randn fill of config 3 (both sweeps full rank): reduced length
-                Lr = 48
-                br, tsr = make_open(3, Lr, D3, Q3, "randn")
+                # ---- C2 on the CPU (oracle), same pipeline ----
+                if "config2" in extra:
+                    from oracle import tt_oracle as O
+                    _, t2 = make_open(2, 128, 64, 2)
+                    Ao = O.TensorTrain(t2)
+                    c0_ = time.perf_counter()
+                    O.orthogonalize_right(Ao, O.TruncThresh(0.0)); O.compress(Ao, O.TruncBond(32), is_orthogonal="right")
+                    c1_ = time.perf_counter()
+                    lzo = O.normalize(Ao); mo = O.marginals(Ao)
+                    c2_ = time.perf_counter()
+                    extra["config2"]["cpu_ms"] = (c2_ - c0_) * 1e3
+                    extra["config2"]["cpu_site_steps_per_s"] = 254 / (c1_ - c0_)
+                    extra["config2"]["matches_cpu"] = bool(T.bond_dims(A2) == O.bond_dims(Ao) and abs(lz2 - lzo) <= 1e-8 * max(1.0, abs(lzo))
+                                                          and all(np.allclose(a, b, rtol=1e-8, atol=1e-12) for a, b in zip(m2, mo)))
+                    parity_fail = parity_fail or not extra["config2"]["matches_cpu"]
+                # ---- C5: fixed global train ids against the oracle (log Z, every pair marginal, retained bonds) ----
+                if batch_info is not None:
+                    from oracle import tt_oracle as O
+                    ids = [0, 1, 777, 2047, 2048, 4095]
+                    ok_ids = []
+                    for g in ids:
+                        raw = gen5(g, g + 1).reshape(L5, D5 * D5 * Q5)
+                        Ao = O.PeriodicTensorTrain([raw[t].reshape((D5, D5, Q5), order="F").copy() for t in range(L5)])
+                        lzo = O.normalize(Ao)
+                        po = O.twovar_marginals(Ao)
+                        O.compress(Ao, O.TruncThresh(1e-6))
+                        okg = abs(c5_check["lz"][g] - lzo) <= 1e-10 * abs(lzo)
+                        i = 0
+                        for t in range(L5 - 1):
+                            for u in range(t + 1, L5):
+                                okg = okg and np.allclose(c5_check["pairs"][g, i], np.reshape(po[(t, u)], -1, order="F"), rtol=1e-9, atol=1e-13)
+                                i += 1
+                        okg = okg and [int(x) for x in c5_check["bonds"][g][:L5]] == [int(x) for x in O.bond_dims(Ao)]
+                        ok_ids.append(bool(okg))
+                    batch_info["oracle_check"] = {"global_train_ids": ids, "ok": ok_ids,
+                                                  "what": "log Z (1e-10), all 2016 pair marginals (1e-9), retained bonds (identical) vs the oracle"}
+                    parity_fail = parity_fail or not all(ok_ids)
+                # ---- randn fill of config 3 at FULL length (both sweeps full rank: every left-sweep step is a 256 x 256 SVD) ----
+                br, tsr = make_open(3, L3, D3, Q3, "randn")
                 Ar = T.TensorTrain(tsr)
+                del tsr
                 T.compress_(Ar.copy(), tr)
+                Pr = Ar.copy()
                 T.compress_(Ar, tr)
                 msr, _ = Ar.last_timing()
-                extra["randn_fill"] = {"workload": f"C3 shape, randn_tt fill (nothing to truncate: every left-sweep step is a full "
-                                                   f"256 x 256 SVD, cluster Jacobi), L={Lr}",
-                                       "site_steps_per_s": 2 * (Lr - 1) / (msr * 1e-3), "ms": msr}
+                Pr.profile(True); T.compress_(Pr, tr); repr_ = Pr.profile_report(); Pr.profile(False)
+                bonds_r = T.bond_dims(Ar)
+                del Pr
+                nsvd = L3 - 1
+                f_svd = 6.0 * 512 * 256 ** 2 + 20.0 * 256 ** 3          # GVL R-SVD, thin U, S, V of the 512 x 256 fold
+                jac = {k: v for k, v in repr_.items() if "jacobi" in k}
+                jac_ms = sum(v[1] for v in jac.values())
+                rn = {"workload": f"C3 shape, randn_tt fill (nothing to truncate: every left-sweep step is a full 256 x 256 SVD), L={L3}, "
+                                  "compress!(TruncThresh(1e-10)) = 510 site-steps",
+                      "site_steps_per_s": nsteps_unit / (msr * 1e-3), "ms": msr, "bonds_after_max": int(max(bonds_r)),
+                      "kernels": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(repr_.items(), key=lambda kv: -kv[1][1])},
+                      "roofline": {"bound": "tensor", "kernel": "k_jacobi_* (QR + one-sided Jacobi SVD of the left sweep)", "unit": "TFLOP/s",
+                                   "achieved": nsvd * f_svd / (jac_ms * 1e-3) / 1e12 if jac_ms else None, "peak": peak,
+                                   "frac": nsvd * f_svd / (jac_ms * 1e-3) / 1e12 / peak if jac_ms and peak else None,
+                                   "alg_flops_per_step": f_svd, "ms": jac_ms,
+                                   "note": "achieved = 255 x F_svd (6 n m^2 + 20 m^3 = 536.9 MFLOP, the LAPACK R-SVD count SURVEY 8d prescribes; "
+                                           "the absorb's 67.1 MFLOP is counted with its own kernel) / CUDA-event time of the Jacobi kernels"}}
+                try:
+                    cpr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--fill", "randn", "--steps", "1",
+                                          "--warmup", "0"], capture_output=True, text=True, timeout=900)
+                    rl = json.loads([ln for ln in cpr.stdout.splitlines() if ln.startswith("{")][-1])
+                    rn["cpu_site_steps_per_s"] = rl["value"]
+                    rn["cpu_sample"] = rl["cpu_baseline"]["sample"]
+                    rn["cpu_blas_threads"] = rl["cpu_baseline"]["cores"]
+                    if rl["config"].get("bonds_after") is not None:
+                        rn["bonds_identical_to_cpu_arm"] = [int(x) for x in bonds_r] == [int(x) for x in rl["config"]["bonds_after"]]
+                        parity_fail = parity_fail or not rn["bonds_identical_to_cpu_arm"]
+                except Exception as ex:
+                    rn["cpu_error"] = repr(ex)
+                extra["randn_fill"] = rn
             except Exception as ex:  # the headline line must still be printed
                 extra["error"] = repr(ex)
         if extra:
             line["extra"] = extra
         print(json.dumps(line))
+        sys.stdout.flush()
+        if parity_fail:
+            raise SystemExit("bench.py: a parity check of this run FAILED (see parity_in_run / matches_cpu / oracle_check in the line)")
     if world > 1:
         dist.destroy_process_group()
 

@@ -141,7 +141,9 @@ int ttb_normalize(ttb_handle h, double* logz_out);
  * (src/MatrixProductStates/mps.jl:154-168) is ttb_dot(psi, psi) + this + ttb_set_z. */
 int ttb_scale_sites(ttb_handle h, const double* divisor);
 int ttb_normalize_eachmatrix(ttb_handle h);
-/* marginals (src/abstract_tensor_train.jl:208-220): out[b][t][x], batch*L*Q doubles */
+/* marginals (src/abstract_tensor_train.jl:208-220): out[b][t][x], batch*L*Q doubles.  `out` of ttb_marginals* and
+ * ttb_twovar_marginals* may be HOST memory (pageable or pinned) or DEVICE memory of the handle's device (unified
+ * addressing decides): a caller that all-gathers the results over NCCL keeps them on the device. */
 int ttb_marginals(ttb_handle h, double* out);
 /* twovar_marginals (src/abstract_tensor_train.jl:231-254): pairs t<u<=t+maxdist in lexicographic
  * order, each Q*Q doubles column-major (x_t fastest); *npairs receives the count per train. */

