@@ -62,6 +62,7 @@ struct Workspace {
   DevBuf samp[10];                    // sampler scratch (offsets, G, uniforms, x, p, hist, sum log p, packed A, packed G)
   DevBuf scr[6];                      // twovar_marginals (pair offsets, out, scratch, GT, Tm) and dot scratch
   DevBuf scr_trace, scr_toff;         // two-phase environment pass: per-site traces and their offset table
+  DevBuf mps[10];                     // MPS (Born machine) environments, sandwiches and item tables (mps.cu)
   // sweep
   double* X[2] = {nullptr, nullptr};  // folded site / absorb output, p_max x n_max col-major
   int64_t x_stride = 0;
@@ -288,6 +289,26 @@ __device__ __forceinline__ double rsqrt_nr(double a) {
   y = fma(0.5 * y, e, y);
   return y;
 }
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                             uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+  c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t sample, uint32_t site) {
+  uint32_t c0 = (uint32_t)sample, c1 = (uint32_t)(sample >> 32), c2 = site, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint64_t bits = ((uint64_t)c0 << 21) ^ ((uint64_t)c1 >> 11);
+  return (double)bits * (1.0 / 9007199254740992.0);
+}
+
 // max-abs with NaN propagation (fmax drops NaN, the reference's maximum(abs, .) keeps it)
 __device__ __forceinline__ double absmax_nan(double acc, double v) {
   double a = fabs(v);

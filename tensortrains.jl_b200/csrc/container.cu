@@ -80,6 +80,7 @@ static void free_ws(ttb_tt* h) {
   cudaFree(w.spectrum); cudaFree(w.envL); cudaFree(w.envR); cudaFree(w.env_log); cudaFree(w.env_sign);
   for (DevBuf& d : w.samp) d.release();
   for (DevBuf& d : w.scr) d.release();
+  for (DevBuf& d : w.mps) d.release();
   w.scr_trace.release(); w.scr_toff.release();
   w = Workspace();
 }
@@ -485,6 +486,7 @@ int ttb_trim(ttb_handle h) {
   TTB_CUDA(cudaStreamSynchronize(h->stream));
   for (DevBuf& d : h->ws.samp) d.release();
   for (DevBuf& d : h->ws.scr) d.release();
+  for (DevBuf& d : h->ws.mps) d.release();
   h->ws.scr_trace.release();
   return TTB_OK;
 }

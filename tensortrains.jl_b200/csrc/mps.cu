@@ -1,0 +1,672 @@
+// mps.cu -- the Born-machine wrapper MPS (p(x) = |psi(x)|^2) over an OPEN train psi:
+//   accumulate_L / accumulate_R   src/MatrixProductStates/mps.jl:60-103   (the "d^4" environments)
+//   marginals                     :176-196
+//   accumulate_M / twovar_marginals  :105-126, :206-232
+//   sample!                       :264-290
+//
+// For an open train (d_1 = d_{L+1} = 1) the reference's four-index environments Ll[a1, al, b1, bl] have
+// a1 = b1 = 1: they ARE d x d matrices, and every contraction of the file is a "sandwich"
+//     up:    E' = sum_x A(x)^T E A(x)        (left environment, accumulate_M transfer)
+//     down:  R' = sum_x A(x) R A(x)^T        (right environment)
+// i.e. two d^3 GEMMs per physical value -- dense FP64 tensor-core work (mma.sync m16n8k8, `k_gemm_items`:
+// one launch serves a whole table of products with their own shapes, so all sites / all pairs of one distance
+// are one launch).  Per-x sandwiches are kept:  S_t(x) = A_t(x) r_{t+1} A_t(x)^T  gives
+//     marginals        p_t[x]        = <l_{t-1}, S_t(x)>_F
+//     pair marginals   b_tu[x, y]    = <K_tu(x), S_u(y)>_F,  K_t,t+1(x) = A_t(x)^T l_{t-1} A_t(x),
+//                                      K_t,u+1(x) = sym(sum_y A_u(y)^T K_tu(x) A_u(y))   (streamed, never the L x L table)
+//     sampling         p[x | q]      = q S_t(x) q^T,  q <- q A_t(x_t)
+// The reference's quirks are kept: the in-place `Ll ./= nl` also rescales the environment stored one step
+// earlier (stored l[t < L] have max-abs 1, the last one is unscaled), hermiticity is restored after every
+// step ((E + E^T) / 2), z = prod(nl) * trace.  Periodic psi (matrix boundary: genuine d_1^2 d^2 arrays) is not
+// built: TTB_EUNSUPPORTED.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tma_mma.cuh"
+
+namespace ttb {
+
+// one product of a table: C (m x n) = sum_{s < nsum} op(A + s sA) op(B + s sB), column-major operands
+struct GemmItem {
+  const double* A;
+  const double* B;
+  double* C;
+  int m, n, k;
+  int lda, ldb, ldc;
+  int nsum, pad_;
+  int64_t sA, sB;
+};
+
+// TA: A is stored k x m (op(A) = A^T); TB: B is stored n x k (op(B) = B^T).  64 x 64 tile per CTA, 4 warps of
+// 32 x 32 (2 x 4 DMMA tiles), K staged 16 at a time through shared memory with a register prefetch of the
+// next stage.  grid = (max tiles of any item, items): surplus CTAs exit.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(128) k_gemm_items(const GemmItem* __restrict__ items) {
+  const GemmItem it = items[blockIdx.y];
+  const int tiles_m = (it.m + 63) >> 6, tiles_n = (it.n + 63) >> 6;
+  if ((int)blockIdx.x >= tiles_m * tiles_n) return;
+  const int i0 = ((int)blockIdx.x % tiles_m) * 64, j0 = ((int)blockIdx.x / tiles_m) * 64;
+  __shared__ double As[16][72], Bs[16][72];   // [k][m], [k][n]; stride 72 = 8 mod 32: fragment loads conflict-free
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wm = (wid & 1) * 32, wn = (wid >> 1) * 32;
+  double acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.0;
+  const int nst = (it.k + 15) >> 4, total = nst * it.nsum;
+  double ra[8], rb[8];
+  auto load = [&](int st) {
+    const int s = st / nst, k0 = (st - s * nst) * 16;
+    const double* Ap = it.A + (int64_t)s * it.sA;
+    const double* Bp = it.B + (int64_t)s * it.sB;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = tid + 128 * r;
+      int mm, kk;
+      if (TA) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+      const bool ok = (i0 + mm < it.m) && (k0 + kk < it.k);
+      ra[r] = ok ? (TA ? Ap[(k0 + kk) + (int64_t)it.lda * (i0 + mm)] : Ap[(i0 + mm) + (int64_t)it.lda * (k0 + kk)]) : 0.0;
+      int nn, kb;
+      if (TB) { nn = idx & 63; kb = idx >> 6; } else { kb = idx & 15; nn = idx >> 4; }
+      const bool okb = (j0 + nn < it.n) && (k0 + kb < it.k);
+      rb[r] = okb ? (TB ? Bp[(j0 + nn) + (int64_t)it.ldb * (k0 + kb)] : Bp[(k0 + kb) + (int64_t)it.ldb * (j0 + nn)]) : 0.0;
+    }
+  };
+  if (total > 0) load(0);
+  for (int st = 0; st < total; ++st) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = tid + 128 * r;
+      if (TA) As[idx & 15][idx >> 4] = ra[r]; else As[idx >> 6][idx & 63] = ra[r];
+      if (TB) Bs[idx >> 6][idx & 63] = rb[r]; else Bs[idx & 15][idx >> 4] = rb[r];
+    }
+    __syncthreads();
+    if (st + 1 < total) load(st + 1);
+#pragma unroll
+    for (int ks = 0; ks < 16; ks += 8) {
+      double af[2][4], bf[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = wm + 16 * mt + g;
+        af[mt][0] = As[ks + tq][r0]; af[mt][1] = As[ks + tq][r0 + 8];
+        af[mt][2] = As[ks + tq + 4][r0]; af[mt][3] = As[ks + tq + 4][r0 + 8];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c0 = wn + 8 * nt + g;
+        bf[nt][0] = Bs[ks + tq][c0]; bf[nt][1] = Bs[ks + tq + 4][c0];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma_16x8x8(acc[mt][nt], af[mt], bf[nt]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + wm + 16 * mt + g + ((e & 2) ? 8 : 0), j = j0 + wn + 8 * nt + 2 * tq + (e & 1);
+        if (i < it.m && j < it.n) it.C[i + (int64_t)it.ldc * j] = acc[mt][nt][e];
+      }
+}
+
+// out = (raw + raw^T) / 2 (d x d), max-abs of the result into mx[slot] (ordered bits, NaN-propagating)
+struct SymItem { const double* raw; double* out; int d; int slot; };
+__global__ void __launch_bounds__(256) k_mps_sym(const SymItem* __restrict__ items, unsigned long long* mx) {
+  const SymItem it = items[blockIdx.y];
+  const int64_t n = (int64_t)it.d * it.d;
+  double m = 0.0;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(o % it.d), j = (int)(o / it.d);
+    const double v = 0.5 * (it.raw[o] + it.raw[j + (int64_t)it.d * i]);
+    it.out[o] = v;
+    m = absmax_nan(m, v);
+  }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bits, o); bits = ot > bits ? ot : bits; }
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(mx + it.slot, bits);
+}
+
+// buf /= mx[slot] unless the maximum is zero (`!iszero(nl)`, mps.jl:67)
+struct ScaleItem { double* buf; int64_t n; int slot; int pad_; };
+__global__ void __launch_bounds__(256) k_mps_scale(const ScaleItem* __restrict__ items, const unsigned long long* mx) {
+  const ScaleItem it = items[blockIdx.y];
+  const double m = __longlong_as_double((long long)mx[it.slot]);
+  if (m == 0.0) return;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < it.n; o += (int64_t)gridDim.x * blockDim.x) it.buf[o] /= m;
+}
+
+// out[item] = <X, Y>_F over n contiguous doubles
+struct FrobItem { const double* X; const double* Y; double* out; int64_t n; };
+__global__ void __launch_bounds__(256) k_mps_frob(const FrobItem* __restrict__ items) {
+  const FrobItem it = items[blockIdx.x];
+  __shared__ double red[40];
+  double v = 0.0;
+  for (int64_t o = threadIdx.x; o < it.n; o += blockDim.x) v += it.X[o] * it.Y[o];
+  v = block_sum(v, red);
+  if (threadIdx.x == 0) *it.out = v;
+}
+
+// z = prod_{t < nscaled} mx[t] * value -> (log|z|, sign)
+__global__ void k_mps_final(const unsigned long long* mx, int nscaled, const double* last, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double lg = 0.0;
+  for (int t = 0; t < nscaled; ++t) {
+    const double m = __longlong_as_double((long long)mx[t]);
+    if (m != 0.0) lg += log(m);
+  }
+  const double v = *last;
+  out[0] = lg + log(fabs(v));
+  out[1] = v < 0.0 ? -1.0 : 1.0;
+  if (v != v) out[0] = v;
+}
+
+// ---- sampler: one CTA per draw.  q (1 x d_t) is the running product; p[x] = q S_t(x) q^T ----
+struct MpsSampCtx {
+  const double* slab; int64_t tt_off; const int64_t* off; const int64_t* bond; int L, Q, dmax;
+  const double* S; const int64_t* soff;     // S_t(x): d_t x d_t at S + soff[t] + x d_t^2
+  const double* zlog;                       // log z of accumulate_R
+  const double* uniforms; uint64_t seed, first;
+  uint8_t* x_out; double* p_out; int64_t nsamples;
+};
+__global__ void __launch_bounds__(128) k_mps_sample(MpsSampCtx c) {
+  const int64_t s = blockIdx.x;
+  if (s >= c.nsamples) return;
+  extern __shared__ double sm[];
+  double* q = sm;
+  double* qn = sm + c.dmax;
+  double* pw = qn + c.dmax;
+  __shared__ double red[40];
+  __shared__ int s_x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const double* tt = c.slab + c.tt_off;
+  if (tid == 0) q[0] = 1.0;
+  double ls = 0.0;
+  __syncthreads();
+  for (int t = 0; t < c.L; ++t) {
+    const int dl = (int)c.bond[t], dr = (int)c.bond[t + 1];
+    for (int x = 0; x < c.Q; ++x) {
+      const double* Sx = c.S + c.soff[t] + (int64_t)x * dl * dl;
+      double acc = 0.0;
+      for (int j = wid; j < dl; j += nw) {        // column j of S (symmetric up to rounding: use it as stored)
+        double col = 0.0;
+        for (int i = lane; i < dl; i += 32) col += q[i] * Sx[i + (int64_t)dl * j];
+        col = warp_sum(col);
+        if (lane == 0) acc += col * q[j];
+      }
+      acc = block_sum(acc, red);
+      if (tid == 0) pw[x] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int x = 0; x < c.Q; ++x) tot += pw[x];
+      const double u = c.uniforms ? c.uniforms[s * c.L + t] : philox_uniform(c.seed, c.first + (uint64_t)s, (uint32_t)t);
+      int xs = c.Q - 1;
+      double cw = 0.0;
+      for (int x = 0; x < c.Q; ++x) {
+        cw += pw[x] / tot;
+        if (cw > u) { xs = x; break; }
+      }
+      s_x = xs;
+      c.x_out[s * c.L + t] = (uint8_t)xs;
+    }
+    __syncthreads();
+    const int xs = s_x;
+    const double* A = tt + c.off[t] + (int64_t)dl * dr * xs;
+    for (int n = wid; n < dr; n += nw) {
+      double a = 0.0;
+      for (int m = lane; m < dl; m += 32) a += q[m] * A[m + (int64_t)dl * n];
+      a = warp_sum(a);
+      if (lane == 0) qn[n] = a;
+    }
+    __syncthreads();
+    double mx = 0.0;
+    for (int n = tid; n < dr; n += nt) mx = fmax(mx, fabs(qn[n]));
+    mx = block_max(mx, red);
+    if (mx > 0.0 && !isinf(mx)) {
+      for (int n = tid; n < dr; n += nt) qn[n] /= mx;
+      ls += log(mx);
+    }
+    __syncthreads();
+    double* tmp = q; q = qn; qn = tmp;
+  }
+  if (tid == 0 && c.p_out) c.p_out[s] = exp(2.0 * (log(fabs(q[0])) + ls) - c.zlog[0]);   // |tr Q|^2 / z (mps.jl:288)
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MpsPlan {
+  int L = 0, Q = 0, dmax = 1;
+  std::vector<int> bd;                 // current bonds of train b, L + 1
+  std::vector<int64_t> eoffL, eoffR;   // slot t of l (d_{t+1}^2) / of r (d_t^2)
+  std::vector<int64_t> soff, uoff;     // S_t(.) (Q d_t^2) / U_t(.) (Q d_t d_{t+1})
+  const double* tt = nullptr;
+};
+
+static int mps_plan(ttb_tt* h, int64_t b, MpsPlan& p) {
+  TTB_TRY(check_handle(h));
+  if (b < 0 || b >= h->batch) return fail(TTB_EINVAL, "train index out of range");
+  TTB_TRY(sync_bonds_to_host(h));
+  p.L = (int)h->L; p.Q = (int)h->Q;
+  p.bd.assign(h->h_bond.begin() + b * (p.L + 1), h->h_bond.begin() + (b + 1) * (p.L + 1));
+  if (h->periodic || p.bd[0] != 1 || p.bd[p.L] != 1)
+    return fail(TTB_EUNSUPPORTED, "MPS environments are built for open trains (first and last bond 1)");
+  p.eoffL.assign(p.L + 1, 0); p.eoffR.assign(p.L + 1, 0); p.soff.assign(p.L + 1, 0); p.uoff.assign(p.L + 1, 0);
+  for (int t = 0; t < p.L; ++t) {
+    p.dmax = std::max(p.dmax, std::max(p.bd[t], p.bd[t + 1]));
+    p.eoffL[t + 1] = p.eoffL[t] + (int64_t)p.bd[t + 1] * p.bd[t + 1];
+    p.eoffR[t + 1] = p.eoffR[t] + (int64_t)p.bd[t] * p.bd[t];
+    p.soff[t + 1] = p.soff[t] + (int64_t)p.Q * p.bd[t] * p.bd[t];
+    p.uoff[t + 1] = p.uoff[t] + (int64_t)p.Q * p.bd[t] * p.bd[t + 1];
+  }
+  p.tt = h->slab + b * h->tt_stride;
+  return TTB_OK;
+}
+
+static inline unsigned tiles64(int m, int n) { return (unsigned)(((m + 63) / 64) * ((n + 63) / 64)); }
+
+template <bool TA, bool TB>
+static void launch_gemm(ttb_tt* h, const GemmItem* d_items, int nitems, unsigned max_tiles) {
+  if (nitems <= 0) return;
+  TTB_LAUNCH(h, "k_gemm_items", (k_gemm_items<TA, TB><<<dim3(max_tiles, (unsigned)nitems), 128, 0, h->stream>>>(d_items)));
+}
+
+// upload a host table into a handle-owned buffer (grow-only); returns the device pointer
+template <typename Tp>
+static Tp* upload_table(ttb_tt* h, DevBuf& buf, const std::vector<Tp>& v, cudaError_t& e) {
+  if (e == cudaSuccess) e = buf.ensure(std::max<size_t>(sizeof(Tp) * v.size(), 64));
+  if (e == cudaSuccess && !v.empty()) e = cudaMemcpyAsync(buf.p, v.data(), sizeof(Tp) * v.size(), cudaMemcpyHostToDevice, h->stream);
+  return static_cast<Tp*>(buf.p);
+}
+
+// environments of train b into ws.mps[left ? 0 : 1]; (log|z|, sign) into *zout (device, 2 doubles) when non-null.
+// Buffers: mps[0] l, mps[1] r, mps[2] raw / temporaries, mps[3] item tables, mps[4] max-abs slots + outputs.
+static int mps_env(ttb_tt* h, const MpsPlan& p, bool left, int normalize, double* d_zout) {
+  Workspace& w = h->ws;
+  const int L = p.L, Q = p.Q;
+  const int64_t d2 = (int64_t)p.dmax * p.dmax;
+  cudaError_t e = w.mps[left ? 0 : 1].ensure(sizeof(double) * std::max<int64_t>(left ? p.eoffL[L] : p.eoffR[L], 1));
+  if (e == cudaSuccess) e = w.mps[2].ensure(sizeof(double) * (Q + 1) * d2);
+  if (e == cudaSuccess) e = w.mps[4].ensure(sizeof(unsigned long long) * (L + 8) + 64);
+  if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS environments: %s", cudaGetErrorString(e));
+  double* env = static_cast<double*>(w.mps[left ? 0 : 1].p);
+  double* Tx = static_cast<double*>(w.mps[2].p);          // Q temporaries, then the raw sum
+  double* raw = Tx + Q * d2;
+  unsigned long long* mx = static_cast<unsigned long long*>(w.mps[4].p);
+  // tables: per site Q products E A(x) (or A(x) R), one summed product, one sym, one scale
+  std::vector<GemmItem> g1((size_t)L * Q), g2(L);
+  std::vector<SymItem> sy(L);
+  std::vector<ScaleItem> sc(L);
+  for (int step = 0; step < L; ++step) {
+    const int t = left ? step : L - 1 - step;
+    const int dl = p.bd[t], dr = p.bd[t + 1];
+    const double* At = p.tt + h->off[t];
+    // incoming environment: the previous slot (already scaled), or the 1 x 1 identity kept at raw[d2 - 1 ..]
+    const double* Ein = step == 0 ? nullptr : (left ? env + p.eoffL[t - 1] : env + p.eoffR[t + 1]);
+    for (int x = 0; x < Q; ++x) {
+      GemmItem& it = g1[(size_t)step * Q + x];
+      it = GemmItem{};
+      if (left) {   // T_x = E (dl x dl) A(x) (dl x dr)
+        it.A = Ein; it.lda = dl; it.B = At + (int64_t)x * dl * dr; it.ldb = dl; it.m = dl; it.n = dr; it.k = dl;
+      } else {      // T_x = A(x) (dl x dr) R (dr x dr)
+        it.A = At + (int64_t)x * dl * dr; it.lda = dl; it.B = Ein; it.ldb = dr; it.m = dl; it.n = dr; it.k = dr;
+      }
+      it.C = Tx + x * d2; it.ldc = dl; it.nsum = 1;
+    }
+    GemmItem& s2 = g2[step];
+    s2 = GemmItem{};
+    s2.nsum = Q;
+    if (left) {     // E' = sum_x A(x)^T T_x : A stored k x m = dl x dr (TA)
+      s2.A = At; s2.lda = dl; s2.sA = (int64_t)dl * dr; s2.B = Tx; s2.ldb = dl; s2.sB = d2; s2.m = dr; s2.n = dr; s2.k = dl; s2.ldc = dr;
+    } else {        // R' = sum_x T_x A(x)^T : B stored n x k = dl x dr (TB)
+      s2.A = Tx; s2.lda = dl; s2.sA = d2; s2.B = At; s2.ldb = dl; s2.sB = (int64_t)dl * dr; s2.m = dl; s2.n = dl; s2.k = dr; s2.ldc = dl;
+    }
+    s2.C = raw;
+    const int dn = left ? dr : dl;
+    double* slot = env + (left ? p.eoffL[t] : p.eoffR[t]);
+    sy[step] = SymItem{raw, slot, dn, step};
+    sc[step] = ScaleItem{slot, (int64_t)dn * dn, step, 0};
+  }
+  // the first step's incoming environment is the 1 x 1 identity: a device constant kept behind the max slots
+  double* one = reinterpret_cast<double*>(mx + L + 4);
+  for (int x = 0; x < Q; ++x) { GemmItem& it = g1[x]; if (left) it.A = one; else it.B = one; }
+  std::vector<unsigned char> blob(sizeof(GemmItem) * (g1.size() + g2.size()) + sizeof(SymItem) * sy.size() + sizeof(ScaleItem) * sc.size());
+  unsigned char* bp = blob.data();
+  const size_t o1 = 0, o2 = o1 + sizeof(GemmItem) * g1.size(), o3 = o2 + sizeof(GemmItem) * g2.size(), o4 = o3 + sizeof(SymItem) * sy.size();
+  memcpy(bp + o1, g1.data(), sizeof(GemmItem) * g1.size());
+  memcpy(bp + o2, g2.data(), sizeof(GemmItem) * g2.size());
+  memcpy(bp + o3, sy.data(), sizeof(SymItem) * sy.size());
+  memcpy(bp + o4, sc.data(), sizeof(ScaleItem) * sc.size());
+  unsigned char* d_blob = upload_table(h, w.mps[3], blob, e);
+  const double h_one = 1.0;
+  if (e == cudaSuccess) e = cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * (L + 4), h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(one, &h_one, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // blob / h_one are stack or local storage
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS environments: %s", cudaGetErrorString(e));
+  const GemmItem* d1 = reinterpret_cast<const GemmItem*>(d_blob + o1);
+  const GemmItem* d2i = reinterpret_cast<const GemmItem*>(d_blob + o2);
+  const SymItem* d3 = reinterpret_cast<const SymItem*>(d_blob + o3);
+  const ScaleItem* d4 = reinterpret_cast<const ScaleItem*>(d_blob + o4);
+  for (int step = 0; step < L; ++step) {
+    const int t = left ? step : L - 1 - step;
+    const int dl = p.bd[t], dr = p.bd[t + 1], dn = left ? dr : dl;
+    launch_gemm<false, false>(h, d1 + (size_t)step * Q, Q, tiles64(dl, dr));
+    if (left) launch_gemm<true, false>(h, d2i + step, 1, tiles64(dn, dn));
+    else launch_gemm<false, true>(h, d2i + step, 1, tiles64(dn, dn));
+    const unsigned gs = (unsigned)std::min<int64_t>(((int64_t)dn * dn + 255) / 256, 256);
+    TTB_LAUNCH(h, "k_mps_sym", (k_mps_sym<<<dim3(gs, 1), 256, 0, h->stream>>>(d3 + step, mx)));
+    // `Ll ./= nl` at the START of the next iteration, in place on the stored array (mps.jl:65-69): every stored
+    // environment but the last has max-abs 1
+    if (normalize && step < L - 1) TTB_LAUNCH(h, "k_mps_scale", (k_mps_scale<<<dim3(gs, 1), 256, 0, h->stream>>>(d4 + step, mx)));
+  }
+  if (d_zout) {
+    const double* last = env + (left ? p.eoffL[L - 1] : p.eoffR[0]);   // 1 x 1: its trace is the value
+    TTB_LAUNCH(h, "k_mps_final", (k_mps_final<<<1, 32, 0, h->stream>>>(mx, normalize ? L - 1 : 0, last, d_zout)));
+  }
+  return TTB_OK;
+}
+
+// S_t(x) = A_t(x) r_{t+1} A_t(x)^T for all (t, x) into mps[5] (U in mps[6]); r must be in mps[1]
+static int mps_sandwich_R(ttb_tt* h, const MpsPlan& p) {
+  Workspace& w = h->ws;
+  const int L = p.L, Q = p.Q;
+  cudaError_t e = w.mps[5].ensure(sizeof(double) * std::max<int64_t>(p.soff[L], 1));
+  if (e == cudaSuccess) e = w.mps[6].ensure(sizeof(double) * std::max<int64_t>(p.uoff[L], 1));
+  if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS sandwiches: %s", cudaGetErrorString(e));
+  double* S = static_cast<double*>(w.mps[5].p);
+  double* U = static_cast<double*>(w.mps[6].p);
+  const double* r = static_cast<const double*>(w.mps[1].p);
+  const double* one = reinterpret_cast<const double*>(static_cast<unsigned long long*>(w.mps[4].p) + L + 4);
+  std::vector<GemmItem> g((size_t)2 * L * Q);
+  unsigned tu = 1, ts = 1;
+  for (int t = 0; t < L; ++t) {
+    const int dl = p.bd[t], dr = p.bd[t + 1];
+    for (int x = 0; x < Q; ++x) {
+      const double* Ax = p.tt + h->off[t] + (int64_t)x * dl * dr;
+      GemmItem& a = g[(size_t)t * Q + x];
+      a = GemmItem{};
+      a.A = Ax; a.lda = dl; a.B = t < L - 1 ? r + p.eoffR[t + 1] : one; a.ldb = dr; a.m = dl; a.n = dr; a.k = dr;
+      a.C = U + p.uoff[t] + (int64_t)x * dl * dr; a.ldc = dl; a.nsum = 1;
+      GemmItem& b = g[(size_t)L * Q + (size_t)t * Q + x];
+      b = GemmItem{};
+      b.A = a.C; b.lda = dl; b.B = Ax; b.ldb = dl; b.m = dl; b.n = dl; b.k = dr;
+      b.C = S + p.soff[t] + (int64_t)x * dl * dl; b.ldc = dl; b.nsum = 1;
+      tu = std::max(tu, tiles64(dl, dr)); ts = std::max(ts, tiles64(dl, dl));
+    }
+  }
+  GemmItem* dg = upload_table(h, w.mps[7], g, e);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS sandwiches: %s", cudaGetErrorString(e));
+  launch_gemm<false, false>(h, dg, L * Q, tu);
+  launch_gemm<false, true>(h, dg + (size_t)L * Q, L * Q, ts);
+  return TTB_OK;
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_mps_env_size(ttb_handle h, int64_t b, int left, int64_t* n_doubles) {
+  if (!n_doubles) return fail(TTB_EINVAL, "null argument");
+  MpsPlan p;
+  TTB_TRY(mps_plan(h, b, p));
+  *n_doubles = left ? p.eoffL[p.L] : p.eoffR[p.L];
+  return TTB_OK;
+}
+
+int ttb_mps_accumulate(ttb_handle h, int64_t b, int left, int normalize, double* env_out, double* logabs, int* sign) {
+  MpsPlan p;
+  TTB_TRY(mps_plan(h, b, p));
+  Workspace& w = h->ws;
+  if (w.mps[8].ensure(256) != cudaSuccess) return fail(TTB_ENOMEM, "MPS outputs");
+  double* d_z = static_cast<double*>(w.mps[8].p);
+  CallTimer tm(h);
+  int rc = mps_env(h, p, left != 0, normalize, d_z);
+  if (rc == TTB_OK) rc = tm.finish();
+  if (rc != TTB_OK) return rc;
+  double hz[2];
+  TTB_CUDA(cudaMemcpy(hz, d_z, sizeof(hz), cudaMemcpyDeviceToHost));
+  if (logabs) *logabs = hz[0];
+  if (sign) *sign = hz[1] < 0.0 ? -1 : 1;
+  if (env_out) TTB_CUDA(cudaMemcpy(env_out, w.mps[left ? 0 : 1].p, sizeof(double) * (left ? p.eoffL[p.L] : p.eoffR[p.L]), cudaMemcpyDefault));
+  return TTB_OK;
+}
+
+int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) {
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  MpsPlan p;
+  TTB_TRY(mps_plan(h, b, p));
+  Workspace& w = h->ws;
+  const int L = p.L, Q = p.Q;
+  if (w.mps[8].ensure(sizeof(double) * ((size_t)L * Q + 32)) != cudaSuccess) return fail(TTB_ENOMEM, "MPS outputs");
+  double* d_p = static_cast<double*>(w.mps[8].p) + 32;
+  CallTimer tm(h);
+  int rc = mps_env(h, p, true, 1, nullptr);
+  if (rc == TTB_OK) rc = mps_env(h, p, false, 1, nullptr);
+  if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
+  if (rc != TTB_OK) return rc;
+  const double* l = static_cast<const double*>(w.mps[0].p);
+  const double* S = static_cast<const double*>(w.mps[5].p);
+  const double* one = reinterpret_cast<const double*>(static_cast<unsigned long long*>(w.mps[4].p) + L + 4);
+  std::vector<FrobItem> f((size_t)L * Q);
+  for (int t = 0; t < L; ++t)
+    for (int x = 0; x < Q; ++x)
+      f[(size_t)t * Q + x] = FrobItem{t > 0 ? l + p.eoffL[t - 1] : one, S + p.soff[t] + (int64_t)x * p.bd[t] * p.bd[t], d_p + (size_t)t * Q + x,
+                                      (int64_t)p.bd[t] * p.bd[t]};
+  cudaError_t e = cudaSuccess;
+  FrobItem* df = upload_table(h, w.mps[9], f, e);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS marginals: %s", cudaGetErrorString(e));
+  TTB_LAUNCH(h, "k_mps_frob", (k_mps_frob<<<(unsigned)(L * Q), 256, 0, h->stream>>>(df)));
+  rc = tm.finish();
+  if (rc != TTB_OK) return rc;
+  std::vector<double> hp((size_t)L * Q);
+  TTB_CUDA(cudaMemcpy(hp.data(), d_p, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost));
+  for (int t = 0; t < L; ++t) {     // p ./= sum(p)  (mps.jl:190)
+    double s = 0.0;
+    for (int x = 0; x < Q; ++x) s += hp[(size_t)t * Q + x];
+    for (int x = 0; x < Q; ++x) out[(size_t)t * Q + x] = hp[(size_t)t * Q + x] / s;
+  }
+  return TTB_OK;
+}
+
+int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* out) {
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  MpsPlan p;
+  TTB_TRY(mps_plan(h, b, p));
+  Workspace& w = h->ws;
+  const int L = p.L, Q = p.Q;
+  if (maxdist <= 0 || maxdist > L - 1) maxdist = L - 1;
+  std::vector<int64_t> poff(L + 1, 0);
+  for (int t = 0; t < L - 1; ++t) poff[t + 1] = poff[t] + (std::min<int64_t>(L - 1, t + maxdist) - t);
+  const int64_t npairs = poff[L - 1];
+  if (npairs == 0) return TTB_OK;
+  const int64_t d2 = (int64_t)p.dmax * p.dmax;
+  cudaError_t e = w.mps[8].ensure(sizeof(double) * ((size_t)npairs * Q * Q + 32));
+  // K (current, raw) for every (t, x), T for every (t, x, y)
+  if (e == cudaSuccess) e = w.mps[2].ensure(sizeof(double) * (size_t)L * Q * d2 * (2 + Q));
+  if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS pair marginals: %s", cudaGetErrorString(e));
+  double* d_out = static_cast<double*>(w.mps[8].p) + 32;
+  CallTimer tm(h);
+  int rc = mps_env(h, p, true, 1, nullptr);
+  if (rc == TTB_OK) rc = mps_env(h, p, false, 1, nullptr);
+  if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
+  if (rc != TTB_OK) return rc;
+  // (mps_env used mps[2] as its temporary: it is free again from here)
+  double* K = static_cast<double*>(w.mps[2].p);
+  double* Kraw = K + (size_t)L * Q * d2;
+  double* Tm = Kraw + (size_t)L * Q * d2;
+  const double* l = static_cast<const double*>(w.mps[0].p);
+  const double* S = static_cast<const double*>(w.mps[5].p);
+  unsigned long long* mx = static_cast<unsigned long long*>(w.mps[4].p);   // slots 0 .. L-1 reused per distance
+  const double* one = reinterpret_cast<const double*>(mx + L + 4);
+  auto Kp = [&](double* base, int t, int x) { return base + ((size_t)t * Q + x) * d2; };
+  auto Tp = [&](int t, int x, int y) { return Tm + (((size_t)t * Q + x) * Q + y) * d2; };
+  // ---- tables for all distances, one upload ----
+  std::vector<GemmItem> gi;
+  std::vector<SymItem> si;
+  std::vector<ScaleItem> ci;
+  std::vector<FrobItem> fi;
+  struct Step { size_t g1, n1, g2, n2, s, ns, f, nf; unsigned t1, t2; };
+  std::vector<Step> steps;
+  // distance 0 -> 1: K_{t,t+1}(x) = A_t(x)^T l_{t-1} A_t(x)
+  {
+    Step st{}; st.g1 = gi.size(); st.t1 = 1; st.t2 = 1;
+    for (int t = 0; t < L - 1; ++t)
+      for (int x = 0; x < Q; ++x) {
+        const int dl = p.bd[t], dr = p.bd[t + 1];
+        GemmItem a{};
+        a.A = t > 0 ? l + p.eoffL[t - 1] : one; a.lda = dl; a.B = p.tt + h->off[t] + (int64_t)x * dl * dr; a.ldb = dl;
+        a.m = dl; a.n = dr; a.k = dl; a.C = Tp(t, x, 0); a.ldc = dl; a.nsum = 1;
+        gi.push_back(a); st.t1 = std::max(st.t1, tiles64(dl, dr));
+      }
+    st.n1 = gi.size() - st.g1; st.g2 = gi.size();
+    for (int t = 0; t < L - 1; ++t)
+      for (int x = 0; x < Q; ++x) {
+        const int dl = p.bd[t], dr = p.bd[t + 1];
+        GemmItem a{};
+        a.A = p.tt + h->off[t] + (int64_t)x * dl * dr; a.lda = dl; a.B = Tp(t, x, 0); a.ldb = dl;
+        a.m = dr; a.n = dr; a.k = dl; a.C = Kp(K, t, x); a.ldc = dr; a.nsum = 1;
+        gi.push_back(a); st.t2 = std::max(st.t2, tiles64(dr, dr));
+      }
+    st.n2 = gi.size() - st.g2;
+    steps.push_back(st);
+  }
+  for (int64_t dist = 1; dist <= maxdist; ++dist) {
+    Step st{}; st.t1 = 1; st.t2 = 1;
+    st.f = fi.size();
+    for (int t = 0; t + dist <= L - 1; ++t) {
+      const int u = t + (int)dist, du = p.bd[u];
+      for (int x = 0; x < Q; ++x)
+        for (int y = 0; y < Q; ++y)
+          fi.push_back(FrobItem{Kp(K, t, x), S + p.soff[u] + (int64_t)y * du * du, d_out + (poff[t] + dist - 1) * Q * Q + x + (size_t)Q * y,
+                                (int64_t)du * du});
+    }
+    st.nf = fi.size() - st.f;
+    st.g1 = gi.size();
+    if (dist < maxdist) {
+      for (int t = 0; t + dist + 1 <= L - 1; ++t) {
+        const int u = t + (int)dist, du = p.bd[u], dn = p.bd[u + 1];
+        for (int x = 0; x < Q; ++x)
+          for (int y = 0; y < Q; ++y) {
+            GemmItem a{};
+            a.A = Kp(K, t, x); a.lda = du; a.B = p.tt + h->off[u] + (int64_t)y * du * dn; a.ldb = du;
+            a.m = du; a.n = dn; a.k = du; a.C = Tp(t, x, y); a.ldc = du; a.nsum = 1;
+            gi.push_back(a); st.t1 = std::max(st.t1, tiles64(du, dn));
+          }
+      }
+      st.n1 = gi.size() - st.g1; st.g2 = gi.size(); st.s = si.size();
+      for (int t = 0; t + dist + 1 <= L - 1; ++t) {
+        const int u = t + (int)dist, du = p.bd[u], dn = p.bd[u + 1];
+        for (int x = 0; x < Q; ++x) {
+          GemmItem a{};
+          a.A = p.tt + h->off[u]; a.lda = du; a.sA = (int64_t)du * dn; a.B = Tp(t, x, 0); a.ldb = du; a.sB = d2;
+          a.m = dn; a.n = dn; a.k = du; a.C = Kp(Kraw, t, x); a.ldc = dn; a.nsum = Q;
+          gi.push_back(a); st.t2 = std::max(st.t2, tiles64(dn, dn));
+          si.push_back(SymItem{Kp(Kraw, t, x), Kp(K, t, x), dn, t});
+          ci.push_back(ScaleItem{Kp(K, t, x), (int64_t)dn * dn, t, 0});
+        }
+      }
+      st.n2 = gi.size() - st.g2; st.ns = si.size() - st.s;
+    }
+    steps.push_back(st);
+  }
+  GemmItem* dg = nullptr; SymItem* ds = nullptr; ScaleItem* dc = nullptr; FrobItem* df = nullptr;
+  {
+    const size_t bg = sizeof(GemmItem) * gi.size(), bs = sizeof(SymItem) * si.size(), bc = sizeof(ScaleItem) * ci.size(), bf = sizeof(FrobItem) * fi.size();
+    std::vector<unsigned char> blob(bg + bs + bc + bf + 64);
+    memcpy(blob.data(), gi.data(), bg);
+    memcpy(blob.data() + bg, si.data(), bs);
+    memcpy(blob.data() + bg + bs, ci.data(), bc);
+    memcpy(blob.data() + bg + bs + bc, fi.data(), bf);
+    unsigned char* d_blob = upload_table(h, w.mps[9], blob, e);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS pair marginals: %s", cudaGetErrorString(e));
+    dg = reinterpret_cast<GemmItem*>(d_blob); ds = reinterpret_cast<SymItem*>(d_blob + bg);
+    dc = reinterpret_cast<ScaleItem*>(d_blob + bg + bs); df = reinterpret_cast<FrobItem*>(d_blob + bg + bs + bc);
+  }
+  const unsigned gsz = (unsigned)std::min<int64_t>((d2 + 255) / 256, 64);
+  for (size_t i = 0; i < steps.size(); ++i) {
+    const Step& st = steps[i];
+    if (i == 0) {
+      launch_gemm<false, false>(h, dg + st.g1, (int)st.n1, st.t1);
+      launch_gemm<true, false>(h, dg + st.g2, (int)st.n2, st.t2);
+      continue;
+    }
+    if (st.nf) TTB_LAUNCH(h, "k_mps_frob", (k_mps_frob<<<(unsigned)st.nf, 256, 0, h->stream>>>(df + st.f)));
+    if (st.n1) {
+      launch_gemm<false, false>(h, dg + st.g1, (int)st.n1, st.t1);
+      launch_gemm<true, false>(h, dg + st.g2, (int)st.n2, st.t2);
+      cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * L, h->stream);
+      // (K_tu(x) + K_tu(x)^T) / 2 like accumulate_M (mps.jl:118); one common scale per first site keeps b_tu exact
+      TTB_LAUNCH(h, "k_mps_sym", (k_mps_sym<<<dim3(gsz, (unsigned)st.ns), 256, 0, h->stream>>>(ds + st.s, mx)));
+      TTB_LAUNCH(h, "k_mps_scale", (k_mps_scale<<<dim3(gsz, (unsigned)st.ns), 256, 0, h->stream>>>(dc + st.s, mx)));
+    }
+  }
+  rc = tm.finish();
+  if (rc != TTB_OK) return rc;
+  TTB_CUDA(cudaMemcpy(out, d_out, sizeof(double) * npairs * Q * Q, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < npairs; ++i) {   // b ./= sum(b)  (mps.jl:227)
+    double s = 0.0;
+    for (int j = 0; j < Q * Q; ++j) s += out[i * Q * Q + j];
+    for (int j = 0; j < Q * Q; ++j) out[i * Q * Q + j] /= s;
+  }
+  return TTB_OK;
+}
+
+int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index, const double* uniforms,
+                   uint8_t* x_out, double* p_out) {
+  if (!x_out) return fail(TTB_EINVAL, "null x_out");
+  if (nsamples < 0) return fail(TTB_EINVAL, "nsamples must be >= 0");
+  if (nsamples == 0) return TTB_OK;
+  MpsPlan p;
+  TTB_TRY(mps_plan(h, b, p));
+  if (p.Q > 256) return fail(TTB_EUNSUPPORTED, "sample supports Q <= 256 (uint8 output)");
+  Workspace& w = h->ws;
+  const int L = p.L;
+  cudaError_t e = w.mps[8].ensure(sizeof(double) * ((size_t)nsamples * (uniforms ? L + 1 : 1) + 32) + (size_t)nsamples * L + 64);
+  if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS sample buffers: %s", cudaGetErrorString(e));
+  double* d_z = static_cast<double*>(w.mps[8].p);
+  double* d_pq = d_z + 32;
+  double* d_u = uniforms ? d_pq + nsamples : nullptr;
+  uint8_t* d_x = reinterpret_cast<uint8_t*>(d_pq + nsamples + (uniforms ? (size_t)nsamples * L : 0));
+  if (uniforms) TTB_CUDA(cudaMemcpyAsync(d_u, uniforms, sizeof(double) * nsamples * L, cudaMemcpyHostToDevice, h->stream));
+  CallTimer tm(h);
+  int rc = mps_env(h, p, false, 1, d_z);          // rz = accumulate_R(p) (mps.jl:265)
+  if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
+  if (rc != TTB_OK) return rc;
+  std::vector<int64_t> tab(3 * (L + 1));
+  for (int t = 0; t <= L; ++t) { tab[t] = h->off[t]; tab[L + 1 + t] = p.soff[t]; tab[2 * (L + 1) + t] = p.bd[t]; }
+  int64_t* d_tab = upload_table(h, w.mps[9], tab, e);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS sample: %s", cudaGetErrorString(e));
+  MpsSampCtx c{};
+  c.slab = h->slab; c.tt_off = b * h->tt_stride; c.off = d_tab; c.bond = d_tab + 2 * (L + 1); c.L = L; c.Q = p.Q; c.dmax = p.dmax;
+  c.S = static_cast<const double*>(w.mps[5].p); c.soff = d_tab + L + 1; c.zlog = d_z;
+  c.uniforms = d_u; c.seed = seed; c.first = first_index; c.x_out = d_x; c.p_out = p_out ? d_pq : nullptr; c.nsamples = nsamples;
+  const size_t smem = sizeof(double) * (2 * (size_t)p.dmax + p.Q + 8);
+  if (smem > 48 * 1024) return fail(TTB_EUNSUPPORTED, "MPS sample: bond dimension too large for the one-CTA-per-draw kernel");
+  TTB_LAUNCH(h, "k_mps_sample", (k_mps_sample<<<(unsigned)nsamples, 128, smem, h->stream>>>(c)));
+  rc = tm.finish();
+  if (rc != TTB_OK) return rc;
+  TTB_CUDA(cudaMemcpy(x_out, d_x, (size_t)nsamples * L, cudaMemcpyDeviceToHost));
+  if (p_out) TTB_CUDA(cudaMemcpy(p_out, d_pq, sizeof(double) * nsamples, cudaMemcpyDeviceToHost));
+  return TTB_OK;
+}
+
+}  // extern "C"

@@ -17,25 +17,7 @@
 
 namespace ttb {
 
-// ---- Philox4x32-10 ---------------------------------------------------------------------------
-__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
-                                             uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-  const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-  c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-}
-__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t sample, uint32_t site) {
-  uint32_t c0 = (uint32_t)sample, c1 = (uint32_t)(sample >> 32), c2 = site, c3 = 0u;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    philox_round(c0, c1, c2, c3, k0, k1);
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  const uint64_t bits = ((uint64_t)c0 << 21) ^ ((uint64_t)c1 >> 11);
-  return (double)bits * (1.0 / 9007199254740992.0);
-}
+// (Philox4x32-10: common.cuh, shared with mps.cu)
 
 // ---- evaluate: one CTA per query point ------------------------------------------------------
 struct EvalCtx {

@@ -115,6 +115,11 @@ _sig("ttb_upload_all_async", _h, _pd)
 _sig("ttb_reset", _h)
 _sig("ttb_trim", _h)
 _sig("ttb_dot", _h, _i64, _h, _i64, _pd, _pi)
+_sig("ttb_mps_env_size", _h, _i64, C.c_int, _pi64)
+_sig("ttb_mps_accumulate", _h, _i64, C.c_int, C.c_int, _pd, _pd, _pi)
+_sig("ttb_mps_marginals", _h, _i64, _pd)
+_sig("ttb_mps_twovar_marginals", _h, _i64, _i64, _pd)
+_sig("ttb_mps_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
 _sig("ttb_last_timing", _h, _pd, _pi64)
 _sig("ttb_profile", _h, C.c_int)
 _sig("ttb_profile_report", _h, C.c_char_p, C.c_size_t)
@@ -1017,16 +1022,78 @@ def mps_orthogonalize_right_(p: MPS, svd_trunc=None):
     return p
 
 
-def _mps_not_built(name):
-    def f(p, *a, **k):
-        raise NotImplementedError(f"{name}(::MPS): the d^4 environments of mps.jl:60-126 are not built on the device yet")
-    f.__name__ = name
-    return f
+def _mps_accumulate(p: MPS, left: bool, normalize: bool):
+    A = p.psi
+    n = _i64()
+    _ck(lib.ttb_mps_env_size(A._hd, 0, int(left), C.byref(n)))
+    buf = np.zeros(max(n.value, 1))
+    la, sg = C.c_double(), C.c_int()
+    _ck(lib.ttb_mps_accumulate(A._hd, 0, int(left), int(bool(normalize)), _dp(buf), C.byref(la), C.byref(sg)))
+    bd = [int(v) for v in A.bonds(0)]
+    envs, o = [], 0
+    for t in range(A.L):
+        d = bd[t + 1] if left else bd[t]
+        # the reference's four-index array [a1, a, b1, b] of an open train: a1 = b1 = 1
+        envs.append(buf[o:o + d * d].reshape((d, d), order="F").reshape((1, d, 1, d) if left else (d, 1, d, 1)).copy())
+        o += d * d
+    return envs, Logarithmic(logabs=la.value, sign=sg.value)
 
 
-mps_marginals = _mps_not_built("marginals")
-mps_twovar_marginals = _mps_not_built("twovar_marginals")
-mps_sample = _mps_not_built("sample")
+def mps_accumulate_L(p: MPS, normalize: bool = True):
+    """``accumulate_L(p::MPS)`` (mps.jl:60-80): ``(l, z)``; ``l[t]`` indexed ``[a1, a_{t+1}, b1, b_{t+1}]`` (open psi:
+    ``a1 = b1 = 1``), hermiticity restored after every step, every ``l[t < L]`` max-abs 1 with ``normalize``."""
+    return _mps_accumulate(p, True, normalize)
+
+
+def mps_accumulate_R(p: MPS, normalize: bool = True):
+    """``accumulate_R(p::MPS)`` (mps.jl:82-103): ``(r, z)``; ``r[t]`` indexed ``[a_t, aL, b_t, bL]`` -- for an open psi
+    ``aL = bL = 1``, shape ``(d, 1, d, 1)``."""
+    return _mps_accumulate(p, False, normalize)
+
+
+def mps_marginals(p: MPS):
+    """``marginals(p::MPS)`` (mps.jl:176-196): list over sites of arrays shaped ``q``"""
+    A = p.psi
+    out = np.zeros((A.L, A.Q))
+    _ck(lib.ttb_mps_marginals(A._hd, 0, _dp(out)))
+    return [out[t].reshape(A.q, order="F") for t in range(A.L)]
+
+
+def mps_twovar_marginals(p: MPS, maxdist: Optional[int] = None):
+    """``twovar_marginals(p::MPS)`` (mps.jl:206-232): dict ``(t, u) -> (q..., q...)`` array, 0-based ``t < u <= t + maxdist``"""
+    A = p.psi
+    md = A.L - 1 if maxdist is None else int(maxdist)
+    n = _i64()
+    _ck(lib.ttb_twovar_count(A._hd, md, C.byref(n)))
+    out = np.zeros((max(n.value, 1), A.Q * A.Q))
+    if n.value:
+        _ck(lib.ttb_mps_twovar_marginals(A._hd, 0, md, _dp(out)))
+    d, i = {}, 0
+    for t in range(A.L - 1):
+        for u in range(t + 1, min(A.L - 1, t + md) + 1):
+            d[(t, u)] = out[i].reshape(A.q + A.q, order="F")
+            i += 1
+    return d
+
+
+def mps_sample(p: MPS, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None):
+    """``sample(p::MPS)`` (mps.jl:264-290, 300-313): ``(X, q)`` like :func:`sample`; ``q = |tr Q|^2 / z``"""
+    A = p.psi
+    single = nsamples is None and uniforms is None
+    if uniforms is not None:
+        uniforms = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(-1, A.L))
+        n = uniforms.shape[0]
+    else:
+        n = 1 if nsamples is None else int(nsamples)
+    X = np.zeros((max(n, 1), A.L), dtype=np.uint8)
+    q = np.zeros(max(n, 1))
+    _ck(lib.ttb_mps_sample(A._hd, 0, n, seed, first_index, _dp(uniforms) if uniforms is not None else None,
+                           X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(q)))
+    if single:
+        return X[0].astype(np.int64), float(q[0])
+    return X[:n].astype(np.int64), q[:n]
+
 
 __all__ += ["MPS", "mps_evaluate", "mps_normalization", "mps_normalize_", "mps_compress_", "mps_orthogonalize_left_",
-            "mps_orthogonalize_right_"]
+            "mps_orthogonalize_right_", "mps_accumulate_L", "mps_accumulate_R", "mps_marginals", "mps_twovar_marginals",
+            "mps_sample"]

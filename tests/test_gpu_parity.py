@@ -743,8 +743,84 @@ def test_mps_wrapper_matches_oracle(z):
     one = T.mps_normalization(p)
     assert abs(one.logabs) <= 1e-12 and one.sign == 1
     assert close(T.mps_evaluate(p, X), O.mps_evaluate(po, X), 1e-9)
+
+
+def _mps_case(name, rng):
+    if name == "ref":                   # test/mps.jl:14-15 (real Float64)
+        shapes = [(1, 5, 2, 2), (5, 4, 2, 2), (4, 10, 2, 2), (10, 1, 2, 2)]
+    elif name == "wide":                # bonds above one 64 x 64 GEMM tile, ragged, Q = 3
+        shapes = [(1, 4, 3), (4, 66, 3), (66, 70, 3), (70, 5, 3), (5, 3, 3), (3, 1, 3)]
+    else:                               # long chain: the per-step rescaling matters
+        shapes = [(1, 6, 2)] + [(6, 6, 2)] * 28 + [(6, 1, 2)]
+    return [rng.standard_normal(s) for s in shapes]
+
+
+@pytest.mark.parametrize("case", ["ref", "wide", "long"])
+def test_mps_environments_marginals_sampling_match_oracle(case):
+    """accumulate_L/R(::MPS) stored, marginals, twovar_marginals, sample! (src/MatrixProductStates/mps.jl:60-126,
+    176-232, 264-290) against the oracle; brute force on the reference's own test case (test/mps.jl:31-33)."""
+    rng = RNG(970)
+    ts = _mps_case(case, rng)
+    psi, psio = pair(ts)
+    p, po = T.MPS(psi), O.MPS(psio)
+    for normalize in (True, False) if case != "long" else (True,):
+        for fg, fo in ((T.mps_accumulate_L, O.mps_accumulate_L), (T.mps_accumulate_R, O.mps_accumulate_R)):
+            eg, zg = fg(p, normalize)
+            eo, zo = fo(po, normalize)
+            assert zg.sign == zo.sign and close(zg.logabs, zo.logabs, 1e-10, 1e-12)
+            for a, b in zip(eg, eo):
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-10, atol=1e-12 * np.abs(b).max())
+    zn = T.mps_normalization(p)
+    zL = T.mps_accumulate_L(p)[1]
+    assert close(zn.logabs, zL.logabs, 1e-10, 1e-12)            # z / abs2(psi.z), psi.z = 1
+    for a, b in zip(T.mps_marginals(p), O.mps_marginals(po)):
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-10, atol=1e-13)
+    bo = O.mps_twovar_marginals(po)
+    bg = T.mps_twovar_marginals(p)
+    assert set(bg) == set(bo)
+    for k in bo:
+        assert np.allclose(bg[k], bo[k], rtol=1e-9, atol=1e-12), k
+    b3 = T.mps_twovar_marginals(p, maxdist=2)
+    assert set(b3) == {k for k in bo if k[1] - k[0] <= 2} and all(np.array_equal(b3[k], bg[k]) for k in b3)
+    if case == "ref":                   # exact_marginals / exact_twovar_marginals (test/exact.jl)
+        qq = O.mps_exact_prob(po).reshape([4] * 4)
+        mg = T.mps_marginals(p)
+        for t in range(4):
+            pt = qq.sum(axis=tuple(i for i in range(4) if i != t))
+            assert np.allclose(pt / pt.sum(), mg[t].reshape(-1, order="F"), rtol=1e-10, atol=0)
+        for (t, u), b in bg.items():
+            ptu = qq.sum(axis=tuple(i for i in range(4) if i not in (t, u)))
+            assert np.allclose(ptu / ptu.sum(), b.reshape(4, 4, order="F"), rtol=1e-10, atol=0)
+    n = 24
+    us = rng.random((n, len(ts)))
+    X, qg = T.mps_sample(p, uniforms=us)
+    zR = O.mps_accumulate_R(po)
+    for i in range(n):
+        xo, qo = O.mps_sample(lambda t: us[i, t], po, rz=zR)
+        flat = [int(np.ravel_multi_index(x, psi.q, order="F")) for x in xo]
+        assert list(X[i]) == flat and close(qg[i], qo, 1e-9)
+    X1, q1 = T.mps_sample(p, 300, seed=5)
+    X2, q2 = T.mps_sample(p, 100, seed=5, first_index=200)
+    assert np.array_equal(X1[200:], X2) and np.allclose(q1[200:], q2, rtol=1e-13)     # Philox counter = global draw index
+
+
+def test_mps_orthogonal_environments_and_unsupported():
+    """test/mps.jl:71-80: after orthogonalize_left!/right! the unnormalised environments are identities;
+    a periodic psi is refused loudly (no CPU path)."""
+    rng = RNG(971)
+    psi, _ = pair(_mps_case("ref", rng))
+    p = T.MPS(psi)
+    T.mps_orthogonalize_left_(p, T.TruncThresh(0.0))
+    for l in T.mps_accumulate_L(p, False)[0][:-1]:
+        d = l.shape[1]
+        assert np.allclose(l.reshape(d, d), np.eye(d), atol=1e-10)
+    T.mps_orthogonalize_right_(p, T.TruncThresh(0.0))
+    for r in T.mps_accumulate_R(p, False)[0][1:]:
+        d = r.shape[0]
+        assert np.allclose(r.reshape(d, d), np.eye(d), atol=1e-10)
+    per, _ = pair(rand_per(rng, [3, 4, 3], (2,)), periodic=True)
     with pytest.raises(NotImplementedError):
-        T.mps_marginals(p)
+        T.mps_marginals(T.MPS(per))
 
 
 @pytest.mark.parametrize("case", ["open_d40", "periodic_d20", "batched"])
