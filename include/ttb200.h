@@ -93,6 +93,9 @@ int ttb_upload_all_async(ttb_handle h, const double* host);
 /* bond dimensions back to the ones the handle was created with, z = 1: reuse the slab and the workspaces
  * for the next train of the same shape */
 int ttb_reset(ttb_handle h);
+/* the bond dimensions the handle was created with (L+1 entries): sweeps only shrink bonds, storage and every
+ * stride derived from it keep this capacity (src/tensor_train.jl:8-24 has no such notion: Julia reallocates) */
+int ttb_get_capacity_bonds(ttb_handle h, int64_t* out);
 /* sample / twovar_marginals / dot keep their device scratch on the handle between calls (grow-only: a
  * cudaFree of a few hundred MB costs up to hundreds of ms of wall clock); this releases it */
 int ttb_trim(ttb_handle h);
@@ -220,6 +223,26 @@ int ttb_mps_marginals(ttb_handle h, int64_t b, double* out);
 int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* out);
 int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index, const double* uniforms,
                    uint8_t* x_out, double* p_out);
+
+/* ---- two-site pieces (the data-parallel parts of 2-site DMRG, src/dmrg.jl:59-151; the optimisation loop itself is
+ *      host control flow and not part of the library).  `t` is the 0-based index of the first site of the pair.
+ *  ttb_merge_tensors (_merge_tensors, src/utils.jl:37-44): out[m, n, xA, xB] = sum_k A_t[m,k,xA] A_{t+1}[k,n,xB],
+ *      d_t x d_{t+2} x Q x Q column-major; `out` may be host or device memory.
+ *  ttb_split_tensor (_split_tensor, src/abstract_tensor_train.jl:283-308): SVD of C[(al,xl),(al1,xl1)] under `tr`,
+ *      left != 0: A_t = U, A_{t+1} = L V' (lr = Left()); left == 0: A_t = U L, A_{t+1} = V' (lr = Right()); the
+ *      sites and the bond between them are replaced in place (z is untouched).  The new bond must fit the capacity
+ *      the handle was created with at that bond (TTB_EUNSUPPORTED otherwise).  *trunc_err (nullable) receives the
+ *      relative truncation error of the step (what TruncBondMax records).
+ *  ttb_data_environments (precompute_left_environments / precompute_right_environments, src/tensor_train.jl:320-334):
+ *      X is n x L flat 0-based indices; env[i][j][0 .. d_j) for j = 0..L with a stride of max(bond capacity) doubles
+ *      per entry: left != 0: entry j = A_0(x_0)...A_{j-1}(x_{j-1}) (entry 0 = [1]); left == 0: entry j =
+ *      A_j(x_j)...A_{L-1}(x_{L-1}) (entry L = [1]).  `env` may be host or device memory.
+ *  ttb_data_env_update (update_environments!, src/dmrg.jl:124-151): after site t changed, left != 0: entry t+1 =
+ *      entry t * A_t(x_t); left == 0: entry t = A_t(x_t) * entry t+1, for every datapoint, in place. */
+int ttb_merge_tensors(ttb_handle h, int64_t b, int64_t t, double* out);
+int ttb_split_tensor(ttb_handle h, int64_t b, int64_t t, const double* C, const ttb_trunc* tr, int left, double* trunc_err);
+int ttb_data_environments(ttb_handle h, int64_t b, const int32_t* X, int64_t n, int left, double* env);
+int ttb_data_env_update(ttb_handle h, int64_t b, const int32_t* X, int64_t n, int64_t t, int left, double* env);
 
 /* ---- dot (src/abstract_tensor_train.jl:395-408) of train ba of `a` with train bb of `b` (same length and
  * physical dimension, same device; open or periodic, bonds may differ).  The value is returned as

@@ -785,6 +785,70 @@ def isapprox(A, B, atol=0.0, rtol=1e-6) -> bool:
 
 
 # ----------------------------------------------------------------------------------------------
+# two-site pieces (2-site DMRG building blocks): src/utils.jl:37-44, src/abstract_tensor_train.jl:283-308,
+# src/tensor_train.jl:320-334, src/dmrg.jl:124-151
+# ----------------------------------------------------------------------------------------------
+def merge_tensors(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """``_merge_tensors`` (``utils.jl:37-44``): ``C[m,n,xA...,xB...] = sum_k A[m,k,xA] B[k,n,xB]``"""
+    sA, sB = A.shape[2:], B.shape[2:]
+    assert len(sA) == len(sB)
+    C = np.einsum("mka,knb->mnab", _reshape1(A), _reshape1(B))
+    return C.reshape((C.shape[0], C.shape[1]) + tuple(sA) + tuple(sB), order="F")
+
+
+def split_tensor(C: np.ndarray, svd_trunc: Optional[SVDTrunc] = None, lr: str = "left"):
+    """``_split_tensor`` (``abstract_tensor_train.jl:283-308``): ``C_resh[(al,xl),(al1,xl1)] = U L V'``;
+    ``lr="left"``: ``A = U, B = L V'``; ``lr="right"``: ``A = U L, B = V'``"""
+    svd_trunc = TruncThresh(0.0) if svd_trunc is None else svd_trunc
+    sC = C.shape[2:]
+    h = len(sC) // 2
+    sA, sB = sC[:h], sC[h:]
+    qa, qb = int(np.prod(sA)), int(np.prod(sB))
+    Cr = C.reshape((C.shape[0], C.shape[1], qa, qb), order="F")
+    # (al, xl) with al fastest, (al1, xl1) with al1 fastest (TensorCast)
+    M = np.transpose(Cr, (0, 2, 1, 3)).reshape((C.shape[0] * qa, C.shape[1] * qb), order="F")
+    U, lam, V = svd_trunc(M)
+    if lr == "left":
+        Ar, Br = U, lam[:, None] * V.T
+    else:
+        Ar, Br = U * lam[None, :], V.T
+    m = len(lam)
+    A = Ar.reshape((C.shape[0], qa, m), order="F").transpose(0, 2, 1)          # A_[i,j,x] = A_resh[(i,x),j]
+    B = Br.reshape((m, C.shape[1], qb), order="F")                             # B_[i,j,x] = B_resh[i,(j,x)]
+    return (np.ascontiguousarray(A).reshape((C.shape[0], m) + tuple(sA), order="F"),
+            np.ascontiguousarray(B).reshape((m, C.shape[1]) + tuple(sB), order="F"))
+
+
+def precompute_left_environments(A, X):
+    """``tensor_train.jl:320-326``: list indexed 0..L, entry j = ``A_1(x_1)...A_j(x_j)`` (entry 0 = ones(1,1))"""
+    out = [np.ones((1, 1))]
+    for Ak, xk in zip(A.tensors, X):
+        out.append(out[-1] @ Ak[(slice(None), slice(None)) + tuple(xk)])
+    return out
+
+
+def precompute_right_environments(A, X):
+    """``tensor_train.jl:328-334``: list indexed 0..L, entry j = ``A_{j+1}(x_{j+1})...A_L(x_L)`` (the reference's
+    ``prodA_right[j+1]``; entry L = ones(1,1))"""
+    out = [np.ones((1, 1))]
+    for Ak, xk in zip(reversed(A.tensors), reversed(list(X))):
+        out.append(Ak[(slice(None), slice(None)) + tuple(xk)] @ out[-1])
+    return out[::-1]
+
+
+def update_environments(prod_left, prod_right, A, k: int, X, lr: str):
+    """``update_environments!`` (``dmrg.jl:124-151``), ``k`` the 0-based first site of the pair just split; the
+    lists are those of :func:`precompute_left_environments` / :func:`precompute_right_environments` per datapoint."""
+    for n, x in enumerate(X):
+        if lr == "left":
+            Anew = A[k][(slice(None), slice(None)) + tuple(x[k])]
+            prod_left[n][k + 1] = prod_left[n][k] @ Anew
+        else:
+            Anew = A[k + 1][(slice(None), slice(None)) + tuple(x[k + 1])]
+            prod_right[n][k + 1] = Anew @ prod_right[n][k + 2]
+
+
+# ----------------------------------------------------------------------------------------------
 # MPS Born-machine wrapper (src/MatrixProductStates/mps.jl), real Float64 (conj is a no-op)
 # ----------------------------------------------------------------------------------------------
 class MPS:

@@ -175,6 +175,7 @@ struct CallTimer {
   }
 };
 
+int create_handle(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_tt** out, bool check_boundary);
 int check_handle(ttb_tt* h);      // validates, selects the device, joins pending asynchronous uploads
 int check_handle_raw(ttb_tt* h);  // same without the join (sweeps that consume the upload chunk by chunk)
 int join_uploads(ttb_tt* h, int need_site);  // main stream waits for the chunks holding sites >= need_site (-1: all)

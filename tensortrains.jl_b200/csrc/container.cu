@@ -114,12 +114,20 @@ int ttb_host_free(void* p) {
 }
 
 int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_handle* out) {
+  return ttb::create_handle(L, bond, Q, periodic, batch, out, true);
+}
+
+}  // extern "C"
+
+// check_boundary = false: an open chain SEGMENT (first / last bond > 1), the temporary two-site train of
+// ttb_split_tensor (twosite.cu); everything else is the public constructor
+int ttb::create_handle(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t batch, ttb_handle* out, bool check_boundary) {
   if (!bond || !out) return fail(TTB_EINVAL, "null argument");
   if (L < 1 || Q < 1 || batch < 1) return fail(TTB_EINVAL, "L, Q and batch must be >= 1 (got %lld, %lld, %lld)",
                                                (long long)L, (long long)Q, (long long)batch);
   for (int64_t t = 0; t <= L; ++t)
     if (bond[t] < 1) return fail(TTB_ESHAPE, "bond %lld is %lld, must be >= 1", (long long)t, (long long)bond[t]);
-  if (!periodic && !(bond[0] == 1 && bond[L] == 1))
+  if (check_boundary && !periodic && !(bond[0] == 1 && bond[L] == 1))
     return fail(TTB_ESHAPE, "First matrix must have 1 row, last matrix must have 1 column");
   if (periodic && bond[L] != bond[0])
     return fail(TTB_ESHAPE, "Matrix indices for matrix product non compatible (bond[L]=%lld != bond[0]=%lld)",
@@ -185,6 +193,8 @@ int ttb_create(int64_t L, const int64_t* bond, int64_t Q, int periodic, int64_t 
   return TTB_OK;
 }
 
+extern "C" {
+
 int ttb_destroy(ttb_handle h) {
   if (!h) return TTB_OK;
   cudaSetDevice(h->device);
@@ -208,6 +218,13 @@ int ttb_destroy(ttb_handle h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return TTB_OK;
+}
+
+int ttb_get_capacity_bonds(ttb_handle h, int64_t* out) {
+  TTB_TRY(check_handle(h));
+  if (!out) return fail(TTB_EINVAL, "null argument");
+  for (int64_t t = 0; t <= h->L; ++t) out[t] = h->bond0[t];
   return TTB_OK;
 }
 

@@ -70,6 +70,7 @@ _sig("ttb_clone", _h, C.POINTER(_h))
 _sig("ttb_compose", _h, _h, C.c_int, C.POINTER(_h))
 _sig("ttb_info", _h, _pi64, _pi64, _pi, _pi64)
 _sig("ttb_get_bonds", _h, _i64, _pi64)
+_sig("ttb_get_capacity_bonds", _h, _pi64)
 _sig("ttb_nparams", _h, _i64, _pi64)
 _sig("ttb_upload_site", _h, _i64, _i64, _pd)
 _sig("ttb_download_site", _h, _i64, _i64, _pd)
@@ -115,6 +116,10 @@ _sig("ttb_upload_all_async", _h, _pd)
 _sig("ttb_reset", _h)
 _sig("ttb_trim", _h)
 _sig("ttb_dot", _h, _i64, _h, _i64, _pd, _pi)
+_sig("ttb_merge_tensors", _h, _i64, _i64, _pd)
+_sig("ttb_split_tensor", _h, _i64, _i64, _pd, C.POINTER(_Trunc), C.c_int, _pd)
+_sig("ttb_data_environments", _h, _i64, C.POINTER(C.c_int32), _i64, C.c_int, _pd)
+_sig("ttb_data_env_update", _h, _i64, C.POINTER(C.c_int32), _i64, _i64, C.c_int, _pd)
 _sig("ttb_mps_env_size", _h, _i64, C.c_int, _pi64)
 _sig("ttb_mps_accumulate", _h, _i64, C.c_int, C.c_int, _pd, _pd, _pi)
 _sig("ttb_mps_marginals", _h, _i64, _pd)
@@ -302,6 +307,12 @@ class AbstractTensorTrain:
             zz = z if isinstance(z, Logarithmic) else Logarithmic(z)
             for b in range(B):
                 _ck(lib.ttb_set_z(self._hd, b, zz.logabs, zz.sign))
+
+    def _dmax(self) -> int:
+        """largest bond the handle was created with (the stride of data-environment entries)"""
+        out = np.zeros(self.L + 1, dtype=np.int64)
+        _ck(lib.ttb_get_capacity_bonds(self._hd, out.ctypes.data_as(_pi64)))
+        return int(out.max())
 
     def _refresh(self):
         L, Q, per, B = _i64(), _i64(), C.c_int(), _i64()
@@ -923,6 +934,60 @@ def sample_stats(A, nsamples: int, seed: int = 0, first_index: int = 0, b: int =
     _ck(lib.ttb_sample_stats_env(A._hd, _env_arg(rz, False, "rz"), b, int(nsamples), C.c_uint64(seed), C.c_uint64(first_index),
                                  hist.ctypes.data_as(_pi64), C.byref(slp)))
     return hist, slp.value
+
+
+# ---- two-site pieces: _merge_tensors / _split_tensor / data environments ------------------
+def merge_tensors(A, t: int, b: int = 0) -> np.ndarray:
+    """``_merge_tensors(A[t], A[t+1])`` (src/utils.jl:37-44), ``t`` 0-based: array ``(d_t, d_{t+2}) + q + q``"""
+    bd = A.bonds(b)
+    if not (0 <= int(t) < A.L - 1):
+        raise ValueError(f"ArgumentError: site pair ({t}, {t + 1}) outside the train")
+    out = np.zeros(int(bd[t]) * int(bd[t + 2]) * A.Q * A.Q)
+    _ck(lib.ttb_merge_tensors(A._hd, b, int(t), _dp(out)))
+    return out.reshape((int(bd[t]), int(bd[t + 2])) + tuple(A.q) + tuple(A.q), order="F")
+
+
+def split_tensor_(A, t: int, Cm: np.ndarray, svd_trunc: Optional[SVDTrunc] = None, lr: str = "left", b: int = 0):
+    """``A[t], A[t+1] = _split_tensor(C; svd_trunc, lr)`` (src/abstract_tensor_train.jl:283-308) in place on the device
+    train; ``lr`` = "left" (``A[t] = U``) or "right" (``A[t+1] = V'``).  Returns the relative truncation error."""
+    if lr not in ("left", "right"):
+        raise ValueError("ArgumentError: lr must be \"left\" or \"right\"")
+    tr = (svd_trunc or TruncThresh(0.0))
+    bd = A.bonds(b)
+    Cf = np.ascontiguousarray(np.reshape(np.asarray(Cm, dtype=np.float64), -1, order="F"))
+    if Cf.size != int(bd[t]) * int(bd[t + 2]) * A.Q * A.Q:
+        raise ValueError("DimensionMismatch: C does not have the shape (d_t, d_{t+2}, q..., q...)")
+    err = C.c_double(0.0)
+    c = tr._c()
+    _ck(lib.ttb_split_tensor(A._hd, b, int(t), _dp(Cf), C.byref(c), 1 if lr == "left" else 0, C.byref(err)))
+    A._refresh()
+    if isinstance(tr, TruncBondMax):
+        tr.maxerr[0] = max(tr.maxerr[0], err.value)
+    return err.value
+
+
+def _x_flat_rows(A, X) -> np.ndarray:
+    return np.ascontiguousarray(np.stack([_flat_x(A, x) for x in X]).astype(np.int32))
+
+
+def data_environments(A, X, left: bool = True, b: int = 0) -> np.ndarray:
+    """``[precompute_left_environments(A, x) for x in X]`` (``left``) / ``precompute_right_environments``
+    (src/tensor_train.jl:320-334) as one array ``(len(X), L + 1, dmax)``: entry ``j`` holds ``d_j`` values (the
+    product of the first ``j`` matrices, resp. of matrices ``j..L-1``), zero padded."""
+    Xf = _x_flat_rows(A, X)
+    env = np.zeros((Xf.shape[0], A.L + 1, A._dmax()))
+    _ck(lib.ttb_data_environments(A._hd, b, Xf.ctypes.data_as(C.POINTER(C.c_int32)), Xf.shape[0], int(bool(left)), _dp(env)))
+    return env
+
+
+def update_environments_(env: np.ndarray, A, t: int, X, left: bool = True, b: int = 0) -> np.ndarray:
+    """``update_environments!`` (src/dmrg.jl:124-151) after site ``t`` (0-based) changed: entry ``t+1`` (``left``) or
+    entry ``t`` of every datapoint's environment list is recomputed in place."""
+    Xf = _x_flat_rows(A, X)
+    if env.shape != (Xf.shape[0], A.L + 1, A._dmax()) or not env.flags.c_contiguous:
+        raise ValueError("ArgumentError: env must be the array data_environments returned")
+    _ck(lib.ttb_data_env_update(A._hd, b, Xf.ctypes.data_as(C.POINTER(C.c_int32)), Xf.shape[0], int(t), int(bool(left)), _dp(env)))
+    return env
 
 
 # ---- dot / norm / norm2m / isapprox (first row after the hot path, SURVEY 8f) -------------------------

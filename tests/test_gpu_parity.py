@@ -1054,3 +1054,94 @@ def test_is_in_domain_and_equality():
     C1, C2 = A.copy(), A.copy()
     T.compress_(C1, T.TruncBond(2)); T.compress_(C2, T.TruncBond(2))
     assert C1 == C2 and not (C1 == A)
+
+
+# ---- two-site pieces: src/utils.jl:37-44, src/abstract_tensor_train.jl:283-308, src/dmrg.jl:124-151 ----
+@pytest.mark.parametrize("q", [(2,), (2, 3)])
+def test_merge_and_split_tensor_match_oracle(q):
+    rng = RNG(980)
+    bonds = [1, 6, 9, 6, 4, 1]
+    ts = rand_open(rng, bonds, q, "randn")
+    A, Ao = pair(ts)
+    Qf = int(np.prod(q))
+    X = rand_points(rng, Ao, 6)
+    e0 = [T.evaluate(A, x) for x in X]
+    for t in range(len(ts) - 1):
+        Cg, Co = T.merge_tensors(A, t), O.merge_tensors(Ao[t], Ao[t + 1])
+        assert Cg.shape == Co.shape and np.allclose(Cg, Co, rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        T.merge_tensors(A, len(ts) - 1)
+    # exact split of the pair (1, 2): rank = the bond 9 it was merged over (<= capacity)
+    for lr in ("left", "right"):
+        B = A.copy()
+        Cm = T.merge_tensors(B, 1)
+        T.split_tensor_(B, 1, Cm, T.TruncBond(9), lr)      # (TruncThresh keeps one value more than the rank: svd_trunc.jl:38-47)
+        Ao1, Ao2 = O.split_tensor(O.merge_tensors(Ao[1], Ao[2]), O.TruncBond(9), lr)
+        assert T.bond_dims(B)[2] == Ao1.shape[1] == 9
+        assert np.allclose(T.merge_tensors(B, 1), Cm, rtol=1e-10, atol=1e-12)          # A * B = C
+        assert all(close(T.evaluate(B, x), e, 1e-9) for x, e in zip(X, e0)) and float(B.z) == float(A.z)
+        a1, a2 = B.site(1), B.site(2)
+        if lr == "left":        # A = U: left-orthonormal; B = L V': rows carry the singular values
+            assert T.is_left_canonical(B, 1)
+            sv = np.sort(np.linalg.norm(a2.reshape(a2.shape[0], -1), axis=1))[::-1]
+            svo = np.sort(np.linalg.norm(Ao2.reshape(Ao2.shape[0], -1), axis=1))[::-1]
+        else:
+            assert T.is_right_canonical(B, 2)
+            sv = np.sort(np.linalg.norm(a1.transpose(1, 0, *range(2, a1.ndim)).reshape(a1.shape[1], -1), axis=1))[::-1]
+            svo = np.sort(np.linalg.norm(Ao1.transpose(1, 0, *range(2, Ao1.ndim)).reshape(Ao1.shape[1], -1), axis=1))[::-1]
+        assert np.allclose(sv, svo, rtol=1e-9, atol=1e-12 * svo[0])
+    # truncating split of a perturbed merged tensor (what a DMRG step hands back)
+    B = A.copy()
+    Cm = T.merge_tensors(B, 1) + 0.05 * rng.standard_normal((6, 6) + q + q)
+    tb = T.TruncBondMax(4)
+    err = T.split_tensor_(B, 1, Cm, tb, "left")
+    So = O.TruncBondMax(4)
+    Ao1, Ao2 = O.split_tensor(Cm, So, "left")
+    assert T.bond_dims(B)[2] == 4 and close(err, So.maxerr[0], 1e-6) and close(tb.maxerr[0], So.maxerr[0], 1e-6)
+    assert np.allclose(T.merge_tensors(B, 1), O.merge_tensors(Ao1, Ao2), rtol=1e-8, atol=1e-10)
+    # a split that would need more than the capacity of the bond is refused, the train is untouched
+    B = A.copy()
+    with pytest.raises(NotImplementedError):
+        T.split_tensor_(B, 1, Cm, T.TruncThresh(0.0), "left")
+    assert T.bond_dims(B) == T.bond_dims(A) and np.array_equal(B.site(1), A.site(1))
+    assert Qf >= 2
+
+
+def test_data_environments_and_updates_match_oracle():
+    rng = RNG(981)
+    q = (2, 2)
+    ts = rand_open(rng, [1, 4, 7, 5, 3, 1], q, "randn")
+    A, Ao = pair(ts)
+    L = len(ts)
+    X = [[tuple(int(rng.integers(0, v)) for v in q) for _ in range(L)] for _ in range(9)]
+    envL, envR = T.data_environments(A, X, left=True), T.data_environments(A, X, left=False)
+    pl = [O.precompute_left_environments(Ao, x) for x in X]
+    pr = [O.precompute_right_environments(Ao, x) for x in X]
+    def check(env, ref):
+        for n in range(len(X)):
+            for j in range(L + 1):
+                v = np.reshape(ref[n][j], -1)
+                assert np.allclose(env[n, j, :v.size], v, rtol=1e-12, atol=1e-14) and not env[n, j, v.size:].any()
+    check(envL, pl); check(envR, pr)
+    # one DMRG-like step at the pair (1, 2): perturb, split keeping the sweep direction's gauge, update the environments
+    for lr, left in (("left", True), ("right", False)):
+        Cm = T.merge_tensors(A, 1) + 0.01 * rng.standard_normal((4, 5) + q + q)
+        T.split_tensor_(A, 1, Cm, T.TruncBond(7), lr)
+        Ao.tensors[1], Ao.tensors[2] = O.split_tensor(Cm, O.TruncBond(7), lr)
+        O.update_environments(pl, pr, Ao, 1, X, lr)
+        if left:
+            T.update_environments_(envL, A, 1, X, left=True)
+        else:
+            T.update_environments_(envR, A, 2, X, left=False)
+        # the two SVDs may differ by a gauge (signs): compare evaluations, and the updated entry with a fresh pass
+        eg = [T.evaluate(A, x) for x in X]
+        eo = [O.evaluate(Ao, x) for x in X]
+        assert np.allclose(eg, eo, rtol=1e-9)
+        full = T.data_environments(A, X, left=left)
+        upd = envL if left else envR
+        j = 2
+        assert np.allclose(upd[:, j], full[:, j], rtol=1e-12, atol=1e-14)
+        if left:
+            envR = T.data_environments(A, X, left=False)
+        else:
+            envL = T.data_environments(A, X, left=True)
