@@ -106,6 +106,18 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
 #pragma unroll
   for (int i = 0; i < RPL; ++i) x[i] = a[OS][i];
   const double x0m = (lane > cc) ? x[0] : 0.0;   // rows <= cc of the first 32 do not belong to the reflector
+#ifdef TTB_PANEL_RAW_EARLY   // measured A/B (round 2): no gain in situ (54.9 vs 54.8 ms per compress!), kept for the record
+  // the raw column goes to shared memory FIRST (it is final at entry): the next owner's dot products with it --
+  // ~750 cycles of loads, FMAs and a transposed butterfly -- then finish before den / tau' are published, and what
+  // is left on the hand-off is the rank-1 update (stamps: the flag used to follow the butterfly, the next owner
+  // finished its dots ~1000 cycles after the publish)
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    if (!STREAM || i < nvi) vcol[lane + 32 * i] = i == 0 ? x0m : x[i];
+  }
+  __syncwarp();
+  *reinterpret_cast<volatile int*>(&raw[cc]) = 1;
+#endif
   double red[NL + 1];
   {
     double p0 = x0m * x0m, p1 = 0.0, p2 = 0.0, p3 = 0.0;
@@ -146,15 +158,19 @@ __device__ __forceinline__ void panel_owner_step(double (&a)[NS][RPL], double* v
     double got[NL + 1];
 #pragma unroll
     for (int k = 0; k <= NL; ++k) got[k] = __shfl_xor_sync(0xffffffffu, red[k], o);
+#ifndef TTB_PANEL_RAW_EARLY
 #pragma unroll
     for (int i = lv * SPL; i < (lv + 1) * SPL; ++i) {
       if (i < RPL && (!STREAM || i < nvi)) vcol[lane + 32 * i] = i == 0 ? x0m : x[i];
     }
+#endif
 #pragma unroll
     for (int k = 0; k <= NL; ++k) red[k] += got[k];
   }
+#ifndef TTB_PANEL_RAW_EARLY
   __syncwarp();
   *reinterpret_cast<volatile int*>(&raw[cc]) = 1;
+#endif
   const double xn2 = red[NL];
 #ifdef TTB_PANEL_FINE
   if (lane == 0 && xn2 != 1.2345) TTB_PANEL_STAMPS[64 + 16 * cc + 2] = clock64();

@@ -34,6 +34,12 @@
 
 namespace ttb {
 
+#ifndef TTB_QS_PUSH_SLEEP
+#define TTB_QS_PUSH_SLEEP 100
+#endif
+#ifndef TTB_QS_CREDIT_LD
+#define TTB_QS_CREDIT_LD ld_acquire_cluster_s32
+#endif
 constexpr int kQsRing = 8;         // reflector slots per consumer CTA
 constexpr int kQsThreads = 256;    // 8 warps, 4 columns each
 constexpr int kQsMaxBlocks = 8;    // portable cluster size
@@ -47,6 +53,7 @@ __host__ __device__ constexpr size_t qs_smem_bytes(int RPL) {
 // timeline stamps (globaltimer ns) of one traced site step: [CTA][0] start, [1 + j] consumed panel j,
 // [20] factor done, [21] all stored, [22 + blk] block done; written only when the step descriptor asks
 __device__ unsigned long long g_qs_trace[16 * 32];
+__device__ unsigned long long g_qs_trace2[4 * 64];   // panel 0 -> CTA 1: [0] pushed, [1] ready seen by the pusher, [2] arrived, [3] applied
 __device__ __forceinline__ unsigned long long qs_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -132,8 +139,13 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       __syncwarp();
       my_next += kQsRing;
     };
+    // A remote reflector costs this CTA ~1200 cycles applied alone (16 loads, 4 dots, one transposed butterfly, the
+    // update) while the factoring CTA forms one every ~1100: the consumer fell behind over a panel and the NEXT panel
+    // started ~4 us after the previous one had finished (globaltimer trace).  Whenever two reflectors have already
+    // arrived they are applied TOGETHER: d0 = v0.a, d1 = v1.a, g = v1.v0 ride the same butterflies,
+    // w0 = tau0 d0, w1 = tau1 (d1 - g w0), a -= w0 v0 + w1 v1 -- one latency chain for two reflectors.
 #pragma unroll 1
-    for (int g = 0; g < nremote; ++g) {
+    for (int g = 0; g < nremote;) {
       try_arm(g);
       const int slot = g & (kQsRing - 1);
       const uint32_t parity = (uint32_t)(g / kQsRing) & 1u;
@@ -141,11 +153,64 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
         try_arm(g);
         if (it > (1u << 24)) __trap();
       }
+#ifdef TTB_QS_TRACE2
+      if (s.trace && b == 0 && kb == 1 && tid == 0 && g < 64) g_qs_trace2[2 * 64 + g] = qs_now();
+#endif
       // register i holds row group (i + kb) mod RPL => two contiguous runs, immediate offsets
       const double* vsl = ring + (size_t)slot * SL;
       const double tau = vsl[LDV];
       const double* pA = vsl + 32 * kb + lane;
       const double* pB = pA - LDV;
+      bool two = false;
+#ifdef TTB_QS_PAIR   // measured A/B on one box (round 2): 55.0 ms per compress! with the pair path, 54.8 without -- the consumers are not the hand-off's bottleneck
+      if (g + 1 < nremote) {
+        try_arm(g + 1);
+        const int slot1 = (g + 1) & (kQsRing - 1);
+        two = __all_sync(0xffffffffu, mbar_try_wait(&bars[slot1], (uint32_t)((g + 1) / kQsRing) & 1u));
+      }
+#endif
+      if (two) {
+        // (both vectors are streamed from shared memory twice -- dots, then update -- instead of living in
+        // registers across the butterflies: the kernel sits at the 255-register limit)
+        const double* vsl1 = ring + (size_t)((g + 1) & (kQsRing - 1)) * SL;
+        const double tau1 = vsl1[LDV];
+        const double* qA = vsl1 + 32 * kb + lane;
+        const double* qB = qA - LDV;
+        double d0[NS], d1[NS], gg = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) { d0[s2] = 0.0; d1[s2] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          const double vi = (i < RPL - kb ? pA : pB)[32 * i], ui = (i < RPL - kb ? qA : qB)[32 * i];
+          gg = fma(ui, vi, gg);
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) { d0[s2] = fma(vi, a[s2][i], d0[s2]); d1[s2] = fma(ui, a[s2][i], d1[s2]); }
+        }
+        const double t0 = warp_reduce_ns<NS>(d0, lane);
+        const double t1 = warp_reduce_ns<NS>(d1, lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
+        double w0[NS], w1[NS];
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) {
+          w0[s2] = tau * __shfl_sync(0xffffffffu, t0, s2 * (32 / NS));
+          w1[s2] = tau1 * fma(-gg, w0[s2], __shfl_sync(0xffffffffu, t1, s2 * (32 / NS)));
+        }
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          const double vi = (i < RPL - kb ? pA : pB)[32 * i], ui = (i < RPL - kb ? qA : qB)[32 * i];
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) a[s2][i] -= fma(vi, w0[s2], ui * w1[s2]);
+        }
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(&done[wid]) = g + 2;
+#ifdef TTB_QS_TRACE2
+        if (s.trace && b == 0 && kb == 1 && tid == 0 && g + 1 < 64) { g_qs_trace2[3 * 64 + g] = qs_now(); g_qs_trace2[3 * 64 + g + 1] = qs_now(); g_qs_trace2[2 * 64 + g + 1] = g_qs_trace2[2 * 64 + g]; }
+#endif
+        if (trace && ((g & 31) == 31 || ((g + 1) & 31) == 31)) g_qs_trace[kb * 32 + 1 + ((g + 1) >> 5)] = qs_now();
+        g += 2;
+        continue;
+      }
       double v[RPL];
 #pragma unroll
       for (int i = 0; i < RPL; ++i) v[i] = (i < RPL - kb ? pA : pB)[32 * i];
@@ -162,6 +227,10 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile int*>(&done[wid]) = g + 1;
       if (trace && (g & 31) == 31) g_qs_trace[kb * 32 + 1 + (g >> 5)] = qs_now();
+#ifdef TTB_QS_TRACE2
+      if (s.trace && b == 0 && kb == 1 && tid == 0 && g < 64) g_qs_trace2[3 * 64 + g] = qs_now();
+#endif
+      ++g;
     }
   }
   // ---- transition: rows above the panel are final R entries; store them, zero the registers
@@ -191,11 +260,18 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
     if (pusher) {
       while (np < nready) {
         const int slot = (j0 + np) & (kQsRing - 1);
-        if (ld_acquire_cluster_s32(&credit[lane * kQsRing + slot]) <= j0 + np) break;   // slot not armed for it yet
+        // relaxed read: the consumer releases the credit AFTER all its warps are done with the slot's previous
+        // occupant and after re-arming the barrier; the bulk copy below is issued after this load has returned.
+        // (An acquire at cluster scope cost the pusher ~0.5 us per reflector: it could not keep up with the last
+        // blocks of a panel -- one reflector every 0.57 us -- and the next panel started ~3 us late.)
+        if (TTB_QS_CREDIT_LD(&credit[lane * kQsRing + slot]) <= j0 + np) break;   // slot not armed for it yet
         const uint32_t bar_r = bars_r + (uint32_t)slot * 8u;
         const uint32_t dst_r = ring_r + (uint32_t)(slot * SL * 8);
         const double* src = vs + (size_t)np * SL;
         bulk_s2remote(dst_r + (uint32_t)(j0 * 8), src, (uint32_t)((LDV - j0 + 2) * 8), bar_r);   // rows j0..LDV of the slot, then tau
+#ifdef TTB_QS_TRACE2
+        if (s.trace && b == 0 && kb == 0 && lane == 1) g_qs_trace2[np] = qs_now();
+#endif
         ++np;
       }
     }
@@ -218,15 +294,20 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
         panel_consume_later<RPL, NS>(a, vs + (size_t)cc * SL, sh_tau, ready, raw, cc, lane, wid != blk + 1, nvi);
     } else if (wid == 0) {
       // warp 0 owns finished columns from the second block on: it only keeps the pushes going (V'^T V' is formed
-      // after the chain, panel_gram_mma)
+      // after the chain, panel_gram_mma).  Lane 0 polls the flags and the whole warp follows its view (a poll
+      // per lane could diverge around the __syncwarp of pump()); no sleep: the last blocks of a panel publish a
+      // reflector every ~0.57 us and a pusher that lags delays the next panel by the same amount
       const int cend = min(c0 + NS, bwc);
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc) {
         unsigned it = 0;
         while (ld_flag(&ready[cc]) == 0) {
-          __nanosleep(100);
+          __nanosleep(TTB_QS_PUSH_SLEEP);
           if (++it > (1u << 26)) __trap();
         }
+#ifdef TTB_QS_TRACE2
+        if (s.trace && b == 0 && kb == 0 && lane == 0) g_qs_trace2[64 + cc] = qs_now();
+#endif
         pump(cc + 1);
       }
     }

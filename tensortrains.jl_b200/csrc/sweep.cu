@@ -1700,6 +1700,12 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
       for (int blk = 0; blk < 8; ++blk) fprintf(stderr, " %5.1f", ((double)tr_h[kb * 32 + 22 + blk] - (double)t0) * 1e-3);
       fprintf(stderr, "\n");
     }
+    unsigned long long t2[4 * 64];
+    cudaMemcpyFromSymbol(t2, g_qs_trace2, sizeof(t2));
+    fprintf(stderr, "[qs trace] panel 0 -> CTA 1, per reflector: ready seen by pusher | pushed | arrived | applied (us)\n");
+    for (int g = 0; g < 32; ++g)
+      fprintf(stderr, "[qs trace]   %2d: %6.2f %6.2f %6.2f %6.2f\n", g, ((double)t2[64 + g] - (double)t0) * 1e-3, ((double)t2[g] - (double)t0) * 1e-3,
+              ((double)t2[128 + g] - (double)t0) * 1e-3, ((double)t2[192 + g] - (double)t0) * 1e-3);
   }
   if (dbg) {
     clock_gettime(CLOCK_MONOTONIC, &t_d);
