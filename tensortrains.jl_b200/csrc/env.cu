@@ -456,6 +456,7 @@ __global__ void k_twovar(TwoCtx c) {
 }  // namespace ttb
 #include "twovar_fast.cuh"
 #include "twovar_mma.cuh"
+#include "twovar_open.cuh"
 #include "env_fast.cuh"
 #include "env_small.cuh"
 namespace ttb {
@@ -1039,7 +1040,10 @@ static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int6
   // fast path: GT_u(x), T_u once per call, then Frobenius products + one small GEMM per pair
   const int64_t kcap = h->bond0[0] * h->dmax;
   const size_t fast_smem = sizeof(double) * (3 * (size_t)Q * kcap + (size_t)h->dmax * h->dmax + 8 * (Q * Q + 1) + Q * Q);
-  const bool use_fast = fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr;
+  // open trains with bonds above the small path: a group of first sites per CTA, K T_u on the tensor cores (twovar_open.cuh)
+  const bool use_open = !h->periodic && h->bond0[0] == 1 && h->dmax > 32 && h->dmax <= 256 && Q <= 8 &&
+                        getenv("TTB_TWOVAR_GENERIC") == nullptr && getenv("TTB_TWOVAR_NOOPEN") == nullptr;
+  const bool use_fast = use_open || (fast_smem <= 200 * 1024 && getenv("TTB_TWOVAR_GENERIC") == nullptr);
   // small bonds (config 5): the per-pair product on the FP64 tensor cores (twovar_mma.cuh); with the
   // small-path precompute its operands are stored zero padded (no per-pair dimension handling)
   const bool use_mma = use_fast && h->dmax <= 32 && Q * h->bond0[0] <= 64 && Q >= 2 && Q <= 4 && getenv("TTB_TWOVAR_NOMMA") == nullptr;
@@ -1084,6 +1088,13 @@ static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int6
     if (padded) { TTB_LAUNCH(h, "k_twovar_mma", (k_twovar_mma<Q_, true><<<gm, 256, bsm, h->stream>>>(fc))); }              \
     else { TTB_LAUNCH(h, "k_twovar_mma", (k_twovar_mma<Q_, false><<<gm, 256, bsm, h->stream>>>(fc))); }                    \
   } while (0)
+        if (use_open) {
+          const int tb = kTvoRows / (int)Q;
+          const size_t osm = tvo_smem((int)h->dmax, (int)Q);
+          TTB_ONCE_PER_DEVICE(h, 10) cudaFuncSetAttribute(k_twovar_open, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+          const dim3 go((unsigned)((t_hi - t_lo + tb - 1) / tb), (unsigned)h->batch);
+          TTB_LAUNCH(h, "k_twovar_open", (k_twovar_open<<<go, 256, osm, h->stream>>>(fc, tb, (int)t_hi)));
+        } else
         if (use_mma && Q == 2) TTB_TV(2);
         else if (use_mma && Q == 3) TTB_TV(3);
         else if (use_mma && Q == 4) TTB_TV(4);

@@ -1145,3 +1145,48 @@ def test_data_environments_and_updates_match_oracle():
             envR = T.data_environments(A, X, left=False)
         else:
             envL = T.data_environments(A, X, left=True)
+
+
+@pytest.mark.parametrize("case", ["ragged_q3", "d96_q2", "maxdist", "batched_q4"])
+def test_twovar_open_group_kernel_matches_oracle(case):
+    """k_twovar_open (open trains, bonds above 32): a group of first sites per CTA, K T_u on the tensor cores --
+    against the oracle's twovar_marginals (src/abstract_tensor_train.jl:231-254) and against the generic kernel."""
+    rng = RNG(990)
+    md = None
+    if case == "ragged_q3":
+        bonds, q = [1, 3, 9, 27, 40, 37, 50, 33, 8, 3, 1], (3,)
+    elif case == "d96_q2":
+        bonds, q = [1] + [96] * 22 + [1], (2,)          # 23 sites: more first sites than one group of 16
+    elif case == "maxdist":
+        bonds, q, md = [1] + [48] * 19 + [1], (2,), 5
+    else:
+        bonds, q = [1, 4, 16, 40, 40, 16, 4, 1], (2, 2)
+    if case == "batched_q4":
+        B = 3
+        tss = [rand_open(rng, bonds, q) for _ in range(B)]
+        A = T.TensorTrain([np.stack([tss[b][t] for b in range(B)]) for t in range(len(bonds) - 1)], batched=True)
+        got = T.twovar_marginals(A)
+        for b in range(B):
+            Ao = O.TensorTrain([a.copy() for a in tss[b]])
+            po = O.twovar_marginals(Ao)
+            assert set(got[b]) == set(po)
+            for k in po:
+                assert np.allclose(got[b][k], po[k], rtol=1e-10, atol=1e-14), (b, k)
+        return
+    ts = rand_open(rng, bonds, q)
+    A, Ao = pair(ts)
+    T.normalize_(A); O.normalize(Ao)
+    got = T.twovar_marginals(A, maxdist=md)
+    po = O.twovar_marginals(Ao, maxdist=md)
+    assert set(got) == set(po)
+    for k in po:
+        assert np.allclose(got[k], po[k], rtol=1e-10, atol=1e-14), k
+    L = len(ts)
+    mdv = L - 1 if md is None else md
+    blk = T.twovar_marginals_block(A, 3, L - 2, mdv)[0]      # a range that starts inside a group
+    i = 0
+    for t in range(3, L - 2):
+        for u in range(t + 1, min(L - 1, t + mdv) + 1):
+            assert np.array_equal(blk[i].reshape(q + q, order="F"), got[(t, u)])
+            i += 1
+    assert i == blk.shape[0]
