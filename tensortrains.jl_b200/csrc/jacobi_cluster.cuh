@@ -80,9 +80,10 @@ __device__ __forceinline__ bool jacobi_pair_fixed(double (&xi)[NE], double (&jx)
     if (e < nv) jj[e] = sn * p + cs * q;
   }
   const double t = sn * ic;
+  const bool big = ga * ga > kJacobiBig2 * al * be;   // counts against convergence (common.cuh)
   al -= t * ga;
   *sqj = be + t * ga;
-  return true;
+  return big;
 }
 
 // copy `rows` rows of `n` doubles between a strided global matrix and a packed shared block; 16-byte

@@ -67,7 +67,7 @@ __device__ __forceinline__ int jacobi_two_pairs(double* B, double* J, double* sq
     cs[k] = rot ? uu * ic : 1.0;
     sn[k] = rot ? 0.5 * s2 * ic : 0.0;
     dsq[k] = sn[k] * ic * ga[k];
-    rotated |= rot ? 1 : 0;
+    rotated |= (rot && ga[k] * ga[k] > kJacobiBig2 * al[k] * be[k]) ? 1 : 0;
   }
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(16 * WR, (WR == 32 && WL == 32) ? 2 : 1) k_jac
           const double t = sn * ic;
           sq[i] = al - t * ga;
           sq[j] = be + t * ga;
-          rotated = 1;
+          if (ga * ga > kJacobiBig2 * al * be) rotated = 1;
         }
       }
       __syncthreads();
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(4 * W, W == 32 ? 8 : 1) k_jacobi_g8(SweepCtx c
           const double t = sn * ic;
           sq[i] = al - t * ga;
           sq[j] = be + t * ga;
-          rotated = 1;
+          if (ga * ga > kJacobiBig2 * al * be) rotated = 1;
         }
       }
       __syncthreads();

@@ -408,7 +408,8 @@ __device__ int rank_rule(const double* lam, int m, int kind, double eps, int cap
 // |bi'|^2 = al - t ga, |bj'|^2 = be + t ga), so a pair costs ONE dot + one warp reduction.  The first
 // 32*NE elements of both rows (32*NJ of the rotation rows) stay in registers between the dot and the
 // update: a round is a latency chain (load -> dot -> 5 shuffles -> angle -> store), not a throughput
-// problem, so every shared-memory round trip taken off it counts.  Returns true when it rotated.
+// problem, so every shared-memory round trip taken off it counts.  Returns true when it made a rotation that
+// counts against convergence (kJacobiBig2, common.cuh).
 // ---------------------------------------------------------------------------------------------
 template <int NE, int NJ>
 __device__ __forceinline__ bool jacobi_pair(double* bi, double* bj, double* ji, double* jj, int len, int nv,
@@ -479,7 +480,7 @@ __device__ __forceinline__ bool jacobi_pair(double* bi, double* bj, double* ji, 
   const double t = sn * ic;   // tan(theta) without a division
   *sqi = al - t * ga;         // same value from every lane
   *sqj = be + t * ga;
-  return true;
+  return ga * ga > kJacobiBig2 * al * be;
 }
 
 // round-robin (circle method) pairing of n (even) players: pair q of round rd, i < j
