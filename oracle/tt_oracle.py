@@ -127,6 +127,8 @@ def _svd(M: np.ndarray):
 # ----------------------------------------------------------------------------------------------
 class SVDTrunc:
     kind = -1
+    capture = None      # test hook: callable(M, lam, mprime) called on every SVD (the high-precision arbiter of
+                        # tests/test_gpu_full_parity.py keeps the matrices whose rank decision sits near the threshold)
 
     def rank(self, lam: np.ndarray) -> int:  # pragma: no cover - abstract
         raise NotImplementedError
@@ -135,6 +137,8 @@ class SVDTrunc:
         U, lam, V = _svd(M)
         mprime = self.rank(lam)
         self.last_spectrum = lam.copy()
+        if self.capture is not None:
+            self.capture(M, lam, mprime)
         return U[:, :mprime], lam[:mprime], V[:, :mprime]
 
 

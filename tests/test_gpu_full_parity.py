@@ -90,6 +90,79 @@ def test_config3_full_length_against_oracle(fill):
         assert np.max(np.abs(g - e)) <= 1e-8 * np.max(np.abs(e)), (g, e)
 
 
+def _thresh_margin(lam, eps):
+    """The two decisive comparisons of TruncThresh (src/svd_trunc.jl:38-47) on a spectrum: returns (mprime, tail sum
+    that reached the threshold / threshold, last tail sum that did not / threshold)."""
+    lam = np.asarray(lam, dtype=np.float64)
+    thr = (float(np.linalg.norm(lam)) * eps) ** 2
+    s = float(lam[-1]) ** 2
+    below = s / thr if s < thr else None          # (the rule starts from lam_m^2 without testing it)
+    for k in range(len(lam) - 1, 0, -1):
+        s += float(lam[k - 1]) ** 2
+        if s >= thr:
+            return k + 1, s / thr, below
+        below = s / thr
+    return 1, None, below
+
+
+def test_config3_threshold_decisions_against_high_precision_svd():
+    """Arbiter for the rank decisions of compress!(TruncThresh(1e-10)) on the config-3 chain (rand fill, L = 256):
+    the reference's LAPACK is MKL gesdd, the oracle's is OpenBLAS gesdd, the CUDA path is a one-sided Jacobi -- for
+    the bonds whose decisive tail sum lies closest to the threshold (all within 10 %, at least the 6 closest) a
+    40-digit SVD (mpmath) of the matrix the oracle handed to its SVD says what the decision IS: retained rank and
+    decisive tail sums of gesdd and of the Jacobi spectrum are compared with it."""
+    import mpmath as mp
+    L, d, q, eps = 256, 256, 2, 1e-10
+    ts = make_open(3, L, d, q, "rand")
+    A = T.TensorTrain(ts)
+    Ao = O.TensorTrain([a.copy() for a in ts])
+    del ts
+    A.record_spectrum(True)
+    T.compress_(A, T.TruncThresh(eps))
+    cand = []
+
+    def capture(M, lam, mprime):
+        mp_, hit, below = _thresh_margin(lam, eps)
+        dist = min(abs(hit - 1.0) if hit is not None else 9.0, abs(1.0 - below) if below is not None else 9.0)
+        cand.append((dist, len(cand), M.copy(), lam.copy(), mprime))
+
+    tr = O.TruncThresh(eps)
+    stats = []
+    with oracle_threads():
+        O.orthogonalize_right(Ao, O.TruncThresh(0.0))
+        tr.capture = capture
+        O.orthogonalize_left(Ao, tr, stats=stats)
+    assert T.bond_dims(A) == O.bond_dims(Ao)
+    order = sorted(range(len(cand)), key=lambda i: cand[i][0])
+    pick = [i for i in order if cand[i][0] < 0.10]
+    n_close = len(pick)
+    pick = (pick + [i for i in order if i not in pick])[:max(len(pick), 6)][:40]
+    mp.mp.dps = 40
+    worst_lapack = worst_jacobi = 0.0
+    for i in pick:
+        dist, idx, M, lam, kept = cand[i]
+        t_site = stats[idx][0]
+        Mt = M if M.shape[0] >= M.shape[1] else M.T
+        sv = np.array([float(x) for x in mp.svd_r(mp.matrix(Mt.tolist()), compute_uv=False)])
+        sv = np.sort(sv)[::-1][:len(lam)]
+        m_ref, hit_ref, below_ref = _thresh_margin(sv, eps)
+        lam_g = A.spectrum(t_site)
+        m_g, hit_g, below_g = _thresh_margin(lam_g, eps)
+        m_o, hit_o, below_o = _thresh_margin(lam, eps)
+        assert m_ref == m_o == kept == m_g, (t_site, m_ref, m_o, kept, m_g, dist)
+        for a_, b_, who in ((hit_o, hit_ref, "l"), (below_o, below_ref, "l"), (hit_g, hit_ref, "j"), (below_g, below_ref, "j")):
+            if a_ is None or b_ is None:
+                continue
+            err = abs(a_ / b_ - 1.0)
+            if who == "l":
+                worst_lapack = max(worst_lapack, err)
+            else:
+                worst_jacobi = max(worst_jacobi, err)
+    print(f"[C3 arbiter] {n_close} bonds within 10 % of the threshold, {len(pick)} examined, closest margin {cand[order[0]][0]:.3f}; decisive tail sums vs 40-digit SVD: "
+          f"gesdd {worst_lapack:.1e}, Jacobi (different rounding history of the sweep included) {worst_jacobi:.1e}")
+    assert worst_lapack < 1e-3 and worst_jacobi < 1e-3
+
+
 def test_config5_bench_trains_against_oracle():
     """C5 at full length (64 sites, bond 32, q=2): the first 8 trains of bench.py's chunks 0 and 3840 (seeds
     5000 + chunk start): normalize! + twovar_marginals + compress!(TruncThresh(1e-6)) against the oracle."""
