@@ -1017,7 +1017,9 @@ static int twovar_impl(ttb_tt* h, const ttb_env* lenv, const ttb_env* renv, int6
   int64_t npairs = 0;
   ttb_twovar_count(h, maxdist, &npairs);
   if (npairs == 0 || t_lo == t_hi) return TTB_OK;
-  if (Q * Q * sizeof(double) > 40 * 1024) return fail(TTB_EUNSUPPORTED, "twovar_marginals supports Q <= 71");
+  // the Q x Q table of one pair lives in shared memory; large Q takes the generic kernel (k_twovar), whose only
+  // Q-dependent resource is that table
+  if (Q * Q * sizeof(double) > 200 * 1024) return fail(TTB_EUNSUPPORTED, "twovar_marginals supports Q <= 160");
   TTB_TRY(ensure_env_ws(h));
   Workspace& w = h->ws;
   EnvSide s; EnvOffsets eo;

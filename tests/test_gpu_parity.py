@@ -1190,3 +1190,18 @@ def test_twovar_open_group_kernel_matches_oracle(case):
             assert np.array_equal(blk[i].reshape(q + q, order="F"), got[(t, u)])
             i += 1
     assert i == blk.shape[0]
+
+
+def test_twovar_marginals_large_physical_dimension():
+    """Q = 90 (> 71, the round-1 limit): the Q x Q table of a pair goes through the generic kernel"""
+    rng = RNG(991)
+    ts = rand_open(rng, [1, 3, 4, 2, 1], (90,))
+    A, Ao = pair(ts)
+    got, po = T.twovar_marginals(A), O.twovar_marginals(Ao)
+    assert set(got) == set(po)
+    for k in po:
+        assert got[k].shape == (90, 90) and np.allclose(got[k], po[k], rtol=1e-10, atol=1e-15), k
+    per, pero = pair(rand_per(rng, [2, 3, 2], (75,)), periodic=True)
+    g2, p2 = T.twovar_marginals(per), O.twovar_marginals(pero)
+    for k in p2:
+        assert np.allclose(g2[k], p2[k], rtol=1e-10, atol=1e-15), k
