@@ -22,6 +22,12 @@ namespace cg = cooperative_groups;
 constexpr int kJcCluster = 8;            // CTAs per cluster (portable maximum)
 constexpr int kJcBlocks = 2 * kJcCluster;
 constexpr int kJcThreads = 512;
+#ifdef TTB_JC_STAMPS
+__device__ long long g_jc_stamps[8];   // cycles of CTA 0: load, norms, in-block, cross, store+fence, cluster sync, sweeps, block-rounds
+#define JC_T(i) do { if (tid == 0) { const long long t_ = clock64(); acc_[i] += t_ - last_; last_ = t_; } } while (0)
+#else
+#define JC_T(i) do { } while (0)
+#endif
 
 __host__ __device__ inline int jc_rows_per_block(int nv) {
   int rb = (nv + kJcBlocks - 1) / kJcBlocks;
@@ -170,6 +176,9 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
   const double tol = sqrt((double)max(len, 2)) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
   int* rot = c.st[b].rot;
+#ifdef TTB_JC_STAMPS
+  long long acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
   bool conv = (nv < 2);
   int sweep = 0;
   for (; sweep < s.max_sweeps && !conv; ++sweep) {
@@ -184,6 +193,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
         jc_copy_rows<true>(Jg, c.ldj, Js + (size_t)half * rb * nv, nv, rb, g0, nv, tid);
       }
       __syncthreads();
+      JC_T(0);
       for (int v = wid; v < rb2; v += NW) {
         const double* row = Bs + (size_t)v * len;
         double a0 = 0.0, a1 = 0.0;
@@ -194,6 +204,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
         if (lane == 0) sq[v] = al;
       }
       __syncthreads();
+      JC_T(1);
       bool did = false;
       // ---- rotations inside each block, once per sweep (first block-round): rb/2 + rb/2 pairs per sub-round
       if (kr == 0) {
@@ -209,6 +220,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
           __syncthreads();
         }
       }
+      JC_T(2);
       // ---- rotations between the two blocks: rb sub-rounds of rb disjoint pairs
       if (len <= 32 * NE && nv <= 32 * NE) {
         // warp w keeps its row i = w (and the rotation row) in registers through all rb sub-rounds
@@ -252,6 +264,7 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
         }
       }
       if (did && lane == 0) rotated = 1;
+      JC_T(3);
       // ---- blocks back to their home rows
       for (int half = 0; half < 2; ++half) {
         const int g0 = (half ? bj : bi) * rb;
@@ -264,12 +277,20 @@ __global__ void __cluster_dims__(kJcCluster, 1, 1) __launch_bounds__(kJcThreads,
         if (rotated) atomicAdd(&rot[sweep & 1], 1);
         __threadfence();
       }
+      JC_T(4);
       cl.sync();
+      JC_T(5);
+#ifdef TTB_JC_STAMPS
+      if (tid == 0) acc_[7] += 1;
+#endif
     }
     const int total = __ldcg(&rot[sweep & 1]);  // L2 load: identical in every CTA after the barrier
     if (rank == 0 && tid == 0) rot[(sweep + 1) & 1] = 0;  // ordered before its next use by 15 cluster barriers
     conv = (total == 0);
   }
+#ifdef TTB_JC_STAMPS
+  if (rank == 0 && tid == 0 && b == 0) { acc_[6] = sweep; for (int i = 0; i < 8; ++i) g_jc_stamps[i] = acc_[i]; }
+#endif
   if (!conv && rank == 0 && tid == 0) atomicOr(c.status, ST_NOCONV);
 }
 

@@ -1689,6 +1689,14 @@ int ttb_compress(ttb_handle h, const ttb_trunc* tr, int is_orthogonal) {
   if (!ls.empty()) TTB_TRY(enqueue_sweep(h, 1, tr, ls, ub, lb));
   if (dbg) clock_gettime(CLOCK_MONOTONIC, &t_c);
   const int rc = finish_sweeps(h, tm);
+#ifdef TTB_JC_STAMPS
+  if (getenv("TTB_JC_TRACE")) {
+    long long js[8];
+    cudaMemcpyFromSymbol(js, g_jc_stamps, sizeof(js));
+    fprintf(stderr, "[jc trace] last cluster SVD, CTA 0 cycles: load %lld norms %lld in-block %lld cross %lld store+fence %lld cluster-sync %lld | sweeps %lld block-rounds %lld\n",
+            js[0], js[1], js[2], js[3], js[4], js[5], js[6], js[7]);
+  }
+#endif
   if (getenv("TTB_QS_TRACE")) {
     unsigned long long tr_h[16 * 32];
     cudaMemcpyFromSymbol(tr_h, g_qs_trace, sizeof(tr_h));
