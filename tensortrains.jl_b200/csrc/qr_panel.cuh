@@ -399,6 +399,17 @@ __global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag
       // all own columns lie after the block (columns >= bwc are zero and stay zero): rank-1 updates, started on
       // the raw column while the owner is still reducing.  Warps that are not about to take over the chain back
       // off between polls: their spinning would take issue slots from the owner on the same SM sub-partition
+#ifdef TTB_PANEL_DEFER   // measured A/B (round 2): no effect -- the step in the block times at block 4 is NOT sub-partition sharing
+      if (NS == 4) {   // the sub-partition partner of the chain warp (blk + 4) applies this block one block later (qr_stream.cuh)
+        if (wid == blk + 4) continue;
+        if (wid == blk + 3 && blk >= 1) {
+          const int d0 = (blk - 1) * NS;
+#pragma unroll 1
+          for (int cc = d0; cc < d0 + NS; ++cc)
+            panel_consume_later<RPL, NS>(a, vs + (size_t)cc * LDV, sh_tau, ready, raw, cc, lane, false);
+        }
+      }
+#endif
       const int cend = min(c0 + NS, bwc);
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc)

@@ -288,6 +288,19 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       if (s.trace && b == 0 && lane == 0) g_qs_trace[kb * 32 + 22 + blk] = qs_now();
       if (wid == 0) pump(min(c0 + NS, bwc));   // warp 0's own block: its reflectors leave once the block is done
     } else if (wid > blk) {
+#ifdef TTB_PANEL_DEFER   // measured A/B (round 2): no effect -- the step in the block times at block 4 is NOT sub-partition sharing
+      // Warps w and w + 4 share an SM sub-partition (issue port, FP64 pipe): while warp blk is on the chain its
+      // partner blk + 4 stays OFF the pipe and applies this block's four reflectors one block later, when the
+      // owner is blk + 1 (partner blk + 5).  The trace showed a step, not a slope: 3.0 us per block while the
+      // partner consumed (blocks 0-3), 2.3 us once it had nothing left to do (blocks 4-7).
+      if (wid == blk + 4) continue;
+      if (wid == blk + 3 && blk >= 1) {
+        const int d0 = (blk - 1) * NS;
+#pragma unroll 1
+        for (int cc = d0; cc < d0 + NS; ++cc)
+          panel_consume_later<RPL, NS>(a, vs + (size_t)cc * SL, sh_tau, ready, raw, cc, lane, false, nvi);
+      }
+#endif
       const int cend = min(c0 + NS, bwc);
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc)
