@@ -360,6 +360,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk)}
 
+    pre_fail = []      # identity checks of sharded legs against rank 0's own one-GPU run (messages of the ones that failed)
+
     def alone_on_rank0(fn):
         """At N > 1: rank 0 repeats a leg ALONE on the whole workload (the other ranks wait at the barrier), so the
         line carries the 1-GPU figure measured in the same job and speedup_vs_1gpu is arithmetic on two numbers of
@@ -415,10 +417,11 @@ def main():
             one = alone_on_rank0(lambda: draw_range(0, ND))
             if rank == 0:
                 h1, _, ms1, wall1 = one
-                assert np.array_equal(h1, hist_tot), "histogram of the sharded run differs from the one-GPU run"
+                same4 = bool(np.array_equal(h1, hist_tot))       # a mismatch fails the run AFTER the line is printed
+                pre_fail.append(None if same4 else "sharded C4 histogram differs from the one-GPU run")
                 sample_info["one_gpu"] = {"draws_per_s": ND / (ms1 * 1e-3), "e2e_draws_per_s": ND / wall1, "device_ms": ms1}
                 sample_info["speedup_vs_1gpu"] = {"device": ms1 / ms4, "e2e": wall1 / wall4,
-                                                  "histogram_identical_to_one_gpu_run": True}
+                                                  "histogram_identical_to_one_gpu_run": same4}
         del A4, rz4
 
     # ---- config 5: 4096 periodic trains (64 sites, bond 32, q=2) sharded over the ranks by contiguous
@@ -562,12 +565,12 @@ def main():
                 same = (np.array_equal(one["bonds"], c5_check["bonds"]) and
                         np.allclose(one["pairs_host"].numpy(), c5_check["pairs"], rtol=1e-12, atol=0) and
                         np.allclose(one["lz"], c5_check["lz"], rtol=1e-12, atol=0))
-                assert same, "sharded C5 results differ from the one-GPU run"
+                pre_fail.append(None if same else "sharded C5 results differ from the one-GPU run")
                 batch_info["one_gpu"] = {"device_ms": ms1, "device_ms_by_call": one["ms"], "e2e_wall_ms": one["wall"] * 1e3,
                                          "trains_per_s": B5 / (ms1 * 1e-3)}
                 batch_info["speedup_vs_1gpu"] = {"device": ms1 / dev5, "e2e": one["wall"] / wall5,
                                                  "by_call": {k: one["ms"][k] / ms5_max[k] for k in ms5_max},
-                                                 "results_identical_to_one_gpu_run": True}
+                                                 "results_identical_to_one_gpu_run": bool(same)}
             del one
         _pin.clear()
 
@@ -606,7 +609,9 @@ def main():
                 return o[0], A2.last_timing()[0], time.perf_counter() - t0_
             one = alone_on_rank0(one2)
             if rank == 0:
-                assert np.allclose(one[0], full2, rtol=1e-12, atol=0)
+                same3 = bool(np.allclose(one[0], full2, rtol=1e-12, atol=0))
+                pre_fail.append(None if same3 else "sharded pair marginals of one train differ from the one-GPU run")
+                pairs_info["results_identical_to_one_gpu_run"] = same3
                 pairs_info["one_gpu"] = {"device_ms": one[1], "wall_ms": one[2] * 1e3}
                 pairs_info["speedup_vs_1gpu"] = {"device": one[1] / ms2, "e2e": one[2] / wall2}
         del A2
@@ -658,7 +663,9 @@ def main():
                             "whole_step": {"alg_gflop": sum(v[1] for v in fl.values()) / 1e9,
                                            "tflops": sum(v[1] for v in fl.values()) / (dev_ms / K * 1e-3) / 1e12}}
         extra = {}
-        parity_fail = False
+        parity_fail = any(m is not None for m in pre_fail)
+        if parity_fail:
+            line["parity_failures"] = [m for m in pre_fail if m is not None]
         if sample_info is not None:
             sample_info["tflops_minimal_algorithm"] = sample_info["draws_per_s"] * 8.65e6 / 1e12
             sample_info["frac_of_fp64_peak"] = sample_info["tflops_minimal_algorithm"] / (peak * world) if peak else None
