@@ -206,16 +206,17 @@ int ttb_sample_stats_env(ttb_handle h, ttb_env_handle rz, int64_t b, int64_t nsa
 /* ---- MPS: the Born-machine wrapper p(x) = |psi(x)|^2 over the train psi held by `h`
  *      (src/MatrixProductStates/mps.jl).  evaluate / normalization / normalize! / the forwarded sweeps are host
  *      arithmetic on ttb_evaluate, ttb_dot(psi, psi), ttb_scale_sites and the sweep entries; the entries below are
- *      the functions that need the reference's "d^4" environments (mps.jl:60-126).  OPEN trains only (first and
- *      last bond 1: the four-index arrays Ll[a1, al, b1, bl] then have a1 = b1 = 1 and are d x d matrices; a
- *      periodic psi returns TTB_EUNSUPPORTED).  `b` selects the train of a batch.
+ *      the functions that need the reference's "d^4" environments (mps.jl:60-126): the four-index arrays
+ *      Ll[a1, a, b1, b] are kept as d_1^2 boundary slices of d x d (one slice, a1 = b1 = 1, for an open psi).
+ *      `b` selects the train of a batch.
  *  ttb_mps_accumulate: accumulate_L (left != 0, mps.jl:60-80) / accumulate_R (:82-103) -- the stored environments
- *      (slot t: d_{t+1} x d_{t+1} for l[t], d_t x d_t for r[t], column-major, packed in site order; hermiticity
+ *      (slot t: d_1^2 slices (a1 + d_1 b1) of d_{t+1} x d_{t+1} for l[t], of d_t x d_t for r[t], column-major, packed in
+ *      site order; hermiticity
  *      restored after every step; with normalize every stored slot but the last computed has max-abs 1, like the
  *      reference's in-place `Ll ./= nl`) go to env_out when non-NULL, z = prod(nl) * trace to (logabs, sign).
  *  ttb_mps_marginals (:176-196): out[t][x], L*Q doubles.
  *  ttb_mps_twovar_marginals (:206-232, with accumulate_M :105-126 streamed, never stored): pairs t < u <= t + maxdist
- *      in lexicographic order, Q*Q doubles each (x_t fastest), ttb_twovar_count pairs.
+ *      in lexicographic order, Q*Q doubles each (x_t fastest), ttb_twovar_count pairs; TensorTrain psi only (mps.jl:206).
  *  ttb_mps_sample (sample!, :264-290): like ttb_sample; p_out = |tr Q|^2 / z with z of accumulate_R. */
 int ttb_mps_env_size(ttb_handle h, int64_t b, int left, int64_t* n_doubles);
 int ttb_mps_accumulate(ttb_handle h, int64_t b, int left, int normalize, double* env_out, double* logabs, int* sign);

@@ -1,4 +1,4 @@
-// mps.cu -- the Born-machine wrapper MPS (p(x) = |psi(x)|^2) over an OPEN train psi:
+// mps.cu -- the Born-machine wrapper MPS (p(x) = |psi(x)|^2) over a train psi:
 //   accumulate_L / accumulate_R   src/MatrixProductStates/mps.jl:60-103   (the "d^4" environments)
 //   marginals                     :176-196
 //   accumulate_M / twovar_marginals  :105-126, :206-232
@@ -17,8 +17,13 @@
 //     sampling         p[x | q]      = q S_t(x) q^T,  q <- q A_t(x_t)
 // The reference's quirks are kept: the in-place `Ll ./= nl` also rescales the environment stored one step
 // earlier (stored l[t < L] have max-abs 1, the last one is unscaled), hermiticity is restored after every
-// step ((E + E^T) / 2), z = prod(nl) * trace.  Periodic psi (matrix boundary: genuine d_1^2 d^2 arrays) is not
-// built: TTB_EUNSUPPORTED.
+// step ((E + E^T) / 2), z = prod(nl) * trace.
+// A periodic psi has a matrix boundary: the environments are genuine four-index arrays Ll[a1, a, b1, b].  They are
+// kept as S = d_1^2 SLICES E^(a1,b1) (each d x d): every slice obeys the same sandwich, the id4 start is the unit
+// matrix e_a1 e_b1^T, the hermiticity restoration pairs slice (a1,b1) with the transpose of slice (b1,a1), the
+// max-abs scale is common to all slices, trace = sum_{a,b} E^(a,b)[a,b]; marginals and sampling sum their
+// Frobenius products / quadratic forms over the slices.  twovar_marginals(::MPS) is defined for TensorTrain only
+// (mps.jl:206), like the reference.
 #include <math.h>
 #include <string.h>
 
@@ -31,15 +36,16 @@
 
 namespace ttb {
 
-// out = (raw + raw^T) / 2 (d x d), max-abs of the result into mx[slot] (ordered bits, NaN-propagating)
-struct SymItem { const double* raw; double* out; int d; int slot; };
+// out = (raw + rawT^T) / 2 (d x d), max-abs of the result into mx[slot] (ordered bits, NaN-propagating).  rawT is the
+// raw matrix of the transposed boundary slice (b1, a1) -- raw itself for an open train (mps.jl:77-78)
+struct SymItem { const double* raw; const double* rawT; double* out; int d; int slot; };
 __global__ void __launch_bounds__(256) k_mps_sym(const SymItem* __restrict__ items, unsigned long long* mx) {
   const SymItem it = items[blockIdx.y];
   const int64_t n = (int64_t)it.d * it.d;
   double m = 0.0;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(o % it.d), j = (int)(o / it.d);
-    const double v = 0.5 * (it.raw[o] + it.raw[j + (int64_t)it.d * i]);
+    const double v = 0.5 * (it.raw[o] + it.rawT[j + (int64_t)it.d * i]);
     it.out[o] = v;
     m = absmax_nan(m, v);
   }
@@ -47,6 +53,15 @@ __global__ void __launch_bounds__(256) k_mps_sym(const SymItem* __restrict__ ite
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bits, o); bits = ot > bits ? ot : bits; }
   if ((threadIdx.x & 31) == 0 && bits) atomicMax(mx + it.slot, bits);
+}
+
+// id4 (mps.jl:56) as slices: slice s = a1 + d1 b1 is the d1 x d1 unit matrix e_a1 e_b1^T
+__global__ void k_mps_id4(double* out, int d1) {
+  const int64_t n = (int64_t)d1 * d1 * d1 * d1;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = o / ((int64_t)d1 * d1), e = o - s * d1 * d1;
+    out[o] = (e % d1 == s % d1 && e / d1 == s / d1) ? 1.0 : 0.0;
+  }
 }
 
 // buf /= mx[slot] unless the maximum is zero (`!iszero(nl)`, mps.jl:67)
@@ -58,35 +73,42 @@ __global__ void __launch_bounds__(256) k_mps_scale(const ScaleItem* __restrict__
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < it.n; o += (int64_t)gridDim.x * blockDim.x) it.buf[o] /= m;
 }
 
-// out[item] = <X, Y>_F over n contiguous doubles
-struct FrobItem { const double* X; const double* Y; double* out; int64_t n; };
+// out[item] = sum_{s < ns} <X + s sx, Y + s sy>_F, n contiguous doubles per slice
+struct FrobItem { const double* X; const double* Y; double* out; int64_t n; int ns, pad_; int64_t sx, sy; };
 __global__ void __launch_bounds__(256) k_mps_frob(const FrobItem* __restrict__ items) {
   const FrobItem it = items[blockIdx.x];
   __shared__ double red[40];
   double v = 0.0;
-  for (int64_t o = threadIdx.x; o < it.n; o += blockDim.x) v += it.X[o] * it.Y[o];
+  for (int sl = 0; sl < it.ns; ++sl) {
+    const double* X = it.X + sl * it.sx;
+    const double* Y = it.Y + sl * it.sy;
+    for (int64_t o = threadIdx.x; o < it.n; o += blockDim.x) v += X[o] * Y[o];
+  }
   v = block_sum(v, red);
   if (threadIdx.x == 0) *it.out = v;
 }
 
-// z = prod_{t < nscaled} mx[t] * value -> (log|z|, sign)
-__global__ void k_mps_final(const unsigned long long* mx, int nscaled, const double* last, double* out) {
+// z = prod_{t < nscaled} mx[t] * trace(last) -> (log|z|, sign);  trace = sum_{a,b} E^(a,b)[a,b] (mps.jl:128-130)
+__global__ void k_mps_final(const unsigned long long* mx, int nscaled, const double* last, int d1, double* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double lg = 0.0;
   for (int t = 0; t < nscaled; ++t) {
     const double m = __longlong_as_double((long long)mx[t]);
     if (m != 0.0) lg += log(m);
   }
-  const double v = *last;
+  double v = 0.0;
+  for (int a = 0; a < d1; ++a)
+    for (int b = 0; b < d1; ++b) v += last[((int64_t)(a + d1 * b)) * d1 * d1 + a + d1 * b];
   out[0] = lg + log(fabs(v));
   out[1] = v < 0.0 ? -1.0 : 1.0;
   if (v != v) out[0] = v;
 }
 
-// ---- sampler: one CTA per draw.  q (1 x d_t) is the running product; p[x] = q S_t(x) q^T ----
+// ---- sampler: one CTA per draw.  Q (d1 x d_t, d1 = 1 for an open psi) is the running product of the chosen
+//      matrices; p[x] = sum_{a1,b1} Q[a1,:] S_t^(a1,b1)(x) Q[b1,:]^T  (mps.jl:276-279 with S = A r A^T) ----
 struct MpsSampCtx {
-  const double* slab; int64_t tt_off; const int64_t* off; const int64_t* bond; int L, Q, dmax;
-  const double* S; const int64_t* soff;     // S_t(x): d_t x d_t at S + soff[t] + x d_t^2
+  const double* slab; int64_t tt_off; const int64_t* off; const int64_t* bond; int L, Q, dmax, d1;
+  const double* S; const int64_t* soff;     // S_t^(s)(x): d_t x d_t at S + soff[t] + (x d1^2 + s) d_t^2
   const double* zlog;                       // log z of accumulate_R
   const double* uniforms; uint64_t seed, first;
   uint8_t* x_out; double* p_out; int64_t nsamples;
@@ -95,26 +117,31 @@ __global__ void __launch_bounds__(128) k_mps_sample(MpsSampCtx c) {
   const int64_t s = blockIdx.x;
   if (s >= c.nsamples) return;
   extern __shared__ double sm[];
-  double* q = sm;
-  double* qn = sm + c.dmax;
-  double* pw = qn + c.dmax;
+  const int d1 = c.d1, S1 = d1 * d1;
+  double* q = sm;                              // [d1][dmax] row a1 at q + a1 dmax
+  double* qn = sm + (size_t)d1 * c.dmax;
+  double* pw = qn + (size_t)d1 * c.dmax;
   __shared__ double red[40];
   __shared__ int s_x;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   const double* tt = c.slab + c.tt_off;
-  if (tid == 0) q[0] = 1.0;
+  for (int i = tid; i < d1 * c.dmax; i += nt) q[i] = (i % c.dmax == i / c.dmax) ? 1.0 : 0.0;   // Q = I(d1)
   double ls = 0.0;
   __syncthreads();
   for (int t = 0; t < c.L; ++t) {
     const int dl = (int)c.bond[t], dr = (int)c.bond[t + 1];
     for (int x = 0; x < c.Q; ++x) {
-      const double* Sx = c.S + c.soff[t] + (int64_t)x * dl * dl;
+      const double* Sx = c.S + c.soff[t] + (int64_t)x * S1 * dl * dl;
       double acc = 0.0;
-      for (int j = wid; j < dl; j += nw) {        // column j of S (symmetric up to rounding: use it as stored)
-        double col = 0.0;
-        for (int i = lane; i < dl; i += 32) col += q[i] * Sx[i + (int64_t)dl * j];
-        col = warp_sum(col);
-        if (lane == 0) acc += col * q[j];
+      // one warp per (slice, column j): sum_i Q[a1,i] S[i,j], times Q[b1,j]
+      for (int o = wid; o < S1 * dl; o += nw) {
+        const int sl = o / dl, j = o - sl * dl, a1 = sl % d1, b1 = sl / d1;
+        const double* col = Sx + (int64_t)sl * dl * dl + (int64_t)dl * j;
+        const double* qa = q + (size_t)a1 * c.dmax;
+        double v = 0.0;
+        for (int i = lane; i < dl; i += 32) v += qa[i] * col[i];
+        v = warp_sum(v);
+        if (lane == 0) acc += v * q[(size_t)b1 * c.dmax + j];
       }
       acc = block_sum(acc, red);
       if (tid == 0) pw[x] = acc;
@@ -136,32 +163,39 @@ __global__ void __launch_bounds__(128) k_mps_sample(MpsSampCtx c) {
     __syncthreads();
     const int xs = s_x;
     const double* A = tt + c.off[t] + (int64_t)dl * dr * xs;
-    for (int n = wid; n < dr; n += nw) {
+    for (int o = wid; o < d1 * dr; o += nw) {          // Qn[a1, n] = sum_m Q[a1, m] A[m, n]
+      const int a1 = o / dr, n = o - a1 * dr;
+      const double* qa = q + (size_t)a1 * c.dmax;
       double a = 0.0;
-      for (int m = lane; m < dl; m += 32) a += q[m] * A[m + (int64_t)dl * n];
+      for (int m = lane; m < dl; m += 32) a += qa[m] * A[m + (int64_t)dl * n];
       a = warp_sum(a);
-      if (lane == 0) qn[n] = a;
+      if (lane == 0) qn[(size_t)a1 * c.dmax + n] = a;
     }
     __syncthreads();
     double mx = 0.0;
-    for (int n = tid; n < dr; n += nt) mx = fmax(mx, fabs(qn[n]));
+    for (int o = tid; o < d1 * dr; o += nt) mx = fmax(mx, fabs(qn[(size_t)(o / dr) * c.dmax + (o % dr)]));
     mx = block_max(mx, red);
     if (mx > 0.0 && !isinf(mx)) {
-      for (int n = tid; n < dr; n += nt) qn[n] /= mx;
+      for (int o = tid; o < d1 * dr; o += nt) qn[(size_t)(o / dr) * c.dmax + (o % dr)] /= mx;
       ls += log(mx);
     }
     __syncthreads();
     double* tmp = q; q = qn; qn = tmp;
   }
-  if (tid == 0 && c.p_out) c.p_out[s] = exp(2.0 * (log(fabs(q[0])) + ls) - c.zlog[0]);   // |tr Q|^2 / z (mps.jl:288)
+  if (tid == 0 && c.p_out) {
+    double tr = 0.0;
+    for (int a = 0; a < d1; ++a) tr += q[(size_t)a * c.dmax + a];
+    c.p_out[s] = exp(2.0 * (log(fabs(tr)) + ls) - c.zlog[0]);   // |tr Q|^2 / z (mps.jl:288)
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 struct MpsPlan {
   int L = 0, Q = 0, dmax = 1;
+  int d1 = 1, S = 1;                   // boundary bond and number of boundary slices d1^2 (1 for an open psi)
   std::vector<int> bd;                 // current bonds of train b, L + 1
-  std::vector<int64_t> eoffL, eoffR;   // slot t of l (d_{t+1}^2) / of r (d_t^2)
-  std::vector<int64_t> soff, uoff;     // S_t(.) (Q d_t^2) / U_t(.) (Q d_t d_{t+1})
+  std::vector<int64_t> eoffL, eoffR;   // slot t of l (S d_{t+1}^2) / of r (S d_t^2)
+  std::vector<int64_t> soff, uoff;     // S_t(.) (Q S d_t^2) / U_t(.) (Q S d_t d_{t+1})
   const double* tt = nullptr;
 };
 
@@ -171,16 +205,20 @@ static int mps_plan(ttb_tt* h, int64_t b, MpsPlan& p) {
   TTB_TRY(sync_bonds_to_host(h));
   p.L = (int)h->L; p.Q = (int)h->Q;
   p.bd.assign(h->h_bond.begin() + b * (p.L + 1), h->h_bond.begin() + (b + 1) * (p.L + 1));
-  if (h->periodic || p.bd[0] != 1 || p.bd[p.L] != 1)
-    return fail(TTB_EUNSUPPORTED, "MPS environments are built for open trains (first and last bond 1)");
+  if (p.bd[0] != p.bd[p.L]) return fail(TTB_ESHAPE, "MPS: first and last bond of psi differ");
+  p.d1 = p.bd[0]; p.S = p.d1 * p.d1;
   p.eoffL.assign(p.L + 1, 0); p.eoffR.assign(p.L + 1, 0); p.soff.assign(p.L + 1, 0); p.uoff.assign(p.L + 1, 0);
   for (int t = 0; t < p.L; ++t) {
     p.dmax = std::max(p.dmax, std::max(p.bd[t], p.bd[t + 1]));
-    p.eoffL[t + 1] = p.eoffL[t] + (int64_t)p.bd[t + 1] * p.bd[t + 1];
-    p.eoffR[t + 1] = p.eoffR[t] + (int64_t)p.bd[t] * p.bd[t];
-    p.soff[t + 1] = p.soff[t] + (int64_t)p.Q * p.bd[t] * p.bd[t];
-    p.uoff[t + 1] = p.uoff[t] + (int64_t)p.Q * p.bd[t] * p.bd[t + 1];
+    p.eoffL[t + 1] = p.eoffL[t] + (int64_t)p.S * p.bd[t + 1] * p.bd[t + 1];
+    p.eoffR[t + 1] = p.eoffR[t] + (int64_t)p.S * p.bd[t] * p.bd[t];
+    p.soff[t + 1] = p.soff[t] + (int64_t)p.Q * p.S * p.bd[t] * p.bd[t];
+    p.uoff[t + 1] = p.uoff[t] + (int64_t)p.Q * p.S * p.bd[t] * p.bd[t + 1];
   }
+  const int64_t cap = int64_t(1) << 31;   // doubles: 16 GiB per buffer
+  if (std::max(std::max(p.eoffL[p.L], p.eoffR[p.L]), std::max(p.soff[p.L], p.uoff[p.L])) > cap)
+    return fail(TTB_EUNSUPPORTED, "MPS environments: d_1^2 d^2 L Q = %lld doubles exceed the 16 GiB the entry allows per buffer",
+                (long long)p.soff[p.L]);
   p.tt = h->slab + b * h->tt_stride;
   return TTB_OK;
 }
@@ -193,57 +231,73 @@ static Tp* upload_table(ttb_tt* h, DevBuf& buf, const std::vector<Tp>& v, cudaEr
   return static_cast<Tp*>(buf.p);
 }
 
-// environments of train b into ws.mps[left ? 0 : 1]; (log|z|, sign) into *zout (device, 2 doubles) when non-null.
-// Buffers: mps[0] l, mps[1] r, mps[2] raw / temporaries, mps[3] item tables, mps[4] max-abs slots + outputs.
+// id4 slices (S x d1 x d1) live behind the max-abs slots in mps[4]
+static double* mps_id4_ptr(ttb_tt* h, int L) { return reinterpret_cast<double*>(static_cast<unsigned long long*>(h->ws.mps[4].p) + L + 8); }
+static int mps_ensure_id4(ttb_tt* h, const MpsPlan& p) {
+  Workspace& w = h->ws;
+  const size_t bytes = sizeof(unsigned long long) * (p.L + 8) + sizeof(double) * (size_t)p.S * p.S + 64;
+  const bool fresh = bytes > w.mps[4].cap;
+  if (w.mps[4].ensure(bytes) != cudaSuccess) return fail(TTB_ENOMEM, "MPS boundary identity");
+  (void)fresh;
+  k_mps_id4<<<(unsigned)std::min<int64_t>(((int64_t)p.S * p.S + 255) / 256, 1024), 256, 0, h->stream>>>(mps_id4_ptr(h, p.L), p.d1);
+  return TTB_OK;
+}
+
+// environments of train b into ws.mps[left ? 0 : 1]; (log|z|, sign) into *d_zout (device, 2 doubles) when non-null.
+// Buffers: mps[0] l, mps[1] r, mps[2] raw / temporaries, mps[3] item tables, mps[4] max-abs slots + id4 slices.
 static int mps_env(ttb_tt* h, const MpsPlan& p, bool left, int normalize, double* d_zout) {
   Workspace& w = h->ws;
-  const int L = p.L, Q = p.Q;
+  const int L = p.L, Q = p.Q, S = p.S;
   const int64_t d2 = (int64_t)p.dmax * p.dmax;
   cudaError_t e = w.mps[left ? 0 : 1].ensure(sizeof(double) * std::max<int64_t>(left ? p.eoffL[L] : p.eoffR[L], 1));
-  if (e == cudaSuccess) e = w.mps[2].ensure(sizeof(double) * (Q + 1) * d2);
-  if (e == cudaSuccess) e = w.mps[4].ensure(sizeof(unsigned long long) * (L + 8) + 64);
+  if (e == cudaSuccess) e = w.mps[2].ensure(sizeof(double) * (size_t)(Q + 1) * S * d2);
   if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS environments: %s", cudaGetErrorString(e));
+  TTB_TRY(mps_ensure_id4(h, p));
   double* env = static_cast<double*>(w.mps[left ? 0 : 1].p);
-  double* Tx = static_cast<double*>(w.mps[2].p);          // Q temporaries, then the raw sum
-  double* raw = Tx + Q * d2;
+  double* Tx = static_cast<double*>(w.mps[2].p);          // [Q][S] temporaries, then the S raw sums
+  double* raw = Tx + (size_t)Q * S * d2;
   unsigned long long* mx = static_cast<unsigned long long*>(w.mps[4].p);
-  // tables: per site Q products E A(x) (or A(x) R), one summed product, one sym, one scale
-  std::vector<GemmItem> g1((size_t)L * Q), g2(L);
-  std::vector<SymItem> sy(L);
-  std::vector<ScaleItem> sc(L);
+  const double* id4 = mps_id4_ptr(h, L);
+  // tables: per site Q S products E A(x) (or A(x) R), S summed products, S sym, S scale items
+  std::vector<GemmItem> g1((size_t)L * Q * S), g2((size_t)L * S);
+  std::vector<SymItem> sy((size_t)L * S);
+  std::vector<ScaleItem> sc((size_t)L * S);
   for (int step = 0; step < L; ++step) {
     const int t = left ? step : L - 1 - step;
     const int dl = p.bd[t], dr = p.bd[t + 1];
     const double* At = p.tt + h->off[t];
-    // incoming environment: the previous slot (already scaled), or the 1 x 1 identity kept at raw[d2 - 1 ..]
-    const double* Ein = step == 0 ? nullptr : (left ? env + p.eoffL[t - 1] : env + p.eoffR[t + 1]);
-    for (int x = 0; x < Q; ++x) {
-      GemmItem& it = g1[(size_t)step * Q + x];
-      it = GemmItem{};
-      if (left) {   // T_x = E (dl x dl) A(x) (dl x dr)
-        it.A = Ein; it.lda = dl; it.B = At + (int64_t)x * dl * dr; it.ldb = dl; it.m = dl; it.n = dr; it.k = dl;
-      } else {      // T_x = A(x) (dl x dr) R (dr x dr)
-        it.A = At + (int64_t)x * dl * dr; it.lda = dl; it.B = Ein; it.ldb = dr; it.m = dl; it.n = dr; it.k = dr;
-      }
-      it.C = Tx + x * d2; it.ldc = dl; it.nsum = 1;
-    }
-    GemmItem& s2 = g2[step];
-    s2 = GemmItem{};
-    s2.nsum = Q;
-    if (left) {     // E' = sum_x A(x)^T T_x : A stored k x m = dl x dr (TA)
-      s2.A = At; s2.lda = dl; s2.sA = (int64_t)dl * dr; s2.B = Tx; s2.ldb = dl; s2.sB = d2; s2.m = dr; s2.n = dr; s2.k = dl; s2.ldc = dr;
-    } else {        // R' = sum_x T_x A(x)^T : B stored n x k = dl x dr (TB)
-      s2.A = Tx; s2.lda = dl; s2.sA = d2; s2.B = At; s2.ldb = dl; s2.sB = (int64_t)dl * dr; s2.m = dl; s2.n = dl; s2.k = dr; s2.ldc = dl;
-    }
-    s2.C = raw;
-    const int dn = left ? dr : dl;
+    const int din = left ? dl : dr, dn = left ? dr : dl;
+    // incoming environment: the previous slot (already scaled), or the id4 slices (din == d1 there)
+    const double* Ein = step == 0 ? id4 : (left ? env + p.eoffL[t - 1] : env + p.eoffR[t + 1]);
     double* slot = env + (left ? p.eoffL[t] : p.eoffR[t]);
-    sy[step] = SymItem{raw, slot, dn, step};
-    sc[step] = ScaleItem{slot, (int64_t)dn * dn, step, 0};
+    for (int sl = 0; sl < S; ++sl) {
+      const double* Es = Ein + (int64_t)sl * din * din;
+      for (int x = 0; x < Q; ++x) {
+        GemmItem& it = g1[((size_t)step * Q + x) * S + sl];
+        it = GemmItem{};
+        if (left) {   // T_x = E (dl x dl) A(x) (dl x dr)
+          it.A = Es; it.lda = dl; it.B = At + (int64_t)x * dl * dr; it.ldb = dl; it.m = dl; it.n = dr; it.k = dl;
+        } else {      // T_x = A(x) (dl x dr) R (dr x dr)
+          it.A = At + (int64_t)x * dl * dr; it.lda = dl; it.B = Es; it.ldb = dr; it.m = dl; it.n = dr; it.k = dr;
+        }
+        it.C = Tx + ((size_t)x * S + sl) * d2; it.ldc = dl; it.nsum = 1;
+      }
+      GemmItem& s2 = g2[(size_t)step * S + sl];
+      s2 = GemmItem{};
+      s2.nsum = Q;
+      if (left) {     // E' = sum_x A(x)^T T_x : A stored k x m = dl x dr (TA)
+        s2.A = At; s2.lda = dl; s2.sA = (int64_t)dl * dr; s2.B = Tx + (size_t)sl * d2; s2.ldb = dl; s2.sB = (int64_t)S * d2;
+        s2.m = dr; s2.n = dr; s2.k = dl; s2.ldc = dr;
+      } else {        // R' = sum_x T_x A(x)^T : B stored n x k = dl x dr (TB)
+        s2.A = Tx + (size_t)sl * d2; s2.lda = dl; s2.sA = (int64_t)S * d2; s2.B = At; s2.ldb = dl; s2.sB = (int64_t)dl * dr;
+        s2.m = dl; s2.n = dl; s2.k = dr; s2.ldc = dl;
+      }
+      s2.C = raw + (size_t)sl * d2;
+      const int slT = (sl / p.d1) + p.d1 * (sl % p.d1);     // (a1, b1) -> (b1, a1)
+      sy[(size_t)step * S + sl] = SymItem{raw + (size_t)sl * d2, raw + (size_t)slT * d2, slot + (int64_t)sl * dn * dn, dn, step};
+      sc[(size_t)step * S + sl] = ScaleItem{slot + (int64_t)sl * dn * dn, (int64_t)dn * dn, step, 0};
+    }
   }
-  // the first step's incoming environment is the 1 x 1 identity: a device constant kept behind the max slots
-  double* one = reinterpret_cast<double*>(mx + L + 4);
-  for (int x = 0; x < Q; ++x) { GemmItem& it = g1[x]; if (left) it.A = one; else it.B = one; }
   std::vector<unsigned char> blob(sizeof(GemmItem) * (g1.size() + g2.size()) + sizeof(SymItem) * sy.size() + sizeof(ScaleItem) * sc.size());
   unsigned char* bp = blob.data();
   const size_t o1 = 0, o2 = o1 + sizeof(GemmItem) * g1.size(), o3 = o2 + sizeof(GemmItem) * g2.size(), o4 = o3 + sizeof(SymItem) * sy.size();
@@ -252,67 +306,71 @@ static int mps_env(ttb_tt* h, const MpsPlan& p, bool left, int normalize, double
   memcpy(bp + o3, sy.data(), sizeof(SymItem) * sy.size());
   memcpy(bp + o4, sc.data(), sizeof(ScaleItem) * sc.size());
   unsigned char* d_blob = upload_table(h, w.mps[3], blob, e);
-  const double h_one = 1.0;
   if (e == cudaSuccess) e = cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * (L + 4), h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(one, &h_one, sizeof(double), cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // blob / h_one are stack or local storage
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // blob is local storage
   if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS environments: %s", cudaGetErrorString(e));
-  const GemmItem* d1 = reinterpret_cast<const GemmItem*>(d_blob + o1);
+  const GemmItem* d1i = reinterpret_cast<const GemmItem*>(d_blob + o1);
   const GemmItem* d2i = reinterpret_cast<const GemmItem*>(d_blob + o2);
   const SymItem* d3 = reinterpret_cast<const SymItem*>(d_blob + o3);
   const ScaleItem* d4 = reinterpret_cast<const ScaleItem*>(d_blob + o4);
   for (int step = 0; step < L; ++step) {
     const int t = left ? step : L - 1 - step;
     const int dl = p.bd[t], dr = p.bd[t + 1], dn = left ? dr : dl;
-    launch_gemm<false, false>(h, d1 + (size_t)step * Q, Q, tiles64(dl, dr));
-    if (left) launch_gemm<true, false>(h, d2i + step, 1, tiles64(dn, dn));
-    else launch_gemm<false, true>(h, d2i + step, 1, tiles64(dn, dn));
-    const unsigned gs = (unsigned)std::min<int64_t>(((int64_t)dn * dn + 255) / 256, 256);
-    TTB_LAUNCH(h, "k_mps_sym", (k_mps_sym<<<dim3(gs, 1), 256, 0, h->stream>>>(d3 + step, mx)));
+    launch_gemm<false, false>(h, d1i + (size_t)step * Q * S, Q * S, tiles64(dl, dr));
+    if (left) launch_gemm<true, false>(h, d2i + (size_t)step * S, S, tiles64(dn, dn));
+    else launch_gemm<false, true>(h, d2i + (size_t)step * S, S, tiles64(dn, dn));
+    const unsigned gs = (unsigned)std::min<int64_t>(((int64_t)dn * dn + 255) / 256, 64);
+    TTB_LAUNCH(h, "k_mps_sym", (k_mps_sym<<<dim3(gs, (unsigned)S), 256, 0, h->stream>>>(d3 + (size_t)step * S, mx)));
     // `Ll ./= nl` at the START of the next iteration, in place on the stored array (mps.jl:65-69): every stored
-    // environment but the last has max-abs 1
-    if (normalize && step < L - 1) TTB_LAUNCH(h, "k_mps_scale", (k_mps_scale<<<dim3(gs, 1), 256, 0, h->stream>>>(d4 + step, mx)));
+    // environment but the last has max-abs 1 (one common scale for all boundary slices)
+    if (normalize && step < L - 1)
+      TTB_LAUNCH(h, "k_mps_scale", (k_mps_scale<<<dim3(gs, (unsigned)S), 256, 0, h->stream>>>(d4 + (size_t)step * S, mx)));
   }
   if (d_zout) {
-    const double* last = env + (left ? p.eoffL[L - 1] : p.eoffR[0]);   // 1 x 1: its trace is the value
-    TTB_LAUNCH(h, "k_mps_final", (k_mps_final<<<1, 32, 0, h->stream>>>(mx, normalize ? L - 1 : 0, last, d_zout)));
+    const double* last = env + (left ? p.eoffL[L - 1] : p.eoffR[0]);   // S slices of d1 x d1
+    TTB_LAUNCH(h, "k_mps_final", (k_mps_final<<<1, 32, 0, h->stream>>>(mx, normalize ? L - 1 : 0, last, p.d1, d_zout)));
   }
   return TTB_OK;
 }
 
-// S_t(x) = A_t(x) r_{t+1} A_t(x)^T for all (t, x) into mps[5] (U in mps[6]); r must be in mps[1]
+// S_t^(s)(x) = A_t(x) r_{t+1}^(s) A_t(x)^T for all (t, x, s) into mps[5] (U in mps[6]); r must be in mps[1]
 static int mps_sandwich_R(ttb_tt* h, const MpsPlan& p) {
   Workspace& w = h->ws;
-  const int L = p.L, Q = p.Q;
+  const int L = p.L, Q = p.Q, S = p.S;
   cudaError_t e = w.mps[5].ensure(sizeof(double) * std::max<int64_t>(p.soff[L], 1));
   if (e == cudaSuccess) e = w.mps[6].ensure(sizeof(double) * std::max<int64_t>(p.uoff[L], 1));
   if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS sandwiches: %s", cudaGetErrorString(e));
-  double* S = static_cast<double*>(w.mps[5].p);
+  double* Sb = static_cast<double*>(w.mps[5].p);
   double* U = static_cast<double*>(w.mps[6].p);
   const double* r = static_cast<const double*>(w.mps[1].p);
-  const double* one = reinterpret_cast<const double*>(static_cast<unsigned long long*>(w.mps[4].p) + L + 4);
-  std::vector<GemmItem> g((size_t)2 * L * Q);
+  const double* id4 = mps_id4_ptr(h, L);
+  const size_t nit = (size_t)L * Q * S;
+  std::vector<GemmItem> g(2 * nit);
   unsigned tu = 1, ts = 1;
+  size_t k = 0;
   for (int t = 0; t < L; ++t) {
     const int dl = p.bd[t], dr = p.bd[t + 1];
     for (int x = 0; x < Q; ++x) {
       const double* Ax = p.tt + h->off[t] + (int64_t)x * dl * dr;
-      GemmItem& a = g[(size_t)t * Q + x];
-      a = GemmItem{};
-      a.A = Ax; a.lda = dl; a.B = t < L - 1 ? r + p.eoffR[t + 1] : one; a.ldb = dr; a.m = dl; a.n = dr; a.k = dr;
-      a.C = U + p.uoff[t] + (int64_t)x * dl * dr; a.ldc = dl; a.nsum = 1;
-      GemmItem& b = g[(size_t)L * Q + (size_t)t * Q + x];
-      b = GemmItem{};
-      b.A = a.C; b.lda = dl; b.B = Ax; b.ldb = dl; b.m = dl; b.n = dl; b.k = dr;
-      b.C = S + p.soff[t] + (int64_t)x * dl * dl; b.ldc = dl; b.nsum = 1;
+      for (int sl = 0; sl < S; ++sl, ++k) {
+        const double* rs = (t < L - 1 ? r + p.eoffR[t + 1] : id4) + (int64_t)sl * dr * dr;
+        GemmItem& a = g[k];
+        a = GemmItem{};
+        a.A = Ax; a.lda = dl; a.B = rs; a.ldb = dr; a.m = dl; a.n = dr; a.k = dr;
+        a.C = U + p.uoff[t] + ((int64_t)x * S + sl) * dl * dr; a.ldc = dl; a.nsum = 1;
+        GemmItem& b = g[nit + k];
+        b = GemmItem{};
+        b.A = a.C; b.lda = dl; b.B = Ax; b.ldb = dl; b.m = dl; b.n = dl; b.k = dr;
+        b.C = Sb + p.soff[t] + ((int64_t)x * S + sl) * dl * dl; b.ldc = dl; b.nsum = 1;
+      }
       tu = std::max(tu, tiles64(dl, dr)); ts = std::max(ts, tiles64(dl, dl));
     }
   }
   GemmItem* dg = upload_table(h, w.mps[7], g, e);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS sandwiches: %s", cudaGetErrorString(e));
-  launch_gemm<false, false>(h, dg, L * Q, tu);
-  launch_gemm<false, true>(h, dg + (size_t)L * Q, L * Q, ts);
+  for (size_t o = 0; o < nit; o += 32768) launch_gemm<false, false>(h, dg + o, (int)std::min<size_t>(32768, nit - o), tu);
+  for (size_t o = 0; o < nit; o += 32768) launch_gemm<false, true>(h, dg + nit + o, (int)std::min<size_t>(32768, nit - o), ts);
   return TTB_OK;
 }
 
@@ -362,13 +420,15 @@ int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) {
   if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
   if (rc != TTB_OK) return rc;
   const double* l = static_cast<const double*>(w.mps[0].p);
-  const double* S = static_cast<const double*>(w.mps[5].p);
-  const double* one = reinterpret_cast<const double*>(static_cast<unsigned long long*>(w.mps[4].p) + L + 4);
+  const double* Sb = static_cast<const double*>(w.mps[5].p);
+  const double* id4 = mps_id4_ptr(h, L);
   std::vector<FrobItem> f((size_t)L * Q);
   for (int t = 0; t < L; ++t)
-    for (int x = 0; x < Q; ++x)
-      f[(size_t)t * Q + x] = FrobItem{t > 0 ? l + p.eoffL[t - 1] : one, S + p.soff[t] + (int64_t)x * p.bd[t] * p.bd[t], d_p + (size_t)t * Q + x,
-                                      (int64_t)p.bd[t] * p.bd[t]};
+    for (int x = 0; x < Q; ++x) {     // p_t[x] = sum over boundary slices of <l_{t-1}^(s), S_t^(s)(x)>_F
+      const int64_t n = (int64_t)p.bd[t] * p.bd[t];
+      f[(size_t)t * Q + x] = FrobItem{t > 0 ? l + p.eoffL[t - 1] : id4, Sb + p.soff[t] + (int64_t)x * p.S * n, d_p + (size_t)t * Q + x,
+                                      n, p.S, 0, n, n};
+    }
   cudaError_t e = cudaSuccess;
   FrobItem* df = upload_table(h, w.mps[9], f, e);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -390,6 +450,7 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
   if (!out) return fail(TTB_EINVAL, "null argument");
   MpsPlan p;
   TTB_TRY(mps_plan(h, b, p));
+  if (h->periodic || p.S != 1) return fail(TTB_EINVAL, "twovar_marginals(::MPS) is defined for a TensorTrain psi only (mps.jl:206)");
   Workspace& w = h->ws;
   const int L = p.L, Q = p.Q;
   if (maxdist <= 0 || maxdist > L - 1) maxdist = L - 1;
@@ -415,7 +476,7 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
   const double* l = static_cast<const double*>(w.mps[0].p);
   const double* S = static_cast<const double*>(w.mps[5].p);
   unsigned long long* mx = static_cast<unsigned long long*>(w.mps[4].p);   // slots 0 .. L-1 reused per distance
-  const double* one = reinterpret_cast<const double*>(mx + L + 4);
+  const double* one = mps_id4_ptr(h, L);   // S = 1: the 1 x 1 identity
   auto Kp = [&](double* base, int t, int x) { return base + ((size_t)t * Q + x) * d2; };
   auto Tp = [&](int t, int x, int y) { return Tm + (((size_t)t * Q + x) * Q + y) * d2; };
   // ---- tables for all distances, one upload ----
@@ -456,7 +517,7 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
       for (int x = 0; x < Q; ++x)
         for (int y = 0; y < Q; ++y)
           fi.push_back(FrobItem{Kp(K, t, x), S + p.soff[u] + (int64_t)y * du * du, d_out + (poff[t] + dist - 1) * Q * Q + x + (size_t)Q * y,
-                                (int64_t)du * du});
+                                (int64_t)du * du, 1, 0, 0, 0});
     }
     st.nf = fi.size() - st.f;
     st.g1 = gi.size();
@@ -479,7 +540,7 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
           a.A = p.tt + h->off[u]; a.lda = du; a.sA = (int64_t)du * dn; a.B = Tp(t, x, 0); a.ldb = du; a.sB = d2;
           a.m = dn; a.n = dn; a.k = du; a.C = Kp(Kraw, t, x); a.ldc = dn; a.nsum = Q;
           gi.push_back(a); st.t2 = std::max(st.t2, tiles64(dn, dn));
-          si.push_back(SymItem{Kp(Kraw, t, x), Kp(K, t, x), dn, t});
+          si.push_back(SymItem{Kp(Kraw, t, x), Kp(Kraw, t, x), Kp(K, t, x), dn, t});
           ci.push_back(ScaleItem{Kp(K, t, x), (int64_t)dn * dn, t, 0});
         }
       }
@@ -557,11 +618,11 @@ int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uin
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(TTB_ECUDA, "MPS sample: %s", cudaGetErrorString(e));
   MpsSampCtx c{};
-  c.slab = h->slab; c.tt_off = b * h->tt_stride; c.off = d_tab; c.bond = d_tab + 2 * (L + 1); c.L = L; c.Q = p.Q; c.dmax = p.dmax;
+  c.slab = h->slab; c.tt_off = b * h->tt_stride; c.off = d_tab; c.bond = d_tab + 2 * (L + 1); c.L = L; c.Q = p.Q; c.dmax = p.dmax; c.d1 = p.d1;
   c.S = static_cast<const double*>(w.mps[5].p); c.soff = d_tab + L + 1; c.zlog = d_z;
   c.uniforms = d_u; c.seed = seed; c.first = first_index; c.x_out = d_x; c.p_out = p_out ? d_pq : nullptr; c.nsamples = nsamples;
-  const size_t smem = sizeof(double) * (2 * (size_t)p.dmax + p.Q + 8);
-  if (smem > 48 * 1024) return fail(TTB_EUNSUPPORTED, "MPS sample: bond dimension too large for the one-CTA-per-draw kernel");
+  const size_t smem = sizeof(double) * (2 * (size_t)p.d1 * p.dmax + p.Q + 8);
+  if (smem > 48 * 1024) return fail(TTB_EUNSUPPORTED, "MPS sample: d_1 * d_max too large for the one-CTA-per-draw kernel");
   TTB_LAUNCH(h, "k_mps_sample", (k_mps_sample<<<(unsigned)nsamples, 128, smem, h->stream>>>(c)));
   rc = tm.finish();
   if (rc != TTB_OK) return rc;

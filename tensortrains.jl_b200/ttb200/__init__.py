@@ -1095,18 +1095,23 @@ def _mps_accumulate(p: MPS, left: bool, normalize: bool):
     la, sg = C.c_double(), C.c_int()
     _ck(lib.ttb_mps_accumulate(A._hd, 0, int(left), int(bool(normalize)), _dp(buf), C.byref(la), C.byref(sg)))
     bd = [int(v) for v in A.bonds(0)]
+    d1 = bd[0]
     envs, o = [], 0
     for t in range(A.L):
         d = bd[t + 1] if left else bd[t]
-        # the reference's four-index array [a1, a, b1, b] of an open train: a1 = b1 = 1
-        envs.append(buf[o:o + d * d].reshape((d, d), order="F").reshape((1, d, 1, d) if left else (d, 1, d, 1)).copy())
-        o += d * d
+        n = d1 * d1 * d * d
+        # the device keeps one d x d slice per boundary pair (a1, b1): [a, b, a1, b1] column-major; the reference's
+        # arrays are Ll[a1, a, b1, b] (mps.jl:60-80) and Rl[a, aL, b, bL] (:82-103); an open train has a1 = b1 = 1
+        blk = buf[o:o + n].reshape((d, d, d1, d1), order="F")
+        envs.append(np.ascontiguousarray(blk.transpose(2, 0, 3, 1) if left else blk.transpose(0, 2, 1, 3)))
+        o += n
     return envs, Logarithmic(logabs=la.value, sign=sg.value)
 
 
 def mps_accumulate_L(p: MPS, normalize: bool = True):
     """``accumulate_L(p::MPS)`` (mps.jl:60-80): ``(l, z)``; ``l[t]`` indexed ``[a1, a_{t+1}, b1, b_{t+1}]`` (open psi:
-    ``a1 = b1 = 1``), hermiticity restored after every step, every ``l[t < L]`` max-abs 1 with ``normalize``."""
+    ``a1 = b1 = 1``; periodic psi: the full ``d_1 x d x d_1 x d`` array), hermiticity restored after every step, every
+    ``l[t < L]`` max-abs 1 with ``normalize``."""
     return _mps_accumulate(p, True, normalize)
 
 

@@ -818,9 +818,44 @@ def test_mps_orthogonal_environments_and_unsupported():
     for r in T.mps_accumulate_R(p, False)[0][1:]:
         d = r.shape[0]
         assert np.allclose(r.reshape(d, d), np.eye(d), atol=1e-10)
-    per, _ = pair(rand_per(rng, [3, 4, 3], (2,)), periodic=True)
-    with pytest.raises(NotImplementedError):
-        T.mps_marginals(T.MPS(per))
+
+
+@pytest.mark.parametrize("bonds,q", [([3, 4, 5, 2], (2,)), ([2, 6, 6, 6, 6, 6, 3], (3,))])
+def test_mps_periodic_psi_matches_oracle(bonds, q):
+    """A periodic psi: the environments are the reference's genuine four-index arrays (mps.jl:60-103), kept on the
+    device as d_1^2 boundary slices; accumulate_L/R, marginals and sample! against the oracle, marginals against
+    brute force; twovar_marginals(::MPS) is TensorTrain-only like the reference (mps.jl:206)."""
+    rng = RNG(972)
+    ts = [rng.standard_normal((bonds[t], bonds[(t + 1) % len(bonds)]) + q) for t in range(len(bonds))]
+    psi, psio = pair(ts, periodic=True)
+    p, po = T.MPS(psi), O.MPS(psio)
+    for normalize in (True, False):
+        for fg, fo in ((T.mps_accumulate_L, O.mps_accumulate_L), (T.mps_accumulate_R, O.mps_accumulate_R)):
+            eg, zg = fg(p, normalize)
+            eo, zo = fo(po, normalize)
+            assert zg.sign == zo.sign and close(zg.logabs, zo.logabs, 1e-10, 1e-12)
+            for a, b in zip(eg, eo):
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-10, atol=1e-12 * np.abs(b).max())
+    zn = T.mps_normalization(p)
+    assert close(zn.logabs, T.mps_accumulate_L(p)[1].logabs, 1e-10, 1e-12)
+    mg = T.mps_marginals(p)
+    for a, b in zip(mg, O.mps_marginals(po)):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-13)
+    Qf = int(np.prod(q))
+    qq = O.mps_exact_prob(po).reshape([Qf] * len(ts))
+    for t in range(len(ts)):
+        pt = qq.sum(axis=tuple(i for i in range(len(ts)) if i != t))
+        assert np.allclose(pt / pt.sum(), mg[t].reshape(-1, order="F"), rtol=1e-10, atol=0)
+    n = 16
+    us = rng.random((n, len(ts)))
+    X, qg = T.mps_sample(p, uniforms=us)
+    zR = O.mps_accumulate_R(po)
+    for i in range(n):
+        xo, qo = O.mps_sample(lambda t: us[i, t], po, rz=zR)
+        flat = [int(np.ravel_multi_index(x, psi.q, order="F")) for x in xo]
+        assert list(X[i]) == flat and close(qg[i], qo, 1e-9)
+    with pytest.raises(ValueError):
+        T.mps_twovar_marginals(p)
 
 
 @pytest.mark.parametrize("case", ["open_d40", "periodic_d20", "batched"])
