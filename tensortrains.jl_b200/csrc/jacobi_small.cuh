@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(4 * W, W == 32 ? 8 : 1) k_jacobi_g8(SweepCtx c
   const int grp = lane >> 3, e0 = (lane & 7) * 2;    // pair slot inside the warp, first element of this lane
   const int q = wid * 4 + grp;                       // pair index of the round handled by this lane group
   bool conv = (nv < 2);
-  for (int sweep = 0; sweep < s.max_sweeps && !conv; ++sweep) {
+  int sweep = 0;
+  for (; sweep < s.max_sweeps && !conv; ++sweep) {
     if (tid < W) {   // cached squared norms, recomputed once per sweep (one row per thread, stride LD: conflict-free)
       double a0 = 0.0;
       if (tid < nv) {
@@ -319,6 +320,9 @@ __global__ void __launch_bounds__(4 * W, W == 32 ? 8 : 1) k_jacobi_g8(SweepCtx c
     conv = (rotated == 0);
     __syncthreads();
   }
+#ifdef TTB_JSYS_DEBUG
+  if (b == 0 && tid == 0) printf("[g8] W=%d nv=%d len=%d sweeps=%d\n", W, nv, len, sweep);
+#endif
   if (!conv && tid == 0) atomicOr(c.status, ST_NOCONV);
   jacobi_finish(c, s, b, B, LD, nv, len, sig, srt);
   double* Bg = c.Bv + (int64_t)b * c.bv_stride;

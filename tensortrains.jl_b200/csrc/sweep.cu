@@ -626,6 +626,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 }  // namespace ttb
 #include "jacobi_cluster.cuh"
 #include "jacobi_small.cuh"
+#include "jacobi_sys.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -1443,6 +1444,18 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
         // many warps per SM: the issue-lean fixed-stride kernel (jacobi_small.cuh)
         static const bool no_g8 = getenv("TTB_JACOBI_NOG8") != nullptr;
         TTB_ONCE_PER_DEVICE(h, 7) cudaFuncSetAttribute(k_jacobi_g8<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jg8_smem(64));
+        static const bool use_sys = getenv("TTB_JACOBI_SYS") != nullptr;
+        TTB_ONCE_PER_DEVICE(h, 11) {
+          cudaFuncSetAttribute(k_jacobi_sys<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsys_smem(64));
+          cudaFuncSetAttribute(k_jacobi_sys<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsys_smem(32));
+        }
+        if (use_sys && nv_ub <= 32 && len_ub <= 32 && nv_ub > 16) {
+          auto kg = k_jacobi_sys<32>;
+          SW_LAUNCH("k_jacobi", kg, B, 128, jsys_smem(32), c, s);
+        } else if (use_sys && !(nv_ub <= 32 && len_ub <= 32) && nv_ub > 32) {
+          auto kg = k_jacobi_sys<64>;
+          SW_LAUNCH("k_jacobi", kg, B, 256, jsys_smem(64), c, s);
+        } else
         if (nv_ub <= 32 && len_ub <= 32 && B >= sm_count && !no_g8) {
           // a batch that fills the GPU is issue-bound: four pairs per warp (k_jacobi_g8)
           auto kg = k_jacobi_g8<32>;
