@@ -1240,3 +1240,32 @@ def test_twovar_marginals_large_physical_dimension():
     g2, p2 = T.twovar_marginals(per), O.twovar_marginals(pero)
     for k in p2:
         assert np.allclose(g2[k], p2[k], rtol=1e-10, atol=1e-15), k
+
+
+def test_new_entries_argument_errors():
+    """argument checking of the round-2 entries: errors come back as status codes -> the reference's exception classes"""
+    rng = RNG(992)
+    ts = rand_open(rng, [1, 3, 4, 1], (2,))
+    A, _ = pair(ts)
+    with pytest.raises(ValueError):
+        T.merge_tensors(A, 2)                                  # no site pair (2, 3)
+    with pytest.raises(ValueError):
+        T.split_tensor_(A, 0, np.zeros((1, 4, 2)))             # wrong shape
+    with pytest.raises(ValueError):
+        T.split_tensor_(A, 0, T.merge_tensors(A, 0), lr="up")
+    with pytest.raises(ValueError):
+        T.data_environments(A, [[0, 1, 2]])                    # x = 2 outside 0:1
+    with pytest.raises(ValueError):
+        T.update_environments_(np.zeros((1, 2, 3)), A, 0, [[0, 1, 0]])
+    with pytest.raises(ValueError):
+        T.twovar_marginals_block(A, 2, 1)                      # empty / reversed range
+    with pytest.raises(ValueError):
+        T.twovar_marginals_block(A, 0, 2, out=np.zeros(3))     # destination too small
+    per, _ = pair(rand_per(rng, [2, 3, 2], (2,)), periodic=True)
+    with pytest.raises(ValueError):
+        T.data_environments(per, [[0, 1, 0]])                  # TensorTrain only (src/tensor_train.jl:320)
+    batched = T.TensorTrain([np.stack([a, a]) for a in ts], batched=True)
+    with pytest.raises(NotImplementedError):
+        T.MPS(batched)
+    assert T.lib.ttb_merge_tensors(A._hd, 0, 0, None) != 0 and T.lib.ttb_mps_marginals(A._hd, 0, None) != 0
+    assert T.lib.ttb_split_tensor(A._hd, 0, 0, None, None, 1, None) != 0
