@@ -6,7 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
-__device__ long long g_stamps[1024];
+__device__ long long g_stamps[2048];
 #define TTB_PANEL_STAMPS g_stamps
 #include "common.cuh"
 namespace ttb {
@@ -75,17 +75,17 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
     }
-    long long st[1024];
+    long long st[2048];
     cudaMemcpyFromSymbol(st, g_stamps, sizeof(st));
 #ifdef TTB_PANEL_FINE
     printf("  col(OS): prev publish->entry | partial sums | butterfly | scalars | v + publish | own updates\n");
-    for (int cc = 8; cc < 16; ++cc) {
+    for (int cc = 1; cc < 32; ++cc) {
       long long* a = &st[64 + 16 * cc];
       printf("  %2d(%d): %5lld | %5lld | %5lld | %5lld | %5lld | %5lld\n", cc, cc % 4, a[0] - st[8 + cc - 1], a[1] - a[0], a[2] - a[1],
              a[3] - a[2], a[4] - a[3], a[5] - a[4]);
     }
     printf("  next owner as consumer of reflector cc: owner entry->raw seen | early dots | wait ready (vs publish) | update | -> its owner step entry\n");
-    for (int cc = 8; cc < 16; ++cc) {
+    for (int cc = 1; cc < 31; ++cc) {
       long long* a = &st[64 + 16 * cc];
       printf("  %2d: %5lld | %5lld | %5lld (%5lld after publish) | %5lld | %5lld\n", cc, a[6] - a[0], a[7] - a[6], a[8] - a[7], a[8] - st[8 + cc], a[9] - a[8],
              (cc % 4 == 3) ? st[64 + 16 * (cc + 1)] - a[9] : 0LL);
@@ -94,7 +94,7 @@ int main() {
     printf("panel %d: kernel %.1f us (%s)  cycles: loop %lld  Tbuild %lld  store %lld\n", panel, best * 1e3,
            cudaGetErrorString(cudaGetLastError()), st[1] - st[0], st[2] - st[1], st[3] - st[2]);
     printf("  ready-to-ready:");
-    for (int cc = 1; cc < (NCOLS < 32 ? NCOLS : 32); cc += (NCOLS < 32 ? 1 : 3)) printf(" %lld", st[8 + cc] - st[8 + cc - 1]);
+    for (int cc = 1; cc < (NCOLS < 32 ? NCOLS : 32); cc += 1) printf(" %lld", st[8 + cc] - st[8 + cc - 1]);
     printf("\n");
   }
   return 0;
