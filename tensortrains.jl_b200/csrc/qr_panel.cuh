@@ -288,6 +288,80 @@ __device__ __forceinline__ void panel_consume_later(double (&a)[NS][RPL], const 
 #endif
 }
 
+// Two reflectors of the block in flight (cc, cc + 1) applied TOGETHER.  Stamps (profiles/r2_micro_panel.txt): applying
+// one reflector costs a consuming warp ~935 cycles (16 loads, 64 FMAs of dots, a transposed butterfly, the flag wait,
+// 64 FMAs of update) while the owner forms one every 680-960 -- the NEXT owner falls behind inside the block and still
+// has ~1.5 reflectors of work left when the block's last reflector is published: that, not the flag latency, is the
+// 1000-2400 cycles of every hand-off.  With V0 = den0 e_cc + x0, V1 = den1 e_{cc+1} + x1:
+//   d0 = V0.a, d1 = V1.a (both on the ORIGINAL a), g = V1.V0 = den1 x0[cc+1] + x1.x0,
+//   w0 = tau0 d0, w1 = tau1 (d1 - g w0), a -= w0 V0 + w1 V1
+// -- one set of loads, one round of butterflies, one wait and one update pass for two reflectors.  The raw dots start
+// when raw[cc + 1] is up (x1 is the column AFTER the owner applied reflector cc to it); both columns are streamed
+// from shared memory twice instead of living in registers across the butterflies (k_qr_stream sits at 254 registers).
+template <int RPL, int NS>
+__device__ __forceinline__ void panel_consume_pair(double (&a)[NS][RPL], const double* v0c, const double* v1c, const double* sh_tau,
+                                                   const int* ready, const int* raw, int cc, int lane, bool relaxed, int nvi = RPL) {
+  unsigned it = 0;
+  while (ld_flag(&raw[cc + 1]) == 0) {
+    if (relaxed) __nanosleep(100);
+    if (++it > (1u << 26)) __trap();
+  }
+  double d0[NS], d1[NS], g = 0.0;
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) { d0[s2] = 0.0; d1[s2] = 0.0; }
+  const double x00 = lane > cc ? v0c[lane] : 0.0;          // rows <= cc do not belong to reflector cc
+  const double x10 = lane > cc + 1 ? v1c[lane] : 0.0;
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    const double x0 = i == 0 ? x00 : (i < nvi ? v0c[lane + 32 * i] : 0.0);
+    const double x1 = i == 0 ? x10 : (i < nvi ? v1c[lane + 32 * i] : 0.0);
+    g = fma(x1, x0, g);
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) { d0[s2] = fma(x0, a[s2][i], d0[s2]); d1[s2] = fma(x1, a[s2][i], d1[s2]); }
+  }
+  double acc0[NS], acc1[NS];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    acc0[s2] = __shfl_sync(0xffffffffu, a[s2][0], cc);
+    acc1[s2] = __shfl_sync(0xffffffffu, a[s2][0], cc + 1);
+  }
+  const double x0c1 = __shfl_sync(0xffffffffu, x00, cc + 1);   // x0[cc + 1]
+  const double t0 = warp_reduce_ns<NS>(d0, lane);
+  const double t1 = warp_reduce_ns<NS>(d1, lane);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  double ts0[NS], ts1[NS];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    ts0[s2] = __shfl_sync(0xffffffffu, t0, s2 * (32 / NS));
+    ts1[s2] = __shfl_sync(0xffffffffu, t1, s2 * (32 / NS));
+  }
+  it = 0;
+  while (ld_flag(&ready[cc + 1]) == 0) {
+    if (++it > (1u << 26)) __trap();
+  }
+  const double den0 = *reinterpret_cast<const volatile double*>(&v0c[cc]);
+  const double tau0 = *reinterpret_cast<const volatile double*>(&sh_tau[cc]);
+  const double den1 = *reinterpret_cast<const volatile double*>(&v1c[cc + 1]);
+  const double tau1 = *reinterpret_cast<const volatile double*>(&sh_tau[cc + 1]);
+  const double gg = fma(den1, x0c1, g);
+  double w0[NS], w1[NS];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    w0[s2] = tau0 * fma(den0, acc0[s2], ts0[s2]);
+    w1[s2] = tau1 * (fma(den1, acc1[s2], ts1[s2]) - gg * w0[s2]);
+  }
+  const double v00 = lane == cc ? den0 : x00;
+  const double v10 = lane == cc + 1 ? den1 : x10;
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    const double x0 = i == 0 ? v00 : (i < nvi ? v0c[lane + 32 * i] : 0.0);
+    const double x1 = i == 0 ? v10 : (i < nvi ? v1c[lane + 32 * i] : 0.0);
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) a[s2][i] -= fma(x0, w0[s2], x1 * w1[s2]);
+  }
+}
+
 // V'^T V' of the whole panel on the FP64 tensor cores, once, off the chain: G[i + 32 j] = sum_r v'_i[r] v'_j[r] for
 // i < j < bwc from the published reflectors (shared memory, column stride SL, rows 0 .. krows-1 valid, zeros above
 // each diagonal and den on it).  While the chain runs, warps whose columns are finished do NOTHING -- their dots
@@ -411,9 +485,22 @@ __global__ void __launch_bounds__(1024 / NS, (RPL <= 2 ? 4 : 1)) k_qr_panel_flag
       }
 #endif
       const int cend = min(c0 + NS, bwc);
+#ifdef TTB_PANEL_PAIR   // measured (micro_panel2, round 2): hand-offs 15-30 % LONGER -- the pair's dots start at the second raw column and are twice the work
+#pragma unroll 1
+      for (int cc = c0; cc < cend;) {
+        if (cc + 1 < cend) {
+          panel_consume_pair<RPL, NS>(a, vs + (size_t)cc * LDV, vs + (size_t)(cc + 1) * LDV, sh_tau, ready, raw, cc, lane, wid != blk + 1);
+          cc += 2;
+        } else {
+          panel_consume_later<RPL, NS>(a, vs + (size_t)cc * LDV, sh_tau, ready, raw, cc, lane, wid != blk + 1);
+          cc += 1;
+        }
+      }
+#else
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc)
         panel_consume_later<RPL, NS>(a, vs + (size_t)cc * LDV, sh_tau, ready, raw, cc, lane, wid != blk + 1);
+#endif
     }
     // (warps whose columns are finished reflectors have nothing to do: V'^T V' is formed after the chain)
   }

@@ -302,9 +302,22 @@ __global__ void __launch_bounds__(kQsThreads, 1) k_qr_stream(SweepCtx c, StepDes
       }
 #endif
       const int cend = min(c0 + NS, bwc);
+#ifdef TTB_PANEL_PAIR   // measured (micro_panel2, round 2): hand-offs 15-30 % LONGER -- the pair's dots start at the second raw column and are twice the work
+#pragma unroll 1
+      for (int cc = c0; cc < cend;) {     // two reflectors at a time: the consuming warps must be faster than the owner (qr_panel.cuh)
+        if (cc + 1 < cend) {
+          panel_consume_pair<RPL, NS>(a, vs + (size_t)cc * SL, vs + (size_t)(cc + 1) * SL, sh_tau, ready, raw, cc, lane, wid != blk + 1, nvi);
+          cc += 2;
+        } else {
+          panel_consume_later<RPL, NS>(a, vs + (size_t)cc * SL, sh_tau, ready, raw, cc, lane, wid != blk + 1, nvi);
+          cc += 1;
+        }
+      }
+#else
 #pragma unroll 1
       for (int cc = c0; cc < cend; ++cc)
         panel_consume_later<RPL, NS>(a, vs + (size_t)cc * SL, sh_tau, ready, raw, cc, lane, wid != blk + 1, nvi);
+#endif
     } else if (wid == 0) {
       // warp 0 owns finished columns from the second block on: it only keeps the pushes going (V'^T V' is formed
       // after the chain, panel_gram_mma).  Lane 0 polls the flags and the whole warp follows its view (a poll
