@@ -1269,3 +1269,33 @@ def test_new_entries_argument_errors():
         T.MPS(batched)
     assert T.lib.ttb_merge_tensors(A._hd, 0, 0, None) != 0 and T.lib.ttb_mps_marginals(A._hd, 0, None) != 0
     assert T.lib.ttb_split_tensor(A._hd, 0, 0, None, None, 1, None) != 0
+
+
+def test_mps_entries_on_a_train_of_a_batch():
+    """the C entries take the train index b of a batched handle (the Python MPS mirror wraps single trains only)"""
+    import ctypes as C
+    rng = RNG(993)
+    bonds, q = [1, 4, 6, 3, 1], (2,)
+    tss = [[rng.standard_normal((bonds[t], bonds[t + 1]) + q) for t in range(4)] for _ in range(3)]
+    A = T.TensorTrain([np.stack([tss[b][t] for b in range(3)]) for t in range(4)], batched=True)
+    for b in (0, 2):
+        po = O.MPS(O.TensorTrain([a.copy() for a in tss[b]]))
+        out = np.zeros((4, 2))
+        T._ck(T.lib.ttb_mps_marginals(A._hd, b, T._dp(out)))
+        for t, m in enumerate(O.mps_marginals(po)):
+            assert np.allclose(out[t], m.reshape(-1, order="F"), rtol=1e-10, atol=1e-13)
+        la, sg = C.c_double(), C.c_int()
+        T._ck(T.lib.ttb_mps_accumulate(A._hd, b, 1, 1, None, C.byref(la), C.byref(sg)))
+        zo = O.mps_accumulate_L(po)[1]
+        assert sg.value == zo.sign and close(la.value, zo.logabs, 1e-10, 1e-12)
+        n = C.c_int64()
+        T._ck(T.lib.ttb_twovar_count(A._hd, 3, C.byref(n)))
+        pairs = np.zeros((n.value, 4))
+        T._ck(T.lib.ttb_mps_twovar_marginals(A._hd, b, 3, T._dp(pairs)))
+        bo = O.mps_twovar_marginals(po)
+        i = 0
+        for t in range(3):
+            for u in range(t + 1, 4):
+                assert np.allclose(pairs[i], bo[(t, u)].reshape(-1, order="F"), rtol=1e-9, atol=1e-12)
+                i += 1
+    assert T.lib.ttb_mps_marginals(A._hd, 3, T._dp(np.zeros((4, 2)))) != 0      # train index out of range
