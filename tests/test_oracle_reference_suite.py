@@ -387,3 +387,39 @@ def test_mps_normalization_and_marginals_vs_brute_force(z):
     assert math.isclose(math.exp(logz), zn, rel_tol=1e-12)
     O.mps_normalize(pc)
     assert math.isclose(float(O.mps_normalization(pc)), 1.0, rel_tol=1e-12)
+
+
+# ---- two-site pieces (src/utils.jl:37-44, src/abstract_tensor_train.jl:283-308, src/tensor_train.jl:320-349) --------
+@pytest.mark.parametrize("lr", ["left", "right"])
+def test_merge_split_and_data_environments_invariants(lr):
+    """_split_tensor(_merge_tensors(A, B)) reproduces the product and leaves the requested factor orthonormal; the
+    per-datapoint environments give back evaluate (grad_evaluate_two_site's `val`, tensor_train.jl:339-349)."""
+    rng = RNG(820)
+    q = (2, 3)
+    ts = [rng.standard_normal(s + q) for s in [(1, 4), (4, 6), (6, 3), (3, 1)]]
+    A = O.TensorTrain([a.copy() for a in ts])
+    C = O.merge_tensors(A[1], A[2])
+    assert C.shape == (4, 3) + q + q
+    x1, x2 = (1, 2), (0, 1)
+    assert np.allclose(C[(slice(None), slice(None)) + x1 + x2], A[1][(slice(None), slice(None)) + x1] @ A[2][(slice(None), slice(None)) + x2])
+    a, b = O.split_tensor(C, O.TruncBond(6), lr)
+    assert np.allclose(O.merge_tensors(a, b), C, rtol=1e-12, atol=1e-13)
+    if lr == "left":
+        assert O.is_left_canonical(a)
+    else:
+        assert O.is_right_canonical(b)
+    a4, b4 = O.split_tensor(C, O.TruncBond(2), lr)
+    assert a4.shape[1] == b4.shape[0] == 2
+    X = [tuple(int(rng.integers(0, v)) for v in q) for _ in range(4)]
+    pl, pr = O.precompute_left_environments(A, X), O.precompute_right_environments(A, X)
+    assert pl[0].shape == (1, 1) and pr[4].shape == (1, 1)
+    for k in range(3):   # val = Ax_left * Ax_center * Ax_right / z
+        center = O.merge_tensors(A[k], A[k + 1])[(slice(None), slice(None)) + X[k] + X[k + 1]]
+        assert math.isclose((pl[k] @ center @ pr[k + 2]).item(), O.evaluate(A, X), rel_tol=1e-12)
+    A.tensors[1], A.tensors[2] = a, b
+    O.update_environments([pl], [pr], A, 1, [X], lr)
+    assert math.isclose(O.evaluate(A, X), O.evaluate(O.TensorTrain(ts), X), rel_tol=1e-10)       # the split changed the gauge only
+    if lr == "left":
+        assert np.allclose(pl[2], pl[1] @ a[(slice(None), slice(None)) + X[1]])
+    else:
+        assert np.allclose(pr[2], b[(slice(None), slice(None)) + X[2]] @ pr[3])
