@@ -224,6 +224,14 @@ int ttb_mps_marginals(ttb_handle h, int64_t b, double* out);
 int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* out);
 int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index, const double* uniforms,
                    uint8_t* x_out, double* p_out);
+/* the same with the keyword arguments l= / r= / rz= (mps.jl:176-177, 206-208, 264-265): environments as
+ * ttb_mps_accumulate(normalize = 1) returned them (host or device memory), NULL = compute here like the reference's
+ * default keyword; z_logabs = log z of accumulate_R (the second element of rz).  M= of twovar_marginals has no
+ * counterpart: accumulate_M is streamed. */
+int ttb_mps_marginals_env(ttb_handle h, int64_t b, const double* l_env, const double* r_env, double* out);
+int ttb_mps_twovar_marginals_env(ttb_handle h, int64_t b, const double* l_env, const double* r_env, int64_t maxdist, double* out);
+int ttb_mps_sample_env(ttb_handle h, int64_t b, const double* r_env, double z_logabs, int64_t nsamples, uint64_t seed,
+                       uint64_t first_index, const double* uniforms, uint8_t* x_out, double* p_out);
 
 /* ---- two-site pieces (the data-parallel parts of 2-site DMRG, src/dmrg.jl:59-151; the optimisation loop itself is
  *      host control flow and not part of the library).  `t` is the 0-based index of the first site of the pair.

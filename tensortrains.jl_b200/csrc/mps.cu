@@ -374,6 +374,19 @@ static int mps_sandwich_R(ttb_tt* h, const MpsPlan& p) {
   return TTB_OK;
 }
 
+// the keyword arguments l= / r= / rz= of marginals, twovar_marginals and sample! for an MPS (mps.jl:176-177, 206-208,
+// 264-265): a caller-supplied environment (the array ttb_mps_accumulate returned: host or device memory) is copied into
+// the workspace slot instead of being recomputed; NULL = the reference's default keyword (compute it here)
+static int mps_provide_env(ttb_tt* h, const MpsPlan& p, bool left, const double* given, double* d_zout) {
+  if (!given) return mps_env(h, p, left, 1, d_zout);
+  Workspace& w = h->ws;
+  const int64_t n = left ? p.eoffL[p.L] : p.eoffR[p.L];
+  if (w.mps[left ? 0 : 1].ensure(sizeof(double) * std::max<int64_t>(n, 1)) != cudaSuccess) return fail(TTB_ENOMEM, "MPS environments");
+  TTB_TRY(mps_ensure_id4(h, p));
+  TTB_CUDA(cudaMemcpyAsync(w.mps[left ? 0 : 1].p, given, sizeof(double) * n, cudaMemcpyDefault, h->stream));
+  return TTB_OK;
+}
+
 }  // namespace ttb
 
 using namespace ttb;
@@ -406,7 +419,9 @@ int ttb_mps_accumulate(ttb_handle h, int64_t b, int left, int normalize, double*
   return TTB_OK;
 }
 
-int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) {
+int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) { return ttb_mps_marginals_env(h, b, nullptr, nullptr, out); }
+
+int ttb_mps_marginals_env(ttb_handle h, int64_t b, const double* l_env, const double* r_env, double* out) {
   if (!out) return fail(TTB_EINVAL, "null argument");
   MpsPlan p;
   TTB_TRY(mps_plan(h, b, p));
@@ -415,8 +430,8 @@ int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) {
   if (w.mps[8].ensure(sizeof(double) * ((size_t)L * Q + 32)) != cudaSuccess) return fail(TTB_ENOMEM, "MPS outputs");
   double* d_p = static_cast<double*>(w.mps[8].p) + 32;
   CallTimer tm(h);
-  int rc = mps_env(h, p, true, 1, nullptr);
-  if (rc == TTB_OK) rc = mps_env(h, p, false, 1, nullptr);
+  int rc = mps_provide_env(h, p, true, l_env, nullptr);
+  if (rc == TTB_OK) rc = mps_provide_env(h, p, false, r_env, nullptr);
   if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
   if (rc != TTB_OK) return rc;
   const double* l = static_cast<const double*>(w.mps[0].p);
@@ -447,6 +462,10 @@ int ttb_mps_marginals(ttb_handle h, int64_t b, double* out) {
 }
 
 int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* out) {
+  return ttb_mps_twovar_marginals_env(h, b, nullptr, nullptr, maxdist, out);
+}
+
+int ttb_mps_twovar_marginals_env(ttb_handle h, int64_t b, const double* l_env, const double* r_env, int64_t maxdist, double* out) {
   if (!out) return fail(TTB_EINVAL, "null argument");
   MpsPlan p;
   TTB_TRY(mps_plan(h, b, p));
@@ -465,8 +484,8 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
   if (e != cudaSuccess) return fail(TTB_ENOMEM, "MPS pair marginals: %s", cudaGetErrorString(e));
   double* d_out = static_cast<double*>(w.mps[8].p) + 32;
   CallTimer tm(h);
-  int rc = mps_env(h, p, true, 1, nullptr);
-  if (rc == TTB_OK) rc = mps_env(h, p, false, 1, nullptr);
+  int rc = mps_provide_env(h, p, true, l_env, nullptr);
+  if (rc == TTB_OK) rc = mps_provide_env(h, p, false, r_env, nullptr);
   if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
   if (rc != TTB_OK) return rc;
   // (mps_env used mps[2] as its temporary: it is free again from here)
@@ -593,6 +612,11 @@ int ttb_mps_twovar_marginals(ttb_handle h, int64_t b, int64_t maxdist, double* o
 
 int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uint64_t first_index, const double* uniforms,
                    uint8_t* x_out, double* p_out) {
+  return ttb_mps_sample_env(h, b, nullptr, 0.0, nsamples, seed, first_index, uniforms, x_out, p_out);
+}
+
+int ttb_mps_sample_env(ttb_handle h, int64_t b, const double* r_env, double z_logabs, int64_t nsamples, uint64_t seed,
+                       uint64_t first_index, const double* uniforms, uint8_t* x_out, double* p_out) {
   if (!x_out) return fail(TTB_EINVAL, "null x_out");
   if (nsamples < 0) return fail(TTB_EINVAL, "nsamples must be >= 0");
   if (nsamples == 0) return TTB_OK;
@@ -609,7 +633,12 @@ int ttb_mps_sample(ttb_handle h, int64_t b, int64_t nsamples, uint64_t seed, uin
   uint8_t* d_x = reinterpret_cast<uint8_t*>(d_pq + nsamples + (uniforms ? (size_t)nsamples * L : 0));
   if (uniforms) TTB_CUDA(cudaMemcpyAsync(d_u, uniforms, sizeof(double) * nsamples * L, cudaMemcpyHostToDevice, h->stream));
   CallTimer tm(h);
-  int rc = mps_env(h, p, false, 1, d_z);          // rz = accumulate_R(p) (mps.jl:265)
+  int rc = mps_provide_env(h, p, false, r_env, d_z);          // rz = accumulate_R(p) (mps.jl:265), or the caller's (r, z)
+  if (rc == TTB_OK && r_env) {
+    const double hz[2] = {z_logabs, 1.0};
+    cudaMemcpyAsync(d_z, hz, sizeof(hz), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);   // hz is a stack array
+  }
   if (rc == TTB_OK) rc = mps_sandwich_R(h, p);
   if (rc != TTB_OK) return rc;
   std::vector<int64_t> tab(3 * (L + 1));

@@ -123,6 +123,9 @@ _sig("ttb_data_env_update", _h, _i64, C.POINTER(C.c_int32), _i64, _i64, C.c_int,
 _sig("ttb_mps_env_size", _h, _i64, C.c_int, _pi64)
 _sig("ttb_mps_accumulate", _h, _i64, C.c_int, C.c_int, _pd, _pd, _pi)
 _sig("ttb_mps_marginals", _h, _i64, _pd)
+_sig("ttb_mps_marginals_env", _h, _i64, _pd, _pd, _pd)
+_sig("ttb_mps_twovar_marginals_env", _h, _i64, _pd, _pd, _i64, _pd)
+_sig("ttb_mps_sample_env", _h, _i64, _pd, C.c_double, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
 _sig("ttb_mps_twovar_marginals", _h, _i64, _i64, _pd)
 _sig("ttb_mps_sample", _h, _i64, _i64, C.c_uint64, C.c_uint64, _pd, C.POINTER(C.c_uint8), _pd)
 _sig("ttb_last_timing", _h, _pd, _pi64)
@@ -1121,23 +1124,50 @@ def mps_accumulate_R(p: MPS, normalize: bool = True):
     return _mps_accumulate(p, False, normalize)
 
 
-def mps_marginals(p: MPS):
-    """``marginals(p::MPS)`` (mps.jl:176-196): list over sites of arrays shaped ``q``"""
+def _mps_pack_env(envs, left: bool):
+    """list of the reference's four-index arrays (what mps_accumulate_L / _R returned) -> the device layout"""
+    if envs is None:
+        return None
+    parts = []
+    for e in envs:
+        e = np.asarray(e, dtype=np.float64)
+        if e.ndim != 4:
+            raise ValueError("ArgumentError: an MPS environment is a list of four-index arrays")
+        blk = e.transpose(1, 3, 0, 2) if left else e.transpose(0, 2, 1, 3)      # -> [a, b, a1, b1]
+        parts.append(np.reshape(blk, -1, order="F"))
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+def _mps_check_env(A, buf, left: bool, name: str):
+    if buf is None:
+        return None
+    n = _i64()
+    _ck(lib.ttb_mps_env_size(A._hd, 0, int(left), C.byref(n)))
+    if buf.size != n.value:
+        raise ValueError(f"ArgumentError: {name}= does not fit this train (expected {n.value} values, got {buf.size})")
+    return _dp(buf)
+
+
+def mps_marginals(p: MPS, l=None, r=None):
+    """``marginals(p::MPS; l, r)`` (mps.jl:176-196): list over sites of arrays shaped ``q``; ``l`` / ``r``: the lists
+    ``mps_accumulate_L(p)[0]`` / ``mps_accumulate_R(p)[0]`` computed once for many calls"""
     A = p.psi
+    lb, rb = _mps_pack_env(l, True), _mps_pack_env(r, False)
     out = np.zeros((A.L, A.Q))
-    _ck(lib.ttb_mps_marginals(A._hd, 0, _dp(out)))
+    _ck(lib.ttb_mps_marginals_env(A._hd, 0, _mps_check_env(A, lb, True, "l"), _mps_check_env(A, rb, False, "r"), _dp(out)))
     return [out[t].reshape(A.q, order="F") for t in range(A.L)]
 
 
-def mps_twovar_marginals(p: MPS, maxdist: Optional[int] = None):
-    """``twovar_marginals(p::MPS)`` (mps.jl:206-232): dict ``(t, u) -> (q..., q...)`` array, 0-based ``t < u <= t + maxdist``"""
+def mps_twovar_marginals(p: MPS, maxdist: Optional[int] = None, l=None, r=None, M=None):
+    """``twovar_marginals(p::MPS; l, r, M, maxdist)`` (mps.jl:206-232): dict ``(t, u) -> (q..., q...)`` array, 0-based
+    ``t < u <= t + maxdist``.  ``M`` is accepted for signature parity and not read (``accumulate_M`` is streamed)."""
     A = p.psi
     md = A.L - 1 if maxdist is None else int(maxdist)
     n = _i64()
     _ck(lib.ttb_twovar_count(A._hd, md, C.byref(n)))
     out = np.zeros((max(n.value, 1), A.Q * A.Q))
-    if n.value:
-        _ck(lib.ttb_mps_twovar_marginals(A._hd, 0, md, _dp(out)))
+    lb, rb = _mps_pack_env(l, True), _mps_pack_env(r, False)
+    _ck(lib.ttb_mps_twovar_marginals_env(A._hd, 0, _mps_check_env(A, lb, True, "l"), _mps_check_env(A, rb, False, "r"), md, _dp(out)))
     d, i = {}, 0
     for t in range(A.L - 1):
         for u in range(t + 1, min(A.L - 1, t + md) + 1):
@@ -1146,8 +1176,9 @@ def mps_twovar_marginals(p: MPS, maxdist: Optional[int] = None):
     return d
 
 
-def mps_sample(p: MPS, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None):
-    """``sample(p::MPS)`` (mps.jl:264-290, 300-313): ``(X, q)`` like :func:`sample`; ``q = |tr Q|^2 / z``"""
+def mps_sample(p: MPS, nsamples: Optional[int] = None, seed: int = 0, first_index: int = 0, uniforms=None, rz=None):
+    """``sample(p::MPS; rz)`` (mps.jl:264-290, 300-313): ``(X, q)`` like :func:`sample`; ``q = |tr Q|^2 / z``;
+    ``rz = mps_accumulate_R(p)`` computed once for many calls"""
     A = p.psi
     single = nsamples is None and uniforms is None
     if uniforms is not None:
@@ -1157,8 +1188,13 @@ def mps_sample(p: MPS, nsamples: Optional[int] = None, seed: int = 0, first_inde
         n = 1 if nsamples is None else int(nsamples)
     X = np.zeros((max(n, 1), A.L), dtype=np.uint8)
     q = np.zeros(max(n, 1))
-    _ck(lib.ttb_mps_sample(A._hd, 0, n, seed, first_index, _dp(uniforms) if uniforms is not None else None,
-                           X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(q)))
+    rb, zl = None, 0.0
+    if rz is not None:
+        renv, z = rz
+        rb = _mps_pack_env(renv, False)
+        zl = z.logabs if isinstance(z, Logarithmic) else math.log(abs(float(z)))
+    _ck(lib.ttb_mps_sample_env(A._hd, 0, _mps_check_env(A, rb, False, "rz"), zl, n, seed, first_index,
+                               _dp(uniforms) if uniforms is not None else None, X.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(q)))
     if single:
         return X[0].astype(np.int64), float(q[0])
     return X[:n].astype(np.int64), q[:n]

@@ -799,6 +799,17 @@ def test_mps_environments_marginals_sampling_match_oracle(case):
         xo, qo = O.mps_sample(lambda t: us[i, t], po, rz=zR)
         flat = [int(np.ravel_multi_index(x, psi.q, order="F")) for x in xo]
         assert list(X[i]) == flat and close(qg[i], qo, 1e-9)
+    # keyword arguments l=, r=, rz= (mps.jl:176-177, 206-208, 264-265): same results, the accumulate passes paid once
+    lg, _ = T.mps_accumulate_L(p)
+    rg, zr = T.mps_accumulate_R(p)
+    for a, b in zip(T.mps_marginals(p), T.mps_marginals(p, l=lg, r=rg)):
+        assert np.allclose(a, b, rtol=1e-13, atol=0)
+    b2 = T.mps_twovar_marginals(p, l=lg, r=rg)
+    assert all(np.allclose(b2[k], bg[k], rtol=1e-12, atol=0) for k in bg)
+    Xr, qr = T.mps_sample(p, uniforms=us, rz=(rg, zr))
+    assert np.array_equal(Xr, X) and np.allclose(qr, qg, rtol=1e-12)
+    with pytest.raises(ValueError):
+        T.mps_marginals(p, l=lg[:-1])
     X1, q1 = T.mps_sample(p, 300, seed=5)
     X2, q2 = T.mps_sample(p, 100, seed=5, first_index=200)
     assert np.array_equal(X1[200:], X2) and np.allclose(q1[200:], q2, rtol=1e-13)     # Philox counter = global draw index
