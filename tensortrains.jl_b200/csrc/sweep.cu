@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(MAXT) k_jacobi(SweepCtx c, StepDesc s, int sme
 #include "jacobi_cluster.cuh"
 #include "jacobi_small.cuh"
 #include "jacobi_sys.cuh"
+#include "jacobi_lq.cuh"
 namespace ttb {
 
 // ---------------------------------------------------------------------------------------------
@@ -1476,6 +1477,10 @@ static int enqueue_sweep(ttb_tt* h, int dir, const ttb_trunc* tr, const std::vec
           auto ks = k_jacobi_small<64, 64>;
           SW_LAUNCH("k_jacobi", ks, B, thr, sizeof(double) * (2 * 64 + 2 * 64 * 64), c, s);
         }
+      } else if (nv_ub <= 32 && len_ub <= 256 && len_ub > 32 && getenv("TTB_JACOBI_GENERIC") == nullptr && getenv("TTB_JACOBI_LQ") != nullptr) {
+        // (opt-in, measured slower) wide folds: Householder LQ first, Jacobi on the small square factor (jacobi_lq.cuh)
+        TTB_ONCE_PER_DEVICE(h, 12) cudaFuncSetAttribute(k_jacobi_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jlq_smem());
+        SW_LAUNCH("k_jacobi", k_jacobi_lq, B, 256, jlq_smem(), c, s);
       } else if (nv_ub <= 32 && len_ub <= 256 && getenv("TTB_JACOBI_GENERIC") == nullptr) {
         auto ks = k_jacobi_small<32, 256>;
         SW_LAUNCH("k_jacobi", ks, B, std::min(512, thr), sizeof(double) * (2 * 32 + 32 * 256 + 32 * 32), c, s);
