@@ -10,11 +10,18 @@ rank compresses its own train (seed 3+rank): weak scaling, no data-path collecti
 
 JSON line keys beyond the base contract:
   roofline     dominant kernel of the step, algorithmic FLOPs per launch / CUDA-event time per launch
-               against an FP64 peak measured in this run (cuBLAS DGEMM through torch.matmul)
+               against an FP64 peak measured in this run (cuBLAS DGEMM through torch.matmul); traffic from
+               profiles/ncu_traffic.json (the committed `ncu --set full` summaries)
   cpu_baseline the CPU oracle (NumPy/SciPy-OpenBLAS gesdd restatement of the reference; Julia is not
                installed) on the same workload, host cores of this box
-  extra        the second half of the metric string: sample draws/s on config 4 (L=256,q=4,d=128), the
-               sharded 4096-train batch of config 5, and the randn fill of config 3
+  parity_in_run  retained bond dimensions of the timed compress! against the CPU arm's on the same input
+  extra        every other BASELINE.json configuration, each with its own CPU value and in-run parity check:
+               sample (config 4 at 10^8 draws, strong-scaled over the ranks), batch (config 5: 4096 periodic
+               trains sharded over the ranks, pair marginals all-gathered between device buffers), config2,
+               randn_fill (config 3 with the full-rank fill, L = 256), pairs_of_one_train (the third sharding
+               axis of SURVEY 8e).  At N > 1 rank 0 repeats every sharded leg alone in the same job and the line
+               carries speedup_vs_1gpu next to an identity check of the results.
+A failed parity / identity check is recorded in the line and fails the run (exit code) AFTER the line is printed.
 `--impl reference` times the CPU oracle (the reference's algorithm; kind "port") on a bounded sample
 (`--fill randn` = the full-rank fill of config 3, reported as extra.randn_fill of the main arm); when the sample
 is the full chain its line carries the retained bond dimensions, and the main arm asserts the CUDA path's are
