@@ -456,7 +456,8 @@ def main():
             The pair marginals are written to a DEVICE tensor (no pageable staging)."""
             nb_ = hi - lo
             A = T.PeriodicTensorTrain.empty([D5] * (L5 + 1), (Q5,), batch=nb_)
-            A.upload_all(gen5(lo, hi))
+            packed_ = gen5(lo, hi)                              # generated once, uploaded twice (warm-up copy and timed copy)
+            A.upload_all(packed_)
             T._ck(T.lib.ttb_twovar_count(A._hd, L5 - 1, C.byref(npair)))
             npr = int(npair.value)
             dev_out = torch.empty((nb_, npr, Q5 * Q5), dtype=torch.float64, device=dev)
@@ -479,7 +480,8 @@ def main():
                 return lz, ms
             Wm = A.copy()
             pipeline(Wm)                                       # warm-up on the SAME handle (workspaces, scratch)
-            Wm.reset(); Wm.upload_all(gen5(lo, hi))            # fresh input in the warmed handle
+            Wm.reset(); Wm.upload_all(packed_)                 # fresh input in the warmed handle
+            del packed_
             gathered = gather and world > 1 and B5 % world == 0
             host = pin_pairs((B5 if gathered else nb_, npr, Q5 * Q5))   # pinned destination exists before the clock starts
             full_dev = torch.empty((B5, npr, Q5 * Q5), dtype=torch.float64, device=dev) if gathered else dev_out
